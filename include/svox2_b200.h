@@ -1,0 +1,218 @@
+/*
+ * svox2_b200.h -- C-ABI of the B200-native Plenoxels hot path (libsvox2_b200.so).
+ *
+ * One entry point per operator the reference exports from its pybind module `svox2.csrc`
+ * (svox2/csrc/svox2.cpp:74-172).  Signatures take raw DEVICE pointers, sizes, POD option
+ * structs and a cudaStream_t; they never allocate through a framework, never synchronise
+ * the device and return an int status (0 = ok).  On failure svox2_last_error() holds a
+ * message.  The reference prints CUDA errors and carries on (cuda_util.cuh:18-21); here
+ * they are returned so the host shim can raise.
+ *
+ * Conventions
+ *   - All pointers are device pointers on the CURRENT device unless marked HOST.
+ *   - float32 data, int32 links, uint8 (bool) masks, as in the reference
+ *     (data_spec.hpp:18-135).  Tensors are dense row-major; the two data arrays carry an
+ *     explicit row stride so that 16-byte padded rows (stride 28/32) can be used:
+ *     sh_stride == 3*basis_dim and density_stride == 1 reproduce the reference layout.
+ *   - Gradient outputs are ACCUMULATED into (atomic add), masks are OR-ed into
+ *     (render_util.cuh:137-141); callers zero them as the reference's callers do.
+ *   - Kernels are enqueued on `stream` (the reference uses the legacy default stream).
+ *   - Limits: Q*32, X*Y*Z and N*sh_stride must fit in int64 (the reference: int32).
+ */
+#ifndef SVOX2_B200_H
+#define SVOX2_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SVOX2_API __attribute__((visibility("default")))
+#else
+#define SVOX2_API
+#endif
+
+typedef struct CUstream_st* svox2_stream_t; /* == cudaStream_t */
+
+enum {
+    SVOX2_OK = 0,
+    SVOX2_ERR_INVALID = 1, /* bad argument (the reference: TORCH_CHECK / spec.check())      */
+    SVOX2_ERR_CUDA = 2,    /* CUDA runtime / launch error                                   */
+    SVOX2_ERR_WORKSPACE = 3 /* workspace too small                                          */
+};
+
+/* SparseGridSpec (data_spec.hpp:18-67) + PackedSparseGridSpec (data_spec_packed.cuh:11-62) */
+typedef struct {
+    const float* density_data;      /* [N, density_stride], channel 0 is sigma               */
+    const float* sh_data;           /* [N, sh_stride], first 3*basis_dim floats are used     */
+    const int32_t* links;           /* [X, Y, Z] contiguous                                  */
+    int32_t size[3];                /* X, Y, Z                                               */
+    int32_t basis_dim;              /* 1, 4 or 9 (SH only: basis_type == 1)                  */
+    int64_t n_rows;                 /* N                                                     */
+    int64_t sh_stride;              /* floats between consecutive sh rows                    */
+    int64_t density_stride;         /* floats between consecutive density rows               */
+    float offset[3];                /* SparseGridSpec._offset  (HOST values, by value)       */
+    float scaling[3];               /* SparseGridSpec._scaling                               */
+    const int32_t* background_links; /* [2R, R] or NULL                                      */
+    const float* background_data;   /* [Nbg, L, 4] or NULL                                   */
+    int32_t background_reso;        /* R                                                     */
+    int32_t background_nlayers;     /* L; 0 disables the MSI                                 */
+    int64_t background_rows;        /* Nbg                                                   */
+} svox2_grid_t;
+
+/* RenderOptions (data_spec.hpp:115-135) */
+typedef struct {
+    float background_brightness;
+    float step_size;
+    float sigma_thresh;
+    float stop_thresh;
+    float near_clip;
+    int32_t use_spheric_clip;
+    int32_t last_sample_opaque;
+} svox2_render_opts_t;
+
+/* CameraSpec (data_spec.hpp:82-103): c2w stays on the device, as in the reference */
+typedef struct {
+    const float* c2w;               /* device, [3 or 4, 4] row-major                         */
+    float fx, fy, cx, cy;
+    int32_t width, height;
+    float ndc_coeffx, ndc_coeffy;   /* <= 0 disables NDC                                     */
+} svox2_camera_t;
+
+/* GridOutputGrads (data_spec.hpp:69-80); strides are those of the matching data arrays */
+typedef struct {
+    float* grad_density_out;        /* [N, density_stride] or NULL                           */
+    float* grad_sh_out;             /* [N, sh_stride] or NULL                                */
+    float* grad_background_out;     /* [Nbg, L, 4] or NULL                                   */
+    uint8_t* mask_out;              /* [N] or NULL                                           */
+    uint8_t* mask_background_out;   /* [Nbg, L] or NULL                                      */
+} svox2_grads_t;
+
+/* Extension (not in the reference): per-batch march-loop iteration counts, the unit of the
+ * roofline model.  Device array of 4 int64: skip, visited, active, bg. */
+#define SVOX2_N_COUNTERS 4
+
+SVOX2_API const char* svox2_last_error(void);
+SVOX2_API const char* svox2_version(void);
+/* 1 if a CUDA device is usable from this process (lets host code fail loudly). */
+SVOX2_API int svox2_cuda_available(void);
+
+/* Scratch bytes the renderer entry points need for Q rays (log_transmit + accum). */
+SVOX2_API size_t svox2_render_workspace_bytes(int64_t n_rays);
+
+/* volume_render_cuvol  (svox2.cpp:18, render_lerp_kernel_cuvol.cu:918-958)
+ * out [Q,3].  counters may be NULL. */
+SVOX2_API int svox2_volume_render_cuvol(const svox2_grid_t* grid, const float* origins, const float* dirs,
+                              int64_t n_rays, const svox2_render_opts_t* opt, float* out,
+                              void* workspace, size_t workspace_bytes, int64_t* counters,
+                              svox2_stream_t stream);
+
+/* volume_render_cuvol_image  (svox2.cpp:19-20, cuvol.cu:960-1008); out [H,W,3].
+ * row_begin/row_end restrict the render to image rows [row_begin,row_end) (multi-GPU row
+ * sharding); pass 0,height for the reference behaviour.  workspace for (row_end-row_begin)*W rays. */
+SVOX2_API int svox2_volume_render_cuvol_image(const svox2_grid_t* grid, const svox2_camera_t* cam,
+                                    const svox2_render_opts_t* opt, int32_t row_begin,
+                                    int32_t row_end, float* out, void* workspace,
+                                    size_t workspace_bytes, svox2_stream_t stream);
+
+/* volume_render_cuvol_backward  (svox2.cpp:21-23, cuvol.cu:1010-1068) */
+SVOX2_API int svox2_volume_render_cuvol_backward(const svox2_grid_t* grid, const float* origins,
+                                       const float* dirs, int64_t n_rays,
+                                       const svox2_render_opts_t* opt, const float* grad_out,
+                                       const float* color_cache, const svox2_grads_t* grads,
+                                       void* workspace, size_t workspace_bytes,
+                                       svox2_stream_t stream);
+
+/* volume_render_cuvol_fused  (svox2.cpp:24-26, cuvol.cu:1070-1152)
+ * norm_rays: ray count used in the MSE normalisation 2/(3*norm_rays) and beta_loss/norm_rays.
+ * The reference uses the local batch size (cuvol.cu:736,1127): pass n_rays for drop-in
+ * behaviour, the GLOBAL batch size when the batch is sharded over GPUs. */
+SVOX2_API int svox2_volume_render_cuvol_fused(const svox2_grid_t* grid, const float* origins,
+                                    const float* dirs, int64_t n_rays, int64_t norm_rays,
+                                    const svox2_render_opts_t* opt, const float* rgb_gt,
+                                    float beta_loss, float sparsity_loss, float* rgb_out,
+                                    const svox2_grads_t* grads, void* workspace,
+                                    size_t workspace_bytes, int64_t* counters,
+                                    svox2_stream_t stream);
+
+/* volume_render_expected_term / volume_render_sigma_thresh (svox2.cpp:27-30, cuvol.cu:1154-1195) */
+SVOX2_API int svox2_volume_render_expected_term(const svox2_grid_t* grid, const float* origins,
+                                      const float* dirs, int64_t n_rays,
+                                      const svox2_render_opts_t* opt, float* out,
+                                      svox2_stream_t stream);
+SVOX2_API int svox2_volume_render_sigma_thresh(const svox2_grid_t* grid, const float* origins,
+                                     const float* dirs, int64_t n_rays,
+                                     const svox2_render_opts_t* opt, float sigma_thresh,
+                                     float* out, svox2_stream_t stream);
+
+/* sample_grid / sample_grid_backward  (svox2.cpp:11-17, svox2_kernel.cu:178-267)
+ * out_density [P,1]; out_sh [P,3*basis_dim] or NULL (want_colors=false).
+ * Unlike the reference no extra streams are created and nothing is synchronised. */
+SVOX2_API int svox2_sample_grid(const svox2_grid_t* grid, const float* points, int64_t n_points,
+                      float* out_density, float* out_sh, svox2_stream_t stream);
+SVOX2_API int svox2_sample_grid_backward(const svox2_grid_t* grid, const float* points, int64_t n_points,
+                               const float* grad_out_density, const float* grad_out_sh,
+                               float* grad_density_out, float* grad_sh_out,
+                               svox2_stream_t stream);
+
+/* dilate  (svox2.cpp:60, misc_kernel.cu:20-48,339-354): 3x3x3 OR, clamped borders. */
+SVOX2_API int svox2_dilate(const uint8_t* grid, int32_t X, int32_t Y, int32_t Z, uint8_t* out,
+                 svox2_stream_t stream);
+
+/* accel_dist_prop  (svox2.cpp:61, misc_kernel.cu:109-181,356-416): in place on links.
+ * workspace >= svox2_accel_workspace_bytes(X,Y,Z). */
+SVOX2_API size_t svox2_accel_workspace_bytes(int32_t X, int32_t Y, int32_t Z);
+SVOX2_API int svox2_accel_dist_prop(int32_t* links, int32_t X, int32_t Y, int32_t Z, void* workspace,
+                          size_t workspace_bytes, svox2_stream_t stream);
+
+/* grid_weight_render  (svox2.cpp:62-65, misc_kernel.cu:184-334,418-445)
+ * data / grid_weight_out dense [X,Y,Z]; offset/scaling DEVICE float[3] as in the reference. */
+SVOX2_API int svox2_grid_weight_render(const float* data, int32_t X, int32_t Y, int32_t Z,
+                             const svox2_camera_t* cam, float step_size, float stop_thresh,
+                             int32_t last_sample_opaque, const float* offset,
+                             const float* scaling, float* grid_weight_out,
+                             svox2_stream_t stream);
+
+/* tv / tv_grad / tv_grad_sparse / msi_tv_grad_sparse  (svox2.cpp:32-49, loss_kernel.cu:482-641)
+ * data [N, data_stride] with ddim logical channels.  tv: *out (device scalar) is overwritten. */
+SVOX2_API int svox2_tv(const int32_t* links, int32_t X, int32_t Y, int32_t Z, const float* data,
+             int64_t data_stride, int32_t start_dim, int32_t end_dim, int32_t ignore_edge,
+             float ndc_coeffx, float ndc_coeffy, float* out, svox2_stream_t stream);
+SVOX2_API int svox2_tv_grad(const int32_t* links, int32_t X, int32_t Y, int32_t Z, const float* data,
+                  int64_t data_stride, int32_t start_dim, int32_t end_dim, float scale,
+                  int32_t ignore_edge, float ndc_coeffx, float ndc_coeffy, float* grad_data,
+                  svox2_stream_t stream);
+/* scale_cells: the cell count the scale is divided by (the reference: n_cells,
+ * loss_kernel.cu:584-595; the global count when cells are sharded over GPUs). */
+SVOX2_API int svox2_tv_grad_sparse(const int32_t* links, int32_t X, int32_t Y, int32_t Z,
+                         const float* data, int64_t data_stride, const int32_t* rand_cells,
+                         int64_t n_cells, int64_t scale_cells, uint8_t* mask_out,
+                         int32_t start_dim, int32_t end_dim, float scale, int32_t ignore_edge,
+                         int32_t ignore_last_z, float ndc_coeffx, float ndc_coeffy,
+                         float* grad_data, svox2_stream_t stream);
+SVOX2_API int svox2_msi_tv_grad_sparse(const int32_t* background_links, int32_t reso, const float* msi,
+                             int32_t nlayers, int32_t nchannels, const int32_t* rand_cells,
+                             int64_t n_cells, int64_t scale_cells, uint8_t* mask_out, float scale,
+                             float scale_last, float* grad_msi, svox2_stream_t stream);
+
+/* rmsprop_step / sgd_step  (svox2.cpp:52-58, optim_kernel.cu:154-267)
+ * data/rms/grad [rows, row_stride] with n_channels logical channels; the last channel uses
+ * lr_last (lr_last < 0 => lr).  indexer_kind: 0 dense, 1 uint8 mask[rows], 2 int64 index[n_index].
+ * The grad of every updated element is zeroed. */
+enum { SVOX2_INDEXER_DENSE = 0, SVOX2_INDEXER_MASK = 1, SVOX2_INDEXER_INDEX = 2 };
+SVOX2_API int svox2_rmsprop_step(float* data, float* rms, float* grad, int64_t rows, int32_t n_channels,
+                       int64_t row_stride, int32_t indexer_kind, const uint8_t* mask,
+                       const int64_t* index, int64_t n_index, float beta, float lr, float epsilon,
+                       float minval, float lr_last, svox2_stream_t stream);
+SVOX2_API int svox2_sgd_step(float* data, float* grad, int64_t rows, int32_t n_channels,
+                   int64_t row_stride, int32_t indexer_kind, const uint8_t* mask,
+                   const int64_t* index, int64_t n_index, float lr, float lr_last,
+                   svox2_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVOX2_B200_H */

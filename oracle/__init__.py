@@ -87,6 +87,14 @@ def lib():
     return _lib
 
 
+def set_num_threads(n: int):
+    lib().og_set_num_threads(int(n))
+
+
+def get_max_threads() -> int:
+    return int(lib().og_get_max_threads())
+
+
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 

@@ -13,6 +13,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
 
 /* ---------------------------------------------------------------------------------------
  * small helpers
@@ -20,6 +21,42 @@
 
 /* cuda_util.cuh:72-75 : lerp(a,b,w) = fmaf(w, b-a, a) */
 static inline float lerpf(float a, float b, float w) { return fmaf(w, b - a, a); }
+
+/* Multi-threading for the bench's cpu_baseline leg: the ray loops run on g_threads pthreads
+ * (dynamic chunks of 16 rays); gradient accumulation then uses a CAS loop.  With one thread
+ * (the default, what the tests use) everything is plain sequential code. */
+static int g_threads = 1;
+static inline void add_double(double* p, double v) {
+    if (g_threads <= 1) { *p += v; return; }
+    uint64_t* pu = (uint64_t*)p;
+    uint64_t old = __atomic_load_n(pu, __ATOMIC_RELAXED), neu;
+    do {
+        double d;
+        memcpy(&d, &old, 8);
+        d += v;
+        memcpy(&neu, &d, 8);
+    } while (!__atomic_compare_exchange_n(pu, &old, neu, 1, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+}
+typedef void (*range_fn)(int64_t begin, int64_t end, void* ctx);
+typedef struct { range_fn fn; void* ctx; int64_t n; int64_t next; } pfor_t;
+static void* pfor_worker(void* arg) {
+    pfor_t* p = (pfor_t*)arg;
+    for (;;) {
+        const int64_t b = __atomic_fetch_add(&p->next, 16, __ATOMIC_RELAXED);
+        if (b >= p->n) break;
+        p->fn(b, b + 16 < p->n ? b + 16 : p->n, p->ctx);
+    }
+    return NULL;
+}
+static void parallel_for(int64_t n, range_fn fn, void* ctx) {
+    if (g_threads <= 1 || n <= 16) { fn(0, n, ctx); return; }
+    pfor_t p = {fn, ctx, n, 0};
+    pthread_t th[256];
+    const int nt = g_threads > 256 ? 256 : g_threads;
+    for (int i = 1; i < nt; ++i) pthread_create(&th[i], NULL, pfor_worker, &p);
+    pfor_worker(&p);
+    for (int i = 1; i < nt; ++i) pthread_join(th[i], NULL);
+}
 static inline float minf(float a, float b) { return a < b ? a : b; }
 static inline float maxf(float a, float b) { return a > b ? a : b; }
 static inline int mini(int a, int b) { return a < b ? a : b; }
@@ -330,12 +367,12 @@ static void trace_ray_bwd(const og_grid_t* g, const og_opt_t* opt, ray_t* ray, c
                 const float curr_grad_color = sph[j % B] * grad_common;
                 trilerp_weights(ray->pos, curr_grad_color, w);
                 for (int q = 0; q < 8; ++q)
-                    if (lk[q] >= 0) gr->gsh[(int64_t)lk[q] * D + j] += (double)w[q];
+                    if (lk[q] >= 0) add_double(&gr->gsh[(int64_t)lk[q] * D + j], (double)w[q]);
             }
             trilerp_weights(ray->pos, curr_grad_sigma, w);
             for (int q = 0; q < 8; ++q)
                 if (lk[q] >= 0) {
-                    gr->gd[lk[q]] += (double)w[q];
+                    add_double(&gr->gd[lk[q]], (double)w[q]);
                     if (gr->mask) gr->mask[lk[q]] = 1;
                 }
             if (EXPF(log_transmit) < opt->stop_thresh) break;
@@ -422,8 +459,8 @@ static void trilerp_bg_backward(const ray_t* ray, const og_grid_t* g, const int3
         if (lk[q] < 0) continue;
         const int64_t row = (int64_t)lk[q] * L + ray->l[2];
         if (grad) {
-            grad[row * 4 + idx] += (double)(vals[q] * az);
-            grad[(row + 1) * 4 + idx] += (double)(vals[q] * ray->pos[2]);
+            add_double(&grad[row * 4 + idx], (double)(vals[q] * az));
+            add_double(&grad[(row + 1) * 4 + idx], (double)(vals[q] * ray->pos[2]));
         }
         if (mask) { mask[row] = 1; mask[row + 1] = 1; }
     }
@@ -567,13 +604,29 @@ static void render_one(const og_grid_t* g, const og_opt_t* o, const float* origi
     if (logT_out) *logT_out = logT;
 }
 
+typedef struct {
+    const og_grid_t* g; const og_opt_t* o; const float* origins; const float* dirs;
+    float* rgb_out; float* log_transmit; og_counts_t counts;
+} fwd_ctx_t;
+static void fwd_range(int64_t b, int64_t e, void* vctx) {
+    fwd_ctx_t* c = (fwd_ctx_t*)vctx;
+    og_counts_t loc;
+    memset(&loc, 0, sizeof(loc));
+    for (int64_t r = b; r < e; ++r)
+        render_one(c->g, c->o, c->origins + 3 * r, c->dirs + 3 * r, c->rgb_out + 3 * r,
+                   c->log_transmit ? c->log_transmit + r : NULL, &loc);
+    __atomic_fetch_add(&c->counts.s_skip, loc.s_skip, __ATOMIC_RELAXED);
+    __atomic_fetch_add(&c->counts.s_vis, loc.s_vis, __ATOMIC_RELAXED);
+    __atomic_fetch_add(&c->counts.s_act, loc.s_act, __ATOMIC_RELAXED);
+    __atomic_fetch_add(&c->counts.bg_act, loc.bg_act, __ATOMIC_RELAXED);
+}
+
 void og_volume_render(const og_grid_t* g, const og_opt_t* o, const float* origins,
                       const float* dirs, int64_t Q, float* rgb_out, float* log_transmit,
                       og_counts_t* counts) {
-    if (counts) memset(counts, 0, sizeof(*counts));
-    for (int64_t r = 0; r < Q; ++r)
-        render_one(g, o, origins + 3 * r, dirs + 3 * r, rgb_out + 3 * r,
-                   log_transmit ? log_transmit + r : NULL, counts);
+    fwd_ctx_t c = {g, o, origins, dirs, rgb_out, log_transmit, {0, 0, 0, 0}};
+    parallel_for(Q, fwd_range, &c);
+    if (counts) *counts = c.counts;
 }
 
 void og_volume_render_image(const og_grid_t* g, const og_cam_t* cam, const og_opt_t* o,
@@ -646,15 +699,27 @@ static void backward_one(const og_grid_t* g, const og_opt_t* o, const float* ori
     }
 }
 
+typedef struct {
+    const og_grid_t* g; const og_opt_t* o; const float* origins; const float* dirs;
+    const float* grad_in; const float* color_cache; int fused; int64_t norm_rays;
+    const float* logT; float beta; float sparsity; grads_t* gr;
+} bwd_ctx_t;
+static void bwd_range(int64_t b, int64_t e, void* vctx) {
+    bwd_ctx_t* c = (bwd_ctx_t*)vctx;
+    for (int64_t r = b; r < e; ++r)
+        backward_one(c->g, c->o, c->origins + 3 * r, c->dirs + 3 * r, c->grad_in + 3 * r,
+                     c->color_cache + 3 * r, c->fused, c->norm_rays, c->logT ? c->logT + r : NULL,
+                     c->beta, c->sparsity, c->gr);
+}
+
 void og_volume_render_backward(const og_grid_t* g, const og_opt_t* o, const float* origins,
                                const float* dirs, int64_t Q, const float* grad_out,
                                const float* color_cache, float* grad_density, float* grad_sh,
                                float* grad_bg, uint8_t* mask, uint8_t* mask_bg) {
     grads_t gr;
     grads_begin(g, &gr, grad_bg != NULL, mask, mask_bg);
-    for (int64_t r = 0; r < Q; ++r)
-        backward_one(g, o, origins + 3 * r, dirs + 3 * r, grad_out + 3 * r, color_cache + 3 * r, 0,
-                     Q, NULL, 0.f, 0.f, &gr);
+    bwd_ctx_t c = {g, o, origins, dirs, grad_out, color_cache, 0, Q, NULL, 0.f, 0.f, &gr};
+    parallel_for(Q, bwd_range, &c);
     grads_end(g, &gr, grad_density, grad_sh, grad_bg);
 }
 
@@ -668,9 +733,8 @@ void og_volume_render_fused(const og_grid_t* g, const og_opt_t* o, const float* 
     grads_t gr;
     grads_begin(g, &gr, grad_bg != NULL, mask, mask_bg);
     const float beta = beta_loss / (float)norm_rays; /* cuvol.cu:1127 */
-    for (int64_t r = 0; r < Q; ++r)
-        backward_one(g, o, origins + 3 * r, dirs + 3 * r, rgb_gt + 3 * r, rgb_out + 3 * r, 1,
-                     norm_rays, logT + r, beta, sparsity_loss, &gr);
+    bwd_ctx_t c = {g, o, origins, dirs, rgb_gt, rgb_out, 1, norm_rays, logT, beta, sparsity_loss, &gr};
+    parallel_for(Q, bwd_range, &c);
     grads_end(g, &gr, grad_density, grad_sh, grad_bg);
     free(logT);
 }
@@ -1139,3 +1203,7 @@ void og_sgd_step(float* data, float* grad, int64_t rows, int32_t C, int32_t inde
         }
     }
 }
+
+/* Thread control for the bench's cpu_baseline leg (1 thread = the scalar port). */
+void og_set_num_threads(int n) { g_threads = n > 0 ? n : 1; }
+int og_get_max_threads(void) { return g_threads; }

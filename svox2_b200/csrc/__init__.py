@@ -1,0 +1,546 @@
+"""Drop-in replacement for the reference's pybind module ``svox2.csrc``.
+
+Same attribute names, argument order and meaning as ``svox2/csrc/svox2.cpp:74-172`` of
+sxyu/svox2: 5 spec classes with read/write attributes and the operator functions, looked up
+by name at call time by the Python layer (``svox2.py:239,252,1125,1158-1161``).  Underneath,
+each function adapts torch tensors to raw pointers and calls the C-ABI of
+``libsvox2_b200.so`` (``include/svox2_b200.h``) on torch's CURRENT stream (the reference
+uses the legacy default stream).  Argument violations and CUDA errors raise ``RuntimeError``
+(the reference raises for the former and only prints the latter).
+
+The CUDA sources of the library live next to this file (``*.cu``, ``common.cuh``).
+"""
+import ctypes as C
+
+import torch
+
+from .. import _lib
+from .._lib import CameraT, GradsT, GridT, RenderOptsT, Svox2Error, check
+
+BASIS_TYPE_SH = 1
+
+__all__ = [
+    "SparseGridSpec", "CameraSpec", "RaysSpec", "RenderOptions", "GridOutputGrads",
+    "sample_grid", "sample_grid_backward", "volume_render_cuvol", "volume_render_cuvol_image",
+    "volume_render_cuvol_backward", "volume_render_cuvol_fused", "volume_render_expected_term",
+    "volume_render_sigma_thresh", "volume_render_nvol", "volume_render_nvol_backward",
+    "volume_render_nvol_fused", "volume_render_svox1", "volume_render_svox1_backward",
+    "volume_render_svox1_fused", "dilate", "accel_dist_prop", "grid_weight_render", "tv",
+    "tv_grad", "tv_grad_sparse", "msi_tv_grad_sparse", "lumisphere_tv_grad_sparse",
+    "rmsprop_step", "sgd_step",
+]
+
+
+# ----------------------------------------------------------------------------------------
+# spec classes (data_spec.hpp:18-135): default-constructible, plain read/write attributes;
+# an unset tensor attribute (None) means "absent" (an undefined torch::Tensor upstream).
+# ----------------------------------------------------------------------------------------
+class SparseGridSpec:
+    def __init__(self):
+        self.density_data = None
+        self.sh_data = None
+        self.links = None
+        self._offset = None
+        self._scaling = None
+        self.basis_dim = 0
+        self.basis_type = BASIS_TYPE_SH
+        self.basis_data = None
+        self.background_links = None
+        self.background_data = None
+
+
+class CameraSpec:
+    def __init__(self):
+        self.c2w = None
+        self.fx = self.fy = self.cx = self.cy = 0.0
+        self.width = self.height = 0
+        self.ndc_coeffx = self.ndc_coeffy = -1.0
+
+
+class RaysSpec:
+    def __init__(self):
+        self.origins = None
+        self.dirs = None
+
+
+class RenderOptions:
+    def __init__(self):
+        self.background_brightness = 1.0
+        self.step_size = 0.5
+        self.sigma_thresh = 1e-10
+        self.stop_thresh = 1e-7
+        self.near_clip = 0.0
+        self.use_spheric_clip = False
+        self.last_sample_opaque = False
+
+
+class GridOutputGrads:
+    def __init__(self):
+        self.grad_density_out = None
+        self.grad_sh_out = None
+        self.grad_basis_out = None
+        self.grad_background_out = None
+        self.mask_out = None
+        self.mask_background_out = None
+
+
+# ----------------------------------------------------------------------------------------
+# checks (util.hpp CHECK_INPUT / data_spec.hpp check()) and adapters
+# ----------------------------------------------------------------------------------------
+def _fail(msg):
+    raise RuntimeError(msg)
+
+
+def _defined(t):
+    return t is not None and isinstance(t, torch.Tensor)
+
+
+def _check_cuda(t, name, dtype=None, ndim=None):
+    if not _defined(t):
+        _fail(f"{name} must be a tensor")
+    if not t.is_cuda:
+        _fail(f"{name} must be a CUDA tensor")
+    if dtype is not None and t.dtype != dtype:
+        _fail(f"{name} must have dtype {dtype}, got {t.dtype}")
+    if ndim is not None and t.dim() != ndim:
+        _fail(f"{name} must have {ndim} dimensions, got {t.dim()}")
+
+
+def _check_input(t, name, dtype=None, ndim=None):
+    _check_cuda(t, name, dtype, ndim)
+    if not t.is_contiguous():
+        _fail(f"{name} must be contiguous")
+
+
+def _check_rows(t, name):
+    """2-D float32 CUDA tensor whose rows are contiguous (row stride may be padded)."""
+    _check_cuda(t, name, torch.float32, 2)
+    if t.size(0) > 1 and t.size(1) > 1 and t.stride(1) != 1:
+        _fail(f"{name} must be contiguous")
+    if t.size(0) > 1 and t.stride(0) < t.size(1):
+        _fail(f"{name} must be contiguous")
+
+
+def _row_stride(t):
+    return t.stride(0) if t.size(0) > 1 else max(t.size(1), 1)
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _host3(t, name):
+    if not _defined(t):
+        _fail(f"{name} must be a tensor")
+    if t.is_cuda:
+        _fail(f"{name} must be a CPU tensor")
+    v = t.detach().to(torch.float32).reshape(-1).tolist()
+    if len(v) != 3:
+        _fail(f"{name} must have 3 elements")
+    return v
+
+
+def _grid_struct(spec):
+    """SparseGridSpec.check() (data_spec.hpp:32-51) + PackedSparseGridSpec."""
+    _check_rows(spec.density_data, "density_data")
+    _check_rows(spec.sh_data, "sh_data")
+    _check_input(spec.links, "links", torch.int32, 3)
+    if int(spec.basis_type) != BASIS_TYPE_SH:
+        _fail("svox2_b200 supports basis_type == BASIS_TYPE_SH only (learned bases are out of scope)")
+    g = GridT()
+    g.density_data = spec.density_data.data_ptr()
+    g.sh_data = spec.sh_data.data_ptr()
+    g.links = spec.links.data_ptr()
+    g.size[:] = list(spec.links.shape)
+    g.basis_dim = int(spec.basis_dim)
+    if spec.sh_data.size(1) != 3 * g.basis_dim:
+        _fail(f"sh_data must have 3*basis_dim = {3 * g.basis_dim} channels, got {spec.sh_data.size(1)}")
+    if spec.density_data.size(0) != spec.sh_data.size(0):
+        _fail("density_data and sh_data must have the same number of rows")
+    g.n_rows = spec.sh_data.size(0)
+    g.sh_stride = _row_stride(spec.sh_data)
+    g.density_stride = _row_stride(spec.density_data)
+    g.offset[:] = _host3(spec._offset, "_offset")
+    g.scaling[:] = _host3(spec._scaling, "_scaling")
+    bl, bd = spec.background_links, spec.background_data
+    if _defined(bl) and _defined(bd) and bl.numel() > 0 and bd.numel() > 0:
+        _check_input(bl, "background_links", torch.int32, 2)
+        _check_input(bd, "background_data", torch.float32, 3)
+        if bd.size(2) != 4:
+            _fail("background_data must have 4 channels")
+        g.background_links = bl.data_ptr()
+        g.background_data = bd.data_ptr()
+        g.background_reso = bl.size(1)
+        g.background_nlayers = bd.size(1)
+        g.background_rows = bd.size(0)
+    return g
+
+
+def _opt_struct(opt):
+    return RenderOptsT(float(opt.background_brightness), float(opt.step_size),
+                       float(opt.sigma_thresh), float(opt.stop_thresh), float(opt.near_clip),
+                       int(bool(opt.use_spheric_clip)), int(bool(opt.last_sample_opaque)))
+
+
+def _rays(rays):
+    """RaysSpec.check() (data_spec.hpp:107-112)."""
+    _check_input(rays.origins, "origins", torch.float32, 2)
+    _check_input(rays.dirs, "dirs", torch.float32, 2)
+    if rays.origins.size(1) != 3 or rays.dirs.shape != rays.origins.shape:
+        _fail("origins and dirs must both be [Q, 3]")
+    return rays.origins, rays.dirs
+
+
+def _cam_struct(cam):
+    """CameraSpec.check() (data_spec.hpp:96-101); c2w stays on the device."""
+    _check_input(cam.c2w, "c2w", torch.float32, 2)
+    if cam.c2w.size(1) != 4 or cam.c2w.size(0) < 3:
+        _fail("c2w must be [3|4, 4]")
+    return CameraT(cam.c2w.data_ptr(), float(cam.fx), float(cam.fy), float(cam.cx), float(cam.cy),
+                   int(cam.width), int(cam.height), float(cam.ndc_coeffx), float(cam.ndc_coeffy))
+
+
+def _grads_struct(grads, gspec):
+    """GridOutputGrads.check() (data_spec.hpp:69-80)."""
+    gr = GradsT()
+    keep = []
+    if _defined(grads.grad_density_out):
+        _check_rows(grads.grad_density_out, "grad_density_out")
+        if _row_stride(grads.grad_density_out) != _row_stride(gspec.density_data) or \
+                grads.grad_density_out.size(0) != gspec.density_data.size(0):
+            _fail("grad_density_out must have the layout of density_data")
+        gr.grad_density_out = grads.grad_density_out.data_ptr()
+    if _defined(grads.grad_sh_out):
+        _check_rows(grads.grad_sh_out, "grad_sh_out")
+        if _row_stride(grads.grad_sh_out) != _row_stride(gspec.sh_data) or \
+                grads.grad_sh_out.size(0) != gspec.sh_data.size(0):
+            _fail("grad_sh_out must have the layout of sh_data")
+        gr.grad_sh_out = grads.grad_sh_out.data_ptr()
+    if _defined(grads.grad_background_out) and grads.grad_background_out.numel() > 0:
+        _check_input(grads.grad_background_out, "grad_background_out", torch.float32)
+        gr.grad_background_out = grads.grad_background_out.data_ptr()
+    if _defined(grads.mask_out) and grads.mask_out.numel() > 0:
+        _check_input(grads.mask_out, "mask_out", torch.bool)
+        gr.mask_out = grads.mask_out.data_ptr()
+    if _defined(grads.mask_background_out) and grads.mask_background_out.numel() > 0:
+        _check_input(grads.mask_background_out, "mask_background_out", torch.bool)
+        gr.mask_background_out = grads.mask_background_out.data_ptr()
+    return gr, keep
+
+
+def _workspace(n_rays, device):
+    nbytes = _lib.lib().svox2_render_workspace_bytes(n_rays)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    return ws, nbytes
+
+
+# ----------------------------------------------------------------------------------------
+# operators
+# ----------------------------------------------------------------------------------------
+def sample_grid(grid, points, want_colors):
+    """svox2.cpp:11-13 -> svox2_sample_grid."""
+    g = _grid_struct(grid)
+    _check_input(points, "points", torch.float32, 2)
+    P = points.size(0)
+    dev = points.device
+    out_density = torch.empty((P, grid.density_data.size(1)), dtype=torch.float32, device=dev)
+    out_sh = torch.empty((P if want_colors else 0, grid.sh_data.size(1)), dtype=torch.float32,
+                         device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().svox2_sample_grid(C.byref(g), points.data_ptr(), P, out_density.data_ptr(),
+                                           out_sh.data_ptr() if want_colors else None, _stream()))
+    return out_density, out_sh
+
+
+def sample_grid_backward(grid, points, grad_out_density, grad_out_sh, grad_density_out,
+                         grad_sh_out, want_colors):
+    """svox2.cpp:14-17 -> svox2_sample_grid_backward."""
+    g = _grid_struct(grid)
+    _check_input(points, "points", torch.float32, 2)
+    _check_input(grad_out_density, "grad_out_density", torch.float32, 2)
+    _check_input(grad_out_sh, "grad_out_sh", torch.float32, 2)
+    _check_rows(grad_density_out, "grad_density_out")
+    _check_rows(grad_sh_out, "grad_sh_out")
+    with torch.cuda.device(points.device):
+        check(_lib.lib().svox2_sample_grid_backward(
+            C.byref(g), points.data_ptr(), points.size(0), grad_out_density.data_ptr(),
+            grad_out_sh.data_ptr() if want_colors else None, grad_density_out.data_ptr(),
+            grad_sh_out.data_ptr() if want_colors else None, _stream()))
+
+
+def volume_render_cuvol(grid, rays, opt, _counters=None):
+    """svox2.cpp:18 -> svox2_volume_render_cuvol.  Returns [Q,3]."""
+    g = _grid_struct(grid)
+    origins, dirs = _rays(rays)
+    Q = origins.size(0)
+    out = torch.empty_like(origins)
+    o = _opt_struct(opt)
+    with torch.cuda.device(origins.device):
+        ws, nbytes = _workspace(Q, origins.device)
+        check(_lib.lib().svox2_volume_render_cuvol(
+            C.byref(g), origins.data_ptr(), dirs.data_ptr(), Q, C.byref(o), out.data_ptr(),
+            ws.data_ptr(), nbytes, _ptr(_counters), _stream()))
+    return out
+
+
+def volume_render_cuvol_image(grid, cam, opt, _rows=None, _out=None):
+    """svox2.cpp:19-20 -> svox2_volume_render_cuvol_image.  Returns [H,W,3].
+
+    ``_rows=(begin, end)`` (extension) renders only those image rows into ``_out``."""
+    g = _grid_struct(grid)
+    c = _cam_struct(cam)
+    o = _opt_struct(opt)
+    dev = grid.sh_data.device
+    H, W = int(cam.height), int(cam.width)
+    out = _out if _out is not None else torch.empty((H, W, 3), dtype=torch.float32, device=dev)
+    r0, r1 = (0, H) if _rows is None else _rows
+    with torch.cuda.device(dev):
+        ws, nbytes = _workspace((r1 - r0) * W, dev)
+        check(_lib.lib().svox2_volume_render_cuvol_image(
+            C.byref(g), C.byref(c), C.byref(o), r0, r1, out.data_ptr(), ws.data_ptr(), nbytes,
+            _stream()))
+    return out
+
+
+def volume_render_cuvol_backward(grid, rays, opt, grad_out, color_cache, grads):
+    """svox2.cpp:21-23 -> svox2_volume_render_cuvol_backward."""
+    g = _grid_struct(grid)
+    origins, dirs = _rays(rays)
+    _check_input(grad_out, "grad_out", torch.float32, 2)
+    _check_input(color_cache, "color_cache", torch.float32, 2)
+    gr, _ = _grads_struct(grads, grid)
+    o = _opt_struct(opt)
+    Q = origins.size(0)
+    with torch.cuda.device(origins.device):
+        ws, nbytes = _workspace(Q, origins.device)
+        check(_lib.lib().svox2_volume_render_cuvol_backward(
+            C.byref(g), origins.data_ptr(), dirs.data_ptr(), Q, C.byref(o), grad_out.data_ptr(),
+            color_cache.data_ptr(), C.byref(gr), ws.data_ptr(), nbytes, _stream()))
+
+
+def volume_render_cuvol_fused(grid, rays, opt, rgb_gt, beta_loss, sparsity_loss, rgb_out, grads,
+                              _norm_rays=None, _counters=None):
+    """svox2.cpp:24-26 -> svox2_volume_render_cuvol_fused.
+
+    ``_norm_rays`` (extension): global batch size when the batch is sharded over GPUs."""
+    g = _grid_struct(grid)
+    origins, dirs = _rays(rays)
+    _check_input(rgb_gt, "rgb_gt", torch.float32, 2)
+    _check_input(rgb_out, "rgb_out", torch.float32, 2)
+    gr, _ = _grads_struct(grads, grid)
+    o = _opt_struct(opt)
+    Q = origins.size(0)
+    with torch.cuda.device(origins.device):
+        ws, nbytes = _workspace(Q, origins.device)
+        check(_lib.lib().svox2_volume_render_cuvol_fused(
+            C.byref(g), origins.data_ptr(), dirs.data_ptr(), Q, Q if _norm_rays is None else _norm_rays,
+            C.byref(o), rgb_gt.data_ptr(), float(beta_loss), float(sparsity_loss), rgb_out.data_ptr(),
+            C.byref(gr), ws.data_ptr(), nbytes, _ptr(_counters), _stream()))
+
+
+def volume_render_expected_term(grid, rays, opt):
+    """svox2.cpp:27-28 -> svox2_volume_render_expected_term.  Returns [Q]."""
+    g = _grid_struct(grid)
+    origins, dirs = _rays(rays)
+    o = _opt_struct(opt)
+    out = torch.empty((origins.size(0),), dtype=torch.float32, device=origins.device)
+    with torch.cuda.device(origins.device):
+        check(_lib.lib().svox2_volume_render_expected_term(
+            C.byref(g), origins.data_ptr(), dirs.data_ptr(), origins.size(0), C.byref(o),
+            out.data_ptr(), _stream()))
+    return out
+
+
+def volume_render_sigma_thresh(grid, rays, opt, sigma_thresh):
+    """svox2.cpp:29-30 -> svox2_volume_render_sigma_thresh.  Returns [Q]."""
+    g = _grid_struct(grid)
+    origins, dirs = _rays(rays)
+    o = _opt_struct(opt)
+    out = torch.empty((origins.size(0),), dtype=torch.float32, device=origins.device)
+    with torch.cuda.device(origins.device):
+        check(_lib.lib().svox2_volume_render_sigma_thresh(
+            C.byref(g), origins.data_ptr(), dirs.data_ptr(), origins.size(0), C.byref(o),
+            float(sigma_thresh), out.data_ptr(), _stream()))
+    return out
+
+
+def _out_of_scope(name):
+    def fn(*args, **kwargs):
+        raise NotImplementedError(
+            f"{name}: the nvol / svox1 ablation backends and the lumisphere regulariser are outside "
+            "the B200 hot path (SURVEY.md 2.1); use backend='cuvol'.")
+    fn.__name__ = name
+    return fn
+
+
+# Name-visible in the reference module (svox2.cpp:80-92); ablation backends, not built here.
+volume_render_nvol = _out_of_scope("volume_render_nvol")
+volume_render_nvol_backward = _out_of_scope("volume_render_nvol_backward")
+volume_render_nvol_fused = _out_of_scope("volume_render_nvol_fused")
+volume_render_svox1 = _out_of_scope("volume_render_svox1")
+volume_render_svox1_backward = _out_of_scope("volume_render_svox1_backward")
+volume_render_svox1_fused = _out_of_scope("volume_render_svox1_fused")
+lumisphere_tv_grad_sparse = _out_of_scope("lumisphere_tv_grad_sparse")
+
+
+def dilate(grid):
+    """svox2.cpp:60 -> svox2_dilate.  bool[X,Y,Z] -> new bool[X,Y,Z]."""
+    _check_input(grid, "grid", None, 3)
+    if grid.is_floating_point():
+        _fail("grid must not be floating point")
+    if grid.dtype != torch.bool:
+        _fail("grid must be a bool tensor")
+    out = torch.empty_like(grid)
+    X, Y, Z = grid.shape
+    with torch.cuda.device(grid.device):
+        check(_lib.lib().svox2_dilate(grid.data_ptr(), X, Y, Z, out.data_ptr(), _stream()))
+    return out
+
+
+def accel_dist_prop(grid):
+    """svox2.cpp:61 -> svox2_accel_dist_prop.  In place on the links tensor."""
+    _check_input(grid, "grid", torch.int32, 3)
+    X, Y, Z = grid.shape
+    with torch.cuda.device(grid.device):
+        nbytes = _lib.lib().svox2_accel_workspace_bytes(X, Y, Z)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=grid.device)
+        check(_lib.lib().svox2_accel_dist_prop(grid.data_ptr(), X, Y, Z, ws.data_ptr(), nbytes,
+                                               _stream()))
+
+
+def grid_weight_render(data, cam, step_size, stop_thresh, last_sample_opaque, offset, scaling,
+                       grid_weight_out):
+    """svox2.cpp:62-65 -> svox2_grid_weight_render."""
+    _check_input(data, "data", torch.float32, 3)
+    _check_input(offset, "offset", torch.float32)
+    _check_input(scaling, "scaling", torch.float32)
+    _check_input(grid_weight_out, "grid_weight_out", torch.float32, 3)
+    c = _cam_struct(cam)
+    X, Y, Z = data.shape
+    with torch.cuda.device(data.device):
+        check(_lib.lib().svox2_grid_weight_render(
+            data.data_ptr(), X, Y, Z, C.byref(c), float(step_size), float(stop_thresh),
+            int(bool(last_sample_opaque)), offset.data_ptr(), scaling.data_ptr(),
+            grid_weight_out.data_ptr(), _stream()))
+
+
+def _tv_common(links, data):
+    _check_input(links, "links", torch.int32, 3)
+    _check_rows(data, "data")
+    return links.shape
+
+
+def tv(links, data, start_dim, end_dim, use_logalpha, logalpha_delta, ignore_edge, ndc_coeffx,
+       ndc_coeffy):
+    """svox2.cpp:32-35 -> svox2_tv.  Returns a 0-dim tensor."""
+    X, Y, Z = _tv_common(links, data)
+    out = torch.empty((), dtype=torch.float32, device=data.device)
+    with torch.cuda.device(data.device):
+        check(_lib.lib().svox2_tv(links.data_ptr(), X, Y, Z, data.data_ptr(), _row_stride(data),
+                                  int(start_dim), int(end_dim), int(bool(ignore_edge)),
+                                  float(ndc_coeffx), float(ndc_coeffy), out.data_ptr(), _stream()))
+    return out
+
+
+def tv_grad(links, data, start_dim, end_dim, scale, use_logalpha, logalpha_delta, ignore_edge,
+            ndc_coeffx, ndc_coeffy, grad_data):
+    """svox2.cpp:36-40 -> svox2_tv_grad."""
+    X, Y, Z = _tv_common(links, data)
+    _check_rows(grad_data, "grad_data")
+    with torch.cuda.device(data.device):
+        check(_lib.lib().svox2_tv_grad(links.data_ptr(), X, Y, Z, data.data_ptr(), _row_stride(data),
+                                       int(start_dim), int(end_dim), float(scale),
+                                       int(bool(ignore_edge)), float(ndc_coeffx), float(ndc_coeffy),
+                                       grad_data.data_ptr(), _stream()))
+
+
+def tv_grad_sparse(links, data, rand_cells, mask_out, start_dim, end_dim, scale, use_logalpha,
+                   logalpha_delta, ignore_edge, ignore_last_z, ndc_coeffx, ndc_coeffy, grad_data,
+                   _scale_cells=0):
+    """svox2.cpp:41-46 -> svox2_tv_grad_sparse.  mask_out with dim()==0 or no elements: no mask."""
+    X, Y, Z = _tv_common(links, data)
+    _check_rows(grad_data, "grad_data")
+    _check_input(rand_cells, "rand_cells", torch.int32)
+    _check_input(mask_out, "mask_out")
+    mask_ptr = mask_out.data_ptr() if (mask_out.dim() > 0 and mask_out.numel() > 0) else None
+    if mask_ptr is not None and mask_out.dtype != torch.bool:
+        _fail("mask_out must be a bool tensor")
+    with torch.cuda.device(data.device):
+        check(_lib.lib().svox2_tv_grad_sparse(
+            links.data_ptr(), X, Y, Z, data.data_ptr(), _row_stride(data), rand_cells.data_ptr(),
+            rand_cells.size(0), int(_scale_cells), mask_ptr, int(start_dim), int(end_dim),
+            float(scale), int(bool(ignore_edge)), int(bool(ignore_last_z)), float(ndc_coeffx),
+            float(ndc_coeffy), grad_data.data_ptr(), _stream()))
+
+
+def msi_tv_grad_sparse(links, msi, rand_cells, mask_out, scale, scale_last, grad_msi,
+                       _scale_cells=0):
+    """svox2.cpp:47-49 -> svox2_msi_tv_grad_sparse."""
+    _check_input(links, "links", torch.int32, 2)
+    _check_input(msi, "msi", torch.float32, 3)
+    _check_input(grad_msi, "grad_msi", torch.float32, 3)
+    _check_input(rand_cells, "rand_cells", torch.int32)
+    _check_input(mask_out, "mask_out")
+    mask_ptr = mask_out.data_ptr() if mask_out.numel() > 0 else None
+    with torch.cuda.device(msi.device):
+        check(_lib.lib().svox2_msi_tv_grad_sparse(
+            links.data_ptr(), links.size(1), msi.data_ptr(), msi.size(1), msi.size(2),
+            rand_cells.data_ptr(), rand_cells.size(0), int(_scale_cells), mask_ptr, float(scale),
+            float(scale_last), grad_msi.data_ptr(), _stream()))
+
+
+def _indexer_args(indexer, rows):
+    """Indexer dispatch of optim_kernel.cu:175-215: 0-dim => dense, empty => skip,
+    bool => mask, otherwise int64 indices."""
+    _check_cuda(indexer, "indexer")
+    if indexer.dim() == 0:
+        return 0, None, None, 0
+    if indexer.size(0) == 0:
+        return None
+    if not indexer.is_contiguous():
+        _fail("indexer must be contiguous")
+    if indexer.dtype == torch.bool:
+        if indexer.numel() != rows:
+            _fail("bool indexer must have one entry per row")
+        return 1, indexer.data_ptr(), None, 0
+    if indexer.dtype != torch.int64:
+        _fail("indexer must be bool or int64")
+    return 2, None, indexer.data_ptr(), indexer.size(0)
+
+
+def rmsprop_step(data, rms, grad, indexer, beta, lr, epsilon, minval, lr_last):
+    """svox2.cpp:52-55 -> svox2_rmsprop_step."""
+    _check_rows(data, "data")
+    _check_rows(rms, "rms")
+    _check_rows(grad, "grad")
+    if not (_row_stride(data) == _row_stride(rms) == _row_stride(grad)):
+        _fail("data, rms and grad must share one layout")
+    sel = _indexer_args(indexer, data.size(0))
+    if sel is None:
+        return
+    kind, mask, index, n_index = sel
+    with torch.cuda.device(data.device):
+        check(_lib.lib().svox2_rmsprop_step(
+            data.data_ptr(), rms.data_ptr(), grad.data_ptr(), data.size(0), data.size(1),
+            _row_stride(data), kind, mask, index, n_index, float(beta), float(lr), float(epsilon),
+            float(minval), float(lr_last), _stream()))
+
+
+def sgd_step(data, grad, indexer, lr, lr_last):
+    """svox2.cpp:56-58 -> svox2_sgd_step."""
+    _check_rows(data, "data")
+    _check_rows(grad, "grad")
+    if _row_stride(data) != _row_stride(grad):
+        _fail("data and grad must share one layout")
+    sel = _indexer_args(indexer, data.size(0))
+    if sel is None:
+        return
+    kind, mask, index, n_index = sel
+    with torch.cuda.device(data.device):
+        check(_lib.lib().svox2_sgd_step(
+            data.data_ptr(), grad.data_ptr(), data.size(0), data.size(1), _row_stride(data), kind,
+            mask, index, n_index, float(lr), float(lr_last), _stream()))

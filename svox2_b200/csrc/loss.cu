@@ -1,0 +1,295 @@
+// Total-variation kernels: tv (value), tv_grad (dense), tv_grad_sparse, msi_tv_grad_sparse.
+// Behaviour follows the reference's loss_kernel.cu (citations per kernel).  The exact-zero
+// tests that decide mask bits use the same separately-rounded operations as the reference's
+// sm_100 SASS (FMUL by size/256, FADD sums, FFMA chain inside the rsqrt).
+#include "common.cuh"
+
+namespace svox2b {
+namespace {
+
+constexpr int TV_THREADS = 256;
+
+// calculate_ray_scale, loss_kernel.cu:22-52 (the NDC branch is commented out upstream)
+__device__ __forceinline__ void ray_scale(int X, int Y, int Z, float* s) {
+    s[0] = __fmul_rn((float)X, 1.f / 256.f);
+    s[1] = __fmul_rn((float)Y, 1.f / 256.f);
+    s[2] = __fmul_rn((float)Z, 1.f / 256.f);
+}
+
+__device__ __forceinline__ float inv_delta(float dx, float dy, float dz) {
+    return rsqrtf(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmaf_rn(dx, dx, 1e-9f))));
+}
+
+// tv_kernel, loss_kernel.cu:64-109.  Block-level sum, one atomic per block.
+__global__ void __launch_bounds__(TV_THREADS)
+tv_kernel(const int32_t* __restrict__ links, int X, int Y, int Z, const float* __restrict__ data,
+          int64_t stride, int start_dim, int end_dim, float scale, int64_t Q, int ignore_edge,
+          float* __restrict__ out) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float tresult = 0.f;
+    if (tid < Q) {
+        const int nd = end_dim - start_dim;
+        const int idx = (int)(tid % nd) + start_dim;
+        const int64_t xyz = tid / nd;
+        const int z = (int)(xyz % (Z - 1));
+        const int64_t xy = xyz / (Z - 1);
+        const int y = (int)(xy % (Y - 1));
+        const int x = (int)(xy / (Y - 1));
+        const int64_t offx = (int64_t)Y * Z;
+        const int32_t* lp = links + (x * offx + (int64_t)y * Z + z);
+        const int32_t l000 = __ldg(lp);
+        if (!(ignore_edge && l000 == 0)) {
+            float sc[3];
+            ray_scale(X, Y, Z, sc);
+            const int32_t l100 = __ldg(lp + offx), l010 = __ldg(lp + Z), l001 = __ldg(lp + 1);
+            const float v000 = l000 >= 0 ? __ldg(data + (int64_t)l000 * stride + idx) : 0.f;
+            const float nullv = ignore_edge ? v000 : 0.f;
+            const float v100 = l100 >= 0 ? __ldg(data + (int64_t)l100 * stride + idx) : nullv;
+            const float v010 = l010 >= 0 ? __ldg(data + (int64_t)l010 * stride + idx) : nullv;
+            const float v001 = l001 >= 0 ? __ldg(data + (int64_t)l001 * stride + idx) : nullv;
+            const float dx = (v100 - v000) * sc[0];
+            const float dy = (v010 - v000) * sc[1];
+            const float dz = (v001 - v000) * sc[2];
+            tresult = sqrtf(1e-5f + dx * dx + dy * dy + dz * dz);
+        }
+    }
+    // warp shuffle reduce, then one shared slot per warp
+    __shared__ float warp_sums[TV_THREADS / 32];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) tresult += __shfl_xor_sync(FULL, tresult, off);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = tresult;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < TV_THREADS / 32 ? warp_sums[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int off = 4; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
+        if (threadIdx.x == 0) atomicAdd(out, v * scale);
+    }
+}
+
+// tv_grad_kernel, loss_kernel.cu:111-176
+__global__ void __launch_bounds__(TV_THREADS)
+tv_grad_kernel(const int32_t* __restrict__ links, int X, int Y, int Z,
+               const float* __restrict__ data, int64_t stride, int start_dim, int end_dim,
+               float scale, int64_t Q, int ignore_edge, float* __restrict__ grad) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= Q) return;
+    const int nd = end_dim - start_dim;
+    const int idx = (int)(tid % nd) + start_dim;
+    const int64_t xyz = tid / nd;
+    const int z = (int)(xyz % (Z - 1));
+    const int64_t xy = xyz / (Z - 1);
+    const int y = (int)(xy % (Y - 1));
+    const int x = (int)(xy / (Y - 1));
+    const int64_t offx = (int64_t)Y * Z;
+    const int32_t* lp = links + (x * offx + (int64_t)y * Z + z);
+    const int32_t l000 = __ldg(lp);
+    if (ignore_edge && l000 == 0) return;
+    float sc[3];
+    ray_scale(X, Y, Z, sc);
+    const int32_t l100 = __ldg(lp + offx), l010 = __ldg(lp + Z), l001 = __ldg(lp + 1);
+    float v000 = 0.f, v100 = 0.f, v010 = 0.f, v001 = 0.f;
+    if (l000 >= 0) v000 = __ldg(data + (int64_t)l000 * stride + idx);
+    if (l100 >= 0) v100 = __ldg(data + (int64_t)l100 * stride + idx); else if (ignore_edge) v100 = v000;
+    if (l010 >= 0) v010 = __ldg(data + (int64_t)l010 * stride + idx); else if (ignore_edge) v010 = v000;
+    if (l001 >= 0) v001 = __ldg(data + (int64_t)l001 * stride + idx); else if (ignore_edge) v001 = v000;
+    float dx = __fsub_rn(v100, v000), dy = __fsub_rn(v010, v000), dz = __fsub_rn(v001, v000);
+    const float idelta = __fmul_rn(scale, inv_delta(dx, dy, dz));
+    dx = __fmul_rn(dx, sc[0]);
+    dy = __fmul_rn(dy, sc[1]);
+    dz = __fmul_rn(dz, sc[2]);
+    if (dx != 0.f && l100 >= 0) atomicAdd(grad + (int64_t)l100 * stride + idx, __fmul_rn(dx, idelta));
+    if (dy != 0.f && l010 >= 0) atomicAdd(grad + (int64_t)l010 * stride + idx, __fmul_rn(dy, idelta));
+    if (dz != 0.f && l001 >= 0) atomicAdd(grad + (int64_t)l001 * stride + idx, __fmul_rn(dz, idelta));
+    if (l000 >= 0)
+        atomicAdd(grad + (int64_t)l000 * stride + idx,
+                  __fmul_rn(-__fadd_rn(__fadd_rn(dx, dy), dz), idelta));
+}
+
+// tv_grad_sparse_kernel, loss_kernel.cu:178-246
+__global__ void __launch_bounds__(TV_THREADS)
+tv_grad_sparse_kernel(const int32_t* __restrict__ links, int X, int Y, int Z,
+                      const float* __restrict__ data, int64_t stride,
+                      const int32_t* __restrict__ rand_cells, int start_dim, int end_dim,
+                      float scale, int64_t Q, int ignore_edge, int ignore_last_z,
+                      uint8_t* __restrict__ mask_out, float* __restrict__ grad) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= Q) return;
+    const int nd = end_dim - start_dim;
+    const int idx = (int)(tid % nd) + start_dim;
+    const int xyz = __ldg(rand_cells + tid / nd);
+    const int z = xyz % Z;
+    const int xy = xyz / Z;
+    const int y = xy % Y;
+    const int x = xy / Y;
+    const int64_t offx = (int64_t)Y * Z;
+    const int32_t* lp = links + (x * offx + (int64_t)y * Z + z);
+    const int32_t lnk000 = __ldg(lp);
+    if (ignore_edge && lnk000 == 0) return;
+    float sc[3];
+    ray_scale(X, Y, Z, sc);
+    // out-of-range neighbours read row 0, not "empty" (reference quirk)
+    const int32_t lnk001 = ((z + 1 < Z) && (!ignore_last_z || z != Z - 2)) ? __ldg(lp + 1) : 0;
+    const int32_t lnk010 = y + 1 < Y ? __ldg(lp + Z) : 0;
+    const int32_t lnk100 = x + 1 < X ? __ldg(lp + offx) : 0;
+    if (ignore_last_z && z == Z - 2) return;
+
+    const float v000 = lnk000 >= 0 ? __ldg(data + (int64_t)lnk000 * stride + idx) : 0.f;
+    const float nullv = ignore_edge ? v000 : 0.f;
+    const float v001 = lnk001 >= 0 ? __ldg(data + (int64_t)lnk001 * stride + idx) : nullv;
+    const float v010 = lnk010 >= 0 ? __ldg(data + (int64_t)lnk010 * stride + idx) : nullv;
+    const float v100 = lnk100 >= 0 ? __ldg(data + (int64_t)lnk100 * stride + idx) : nullv;
+    float dx = __fsub_rn(v100, v000), dy = __fsub_rn(v010, v000), dz = __fsub_rn(v001, v000);
+    const float idelta = __fmul_rn(scale, inv_delta(dx, dy, dz));
+    dx = __fmul_rn(dx, sc[0]);
+    dy = __fmul_rn(dy, sc[1]);
+    dz = __fmul_rn(dz, sc[2]);
+    const float sm = -__fadd_rn(__fadd_rn(dx, dy), dz);
+#define MAYBE_ADD_SET(lnk, val)                                                      \
+    if ((lnk) >= 0 && (val) != 0.f) {                                                \
+        atomicAdd(grad + (int64_t)(lnk) * stride + idx, __fmul_rn((val), idelta));   \
+        if (mask_out) mask_out[(lnk)] = 1;                                           \
+    }
+    MAYBE_ADD_SET(lnk000, sm);
+    MAYBE_ADD_SET(lnk001, dz);
+    MAYBE_ADD_SET(lnk010, dy);
+    MAYBE_ADD_SET(lnk100, dx);
+#undef MAYBE_ADD_SET
+}
+
+// msi_tv_grad_sparse_kernel, loss_kernel.cu:248-333
+__global__ void __launch_bounds__(TV_THREADS)
+msi_tv_grad_sparse_kernel(const int32_t* __restrict__ links, int reso,
+                          const float* __restrict__ msi, int nlayers, int nchan,
+                          const int32_t* __restrict__ rand_cells, float scale, float scale_last,
+                          int64_t Q, uint8_t* __restrict__ mask, float* __restrict__ grad) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= Q) return;
+    const int LX = 2 * reso, LY = reso;
+    const int ch = (int)(tid % nchan);
+    const int msi_idx = __ldg(rand_cells + tid / nchan);
+    const int z = msi_idx % nlayers;
+    const int tmp = msi_idx / nlayers;
+    const int y = tmp % LY;
+    const int x = tmp / LY;
+    const int nx = (x == LX - 1) ? 0 : x + 1;
+    const int ny = (y == LY - 1) ? 0 : y + 1;
+    const int lnk00 = __ldg(links + x * LY + y);
+    const int lnk01 = __ldg(links + x * LY + ny);
+    const int lnk10 = __ldg(links + nx * LY + y);
+#define MSI_AT(l, zz) (((int64_t)(l) * nlayers + (zz)) * nchan + ch)
+    const float v00 = lnk00 >= 0 ? __ldg(msi + MSI_AT(lnk00, z)) : 0.f;
+    const float v_nxl = (lnk00 >= 0 && z + 1 < nlayers) ? __ldg(msi + MSI_AT(lnk00, z + 1))
+                                                        : ((ch == nchan - 1) ? 0.f : v00);
+    const float v01 = lnk01 >= 0 ? __ldg(msi + MSI_AT(lnk01, z)) : 0.f;
+    const float v10 = lnk10 >= 0 ? __ldg(msi + MSI_AT(lnk10, z)) : 0.f;
+    if (ch == nchan - 1) scale = scale_last;
+    float dx = __fsub_rn(v10, v00), dy = __fsub_rn(v01, v00), dz = __fsub_rn(v_nxl, v00);
+    const float idelta = __fmul_rn(scale, inv_delta(dx, dy, dz));
+    dx = __fmul_rn(dx, __fmul_rn((float)LX, 1.f / 256.f));
+    dy = __fmul_rn(dy, __fmul_rn((float)LY, 1.f / 256.f));
+    dz = __fmul_rn(dz, __fmul_rn((float)nlayers, 1.f / 256.f));
+    const float sm = -__fadd_rn(__fadd_rn(dx, dy), dz);
+#define MAYBE_ADD_SET(link, zz, val)                                       \
+    if ((link) >= 0 && (val) != 0.f) {                                     \
+        atomicAdd(grad + MSI_AT(link, zz), __fmul_rn((val), idelta));      \
+        if (mask) mask[(int64_t)(link) * nlayers + (zz)] = 1;              \
+    }
+    MAYBE_ADD_SET(lnk00, z, sm);
+    if (z + 1 < nlayers) { MAYBE_ADD_SET(lnk00, z + 1, dz); }
+    MAYBE_ADD_SET(lnk01, z, dy);
+    MAYBE_ADD_SET(lnk10, z, dx);
+#undef MAYBE_ADD_SET
+#undef MSI_AT
+}
+
+int check_tv_args(const int32_t* links, int X, int Y, int Z, const float* data, int64_t stride,
+                  int start_dim, int end_dim, const char* who) {
+    if (!links || !data) {
+        set_error("%s: links/data must not be null", who);
+        return SVOX2_ERR_INVALID;
+    }
+    if (X < 2 || Y < 2 || Z < 2) {
+        set_error("%s: links must be 3-D with every dimension >= 2", who);
+        return SVOX2_ERR_INVALID;
+    }
+    if (start_dim < 0 || end_dim <= start_dim || end_dim > stride) {
+        set_error("%s: bad channel range [%d,%d) for row stride %lld", who, start_dim, end_dim,
+                  (long long)stride);
+        return SVOX2_ERR_INVALID;
+    }
+    return SVOX2_OK;
+}
+
+}  // namespace
+}  // namespace svox2b
+
+using namespace svox2b;
+
+extern "C" SVOX2_API int svox2_tv(const int32_t* links, int32_t X, int32_t Y, int32_t Z, const float* data,
+                        int64_t data_stride, int32_t start_dim, int32_t end_dim,
+                        int32_t ignore_edge, float ndc_coeffx, float ndc_coeffy, float* out,
+                        svox2_stream_t stream) {
+    (void)ndc_coeffx; (void)ndc_coeffy;
+    if (int e = check_tv_args(links, X, Y, Z, data, data_stride, start_dim, end_dim, __func__)) return e;
+    SVOX2_REQUIRE(out, "out must not be null");
+    const int nl = (X - 1) * (Y - 1) * (Z - 1);
+    const int64_t Q = (int64_t)nl * (end_dim - start_dim);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(out, 0, sizeof(float), st);
+    tv_kernel<<<div_up(Q, TV_THREADS), TV_THREADS, 0, st>>>(links, X, Y, Z, data, data_stride,
+                                                            start_dim, end_dim, 1.f / nl, Q,
+                                                            ignore_edge, out);
+    return check_launch(__func__);
+}
+
+extern "C" SVOX2_API int svox2_tv_grad(const int32_t* links, int32_t X, int32_t Y, int32_t Z,
+                             const float* data, int64_t data_stride, int32_t start_dim,
+                             int32_t end_dim, float scale, int32_t ignore_edge, float ndc_coeffx,
+                             float ndc_coeffy, float* grad_data, svox2_stream_t stream) {
+    (void)ndc_coeffx; (void)ndc_coeffy;
+    if (int e = check_tv_args(links, X, Y, Z, data, data_stride, start_dim, end_dim, __func__)) return e;
+    SVOX2_REQUIRE(grad_data, "grad_data must not be null");
+    const int nl = (X - 1) * (Y - 1) * (Z - 1);
+    const int64_t Q = (int64_t)nl * (end_dim - start_dim);
+    tv_grad_kernel<<<div_up(Q, TV_THREADS), TV_THREADS, 0, (cudaStream_t)stream>>>(
+        links, X, Y, Z, data, data_stride, start_dim, end_dim, scale / nl, Q, ignore_edge, grad_data);
+    return check_launch(__func__);
+}
+
+extern "C" SVOX2_API int svox2_tv_grad_sparse(const int32_t* links, int32_t X, int32_t Y, int32_t Z,
+                                    const float* data, int64_t data_stride,
+                                    const int32_t* rand_cells, int64_t n_cells,
+                                    int64_t scale_cells, uint8_t* mask_out, int32_t start_dim,
+                                    int32_t end_dim, float scale, int32_t ignore_edge,
+                                    int32_t ignore_last_z, float ndc_coeffx, float ndc_coeffy,
+                                    float* grad_data, svox2_stream_t stream) {
+    (void)ndc_coeffx; (void)ndc_coeffy;
+    if (int e = check_tv_args(links, X, Y, Z, data, data_stride, start_dim, end_dim, __func__)) return e;
+    SVOX2_REQUIRE(grad_data, "grad_data must not be null");
+    SVOX2_REQUIRE(n_cells >= 0 && (n_cells == 0 || rand_cells), "rand_cells must not be null");
+    if (n_cells == 0) return SVOX2_OK;
+    if (scale_cells <= 0) scale_cells = n_cells;
+    const int64_t Q = n_cells * (end_dim - start_dim);
+    tv_grad_sparse_kernel<<<div_up(Q, TV_THREADS), TV_THREADS, 0, (cudaStream_t)stream>>>(
+        links, X, Y, Z, data, data_stride, rand_cells, start_dim, end_dim,
+        scale / (float)(int)scale_cells, Q, ignore_edge, ignore_last_z, mask_out, grad_data);
+    return check_launch(__func__);
+}
+
+extern "C" SVOX2_API int svox2_msi_tv_grad_sparse(const int32_t* background_links, int32_t reso,
+                                        const float* msi, int32_t nlayers, int32_t nchannels,
+                                        const int32_t* rand_cells, int64_t n_cells,
+                                        int64_t scale_cells, uint8_t* mask_out, float scale,
+                                        float scale_last, float* grad_msi, svox2_stream_t stream) {
+    SVOX2_REQUIRE(background_links && msi && grad_msi, "null argument");
+    SVOX2_REQUIRE(reso > 0 && nlayers > 0 && nchannels > 0, "bad MSI shape");
+    SVOX2_REQUIRE(n_cells >= 0 && (n_cells == 0 || rand_cells), "rand_cells must not be null");
+    if (n_cells == 0) return SVOX2_OK;
+    if (scale_cells <= 0) scale_cells = n_cells;
+    const int64_t Q = n_cells * nchannels;
+    msi_tv_grad_sparse_kernel<<<div_up(Q, TV_THREADS), TV_THREADS, 0, (cudaStream_t)stream>>>(
+        background_links, reso, msi, nlayers, nchannels, rand_cells,
+        scale / (float)(int)scale_cells, scale_last / (float)(int)scale_cells, Q, mask_out, grad_msi);
+    return check_launch(__func__);
+}

@@ -1,0 +1,113 @@
+"""CPU tests of the host side: grid construction vs reference goldens, C-ABI exports."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import svox2_b200 as sv
+from svox2_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "structure.npz")
+
+
+@pytest.mark.parametrize("key,reso,zo,sph", [
+    ("links_16_1_1", 16, True, True), ("links_16_0_1", 16, False, True),
+    ("links_[8,12,10]_0_1", [8, 12, 10], False, True), ("links_8_1_0", 8, True, False)])
+def test_links_construction_bit_exact(key, reso, zo, sph):
+    z = np.load(GOLD)
+    g = sv.SparseGrid(reso=reso, use_z_order=zo, use_sphere_bound=sph, device="cpu")
+    assert np.array_equal(g.links.numpy(), z[key])
+    assert int(g.capacity) == int(z[key + "_cap"])
+    assert g.density_data.shape == (g.capacity, 1) and g.sh_data.shape == (g.capacity, 27)
+
+
+def test_morton_sh_and_camera_rays():
+    z = np.load(GOLD)
+    assert np.array_equal(sv.utils.gen_morton(8).numpy(), z["morton8"])
+    d = torch.from_numpy(z["sh_dirs"])
+    for bd in (1, 4, 9):
+        assert np.array_equal(sv.utils.eval_sh_bases(bd, d).numpy(), z[f"sh_bases_{bd}"])
+    cam = sv.Camera(torch.from_numpy(z["cam_c2w"]), fx=40.0, fy=42.0, cx=15.5, cy=11.0, width=32, height=24)
+    r = cam.gen_rays()
+    assert np.array_equal(r.origins.numpy(), z["cam_origins"])
+    assert np.abs(r.dirs.numpy() - z["cam_dirs"]).max() < 1e-7
+    cam2 = sv.Camera(torch.from_numpy(z["ndc_c2w"]), fx=40.0, fy=42.0, cx=15.5, cy=11.0, width=32,
+                     height=24, ndc_coeffs=(2 * 40.0 / 32, 2 * 42.0 / 24))
+    r2 = cam2.gen_rays()
+    assert np.abs(r2.origins.numpy() - z["ndc_origins"]).max() < 1e-6
+    assert np.abs(r2.dirs.numpy() - z["ndc_dirs"]).max() < 1e-6
+
+
+def test_world_grid_roundtrip_and_rand_cells():
+    g = sv.SparseGrid(reso=[8, 12, 10], radius=[1.0, 0.8, 1.2], center=[0.1, 0.0, -0.2], device="cpu")
+    p = torch.randn(20, 3)
+    assert torch.allclose(g.grid2world(g.world2grid(p)), p, atol=1e-5)
+    np.random.seed(3)
+    cells = g._get_rand_cells(0.25)
+    n = 8 * 12 * 10
+    assert cells.dtype == torch.int32 and cells.numel() == int(0.25 * n)
+    assert ((cells >= 0) & (cells < n)).all()
+    d = (cells[1:] - cells[:-1]).numpy()
+    assert ((d == 1) | (d == 1 - n)).all()          # contiguous run, wrapped once at most
+    assert g._get_rand_cells(1.0) is None
+
+
+def test_no_silent_cpu_fallback():
+    g = sv.SparseGrid(reso=8, device="cpu")
+    rays = sv.Rays(torch.zeros(4, 3), torch.ones(4, 3))
+    with pytest.raises(NotImplementedError):
+        g.volume_render(rays, use_kernel=False)
+    with pytest.raises(NotImplementedError):
+        g.volume_render(rays)
+    with pytest.raises(NotImplementedError):
+        g.sample(torch.zeros(3, 3))
+    with pytest.raises(NotImplementedError):
+        g.volume_render_fused(rays, torch.zeros(4, 3))
+    with pytest.raises(NotImplementedError):
+        sv.SparseGrid(reso=8, basis_type=sv.BASIS_TYPE_MLP)
+
+
+def test_save_load_roundtrip(tmp_path):
+    g = sv.SparseGrid(reso=8, basis_dim=4, use_sphere_bound=True, device="cpu")
+    with torch.no_grad():
+        g.density_data[:] = torch.rand_like(g.density_data)
+        g.sh_data[:] = torch.randn_like(g.sh_data)
+    path = str(tmp_path / "ckpt.npz")
+    g.save(path)
+    z = np.load(path)
+    assert z["sh_data"].dtype == np.float16 and z["links"].dtype == np.int32
+    g2 = sv.SparseGrid.load(path)
+    assert torch.equal(g2.links, g.links) and g2.basis_dim == 4
+    assert torch.equal(g2.density_data, g.density_data)
+    assert torch.allclose(g2.sh_data, g.sh_data, atol=2e-3, rtol=1e-3)
+
+
+def test_cabi_library_loads_and_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "svox2_b200.h")).read()
+    declared = set(re.findall(r"SVOX2_API[^;(]*?\b(svox2_\w+)\s*\(", hdr))
+    assert len(declared) >= 22
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(handle, name), f"{name} declared in include/svox2_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), "ctypes table out of sync with the header"
+    lib = _lib.lib()
+    assert b"sm_100a" in lib.svox2_version()
+    assert lib.svox2_render_workspace_bytes(5000) >= 5000 * 8
+    # 128^3 pyramid: 64^3 + 32^3 + ... + 1
+    assert lib.svox2_accel_workspace_bytes(128, 128, 128) == sum((128 >> k) ** 3 for k in range(1, 8))
+
+
+def test_cabi_argument_errors_are_reported_not_printed():
+    lib = _lib.lib()
+    g = _lib.GridT()  # all-null grid
+    o = _lib.RenderOptsT()
+    st = lib.svox2_volume_render_cuvol(ctypes.byref(g), None, None, 0, ctypes.byref(o), None, None, 0,
+                                       None, None)
+    assert st == 1
+    assert b"non-null" in lib.svox2_last_error()
+    with pytest.raises(_lib.Svox2Error):
+        _lib.check(st)
