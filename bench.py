@@ -1,0 +1,551 @@
+#!/usr/bin/env python
+"""Benchmark of the Plenoxels hot path: train rays/s of the fused train step on a 512^3 SH-deg-2
+sparse grid (BASELINE.json metric, config C3 of SURVEY.md 8d).
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
+    python bench.py --impl reference ...                      (CPU arm, rank 0 only)
+
+A step = SparseGrid.volume_render_fused (fused fwd+bwd ray march, MSE gradient) +
+inplace_tv_grad + inplace_tv_color_grad + optim_density_step + optim_sh_step on one batch of
+5000 rays per GPU (syn.json hyper-parameters; opt/opt.py:474-603), replicated grid, rays
+sharded over ranks, masked gradient exchange over NCCL when N>1.  Prints ONE JSON line.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 5000                      # rays per GPU per step (opt/opt.py batch_size)
+POOL = 8                          # distinct ray batches cycled through (no L2-resident reuse)
+SYN = dict(lr_sigma=30.0, lr_sh=1e-2, lambda_tv=1e-5, lambda_tv_sh=1e-3, tv_sparsity=0.01,
+           rms_beta=0.95)         # opt/configs/syn.json + opt.py defaults
+RENDER = dict(step_size=0.5, sigma_thresh=1e-8, stop_thresh=1e-7, background_brightness=1.0)
+WORKLOADS = {
+    "c3": dict(reso=512, occupancy=0.10, name="C3: 512^3 sparse (~10% occupancy) SH deg 2"),
+    "c2": dict(reso=256, occupancy=0.25, name="C2-like: 256^3 sparse SH deg 2"),
+    "small": dict(reso=128, occupancy=0.25, name="dev: 128^3 sparse SH deg 2"),
+}
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic scene (identical for both arms; torch ops only, seeded)
+# ----------------------------------------------------------------------------------------------
+def _inside_blobs(reso, centers, radii, scale, device):
+    ax = (torch.arange(reso, device=device, dtype=torch.float32) + 0.5) / reso * 2 - 1
+    inside = torch.zeros((reso, reso, reso), dtype=torch.bool, device=device)
+    X, Y, Z = ax[:, None, None], ax[None, :, None], ax[None, None, :]
+    for c, r in zip(centers.tolist(), radii.tolist()):
+        d2 = ((X - c[0]) / (r[0] * scale)) ** 2 + ((Y - c[1]) / (r[1] * scale)) ** 2 + \
+             ((Z - c[2]) / (r[2] * scale)) ** 2
+        inside |= d2 < 1.0
+    return inside
+
+
+def _dilate(mask, iters):
+    m = mask[None, None].float()
+    for _ in range(iters):
+        m = torch.nn.functional.max_pool3d(m, 3, stride=1, padding=1)
+    return m[0, 0] > 0
+
+
+def build_scene(workload, device, seed=20200823):
+    """sigma = 30 inside a union of seeded ellipsoids, SH ~ N(0, 0.1^2) with DC 0.5, voxels kept =
+    dilate^2(occupied); blob scale bisected so that the stored fraction hits the target."""
+    cfg = WORKLOADS[workload]
+    reso, target = cfg["reso"], cfg["occupancy"]
+    gen = torch.Generator().manual_seed(seed)
+    nb = 40
+    centers = (torch.rand(nb, 3, generator=gen) - 0.5) * 1.3
+    radii = torch.rand(nb, 3, generator=gen) * 0.17 + 0.08
+    lo, hi = 0.2, 3.0
+    for _ in range(10):
+        mid = 0.5 * (lo + hi)
+        keep = _dilate(_inside_blobs(reso, centers, radii, mid, device), 2)
+        frac = keep.float().mean().item()
+        lo, hi = (mid, hi) if frac < target else (lo, mid)
+    scale = 0.5 * (lo + hi)
+    inside = _inside_blobs(reso, centers, radii, scale, device)
+    keep = _dilate(inside, 2)
+    links = torch.cumsum(keep.view(-1).to(torch.int32), 0, dtype=torch.int32) - 1
+    links[~keep.view(-1)] = -1
+    links = links.view(reso, reso, reso).contiguous()
+    n_rows = int(keep.sum().item())
+    density = (inside[keep].float() * 30.0).view(n_rows, 1).contiguous()
+    ggen = torch.Generator(device=device).manual_seed(seed + 1)
+    sh = torch.randn(n_rows, 27, generator=ggen, device=device) * 0.1
+    sh[:, ::9] += 0.5
+    return dict(links=links, density=density, sh=sh.contiguous(), n_rows=n_rows, reso=reso,
+                occupancy=n_rows / reso ** 3, name=cfg["name"])
+
+
+def build_rays(n_total, device, seed=20200823):
+    """NeRF-synthetic-shaped rays: 100 cameras on the r=2.687 upper hemisphere looking at the
+    origin, 800x800, fx=1111.11 (OpenCV convention); random (camera, pixel) per ray."""
+    gen = torch.Generator().manual_seed(seed + 7)
+    ncam = 100
+    u = torch.rand(ncam, generator=gen)
+    phi = torch.rand(ncam, generator=gen) * 2 * math.pi
+    zc = 0.1 + 0.85 * u
+    rxy = torch.sqrt(1 - zc * zc)
+    pos = torch.stack([rxy * torch.cos(phi), rxy * torch.sin(phi), zc], -1).double() * 2.687
+    fwd = -pos / pos.norm(dim=-1, keepdim=True)
+    up = torch.tensor([0.0, 0.0, 1.0], dtype=torch.float64).expand_as(fwd)
+    right = torch.cross(fwd, up, dim=-1)
+    right = right / right.norm(dim=-1, keepdim=True)
+    down = torch.cross(fwd, right, dim=-1)
+    R = torch.stack([right, down, fwd], dim=-1)                 # columns: x, y, z of the camera
+    cam = torch.randint(0, ncam, (n_total,), generator=gen)
+    px = torch.randint(0, 800, (n_total, 2), generator=gen).double() + 0.5
+    d = torch.stack([(px[:, 0] - 400.0) / 1111.11, (px[:, 1] - 400.0) / 1111.11,
+                     torch.ones(n_total, dtype=torch.float64)], -1)
+    d = d / d.norm(dim=-1, keepdim=True)
+    dirs = torch.einsum("nij,nj->ni", R[cam], d)
+    dirs = (dirs / dirs.norm(dim=-1, keepdim=True)).float()
+    origins = pos[cam].float()
+    return origins.to(device).contiguous(), dirs.to(device).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        self.lines = []
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes_fused(q, c):
+    """fused fwd+bwd bytes = 84 Q + 8 S_skip + 128 S_vis + 3528 S_act (SH deg 2)."""
+    return 84 * q + 8 * c[0] + 128 * c[1] + 3528 * c[2]
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import svox2_b200 as sv
+    from svox2_b200 import csrc as C
+    from svox2_b200.dist import ShardedTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    sc = build_scene(args.workload, dev)
+    grid = sv.SparseGrid(reso=sc["reso"], basis_dim=9, device=dev)
+    grid.links = sc["links"]
+    grid.density_data = torch.nn.Parameter(sc["density"])
+    grid.sh_data = torch.nn.Parameter(sc["sh"])
+    grid.capacity = sc["n_rows"]
+    grid.accelerate()
+    for k, v in RENDER.items():
+        setattr(grid.opt, k, v)
+
+    # global ray pool: POOL batches of BATCH*world rays; rank r owns a contiguous slice of each
+    gq = BATCH * world
+    origins, dirs = build_rays(POOL * gq, dev)
+    with torch.no_grad():
+        gt = torch.cat([grid.volume_render(sv.Rays(origins[i:i + 50000], dirs[i:i + 50000]))
+                        for i in range(0, POOL * gq, 50000)])
+        ggen = torch.Generator(device=dev).manual_seed(99)
+        gt = (gt + 0.02 * torch.randn(gt.shape, generator=ggen, device=dev)).clamp_(0, 1)
+    sl = [slice(b * gq + rank * BATCH, b * gq + (rank + 1) * BATCH) for b in range(POOL)]
+    batches = [(origins[s].contiguous(), dirs[s].contiguous(), gt[s].contiguous()) for s in sl]
+    host = [tuple(x.cpu().pin_memory() for x in b) for b in batches]
+
+    trainer = ShardedTrainer(grid, world_size=world, rank=rank, **SYN)
+    np.random.seed(1234)
+
+    def step(o, d, g):
+        return trainer.step(sv.Rays(o, d), g, global_batch=gq)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # counts of the roofline model, one counting pass per pooled batch (untimed)
+    counters = torch.zeros(4, dtype=torch.int64, device=dev)
+    for o, d, g in batches:
+        C.volume_render_cuvol(grid._to_cpp(), sv.Rays(o, d)._to_cpp(), grid.opt._to_cpp(),
+                              _counters=counters)
+    torch.cuda.synchronize()
+    cnt = [c / POOL for c in counters.cpu().tolist()]
+
+    for i in range(args.warmup):
+        step(*batches[i % POOL])
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(*batches[i % POOL])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+
+    # end to end: pinned host inputs -> H2D, step, D2H of the loss, every step
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    loss_val = 0.0
+    for i in range(args.steps):
+        ho, hd, hg = host[i % POOL]
+        o, d, g = (ho.to(dev, non_blocking=True), hd.to(dev, non_blocking=True),
+                   hg.to(dev, non_blocking=True))
+        rgb = step(o, d, g)
+        loss_val = torch.mean((rgb - g) ** 2).item()         # opt.py:505-508 (host sync per step)
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1)
+    clocks = sampler.stop() if sampler else None
+
+    # dominant kernels alone: the fused fwd+bwd march pair
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    spec, ropt = grid._to_cpp(), grid.opt._to_cpp()
+    holder = C.GridOutputGrads()
+    holder.grad_density_out, holder.grad_sh_out = grid.density_data.grad, grid.sh_data.grad
+    holder.mask_out = torch.zeros(sc["n_rows"], dtype=torch.bool, device=dev)
+    rgb_out = torch.zeros_like(batches[0][2])
+    rspecs = [sv.Rays(o, d)._to_cpp() for o, d, _ in batches]
+    for i in range(3):
+        C.volume_render_cuvol_fused(spec, rspecs[i % POOL], ropt, batches[i % POOL][2], 0.0, 0.0,
+                                    rgb_out, holder, _norm_rays=gq)
+    torch.cuda.synchronize()
+    k0.record()
+    for i in range(args.steps):
+        C.volume_render_cuvol_fused(spec, rspecs[i % POOL], ropt, batches[i % POOL][2], 0.0, 0.0,
+                                    rgb_out, holder, _norm_rays=gq)
+    k1.record()
+    torch.cuda.synchronize()
+    ms_fused = k0.elapsed_time(k1) / args.steps
+    grid.density_data.grad.zero_()
+    grid.sh_data.grad.zero_()
+
+    times = torch.tensor([ms, ms_e2e, ms_fused], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, ms_e2e, ms_fused = times.tolist()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    abytes = algorithmic_bytes_fused(BATCH, cnt)
+    achieved = abytes / (ms_fused * 1e-3) / 1e9
+    line = {
+        "metric": "train rays/sec (fused fwd+bwd step) at 512^3 SH2",
+        "value": gq * args.steps / (ms * 1e-3),
+        "unit": "rays/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": sc["name"], "reso": sc["reso"], "stored_voxels": sc["n_rows"],
+            "occupancy": round(sc["occupancy"], 4), "rays_per_gpu": BATCH, "global_batch": gq,
+            "step": "volume_render_fused + tv_grad_sparse(sigma,sh) + rmsprop(sigma,sh)",
+            "l2": "inputs larger than L2 (grid+grads+rms >> 126 MB); 8 distinct ray batches cycled",
+            "parallelism": f"ray-sharded x{world}, replicated grid" +
+                           (", masked packed grad all-reduce (NCCL)" if world > 1 else ""),
+            "samples_per_ray": {"skip": cnt[0] / BATCH, "visited": cnt[1] / BATCH,
+                                "active": cnt[2] / BATCH},
+        },
+        "e2e": {"value": gq * args.steps / (ms_e2e * 1e-3), "unit": "rays/s",
+                "h2d_bytes_per_step": 3 * BATCH * 3 * 4, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps, "last_loss": loss_val},
+        "gpu_launches": trainer.kernels_per_step * args.steps,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "march_fwd_kernel + march_bwd_kernel (fused call)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes,
+                     "ms_per_launch": ms_fused, "traffic": None},
+    }
+    if args.cpu_baseline:
+        line["cpu_baseline"] = cpu_port_baseline(sc, grid, batches[0], budget_rays=args.cpu_rays)
+    if args.ref_cuda:
+        line["ref_cuda"] = reference_cuda_baseline(sc, grid, batches, args, gq)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------
+# baselines
+# ----------------------------------------------------------------------------------------------
+def cpu_port_baseline(sc, grid, batch, budget_rays=1024):
+    """The oracle (a C port of the reference algorithm) timed on the host cores on a bounded
+    sample of the SAME workload: the first `budget_rays` rays of batch 0, fused fwd+bwd."""
+    import oracle as og
+    links = grid.links.cpu().numpy()
+    g = og.Grid(links, sc["density"].cpu().numpy(), sc["sh"].cpu().numpy(),
+                (grid._offset * grid._grid_size() - 0.5).numpy(),
+                (grid._scaling * grid._grid_size()).numpy())
+    opt = og.make_opt(**RENDER)
+    o, d, gt = (x[:budget_rays].cpu().numpy() for x in batch)
+    cores = os.cpu_count() or 1
+    og.set_num_threads(cores)
+    og.set_accum_float(True)
+    gd = np.zeros(g.density.shape[0], np.float32)
+    gsh = np.zeros(g.sh.shape, np.float32)
+    mask = np.zeros(g.density.shape[0], np.uint8)
+    rgb = np.zeros((o.shape[0], 3), np.float32)
+    import ctypes as CT
+    gc, cnt = g.c(), og._Counts()
+    t = time.perf_counter()
+    og.lib().og_volume_render_fused(CT.byref(gc), CT.byref(opt), og._ptr(o), og._ptr(d),
+                                    CT.c_int64(o.shape[0]), CT.c_int64(o.shape[0]), og._ptr(gt),
+                                    CT.c_float(0.0), CT.c_float(0.0), og._ptr(rgb), og._ptr(gd),
+                                    og._ptr(gsh), None, og._ptr(mask), None, CT.byref(cnt))
+    dt = time.perf_counter() - t
+    og.set_num_threads(1)
+    og.set_accum_float(False)
+    return {"value": o.shape[0] / dt, "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": f"first {o.shape[0]} rays of batch 0, fused fwd+bwd march only "
+                      f"(no TV/optimiser), oracle C port, {cores} pthreads, {dt:.2f} s"}
+
+
+def reference_cuda_baseline(sc, grid, batches, args, gq):
+    """The reference's own CUDA extension (built for sm_100, oracle/_ref) on the same workload,
+    same step, same GPU: the kernel to beat."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "svox2")):
+        return {"unavailable": "oracle/_ref not built"}
+    sys.path.insert(0, ref_dir)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import svox2 as ref
+    dev = grid.links.device
+    rg = ref.SparseGrid(reso=sc["reso"], basis_dim=9, device=dev)
+    rg.links = grid.links.clone()
+    rg.density_data = torch.nn.Parameter(sc["density"].clone())
+    rg.sh_data = torch.nn.Parameter(sc["sh"].clone())
+    rg.capacity = sc["n_rows"]
+    for k, v in RENDER.items():
+        setattr(rg.opt, k, v)
+    np.random.seed(1234)
+
+    def rstep(o, d, g):
+        rgb = rg.volume_render_fused(ref.Rays(o, d), g)
+        rg.inplace_tv_grad(rg.density_data.grad, scaling=SYN["lambda_tv"], sparse_frac=SYN["tv_sparsity"])
+        rg.inplace_tv_color_grad(rg.sh_data.grad, scaling=SYN["lambda_tv_sh"], sparse_frac=SYN["tv_sparsity"])
+        rg.optim_density_step(SYN["lr_sigma"], beta=SYN["rms_beta"])
+        rg.optim_sh_step(SYN["lr_sh"], beta=SYN["rms_beta"])
+        return rgb
+
+    for i in range(args.warmup):
+        rstep(*batches[i % POOL])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        rstep(*batches[i % POOL])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    e0.record()
+    for i in range(args.steps):
+        rg.volume_render_fused(ref.Rays(batches[i % POOL][0], batches[i % POOL][1]), batches[i % POOL][2])
+    e1.record()
+    torch.cuda.synchronize()
+    ms_f = e0.elapsed_time(e1) / args.steps
+    return {"value": BATCH / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms,
+            "ms_fused_call": ms_f, "what": "sxyu/svox2 CUDA extension (TORCH_CUDA_ARCH_LIST=10.0), "
+            "same grid/rays/step on this GPU, 1 GPU"}
+
+
+def run_reference(args):
+    """Reference arm: the reference algorithm on the host cores.  The reference's own
+    pure-PyTorch path cannot run the 512^3 workload (its autograd materialises a dense [N,27]
+    gradient per gather: ~50 TB of traffic per batch), so the timed number is the C port of the
+    same algorithm (oracle, all cores) on a bounded sample of each batch; the reference's own
+    Python path is timed beside it on its own CPU-runnable config (C1) and reported as an
+    extra key."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    sc = build_scene(args.workload, dev)
+    import oracle as og
+    links = og.accel_dist_prop(sc["links"].cpu().numpy())
+    gsz = float(sc["reso"])
+    g = og.Grid(links, sc["density"].cpu().numpy(), sc["sh"].cpu().numpy(),
+                np.full(3, 0.5 * gsz - 0.5, np.float32), np.full(3, 0.5 * gsz, np.float32))
+    opt = og.make_opt(**RENDER)
+    world = args.gpus
+    gq = BATCH * world
+    origins, dirs = build_rays(POOL * gq, "cpu")
+    sample = args.cpu_rays
+    cores = os.cpu_count() or 1
+    og.set_num_threads(cores)
+    og.set_accum_float(True)
+    gd = np.zeros(g.density.shape[0], np.float32)
+    gsh = np.zeros(g.sh.shape, np.float32)
+    mask = np.zeros(g.density.shape[0], np.uint8)
+    rng = np.random.default_rng(0)
+    import ctypes as CT
+    gc, cnt = g.c(), og._Counts()
+
+    def one(i):
+        s = (i % POOL) * gq
+        o = np.ascontiguousarray(origins[s:s + sample].numpy())
+        d = np.ascontiguousarray(dirs[s:s + sample].numpy())
+        gt = rng.uniform(0, 1, o.shape).astype(np.float32)
+        rgb = np.zeros_like(o)
+        og.lib().og_volume_render_fused(CT.byref(gc), CT.byref(opt), og._ptr(o), og._ptr(d),
+                                        CT.c_int64(sample), CT.c_int64(sample), og._ptr(gt),
+                                        CT.c_float(0.0), CT.c_float(0.0), og._ptr(rgb), og._ptr(gd),
+                                        og._ptr(gsh), None, og._ptr(mask), None, CT.byref(cnt))
+
+    for i in range(min(args.warmup, 1)):
+        one(i)
+    t = time.perf_counter()
+    for i in range(args.steps):
+        one(i)
+    dt = time.perf_counter() - t
+    val = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "train rays/sec (fused fwd+bwd step) at 512^3 SH2",
+        "value": val, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": sc["name"], "reso": sc["reso"], "stored_voxels": sc["n_rows"],
+                   "rays_per_step": sample},
+        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} rays of each pooled batch per step, fused fwd+bwd march "
+                                   f"(oracle C port of the reference algorithm, {cores} pthreads)"},
+        "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    if args.ref_pytorch:
+        line["reference_pytorch_c1"] = reference_pytorch_c1(args.ref_pytorch_rays)
+    print(json.dumps(line), flush=True)
+
+
+def reference_pytorch_c1(n_rays):
+    """The reference's own pure-PyTorch lerp renderer + autograd (oracle/_ref, unmodified) on
+    its CPU-runnable config C1: 128^3 dense, SH9, rays from the r=2.687 sphere."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "svox2")):
+        return {"unavailable": "oracle/_ref not built"}
+    sys.path.insert(0, ref_dir)
+    import warnings
+    warnings.filterwarnings("ignore")
+    import svox2 as ref
+    torch.set_num_threads(os.cpu_count() or 1)
+    gen = torch.Generator().manual_seed(1234)
+    grid = ref.SparseGrid(reso=128, basis_dim=9, use_z_order=False, use_sphere_bound=False, device="cpu")
+    with torch.no_grad():
+        grid.sh_data[:] = torch.randn(grid.sh_data.shape, generator=gen) * 0.1
+        grid.sh_data[:, ::9] = 0.5
+        grid.density_data[:] = torch.rand(grid.density_data.shape, generator=gen) * 2
+    for k, v in RENDER.items():
+        setattr(grid.opt, k, v)
+    v = torch.nn.functional.normalize(torch.randn(n_rays, 3, generator=gen), dim=-1)
+    origins = v * 2.687
+    targets = torch.rand(n_rays, 3, generator=gen) - 0.5
+    dirs = torch.nn.functional.normalize(targets - origins, dim=-1)
+    gt = torch.rand(n_rays, 3, generator=gen)
+    t = time.perf_counter()
+    rgb = grid.volume_render(ref.Rays(origins, dirs), use_kernel=False)
+    t_f = time.perf_counter() - t
+    torch.nn.functional.mse_loss(rgb, gt).backward()
+    t_all = time.perf_counter() - t
+    return {"config": "C1: SparseGrid 128^3 dense, basis_dim=9, volume_render(use_kernel=False) + autograd",
+            "rays": n_rays, "cores": os.cpu_count(), "torch_threads": torch.get_num_threads(),
+            "fwd_s": t_f, "fwd_bwd_s": t_all, "fwd_rays_per_s": n_rays / t_f,
+            "fwd_bwd_rays_per_s": n_rays / t_all}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
+    ap.add_argument("--cpu-rays", type=int, default=2048, help="bounded CPU sample (rays)")
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-ref-cuda", dest="ref_cuda", action="store_false")
+    ap.add_argument("--no-ref-pytorch", dest="ref_pytorch", action="store_false")
+    ap.add_argument("--ref-pytorch-rays", type=int, default=256)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

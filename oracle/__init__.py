@@ -91,6 +91,10 @@ def set_num_threads(n: int):
     lib().og_set_num_threads(int(n))
 
 
+def set_accum_float(on: bool):
+    lib().og_set_accum_float(int(bool(on)))
+
+
 def get_max_threads() -> int:
     return int(lib().og_get_max_threads())
 

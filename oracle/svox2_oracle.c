@@ -299,9 +299,34 @@ typedef struct {
     double* gd;   /* [N] */
     double* gsh;  /* [N*D] */
     double* gbg;  /* [Nbg*L*4] or NULL */
+    float* fgd;   /* float-accumulation mode (bench): accumulate straight into the outputs */
+    float* fgsh;
+    float* fgbg;
     uint8_t* mask;
     uint8_t* mask_bg;
 } grads_t;
+
+static int g_accum_float = 0;
+static inline void add_float(float* p, float v) {
+    if (g_threads <= 1) { *p += v; return; }
+    uint32_t* pu = (uint32_t*)p;
+    uint32_t old = __atomic_load_n(pu, __ATOMIC_RELAXED), neu;
+    do {
+        float d;
+        memcpy(&d, &old, 4);
+        d += v;
+        memcpy(&neu, &d, 4);
+    } while (!__atomic_compare_exchange_n(pu, &old, neu, 1, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+}
+static inline void acc_sh(grads_t* gr, int64_t i, float v) {
+    if (gr->fgsh) add_float(&gr->fgsh[i], v); else add_double(&gr->gsh[i], (double)v);
+}
+static inline void acc_d(grads_t* gr, int64_t i, float v) {
+    if (gr->fgd) add_float(&gr->fgd[i], v); else add_double(&gr->gd[i], (double)v);
+}
+static inline void acc_bg(grads_t* gr, int64_t i, float v) {
+    if (gr->fgbg) add_float(&gr->fgbg[i], v); else if (gr->gbg) add_double(&gr->gbg[i], (double)v);
+}
 
 static void trace_ray_bwd(const og_grid_t* g, const og_opt_t* opt, ray_t* ray, const float* sph,
                           const float* grad_output, const float* color_cache,
@@ -367,12 +392,12 @@ static void trace_ray_bwd(const og_grid_t* g, const og_opt_t* opt, ray_t* ray, c
                 const float curr_grad_color = sph[j % B] * grad_common;
                 trilerp_weights(ray->pos, curr_grad_color, w);
                 for (int q = 0; q < 8; ++q)
-                    if (lk[q] >= 0) add_double(&gr->gsh[(int64_t)lk[q] * D + j], (double)w[q]);
+                    if (lk[q] >= 0) acc_sh(gr, (int64_t)lk[q] * D + j, w[q]);
             }
             trilerp_weights(ray->pos, curr_grad_sigma, w);
             for (int q = 0; q < 8; ++q)
                 if (lk[q] >= 0) {
-                    add_double(&gr->gd[lk[q]], (double)w[q]);
+                    acc_d(gr, lk[q], w[q]);
                     if (gr->mask) gr->mask[lk[q]] = 1;
                 }
             if (EXPF(log_transmit) < opt->stop_thresh) break;
@@ -447,7 +472,7 @@ static float trilerp_bg(const ray_t* ray, const og_grid_t* g, const int32_t* lk,
 }
 
 static void trilerp_bg_backward(const ray_t* ray, const og_grid_t* g, const int32_t* lk,
-                                double* grad, uint8_t* mask, float grad_out, int idx) {
+                                grads_t* gr, uint8_t* mask, float grad_out, int idx) {
     const int L = g->bg_nlayers;
     const float ay = 1.f - ray->pos[1], az = 1.f - ray->pos[2];
     float vals[4];
@@ -458,10 +483,8 @@ static void trilerp_bg_backward(const ray_t* ray, const og_grid_t* g, const int3
     for (int q = 0; q < 4; ++q) {
         if (lk[q] < 0) continue;
         const int64_t row = (int64_t)lk[q] * L + ray->l[2];
-        if (grad) {
-            add_double(&grad[row * 4 + idx], (double)(vals[q] * az));
-            add_double(&grad[(row + 1) * 4 + idx], (double)(vals[q] * ray->pos[2]));
-        }
+        acc_bg(gr, row * 4 + idx, vals[q] * az);
+        acc_bg(gr, (row + 1) * 4 + idx, vals[q] * ray->pos[2]);
         if (mask) { mask[row] = 1; mask[row + 1] = 1; }
     }
 }
@@ -528,7 +551,7 @@ static void render_background_backward(const og_grid_t* g, const og_opt_t* opt, 
                 total_color += fmaxf(color, 0.f) * grad_output[k];
                 if (color > 0.f) {
                     const float curr_grad_color = SH_C0 * weight * grad_output[k];
-                    trilerp_bg_backward(ray, g, lk, gr->gbg, NULL, curr_grad_color, k);
+                    trilerp_bg_backward(ray, g, lk, gr, NULL, curr_grad_color, k);
                 }
             }
             accum -= weight * total_color;
@@ -536,7 +559,7 @@ static void render_background_backward(const og_grid_t* g, const og_opt_t* opt, 
                                     (total_color * EXPF(log_transmit) - accum);
             if (sparsity_loss > 0.f)
                 curr_grad_sigma += sparsity_loss * (4 * sigma / (1 + 2 * (sigma * sigma)));
-            trilerp_bg_backward(ray, g, lk, gr->gbg, gr->mask_bg, curr_grad_sigma, 3);
+            trilerp_bg_backward(ray, g, lk, gr, gr->mask_bg, curr_grad_sigma, 3);
             if (EXPF(log_transmit) < opt->stop_thresh) break;
         }
         invr_last = invr_mid;
@@ -639,9 +662,12 @@ void og_volume_render_image(const og_grid_t* g, const og_cam_t* cam, const og_op
         }
 }
 
+static void grads_begin_f(const og_grid_t* g, grads_t* gr, float* grad_density, float* grad_sh,
+                          float* grad_bg, uint8_t* mask, uint8_t* mask_bg);
 static void grads_begin(const og_grid_t* g, grads_t* gr, int want_bg, uint8_t* mask,
                         uint8_t* mask_bg) {
     const int D = 3 * g->basis_dim;
+    gr->fgd = gr->fgsh = gr->fgbg = NULL;
     gr->gd = (double*)calloc((size_t)g->n_rows, sizeof(double));
     gr->gsh = (double*)calloc((size_t)g->n_rows * D, sizeof(double));
     gr->gbg = (want_bg && g->bg_nlayers > 0)
@@ -650,9 +676,19 @@ static void grads_begin(const og_grid_t* g, grads_t* gr, int want_bg, uint8_t* m
     gr->mask = mask;
     gr->mask_bg = mask_bg;
 }
+/* bench mode: accumulate in float directly into the caller's arrays (what the reference's
+ * atomicAdd does), so the timed call carries no O(N) staging pass. */
+static void grads_begin_f(const og_grid_t* g, grads_t* gr, float* grad_density, float* grad_sh,
+                          float* grad_bg, uint8_t* mask, uint8_t* mask_bg) {
+    if (!g_accum_float) { grads_begin(g, gr, grad_bg != NULL, mask, mask_bg); return; }
+    gr->gd = gr->gsh = gr->gbg = NULL;
+    gr->fgd = grad_density; gr->fgsh = grad_sh; gr->fgbg = (g->bg_nlayers > 0) ? grad_bg : NULL;
+    gr->mask = mask; gr->mask_bg = mask_bg;
+}
 static void grads_end(const og_grid_t* g, grads_t* gr, float* grad_density, float* grad_sh,
                       float* grad_bg) {
     const int D = 3 * g->basis_dim;
+    if (gr->fgd) return;
     for (int64_t i = 0; i < g->n_rows; ++i) grad_density[i] = (float)((double)grad_density[i] + gr->gd[i]);
     for (int64_t i = 0; i < g->n_rows * D; ++i) grad_sh[i] = (float)((double)grad_sh[i] + gr->gsh[i]);
     if (gr->gbg && grad_bg) {
@@ -685,7 +721,7 @@ static void backward_one(const og_grid_t* g, const og_opt_t* o, const float* ori
     trace_ray_bwd(g, o, &ray, sph, gout, color_cache,
                   (fused && beta_loss > 0.f && logT_fwd) ? *logT_fwd : 0.f,
                   fused ? beta_loss : 0.f, fused ? sparsity_loss : 0.f, gr, &accum, &logT_bwd);
-    if (has_bg && gr->gbg) {
+    if (has_bg && (gr->gbg || gr->fgbg)) {
         /* fused: bg kernels read the FORWARD log_transmit (cuvol.cu:1143); non-fused: the
          * value re-derived by the backward march (cuvol.cu:1048,1059). */
         const float logT = fused ? *logT_fwd : logT_bwd;
@@ -717,7 +753,7 @@ void og_volume_render_backward(const og_grid_t* g, const og_opt_t* o, const floa
                                const float* color_cache, float* grad_density, float* grad_sh,
                                float* grad_bg, uint8_t* mask, uint8_t* mask_bg) {
     grads_t gr;
-    grads_begin(g, &gr, grad_bg != NULL, mask, mask_bg);
+    grads_begin_f(g, &gr, grad_density, grad_sh, grad_bg, mask, mask_bg);
     bwd_ctx_t c = {g, o, origins, dirs, grad_out, color_cache, 0, Q, NULL, 0.f, 0.f, &gr};
     parallel_for(Q, bwd_range, &c);
     grads_end(g, &gr, grad_density, grad_sh, grad_bg);
@@ -731,7 +767,7 @@ void og_volume_render_fused(const og_grid_t* g, const og_opt_t* o, const float* 
     float* logT = (float*)malloc(sizeof(float) * (size_t)(Q > 0 ? Q : 1));
     og_volume_render(g, o, origins, dirs, Q, rgb_out, logT, counts);
     grads_t gr;
-    grads_begin(g, &gr, grad_bg != NULL, mask, mask_bg);
+    grads_begin_f(g, &gr, grad_density, grad_sh, grad_bg, mask, mask_bg);
     const float beta = beta_loss / (float)norm_rays; /* cuvol.cu:1127 */
     bwd_ctx_t c = {g, o, origins, dirs, rgb_gt, rgb_out, 1, norm_rays, logT, beta, sparsity_loss, &gr};
     parallel_for(Q, bwd_range, &c);
@@ -1206,4 +1242,5 @@ void og_sgd_step(float* data, float* grad, int64_t rows, int32_t C, int32_t inde
 
 /* Thread control for the bench's cpu_baseline leg (1 thread = the scalar port). */
 void og_set_num_threads(int n) { g_threads = n > 0 ? n : 1; }
+void og_set_accum_float(int on) { g_accum_float = on ? 1 : 0; }
 int og_get_max_threads(void) { return g_threads; }
