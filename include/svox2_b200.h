@@ -89,6 +89,8 @@ typedef struct {
     float* grad_background_out;     /* [Nbg, L, 4] or NULL                                   */
     uint8_t* mask_out;              /* [N] or NULL                                           */
     uint8_t* mask_background_out;   /* [Nbg, L] or NULL                                      */
+    int64_t grad_sh_stride;         /* floats between grad_sh rows; 0 = grid->sh_stride      */
+    int64_t grad_density_stride;    /* floats between grad_density rows; 0 = density_stride  */
 } svox2_grads_t;
 
 /* Extension (not in the reference): per-batch march-loop iteration counts, the unit of the
@@ -155,7 +157,8 @@ SVOX2_API int svox2_sample_grid(const svox2_grid_t* grid, const float* points, i
                       float* out_density, float* out_sh, svox2_stream_t stream);
 SVOX2_API int svox2_sample_grid_backward(const svox2_grid_t* grid, const float* points, int64_t n_points,
                                const float* grad_out_density, const float* grad_out_sh,
-                               float* grad_density_out, float* grad_sh_out,
+                               float* grad_density_out, int64_t grad_density_stride,
+                               float* grad_sh_out, int64_t grad_sh_stride,
                                svox2_stream_t stream);
 
 /* dilate  (svox2.cpp:60, misc_kernel.cu:20-48,339-354): 3x3x3 OR, clamped borders. */
@@ -177,14 +180,15 @@ SVOX2_API int svox2_grid_weight_render(const float* data, int32_t X, int32_t Y, 
                              svox2_stream_t stream);
 
 /* tv / tv_grad / tv_grad_sparse / msi_tv_grad_sparse  (svox2.cpp:32-49, loss_kernel.cu:482-641)
- * data [N, data_stride] with ddim logical channels.  tv: *out (device scalar) is overwritten. */
+ * data [N, data_stride] with ddim logical channels; grad_data [N, grad_stride] (0 = data_stride).
+ * tv: *out (device scalar) is overwritten. */
 SVOX2_API int svox2_tv(const int32_t* links, int32_t X, int32_t Y, int32_t Z, const float* data,
              int64_t data_stride, int32_t start_dim, int32_t end_dim, int32_t ignore_edge,
              float ndc_coeffx, float ndc_coeffy, float* out, svox2_stream_t stream);
 SVOX2_API int svox2_tv_grad(const int32_t* links, int32_t X, int32_t Y, int32_t Z, const float* data,
                   int64_t data_stride, int32_t start_dim, int32_t end_dim, float scale,
                   int32_t ignore_edge, float ndc_coeffx, float ndc_coeffy, float* grad_data,
-                  svox2_stream_t stream);
+                  int64_t grad_stride, svox2_stream_t stream);
 /* scale_cells: the cell count the scale is divided by (the reference: n_cells,
  * loss_kernel.cu:584-595; the global count when cells are sharded over GPUs). */
 SVOX2_API int svox2_tv_grad_sparse(const int32_t* links, int32_t X, int32_t Y, int32_t Z,
@@ -192,7 +196,7 @@ SVOX2_API int svox2_tv_grad_sparse(const int32_t* links, int32_t X, int32_t Y, i
                          int64_t n_cells, int64_t scale_cells, uint8_t* mask_out,
                          int32_t start_dim, int32_t end_dim, float scale, int32_t ignore_edge,
                          int32_t ignore_last_z, float ndc_coeffx, float ndc_coeffy,
-                         float* grad_data, svox2_stream_t stream);
+                         float* grad_data, int64_t grad_stride, svox2_stream_t stream);
 SVOX2_API int svox2_msi_tv_grad_sparse(const int32_t* background_links, int32_t reso, const float* msi,
                              int32_t nlayers, int32_t nchannels, const int32_t* rand_cells,
                              int64_t n_cells, int64_t scale_cells, uint8_t* mask_out, float scale,

@@ -63,6 +63,8 @@ class GradsT(C.Structure):
         ("grad_background_out", C.c_void_p),
         ("mask_out", C.c_void_p),
         ("mask_background_out", C.c_void_p),
+        ("grad_sh_stride", C.c_int64),
+        ("grad_density_stride", C.c_int64),
     ]
 
 
@@ -84,15 +86,15 @@ SIGNATURES = {
     "svox2_volume_render_expected_term": (C.c_int, [_G, _P, _P, _I64, _O, _P, _P]),
     "svox2_volume_render_sigma_thresh": (C.c_int, [_G, _P, _P, _I64, _O, _F, _P, _P]),
     "svox2_sample_grid": (C.c_int, [_G, _P, _I64, _P, _P, _P]),
-    "svox2_sample_grid_backward": (C.c_int, [_G, _P, _I64, _P, _P, _P, _P, _P]),
+    "svox2_sample_grid_backward": (C.c_int, [_G, _P, _I64, _P, _P, _P, _I64, _P, _I64, _P]),
     "svox2_dilate": (C.c_int, [_P, _I32, _I32, _I32, _P, _P]),
     "svox2_accel_workspace_bytes": (_SZ, [_I32, _I32, _I32]),
     "svox2_accel_dist_prop": (C.c_int, [_P, _I32, _I32, _I32, _P, _SZ, _P]),
     "svox2_grid_weight_render": (C.c_int, [_P, _I32, _I32, _I32, _CAM, _F, _F, _I32, _P, _P, _P, _P]),
     "svox2_tv": (C.c_int, [_P, _I32, _I32, _I32, _P, _I64, _I32, _I32, _I32, _F, _F, _P, _P]),
-    "svox2_tv_grad": (C.c_int, [_P, _I32, _I32, _I32, _P, _I64, _I32, _I32, _F, _I32, _F, _F, _P, _P]),
+    "svox2_tv_grad": (C.c_int, [_P, _I32, _I32, _I32, _P, _I64, _I32, _I32, _F, _I32, _F, _F, _P, _I64, _P]),
     "svox2_tv_grad_sparse": (C.c_int, [_P, _I32, _I32, _I32, _P, _I64, _P, _I64, _I64, _P, _I32, _I32,
-                                       _F, _I32, _I32, _F, _F, _P, _P]),
+                                       _F, _I32, _I32, _F, _F, _P, _I64, _P]),
     "svox2_msi_tv_grad_sparse": (C.c_int, [_P, _I32, _P, _I32, _I32, _P, _I64, _I64, _P, _F, _F, _P, _P]),
     "svox2_rmsprop_step": (C.c_int, [_P, _P, _P, _I64, _I32, _I64, _I32, _P, _P, _I64, _F, _F, _F, _F,
                                      _F, _P]),

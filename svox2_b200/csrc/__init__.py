@@ -210,16 +210,16 @@ def _grads_struct(grads, gspec):
     keep = []
     if _defined(grads.grad_density_out):
         _check_rows(grads.grad_density_out, "grad_density_out")
-        if _row_stride(grads.grad_density_out) != _row_stride(gspec.density_data) or \
-                grads.grad_density_out.size(0) != gspec.density_data.size(0):
-            _fail("grad_density_out must have the layout of density_data")
+        if grads.grad_density_out.shape != gspec.density_data.shape:
+            _fail("grad_density_out must have the shape of density_data")
         gr.grad_density_out = grads.grad_density_out.data_ptr()
+        gr.grad_density_stride = _row_stride(grads.grad_density_out)
     if _defined(grads.grad_sh_out):
         _check_rows(grads.grad_sh_out, "grad_sh_out")
-        if _row_stride(grads.grad_sh_out) != _row_stride(gspec.sh_data) or \
-                grads.grad_sh_out.size(0) != gspec.sh_data.size(0):
-            _fail("grad_sh_out must have the layout of sh_data")
+        if grads.grad_sh_out.shape != gspec.sh_data.shape:
+            _fail("grad_sh_out must have the shape of sh_data")
         gr.grad_sh_out = grads.grad_sh_out.data_ptr()
+        gr.grad_sh_stride = _row_stride(grads.grad_sh_out)
     if _defined(grads.grad_background_out) and grads.grad_background_out.numel() > 0:
         _check_input(grads.grad_background_out, "grad_background_out", torch.float32)
         gr.grad_background_out = grads.grad_background_out.data_ptr()
@@ -269,7 +269,8 @@ def sample_grid_backward(grid, points, grad_out_density, grad_out_sh, grad_densi
         check(_lib.lib().svox2_sample_grid_backward(
             C.byref(g), points.data_ptr(), points.size(0), grad_out_density.data_ptr(),
             grad_out_sh.data_ptr() if want_colors else None, grad_density_out.data_ptr(),
-            grad_sh_out.data_ptr() if want_colors else None, _stream()))
+            _row_stride(grad_density_out), grad_sh_out.data_ptr() if want_colors else None,
+            _row_stride(grad_sh_out), _stream()))
 
 
 def volume_render_cuvol(grid, rays, opt, _counters=None):
@@ -335,7 +336,15 @@ def volume_render_cuvol_fused(grid, rays, opt, rgb_gt, beta_loss, sparsity_loss,
     o = _opt_struct(opt)
     Q = origins.size(0)
     with torch.cuda.device(origins.device):
-        ws, nbytes = _workspace(Q, origins.device)
+        # per-ray scalars + forward->backward colour cache: 16 B per active sample, at most one
+        # slot per lattice step along the grid diagonal (capped so the scratch stays <= 256 MB)
+        nbytes = _lib.lib().svox2_render_workspace_bytes(Q)
+        if Q > 0:
+            diag = sum(float(s) ** 2 for s in grid.links.shape) ** 0.5
+            slots = int(diag / max(float(opt.step_size), 1e-3)) + 2
+            slots = max(0, min(slots, 4096, (256 << 20) // (16 * Q)))
+            nbytes += 16 * slots * Q
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=origins.device)
         check(_lib.lib().svox2_volume_render_cuvol_fused(
             C.byref(g), origins.data_ptr(), dirs.data_ptr(), Q, Q if _norm_rays is None else _norm_rays,
             C.byref(o), rgb_gt.data_ptr(), float(beta_loss), float(sparsity_loss), rgb_out.data_ptr(),
@@ -455,7 +464,7 @@ def tv_grad(links, data, start_dim, end_dim, scale, use_logalpha, logalpha_delta
         check(_lib.lib().svox2_tv_grad(links.data_ptr(), X, Y, Z, data.data_ptr(), _row_stride(data),
                                        int(start_dim), int(end_dim), float(scale),
                                        int(bool(ignore_edge)), float(ndc_coeffx), float(ndc_coeffy),
-                                       grad_data.data_ptr(), _stream()))
+                                       grad_data.data_ptr(), _row_stride(grad_data), _stream()))
 
 
 def tv_grad_sparse(links, data, rand_cells, mask_out, start_dim, end_dim, scale, use_logalpha,
@@ -474,7 +483,7 @@ def tv_grad_sparse(links, data, rand_cells, mask_out, start_dim, end_dim, scale,
             links.data_ptr(), X, Y, Z, data.data_ptr(), _row_stride(data), rand_cells.data_ptr(),
             rand_cells.size(0), int(_scale_cells), mask_ptr, int(start_dim), int(end_dim),
             float(scale), int(bool(ignore_edge)), int(bool(ignore_last_z)), float(ndc_coeffx),
-            float(ndc_coeffy), grad_data.data_ptr(), _stream()))
+            float(ndc_coeffy), grad_data.data_ptr(), _row_stride(grad_data), _stream()))
 
 
 def msi_tv_grad_sparse(links, msi, rand_cells, mask_out, scale, scale_last, grad_msi,

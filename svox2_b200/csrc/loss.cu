@@ -71,7 +71,7 @@ tv_kernel(const int32_t* __restrict__ links, int X, int Y, int Z, const float* _
 __global__ void __launch_bounds__(TV_THREADS)
 tv_grad_kernel(const int32_t* __restrict__ links, int X, int Y, int Z,
                const float* __restrict__ data, int64_t stride, int start_dim, int end_dim,
-               float scale, int64_t Q, int ignore_edge, float* __restrict__ grad) {
+               float scale, int64_t Q, int ignore_edge, float* __restrict__ grad, int64_t gstride) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= Q) return;
     const int nd = end_dim - start_dim;
@@ -98,26 +98,30 @@ tv_grad_kernel(const int32_t* __restrict__ links, int X, int Y, int Z,
     dx = __fmul_rn(dx, sc[0]);
     dy = __fmul_rn(dy, sc[1]);
     dz = __fmul_rn(dz, sc[2]);
-    if (dx != 0.f && l100 >= 0) atomicAdd(grad + (int64_t)l100 * stride + idx, __fmul_rn(dx, idelta));
-    if (dy != 0.f && l010 >= 0) atomicAdd(grad + (int64_t)l010 * stride + idx, __fmul_rn(dy, idelta));
-    if (dz != 0.f && l001 >= 0) atomicAdd(grad + (int64_t)l001 * stride + idx, __fmul_rn(dz, idelta));
+    if (dx != 0.f && l100 >= 0) atomicAdd(grad + (int64_t)l100 * gstride + idx, __fmul_rn(dx, idelta));
+    if (dy != 0.f && l010 >= 0) atomicAdd(grad + (int64_t)l010 * gstride + idx, __fmul_rn(dy, idelta));
+    if (dz != 0.f && l001 >= 0) atomicAdd(grad + (int64_t)l001 * gstride + idx, __fmul_rn(dz, idelta));
     if (l000 >= 0)
-        atomicAdd(grad + (int64_t)l000 * stride + idx,
+        atomicAdd(grad + (int64_t)l000 * gstride + idx,
                   __fmul_rn(-__fadd_rn(__fadd_rn(dx, dy), dz), idelta));
 }
 
 // tv_grad_sparse_kernel, loss_kernel.cu:178-246
+// LPC lanes cooperate on one cell (lane = channel, looping when there are more channels than
+// lanes): the cell decode and the four link loads are done once per cell instead of once per
+// (cell, channel) thread, and there is no 64-bit division on the thread index.
+template <int LPC>
 __global__ void __launch_bounds__(TV_THREADS)
 tv_grad_sparse_kernel(const int32_t* __restrict__ links, int X, int Y, int Z,
                       const float* __restrict__ data, int64_t stride,
                       const int32_t* __restrict__ rand_cells, int start_dim, int end_dim,
-                      float scale, int64_t Q, int ignore_edge, int ignore_last_z,
-                      uint8_t* __restrict__ mask_out, float* __restrict__ grad) {
+                      float scale, int64_t n_cells, int ignore_edge, int ignore_last_z,
+                      uint8_t* __restrict__ mask_out, float* __restrict__ grad, int64_t gstride) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= Q) return;
-    const int nd = end_dim - start_dim;
-    const int idx = (int)(tid % nd) + start_dim;
-    const int xyz = __ldg(rand_cells + tid / nd);
+    const int64_t cell = tid / LPC;
+    if (cell >= n_cells) return;
+    const int sub = (int)(tid % LPC);
+    const int xyz = __ldg(rand_cells + cell);
     const int z = xyz % Z;
     const int xy = xyz / Z;
     const int y = xy % Y;
@@ -133,28 +137,31 @@ tv_grad_sparse_kernel(const int32_t* __restrict__ links, int X, int Y, int Z,
     const int32_t lnk010 = y + 1 < Y ? __ldg(lp + Z) : 0;
     const int32_t lnk100 = x + 1 < X ? __ldg(lp + offx) : 0;
     if (ignore_last_z && z == Z - 2) return;
+    if (lnk000 < 0 && lnk001 < 0 && lnk010 < 0 && lnk100 < 0) return;  // nothing to read or write
 
-    const float v000 = lnk000 >= 0 ? __ldg(data + (int64_t)lnk000 * stride + idx) : 0.f;
-    const float nullv = ignore_edge ? v000 : 0.f;
-    const float v001 = lnk001 >= 0 ? __ldg(data + (int64_t)lnk001 * stride + idx) : nullv;
-    const float v010 = lnk010 >= 0 ? __ldg(data + (int64_t)lnk010 * stride + idx) : nullv;
-    const float v100 = lnk100 >= 0 ? __ldg(data + (int64_t)lnk100 * stride + idx) : nullv;
-    float dx = __fsub_rn(v100, v000), dy = __fsub_rn(v010, v000), dz = __fsub_rn(v001, v000);
-    const float idelta = __fmul_rn(scale, inv_delta(dx, dy, dz));
-    dx = __fmul_rn(dx, sc[0]);
-    dy = __fmul_rn(dy, sc[1]);
-    dz = __fmul_rn(dz, sc[2]);
-    const float sm = -__fadd_rn(__fadd_rn(dx, dy), dz);
+    for (int idx = start_dim + sub; idx < end_dim; idx += LPC) {
+        const float v000 = lnk000 >= 0 ? __ldg(data + (int64_t)lnk000 * stride + idx) : 0.f;
+        const float nullv = ignore_edge ? v000 : 0.f;
+        const float v001 = lnk001 >= 0 ? __ldg(data + (int64_t)lnk001 * stride + idx) : nullv;
+        const float v010 = lnk010 >= 0 ? __ldg(data + (int64_t)lnk010 * stride + idx) : nullv;
+        const float v100 = lnk100 >= 0 ? __ldg(data + (int64_t)lnk100 * stride + idx) : nullv;
+        float dx = __fsub_rn(v100, v000), dy = __fsub_rn(v010, v000), dz = __fsub_rn(v001, v000);
+        const float idelta = __fmul_rn(scale, inv_delta(dx, dy, dz));
+        dx = __fmul_rn(dx, sc[0]);
+        dy = __fmul_rn(dy, sc[1]);
+        dz = __fmul_rn(dz, sc[2]);
+        const float sm = -__fadd_rn(__fadd_rn(dx, dy), dz);
 #define MAYBE_ADD_SET(lnk, val)                                                      \
     if ((lnk) >= 0 && (val) != 0.f) {                                                \
-        atomicAdd(grad + (int64_t)(lnk) * stride + idx, __fmul_rn((val), idelta));   \
+        atomicAdd(grad + (int64_t)(lnk) * gstride + idx, __fmul_rn((val), idelta));   \
         if (mask_out) mask_out[(lnk)] = 1;                                           \
     }
-    MAYBE_ADD_SET(lnk000, sm);
-    MAYBE_ADD_SET(lnk001, dz);
-    MAYBE_ADD_SET(lnk010, dy);
-    MAYBE_ADD_SET(lnk100, dx);
+        MAYBE_ADD_SET(lnk000, sm);
+        MAYBE_ADD_SET(lnk001, dz);
+        MAYBE_ADD_SET(lnk010, dy);
+        MAYBE_ADD_SET(lnk100, dx);
 #undef MAYBE_ADD_SET
+    }
 }
 
 // msi_tv_grad_sparse_kernel, loss_kernel.cu:248-333
@@ -246,14 +253,16 @@ extern "C" SVOX2_API int svox2_tv(const int32_t* links, int32_t X, int32_t Y, in
 extern "C" SVOX2_API int svox2_tv_grad(const int32_t* links, int32_t X, int32_t Y, int32_t Z,
                              const float* data, int64_t data_stride, int32_t start_dim,
                              int32_t end_dim, float scale, int32_t ignore_edge, float ndc_coeffx,
-                             float ndc_coeffy, float* grad_data, svox2_stream_t stream) {
+                             float ndc_coeffy, float* grad_data, int64_t grad_stride,
+                             svox2_stream_t stream) {
     (void)ndc_coeffx; (void)ndc_coeffy;
     if (int e = check_tv_args(links, X, Y, Z, data, data_stride, start_dim, end_dim, __func__)) return e;
     SVOX2_REQUIRE(grad_data, "grad_data must not be null");
     const int nl = (X - 1) * (Y - 1) * (Z - 1);
     const int64_t Q = (int64_t)nl * (end_dim - start_dim);
     tv_grad_kernel<<<div_up(Q, TV_THREADS), TV_THREADS, 0, (cudaStream_t)stream>>>(
-        links, X, Y, Z, data, data_stride, start_dim, end_dim, scale / nl, Q, ignore_edge, grad_data);
+        links, X, Y, Z, data, data_stride, start_dim, end_dim, scale / nl, Q, ignore_edge, grad_data,
+        grad_stride > 0 ? grad_stride : data_stride);
     return check_launch(__func__);
 }
 
@@ -263,17 +272,26 @@ extern "C" SVOX2_API int svox2_tv_grad_sparse(const int32_t* links, int32_t X, i
                                     int64_t scale_cells, uint8_t* mask_out, int32_t start_dim,
                                     int32_t end_dim, float scale, int32_t ignore_edge,
                                     int32_t ignore_last_z, float ndc_coeffx, float ndc_coeffy,
-                                    float* grad_data, svox2_stream_t stream) {
+                                    float* grad_data, int64_t grad_stride, svox2_stream_t stream) {
     (void)ndc_coeffx; (void)ndc_coeffy;
     if (int e = check_tv_args(links, X, Y, Z, data, data_stride, start_dim, end_dim, __func__)) return e;
     SVOX2_REQUIRE(grad_data, "grad_data must not be null");
     SVOX2_REQUIRE(n_cells >= 0 && (n_cells == 0 || rand_cells), "rand_cells must not be null");
     if (n_cells == 0) return SVOX2_OK;
     if (scale_cells <= 0) scale_cells = n_cells;
-    const int64_t Q = n_cells * (end_dim - start_dim);
-    tv_grad_sparse_kernel<<<div_up(Q, TV_THREADS), TV_THREADS, 0, (cudaStream_t)stream>>>(
-        links, X, Y, Z, data, data_stride, rand_cells, start_dim, end_dim,
-        scale / (float)(int)scale_cells, Q, ignore_edge, ignore_last_z, mask_out, grad_data);
+    const int nd = end_dim - start_dim;
+    const float s = scale / (float)(int)scale_cells;
+    const int64_t gs = grad_stride > 0 ? grad_stride : data_stride;
+    cudaStream_t st = (cudaStream_t)stream;
+#define TV_LAUNCH(LPC)                                                                          \
+    tv_grad_sparse_kernel<LPC><<<div_up(n_cells * LPC, TV_THREADS), TV_THREADS, 0, st>>>(       \
+        links, X, Y, Z, data, data_stride, rand_cells, start_dim, end_dim, s, n_cells,          \
+        ignore_edge, ignore_last_z, mask_out, grad_data, gs)
+    if (nd <= 1) TV_LAUNCH(1);
+    else if (nd <= 4) TV_LAUNCH(4);
+    else if (nd <= 16) TV_LAUNCH(16);
+    else TV_LAUNCH(32);
+#undef TV_LAUNCH
     return check_launch(__func__);
 }
 

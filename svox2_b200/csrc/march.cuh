@@ -1,0 +1,48 @@
+// Interface of the lattice-batch march kernel (march.cu) used by the C-ABI entry points.
+#pragma once
+#include "common.cuh"
+
+namespace svox2b {
+
+struct MarchArgs {
+    const float* __restrict__ origins;      // [Q,3] (ignored when rays come from the camera)
+    const float* __restrict__ dirs;
+    CamView cam;
+    int row_begin;
+    int64_t n_rays;
+    float* __restrict__ rgb_out;            // forward / fused: [Q,3]
+    float* __restrict__ logT_out;           // forward: final log-transmittance (-1e3 if stopped);
+                                            // backward-only: the backward march's value; or NULL
+    const float* __restrict__ grad_in;      // backward: grad_out [Q,3]; fused seed: rgb_gt
+    const float* __restrict__ color_cache;  // backward-only: forward colours [Q,3]
+    const float* __restrict__ logT_in;      // backward-only: forward log-transmittance (beta loss)
+    float* __restrict__ accum_out;          // backward: MSI hand-over, or NULL
+    float beta_loss;                        // already divided by norm_rays
+    float sparsity_loss;
+    float norm_factor;                      // 2/(3*norm_rays)
+    int fused_seed;                         // 1: gradient seed is (colour - grad_in)*norm_factor
+    unsigned long long* __restrict__ counters;
+    int64_t gsh_stride, gd_stride;          // row strides of the gradient arrays
+    float4* __restrict__ ccache;            // fused: [Q, ccap] forward->backward colour cache, or NULL
+    int ccap;                               // cache slots per ray (overflow samples are re-gathered)
+};
+
+enum { LB_MODE_FWD = 0, LB_MODE_BWD = 1, LB_MODE_FUSED = 2 };
+
+bool march_vec_ok(const GridView& g, const GradView* gr, int64_t gsh_stride);
+void launch_lattice_march(int mode, bool from_cam, const GridView& g, const Opts& opt,
+                          const MarchArgs& a, const GradView& gr, cudaStream_t st);
+
+}  // namespace svox2b
+
+namespace svox2b {
+// launchers defined in render.cu (v1 march kernels, MSI background, depth)
+void launch_v1_fwd(bool from_cam, const GridView& g, const Opts& opt, const MarchArgs& a, cudaStream_t st);
+void launch_v1_bwd(const GridView& g, const Opts& opt, const MarchArgs& a, const GradView& gr, cudaStream_t st);
+void launch_bg_fwd(bool from_cam, const GridView& g, const Opts& opt, const MarchArgs& a,
+                   const float* logT, cudaStream_t st);
+void launch_bg_bwd(const GridView& g, const Opts& opt, const MarchArgs& a, const float* color_cache,
+                   const float* logT, const float* accum, const GradView& gr, cudaStream_t st);
+void launch_depth(bool sigma_thresh_mode, const GridView& g, const Opts& opt, const float* origins,
+                  const float* dirs, int64_t n_rays, float thresh, float* out, cudaStream_t st);
+}  // namespace svox2b

@@ -343,7 +343,8 @@ extern "C" SVOX2_API int svox2_sample_grid(const svox2_grid_t* grid, const float
 extern "C" SVOX2_API int svox2_sample_grid_backward(const svox2_grid_t* grid, const float* points,
                                           int64_t n_points, const float* grad_out_density,
                                           const float* grad_out_sh, float* grad_density_out,
-                                          float* grad_sh_out, svox2_stream_t stream) {
+                                          int64_t grad_density_stride, float* grad_sh_out,
+                                          int64_t grad_sh_stride, svox2_stream_t stream) {
     if (int e = validate_grid(grid, __func__)) return e;
     SVOX2_REQUIRE(n_points >= 0 && (n_points == 0 || (points && grad_out_density && grad_density_out)),
                   "null argument");
@@ -351,9 +352,11 @@ extern "C" SVOX2_API int svox2_sample_grid_backward(const svox2_grid_t* grid, co
     const GridView g = make_grid_view(grid);
     cudaStream_t st = (cudaStream_t)stream;
     sample_backward_kernel<<<div_up(n_points, MISC_THREADS), MISC_THREADS, 0, st>>>(
-        g, points, n_points, grad_out_density, 1, g.density_stride, grad_density_out);
+        g, points, n_points, grad_out_density, 1,
+        grad_density_stride > 0 ? grad_density_stride : g.density_stride, grad_density_out);
     if (grad_out_sh && grad_sh_out)
         sample_backward_kernel<<<div_up(n_points * g.sh_dim, MISC_THREADS), MISC_THREADS, 0, st>>>(
-            g, points, n_points, grad_out_sh, g.sh_dim, g.sh_stride, grad_sh_out);
+            g, points, n_points, grad_out_sh, g.sh_dim,
+            grad_sh_stride > 0 ? grad_sh_stride : g.sh_stride, grad_sh_out);
     return check_launch(__func__);
 }

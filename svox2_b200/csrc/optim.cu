@@ -1,7 +1,11 @@
 // RMSProp / SGD restricted to the sparse gradient mask (reference: optim_kernel.cu).
-// Pure streaming kernels: per updated element read data/rms/grad, write data/rms/grad (24 B).
-// One kernel per optimiser; the row selector (dense / bool mask / int64 index list,
-// optim_kernel.cu:175-215) is a warp-uniform-per-row predicate, channels are the fast axis.
+//
+// Pure streaming work: per updated element read data/rms/grad, write data/rms/grad (24 B).
+// The reference launches one thread per (row, channel) of the WHOLE array for the bool-mask
+// variant (rows*C threads that almost all exit) and therefore converts the mask to an index
+// list on the host first (one device sync per step, svox2.py:2215-2221).  Here a warp scans 32
+// mask bytes with one coalesced load, ballots, and then sweeps only the touched rows with
+// lane = channel (108-byte coalesced rows): cost ~ N/32 warp-steps + touched rows, no sync.
 #include "common.cuh"
 
 namespace svox2b {
@@ -28,48 +32,79 @@ __device__ __forceinline__ void sgd_once(float* __restrict__ d, float* __restric
     *gp = 0.f;
 }
 
-struct RowSel {
-    int kind;                       // SVOX2_INDEXER_*
+struct OptArgs {
+    float* __restrict__ data;
+    float* __restrict__ rms;   // NULL for SGD
+    float* __restrict__ grad;
+    int64_t rows;              // rows of the arrays (dense / mask) or number of indices
+    int C;
+    int64_t stride;
     const uint8_t* __restrict__ mask;
     const int64_t* __restrict__ index;
+    float beta, lr, eps, minval, lr_last;
 };
 
-// Element tid -> (row, channel); returns false when the element is not to be updated.
-__device__ __forceinline__ bool select(const RowSel& s, int64_t tid, int C, int64_t& row, int& ch) {
-    const int64_t r = tid / C;
-    ch = (int)(tid - r * C);
-    if (s.kind == SVOX2_INDEXER_INDEX) {
-        row = __ldg(s.index + r);
-        return true;
+template <bool RMS>
+__device__ __forceinline__ void update_row(const OptArgs& a, int64_t row, int lane) {
+    for (int ch = lane; ch < a.C; ch += WARP) {
+        const int64_t off = row * a.stride + ch;
+        const float lr = (ch == a.C - 1) ? a.lr_last : a.lr;
+        if (RMS) rmsprop_once(a.data + off, a.rms + off, a.grad + off, a.beta, lr, a.eps, a.minval);
+        else sgd_once(a.data + off, a.grad + off, lr);
     }
-    row = r;
-    if (s.kind == SVOX2_INDEXER_MASK) return __ldg(s.mask + r) != 0;
-    return true;
 }
 
+// bool-mask variant, C > 1: a warp owns 32 consecutive rows
+template <bool RMS>
 __global__ void __launch_bounds__(OPT_THREADS)
-rmsprop_kernel(float* __restrict__ data, float* __restrict__ rms, float* __restrict__ grad,
-               int64_t Q, int C, int64_t stride, RowSel sel, float beta, float lr, float eps,
-               float minval, float lr_last) {
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= Q) return;
-    int64_t row;
-    int ch;
-    if (!select(sel, tid, C, row, ch)) return;
-    const int64_t off = row * stride + ch;
-    rmsprop_once(data + off, rms + off, grad + off, beta, ch == C - 1 ? lr_last : lr, eps, minval);
+masked_rows_kernel(OptArgs a) {
+    const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t row0 = warp_id * WARP;
+    if (row0 >= a.rows) return;
+    const int64_t my_row = row0 + lane;
+    const bool on = my_row < a.rows && __ldg(a.mask + my_row) != 0;
+    unsigned m = __ballot_sync(FULL, on);
+    while (m) {
+        const int r = __ffs(m) - 1;
+        m &= m - 1;
+        update_row<RMS>(a, row0 + r, lane);
+    }
 }
 
+// dense / index variants and single-channel arrays: one thread per (row, channel) element
+template <bool RMS, int KIND>
 __global__ void __launch_bounds__(OPT_THREADS)
-sgd_kernel(float* __restrict__ data, float* __restrict__ grad, int64_t Q, int C, int64_t stride,
-           RowSel sel, float lr, float lr_last) {
+elementwise_kernel(OptArgs a, int64_t Q) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= Q) return;
-    int64_t row;
-    int ch;
-    if (!select(sel, tid, C, row, ch)) return;
-    const int64_t off = row * stride + ch;
-    sgd_once(data + off, grad + off, ch == C - 1 ? lr_last : lr);
+    const int64_t r = tid / a.C;
+    const int ch = (int)(tid - r * a.C);
+    int64_t row = r;
+    if (KIND == SVOX2_INDEXER_INDEX) row = __ldg(a.index + r);
+    if (KIND == SVOX2_INDEXER_MASK && __ldg(a.mask + r) == 0) return;
+    const int64_t off = row * a.stride + ch;
+    const float lr = (ch == a.C - 1) ? a.lr_last : a.lr;
+    if (RMS) rmsprop_once(a.data + off, a.rms + off, a.grad + off, a.beta, lr, a.eps, a.minval);
+    else sgd_once(a.data + off, a.grad + off, lr);
+}
+
+template <bool RMS>
+void launch(const OptArgs& a, int kind, int64_t n_index, cudaStream_t st) {
+    if (kind == SVOX2_INDEXER_MASK && a.C > 1) {
+        const int64_t warps = (a.rows + WARP - 1) / WARP;
+        masked_rows_kernel<RMS><<<div_up(warps * WARP, OPT_THREADS), OPT_THREADS, 0, st>>>(a);
+        return;
+    }
+    const int64_t nrow = kind == SVOX2_INDEXER_INDEX ? n_index : a.rows;
+    const int64_t Q = nrow * a.C;
+    const unsigned blocks = div_up(Q, OPT_THREADS);
+    if (kind == SVOX2_INDEXER_DENSE)
+        elementwise_kernel<RMS, SVOX2_INDEXER_DENSE><<<blocks, OPT_THREADS, 0, st>>>(a, Q);
+    else if (kind == SVOX2_INDEXER_MASK)
+        elementwise_kernel<RMS, SVOX2_INDEXER_MASK><<<blocks, OPT_THREADS, 0, st>>>(a, Q);
+    else
+        elementwise_kernel<RMS, SVOX2_INDEXER_INDEX><<<blocks, OPT_THREADS, 0, st>>>(a, Q);
 }
 
 int check_opt_args(const float* data, const float* grad, int64_t rows, int C, int64_t stride,
@@ -105,37 +140,36 @@ int check_opt_args(const float* data, const float* grad, int64_t rows, int C, in
 using namespace svox2b;
 
 extern "C" SVOX2_API int svox2_rmsprop_step(float* data, float* rms, float* grad, int64_t rows,
-                                  int32_t n_channels, int64_t row_stride, int32_t indexer_kind,
-                                  const uint8_t* mask, const int64_t* index, int64_t n_index,
-                                  float beta, float lr, float epsilon, float minval, float lr_last,
-                                  svox2_stream_t stream) {
+                                            int32_t n_channels, int64_t row_stride,
+                                            int32_t indexer_kind, const uint8_t* mask,
+                                            const int64_t* index, int64_t n_index, float beta,
+                                            float lr, float epsilon, float minval, float lr_last,
+                                            svox2_stream_t stream) {
     if (int e = check_opt_args(data, grad, rows, n_channels, row_stride, indexer_kind, mask, index,
                                n_index, __func__))
         return e;
     SVOX2_REQUIRE(rms, "rms must not be null");
     if (lr_last < 0.f) lr_last = lr;  // optim_kernel.cu:171
     const int64_t nrow = indexer_kind == SVOX2_INDEXER_INDEX ? n_index : rows;
-    const int64_t Q = nrow * n_channels;
-    if (Q == 0) return SVOX2_OK;
-    RowSel sel{indexer_kind, mask, index};
-    rmsprop_kernel<<<div_up(Q, OPT_THREADS), OPT_THREADS, 0, (cudaStream_t)stream>>>(
-        data, rms, grad, Q, n_channels, row_stride, sel, beta, lr, epsilon, minval, lr_last);
+    if (nrow * n_channels == 0) return SVOX2_OK;
+    OptArgs a{data, rms, grad, rows, n_channels, row_stride, mask, index,
+              beta, lr, epsilon, minval, lr_last};
+    launch<true>(a, indexer_kind, n_index, (cudaStream_t)stream);
     return check_launch(__func__);
 }
 
 extern "C" SVOX2_API int svox2_sgd_step(float* data, float* grad, int64_t rows, int32_t n_channels,
-                              int64_t row_stride, int32_t indexer_kind, const uint8_t* mask,
-                              const int64_t* index, int64_t n_index, float lr, float lr_last,
-                              svox2_stream_t stream) {
+                                        int64_t row_stride, int32_t indexer_kind,
+                                        const uint8_t* mask, const int64_t* index, int64_t n_index,
+                                        float lr, float lr_last, svox2_stream_t stream) {
     if (int e = check_opt_args(data, grad, rows, n_channels, row_stride, indexer_kind, mask, index,
                                n_index, __func__))
         return e;
     if (lr_last < 0.f) lr_last = lr;
     const int64_t nrow = indexer_kind == SVOX2_INDEXER_INDEX ? n_index : rows;
-    const int64_t Q = nrow * n_channels;
-    if (Q == 0) return SVOX2_OK;
-    RowSel sel{indexer_kind, mask, index};
-    sgd_kernel<<<div_up(Q, OPT_THREADS), OPT_THREADS, 0, (cudaStream_t)stream>>>(
-        data, grad, Q, n_channels, row_stride, sel, lr, lr_last);
+    if (nrow * n_channels == 0) return SVOX2_OK;
+    OptArgs a{data, nullptr, grad, rows, n_channels, row_stride, mask, index,
+              0.f, lr, 0.f, 0.f, lr_last};
+    launch<false>(a, indexer_kind, n_index, (cudaStream_t)stream);
     return check_launch(__func__);
 }

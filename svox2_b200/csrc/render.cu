@@ -9,10 +9,11 @@
 //   MSI       render_lerp_kernel_cuvol.cu:386-607, 775-860
 //   depth     render_lerp_kernel_cuvol.cu:122-225, 862-902
 #include "common.cuh"
+#include "march.cuh"
 
 namespace svox2b {
 
-namespace {
+namespace v1 {
 
 constexpr int MARCH_THREADS = 128;
 constexpr int BG_THREADS = 128;
@@ -550,232 +551,75 @@ depth_kernel(GridView g, Opts opt, const float* __restrict__ origins,
     out[ray_id] = outv;
 }
 
-int validate_rays(const float* origins, const float* dirs, int64_t n, const char* who) {
-    if (n < 0 || (n > 0 && (!origins || !dirs))) {
-        set_error("%s: rays must be non-null [Q,3] float32 device arrays", who);
-        return SVOX2_ERR_INVALID;
-    }
-    if (n * 32 > (int64_t)2147483647 * MARCH_THREADS) {
-        set_error("%s: too many rays", who);
-        return SVOX2_ERR_INVALID;
-    }
-    return SVOX2_OK;
+}  // namespace v1
+
+// ---------------------------------------------------------------------------------------
+// host launchers used by render_abi.cu
+// ---------------------------------------------------------------------------------------
+using namespace v1;
+
+static RaySource make_source(const MarchArgs& a) {
+    return RaySource{a.origins, a.dirs, a.cam, a.row_begin};
 }
 
-GradView make_grad_view(const svox2_grads_t* gr) {
-    GradView v;
-    v.grad_density = gr->grad_density_out;
-    v.grad_sh = gr->grad_sh_out;
-    v.grad_bg = gr->grad_background_out;
-    v.mask = gr->mask_out;
-    v.mask_bg = gr->mask_background_out;
-    return v;
+// v1 (warp-per-ray, lane-per-channel) march kernels: kept as a debugging / A-B reference for the
+// lattice-batch kernel; selected with SVOX2_B200_MARCH=v1.  Gradient strides must equal the
+// data strides on this path.
+void launch_v1_fwd(bool from_cam, const GridView& g, const Opts& opt, const MarchArgs& a,
+                   cudaStream_t st) {
+    const unsigned blocks = div_up(a.n_rays * WARP, MARCH_THREADS);
+    const RaySource src = make_source(a);
+    if (from_cam)
+        march_fwd_kernel<true, false><<<blocks, MARCH_THREADS, 0, st>>>(g, opt, src, a.n_rays, a.rgb_out,
+                                                                       a.logT_out, nullptr);
+    else if (a.counters)
+        march_fwd_kernel<false, true><<<blocks, MARCH_THREADS, 0, st>>>(g, opt, src, a.n_rays, a.rgb_out,
+                                                                       a.logT_out, a.counters);
+    else
+        march_fwd_kernel<false, false><<<blocks, MARCH_THREADS, 0, st>>>(g, opt, src, a.n_rays, a.rgb_out,
+                                                                        a.logT_out, nullptr);
 }
 
-struct Workspace {
-    float* logT;
-    float* accum;
-};
-
-int carve_workspace(void* ws, size_t bytes, int64_t n_rays, Workspace& w, const char* who) {
-    const size_t need = svox2_render_workspace_bytes(n_rays);
-    if (!ws || bytes < need) {
-        set_error("%s: workspace too small (%zu < %zu bytes)", who, bytes, need);
-        return SVOX2_ERR_WORKSPACE;
-    }
-    w.logT = reinterpret_cast<float*>(ws);
-    w.accum = w.logT + ((n_rays + 63) / 64) * 64;
-    return SVOX2_OK;
+void launch_v1_bwd(const GridView& g, const Opts& opt, const MarchArgs& a, const GradView& gr,
+                   cudaStream_t st) {
+    BwdArgs b{};
+    b.grad_in = a.grad_in;
+    b.color_cache = a.color_cache;
+    b.logT_in = a.logT_in;
+    b.accum_out = a.accum_out;
+    b.logT_out = a.logT_out;
+    b.beta_loss = a.beta_loss;
+    b.sparsity_loss = a.sparsity_loss;
+    b.norm_factor = a.norm_factor;
+    b.fused = a.fused_seed;
+    march_bwd_kernel<<<div_up(a.n_rays * WARP, MARCH_THREADS), MARCH_THREADS, 0, st>>>(
+        g, opt, a.origins, a.dirs, a.n_rays, b, gr);
 }
 
-}  // namespace
+void launch_bg_fwd(bool from_cam, const GridView& g, const Opts& opt, const MarchArgs& a,
+                   const float* logT, cudaStream_t st) {
+    const RaySource src = make_source(a);
+    const unsigned blocks = div_up(a.n_rays, BG_THREADS);
+    if (from_cam)
+        bg_fwd_kernel<true><<<blocks, BG_THREADS, 0, st>>>(g, opt, src, a.n_rays, logT, a.rgb_out, a.counters);
+    else
+        bg_fwd_kernel<false><<<blocks, BG_THREADS, 0, st>>>(g, opt, src, a.n_rays, logT, a.rgb_out, a.counters);
+}
+
+void launch_bg_bwd(const GridView& g, const Opts& opt, const MarchArgs& a, const float* color_cache,
+                   const float* logT, const float* accum, const GradView& gr, cudaStream_t st) {
+    bg_bwd_kernel<<<div_up(a.n_rays, BG_THREADS), BG_THREADS, 0, st>>>(
+        g, opt, a.origins, a.dirs, a.n_rays, a.grad_in, color_cache, logT, accum, a.fused_seed,
+        a.norm_factor, a.sparsity_loss, gr);
+}
+
+void launch_depth(bool sigma_thresh_mode, const GridView& g, const Opts& opt, const float* origins,
+                  const float* dirs, int64_t n_rays, float thresh, float* out, cudaStream_t st) {
+    const unsigned blocks = div_up(n_rays, MARCH_THREADS);
+    if (sigma_thresh_mode)
+        depth_kernel<true><<<blocks, MARCH_THREADS, 0, st>>>(g, opt, origins, dirs, n_rays, thresh, out);
+    else
+        depth_kernel<false><<<blocks, MARCH_THREADS, 0, st>>>(g, opt, origins, dirs, n_rays, thresh, out);
+}
 
 }  // namespace svox2b
-
-using namespace svox2b;
-
-extern "C" SVOX2_API size_t svox2_render_workspace_bytes(int64_t n_rays) {
-    const int64_t padded = ((n_rays + 63) / 64) * 64;
-    return (size_t)padded * 2 * sizeof(float) + 256;
-}
-
-extern "C" SVOX2_API int svox2_volume_render_cuvol(const svox2_grid_t* grid, const float* origins,
-                                         const float* dirs, int64_t n_rays,
-                                         const svox2_render_opts_t* opt, float* out,
-                                         void* workspace, size_t workspace_bytes,
-                                         int64_t* counters, svox2_stream_t stream) {
-    if (int e = validate_grid(grid, __func__)) return e;
-    if (int e = validate_rays(origins, dirs, n_rays, __func__)) return e;
-    SVOX2_REQUIRE(opt && (out || n_rays == 0), "opt/out must not be null");
-    if (n_rays == 0) return SVOX2_OK;
-    const GridView g = make_grid_view(grid);
-    const bool has_bg = g.bg_nlayers > 0;
-    Workspace w{nullptr, nullptr};
-    if (has_bg)
-        if (int e = carve_workspace(workspace, workspace_bytes, n_rays, w, __func__)) return e;
-    RaySource src{origins, dirs, CamView{}, 0};
-    const unsigned blocks = div_up(n_rays * WARP, MARCH_THREADS);
-    auto* ctr = reinterpret_cast<unsigned long long*>(counters);
-    if (counters)
-        march_fwd_kernel<false, true><<<blocks, MARCH_THREADS, 0, (cudaStream_t)stream>>>(
-            g, *opt, src, n_rays, out, w.logT, ctr);
-    else
-        march_fwd_kernel<false, false><<<blocks, MARCH_THREADS, 0, (cudaStream_t)stream>>>(
-            g, *opt, src, n_rays, out, w.logT, nullptr);
-    if (has_bg)
-        bg_fwd_kernel<false><<<div_up(n_rays, BG_THREADS), BG_THREADS, 0, (cudaStream_t)stream>>>(
-            g, *opt, src, n_rays, w.logT, out, ctr);
-    return check_launch(__func__);
-}
-
-extern "C" SVOX2_API int svox2_volume_render_cuvol_image(const svox2_grid_t* grid, const svox2_camera_t* cam,
-                                               const svox2_render_opts_t* opt, int32_t row_begin,
-                                               int32_t row_end, float* out, void* workspace,
-                                               size_t workspace_bytes, svox2_stream_t stream) {
-    if (int e = validate_grid(grid, __func__)) return e;
-    SVOX2_REQUIRE(cam && cam->c2w && opt && out, "cam/opt/out must not be null");
-    SVOX2_REQUIRE(cam->width > 0 && cam->height > 0, "camera size must be positive");
-    SVOX2_REQUIRE(row_begin >= 0 && row_end <= cam->height && row_begin <= row_end,
-                  "row range must lie inside the image");
-    const int64_t n_rays = (int64_t)(row_end - row_begin) * cam->width;
-    if (n_rays == 0) return SVOX2_OK;
-    const GridView g = make_grid_view(grid);
-    const bool has_bg = g.bg_nlayers > 0;
-    Workspace w{nullptr, nullptr};
-    if (has_bg)
-        if (int e = carve_workspace(workspace, workspace_bytes, n_rays, w, __func__)) return e;
-    RaySource src{nullptr, nullptr,
-                  CamView{cam->c2w, cam->fx, cam->fy, cam->cx, cam->cy, cam->width, cam->height,
-                          cam->ndc_coeffx, cam->ndc_coeffy},
-                  row_begin};
-    float* out_rows = out + (int64_t)row_begin * cam->width * 3;
-    march_fwd_kernel<true, false>
-        <<<div_up(n_rays * WARP, MARCH_THREADS), MARCH_THREADS, 0, (cudaStream_t)stream>>>(
-            g, *opt, src, n_rays, out_rows, w.logT, nullptr);
-    if (has_bg)
-        bg_fwd_kernel<true><<<div_up(n_rays, BG_THREADS), BG_THREADS, 0, (cudaStream_t)stream>>>(
-            g, *opt, src, n_rays, w.logT, out_rows, nullptr);
-    return check_launch(__func__);
-}
-
-static int validate_grads(const svox2_grid_t* grid, const svox2_grads_t* grads, const char* who) {
-    if (!grads || !grads->grad_density_out || !grads->grad_sh_out) {
-        set_error("%s: grad_density_out and grad_sh_out are required", who);
-        return SVOX2_ERR_INVALID;
-    }
-    (void)grid;
-    return SVOX2_OK;
-}
-
-extern "C" SVOX2_API int svox2_volume_render_cuvol_backward(const svox2_grid_t* grid, const float* origins,
-                                                  const float* dirs, int64_t n_rays,
-                                                  const svox2_render_opts_t* opt,
-                                                  const float* grad_out, const float* color_cache,
-                                                  const svox2_grads_t* grads, void* workspace,
-                                                  size_t workspace_bytes, svox2_stream_t stream) {
-    if (int e = validate_grid(grid, __func__)) return e;
-    if (int e = validate_rays(origins, dirs, n_rays, __func__)) return e;
-    if (int e = validate_grads(grid, grads, __func__)) return e;
-    SVOX2_REQUIRE(opt && grad_out && color_cache, "opt/grad_out/color_cache must not be null");
-    if (n_rays == 0) return SVOX2_OK;
-    const GridView g = make_grid_view(grid);
-    GradView gr = make_grad_view(grads);
-    const bool use_bg = g.bg_nlayers > 0;
-    Workspace w{nullptr, nullptr};
-    if (use_bg)
-        if (int e = carve_workspace(workspace, workspace_bytes, n_rays, w, __func__)) return e;
-    BwdArgs a{};
-    a.grad_in = grad_out;
-    a.color_cache = color_cache;
-    a.logT_in = nullptr;
-    a.accum_out = w.accum;
-    a.logT_out = w.logT;
-    a.beta_loss = 0.f;
-    a.sparsity_loss = 0.f;
-    a.norm_factor = 0.f;
-    a.fused = 0;
-    march_bwd_kernel<<<div_up(n_rays * WARP, MARCH_THREADS), MARCH_THREADS, 0,
-                       (cudaStream_t)stream>>>(g, *opt, origins, dirs, n_rays, a, gr);
-    if (use_bg && gr.grad_bg)
-        bg_bwd_kernel<<<div_up(n_rays, BG_THREADS), BG_THREADS, 0, (cudaStream_t)stream>>>(
-            g, *opt, origins, dirs, n_rays, grad_out, color_cache, w.logT, w.accum, 0, 0.f, 0.f, gr);
-    return check_launch(__func__);
-}
-
-extern "C" SVOX2_API int svox2_volume_render_cuvol_fused(const svox2_grid_t* grid, const float* origins,
-                                               const float* dirs, int64_t n_rays,
-                                               int64_t norm_rays, const svox2_render_opts_t* opt,
-                                               const float* rgb_gt, float beta_loss,
-                                               float sparsity_loss, float* rgb_out,
-                                               const svox2_grads_t* grads, void* workspace,
-                                               size_t workspace_bytes, int64_t* counters,
-                                               svox2_stream_t stream) {
-    if (int e = validate_grid(grid, __func__)) return e;
-    if (int e = validate_rays(origins, dirs, n_rays, __func__)) return e;
-    if (int e = validate_grads(grid, grads, __func__)) return e;
-    SVOX2_REQUIRE(opt && rgb_gt && rgb_out, "opt/rgb_gt/rgb_out must not be null");
-    SVOX2_REQUIRE(norm_rays > 0 || n_rays == 0, "norm_rays must be positive");
-    if (n_rays == 0) return SVOX2_OK;
-    const GridView g = make_grid_view(grid);
-    GradView gr = make_grad_view(grads);
-    const bool use_bg = g.bg_nlayers > 0;
-    const bool need_logT = use_bg || beta_loss > 0.f;
-    Workspace w{nullptr, nullptr};
-    if (need_logT)
-        if (int e = carve_workspace(workspace, workspace_bytes, n_rays, w, __func__)) return e;
-    RaySource src{origins, dirs, CamView{}, 0};
-    const unsigned blocks = div_up(n_rays * WARP, MARCH_THREADS);
-    auto* ctr = reinterpret_cast<unsigned long long*>(counters);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (counters)
-        march_fwd_kernel<false, true><<<blocks, MARCH_THREADS, 0, st>>>(g, *opt, src, n_rays, rgb_out,
-                                                                      w.logT, ctr);
-    else
-        march_fwd_kernel<false, false><<<blocks, MARCH_THREADS, 0, st>>>(g, *opt, src, n_rays,
-                                                                       rgb_out, w.logT, nullptr);
-    if (use_bg)
-        bg_fwd_kernel<false><<<div_up(n_rays, BG_THREADS), BG_THREADS, 0, st>>>(
-            g, *opt, src, n_rays, w.logT, rgb_out, ctr);
-    BwdArgs a{};
-    a.grad_in = rgb_gt;
-    a.color_cache = rgb_out;
-    a.logT_in = beta_loss > 0.f ? w.logT : nullptr;
-    a.accum_out = use_bg ? w.accum : nullptr;
-    a.logT_out = nullptr;
-    a.beta_loss = beta_loss / (float)norm_rays;           // cuvol.cu:1127
-    a.sparsity_loss = sparsity_loss;
-    a.norm_factor = 2.f / (float)(3 * (int)norm_rays);    // cuvol.cu:736
-    a.fused = 1;
-    march_bwd_kernel<<<blocks, MARCH_THREADS, 0, st>>>(g, *opt, origins, dirs, n_rays, a, gr);
-    if (use_bg && gr.grad_bg)
-        bg_bwd_kernel<<<div_up(n_rays, BG_THREADS), BG_THREADS, 0, st>>>(
-            g, *opt, origins, dirs, n_rays, rgb_gt, rgb_out, w.logT, w.accum, 1, a.norm_factor,
-            sparsity_loss, gr);
-    return check_launch(__func__);
-}
-
-extern "C" SVOX2_API int svox2_volume_render_expected_term(const svox2_grid_t* grid, const float* origins,
-                                                 const float* dirs, int64_t n_rays,
-                                                 const svox2_render_opts_t* opt, float* out,
-                                                 svox2_stream_t stream) {
-    if (int e = validate_grid(grid, __func__)) return e;
-    if (int e = validate_rays(origins, dirs, n_rays, __func__)) return e;
-    SVOX2_REQUIRE(opt && (out || n_rays == 0), "opt/out must not be null");
-    if (n_rays == 0) return SVOX2_OK;
-    depth_kernel<false><<<div_up(n_rays, MARCH_THREADS), MARCH_THREADS, 0, (cudaStream_t)stream>>>(
-        make_grid_view(grid), *opt, origins, dirs, n_rays, 0.f, out);
-    return check_launch(__func__);
-}
-
-extern "C" SVOX2_API int svox2_volume_render_sigma_thresh(const svox2_grid_t* grid, const float* origins,
-                                                const float* dirs, int64_t n_rays,
-                                                const svox2_render_opts_t* opt, float sigma_thresh,
-                                                float* out, svox2_stream_t stream) {
-    if (int e = validate_grid(grid, __func__)) return e;
-    if (int e = validate_rays(origins, dirs, n_rays, __func__)) return e;
-    SVOX2_REQUIRE(opt && (out || n_rays == 0), "opt/out must not be null");
-    if (n_rays == 0) return SVOX2_OK;
-    depth_kernel<true><<<div_up(n_rays, MARCH_THREADS), MARCH_THREADS, 0, (cudaStream_t)stream>>>(
-        make_grid_view(grid), *opt, origins, dirs, n_rays, sigma_thresh, out);
-    return check_launch(__func__);
-}

@@ -27,6 +27,30 @@ BASIS_TYPE_3D_TEXTURE = 4
 BASIS_TYPE_MLP = 255
 
 
+def _pad_cols(d: int) -> int:
+    return (d + 3) // 4 * 4
+
+
+def _padded_zeros(n: int, d: int, device, dtype=torch.float32) -> torch.Tensor:
+    """A zero [N, D] view with 16-byte aligned rows (row stride = D rounded up to 4 floats).
+
+    HBM layout of the SH coefficients: 27 floats per voxel are stored in 28-float (112 B) rows so
+    that the march kernel can gather a row with 128-bit loads and scatter its gradient with
+    128-bit vector reductions.  The public tensor keeps the reference's [N, 27] shape."""
+    return torch.zeros((n, _pad_cols(d)), dtype=dtype, device=device)[:, :d]
+
+
+def _padded_copy(t: torch.Tensor) -> torch.Tensor:
+    out = _padded_zeros(t.size(0), t.size(1), t.device, t.dtype)
+    out.copy_(t)
+    return out
+
+
+def _is_padded(t: torch.Tensor) -> bool:
+    return t.dim() == 2 and (t.size(0) <= 1 or t.stride(0) == _pad_cols(t.size(1))) and \
+        t.stride(1) == 1 and t.data_ptr() % 16 == 0
+
+
 def _no_fallback(what):
     raise NotImplementedError(
         f"{what}: svox2_b200 has no pure-PyTorch / CPU path by design; tensors must be CUDA and "
@@ -292,8 +316,7 @@ class SparseGrid(nn.Module):
 
         self.density_data = nn.Parameter(
             torch.zeros(self.capacity, 1, dtype=torch.float32, device=device))
-        self.sh_data = nn.Parameter(
-            torch.zeros(self.capacity, self.basis_dim * 3, dtype=torch.float32, device=device))
+        self.sh_data = nn.Parameter(_padded_zeros(self.capacity, self.basis_dim * 3, device))
         self.basis_data = nn.Parameter(
             torch.empty(0, 0, 0, 0, dtype=torch.float32, device=device), requires_grad=False)
 
@@ -372,7 +395,23 @@ class SparseGrid(nn.Module):
         return torch.addcmul(roffset.to(points.device), points, rscaling.to(points.device))
 
     # ---- spec for the operator boundary (svox2.py:2135-2161) ---------------------------
+    def _ensure_layout(self):
+        """Re-home sh_data (and its grad / RMS state) into 16-byte aligned rows if user code
+        replaced the parameter with a plain contiguous [N, 27] tensor (opt.py / load / tests do).
+        Values are preserved; only the storage stride changes (27 -> 28 floats)."""
+        p = self.sh_data
+        if not p.is_cuda or _is_padded(p.data):
+            return
+        grad = p.grad
+        new = nn.Parameter(_padded_copy(p.data), requires_grad=p.requires_grad)
+        if grad is not None and grad.shape == p.shape:
+            new.grad = _padded_copy(grad)
+        self.sh_data = new
+        if self.sh_rms is not None and self.sh_rms.shape == new.shape and not _is_padded(self.sh_rms):
+            self.sh_rms = _padded_copy(self.sh_rms)
+
     def _to_cpp(self, grid_coords: bool = False, replace_basis_data=None):
+        self._ensure_layout()
         spec = _C.SparseGridSpec()
         spec.density_data = self.density_data
         spec.sh_data = self.sh_data
@@ -399,6 +438,7 @@ class SparseGrid(nn.Module):
         if not (use_kernel and self.links.is_cuda):
             _no_fallback("SparseGrid.sample")
         assert points.is_cuda
+        self._ensure_layout()
         return _SampleGridAutogradFunction.apply(
             self.density_data, self.sh_data, self._to_cpp(grid_coords=grid_coords),
             points.contiguous(), want_colors)
@@ -421,6 +461,7 @@ class SparseGrid(nn.Module):
         if not (use_kernel and self.links.is_cuda):
             _no_fallback("SparseGrid.volume_render")
         assert rays.is_cuda
+        self._ensure_layout()
         return _VolumeRenderFunction.apply(
             self.density_data, self.sh_data,
             self.background_data if self.use_background else None,
@@ -773,13 +814,18 @@ class SparseGrid(nn.Module):
 
     # ---- optimisers (svox2.py:1972-2107) ----------------------------------------------------------
     def _step(self, param, rms_name, indexer, lr, lr_last, beta, epsilon, optim, flat_channels=None):
+        if param.grad is not None and param.grad.stride() != param.data.stride():
+            param.grad = self._zeros_same_layout(param.data).copy_(param.grad)  # e.g. autograd grads
         data, grad = param.data, param.grad
         if flat_channels is not None:
             data, grad = data.view(-1, flat_channels), grad.view(-1, flat_channels)
         if optim == "rmsprop":
             rms = getattr(self, rms_name)
-            if rms is None or rms.shape != param.data.shape:
-                rms = torch.zeros_like(param.data)
+            if rms is None or rms.shape != param.data.shape or rms.stride() != param.data.stride():
+                old = rms if (rms is not None and rms.shape == param.data.shape) else None
+                rms = self._zeros_same_layout(param.data)
+                if old is not None:
+                    rms.copy_(old)
                 setattr(self, rms_name, rms)
             rms_v = rms.view(-1, flat_channels) if flat_channels is not None else rms
             _C.rmsprop_step(data, rms_v, grad, indexer, beta, lr, epsilon, -1e9, lr_last)
@@ -798,6 +844,7 @@ class SparseGrid(nn.Module):
     def optim_sh_step(self, lr: float, beta: float = 0.9, epsilon: float = 1e-8,
                       optim: str = "rmsprop"):
         self._require_cuda("SparseGrid.optim_sh_step")
+        self._ensure_layout()
         self._step(self.sh_data, "sh_rms", self._maybe_convert_sparse_grad_indexer(sh=True),
                    lr, lr, beta, epsilon, optim)
 
@@ -815,15 +862,25 @@ class SparseGrid(nn.Module):
         raise NotImplementedError("learned bases are out of scope (basis_type is SH)")
 
     # ---- gradient / mask plumbing (svox2.py:2166-2260) ------------------------------------------
+    @staticmethod
+    def _zeros_same_layout(t):
+        if t.dim() == 2 and _is_padded(t) and t.size(1) != _pad_cols(t.size(1)):
+            return _padded_zeros(t.size(0), t.size(1), t.device, t.dtype)
+        return torch.zeros_like(t)
+
     def _get_data_grads(self):
+        self._ensure_layout()
         out = []
         for name in ("density_data", "sh_data", "background_data"):
             p = getattr(self, name)
             if not p.requires_grad:
-                out.append(torch.zeros_like(p.data))
+                out.append(self._zeros_same_layout(p.data))
                 continue
-            if p.grad is None or p.grad.shape != p.data.shape:
-                p.grad = torch.zeros_like(p.data)
+            if p.grad is None or p.grad.shape != p.data.shape or p.grad.stride() != p.data.stride():
+                old = p.grad if (p.grad is not None and p.grad.shape == p.data.shape) else None
+                p.grad = self._zeros_same_layout(p.data)
+                if old is not None:
+                    p.grad.copy_(old)
             out.append(p.grad)
         return out
 
