@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libsvox2_b200.so")
+# SVOX2_B200_LIB selects an A/B build variant (tools/build_variants.sh); default: the in-tree build
+LIB_PATH = os.environ.get("SVOX2_B200_LIB") or os.path.join(_HERE, "csrc", "libsvox2_b200.so")
 
 
 class Svox2Error(RuntimeError):

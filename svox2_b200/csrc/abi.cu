@@ -45,6 +45,15 @@ int validate_grid(const svox2_grid_t* g, const char* who) {
         set_error("%s: basis_dim must be 1, 4 or 9 (SH basis; 3*basis_dim <= 32 lanes)", who);
         return SVOX2_ERR_INVALID;
     }
+    if (g->sh_stride > (1 << 20) || g->density_stride > (1 << 20)) {
+        set_error("%s: row strides above 2^20 floats are not supported", who);
+        return SVOX2_ERR_INVALID;
+    }
+    if (g->n_rows < 1) {
+        // the march kernel loads row 0 unconditionally for empty corners
+        set_error("%s: the grid must store at least one voxel row", who);
+        return SVOX2_ERR_INVALID;
+    }
     if (g->sh_stride < 3 * g->basis_dim || g->density_stride < 1 || g->n_rows < 0) {
         set_error("%s: bad row strides (sh_stride %lld, density_stride %lld)", who,
                   (long long)g->sh_stride, (long long)g->density_stride);

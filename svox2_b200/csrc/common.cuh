@@ -44,8 +44,8 @@ struct GridView {
     int size[3];
     int basis_dim;
     int sh_dim;  // 3 * basis_dim
-    int64_t sh_stride;
-    int64_t density_stride;
+    int sh_stride;      // floats per row (32-bit so row*stride is one IMAD.WIDE)
+    int density_stride;
     int64_t offx;  // Y*Z
     int offy;      // Z
     float offset[3];
@@ -85,8 +85,8 @@ inline GridView make_grid_view(const svox2_grid_t* g) {
     }
     v.basis_dim = g->basis_dim;
     v.sh_dim = 3 * g->basis_dim;
-    v.sh_stride = g->sh_stride;
-    v.density_stride = g->density_stride;
+    v.sh_stride = (int)g->sh_stride;
+    v.density_stride = (int)g->density_stride;
     v.offx = (int64_t)g->size[1] * g->size[2];
     v.offy = g->size[2];
     const bool bg = g->background_links && g->background_data && g->background_nlayers > 0 &&

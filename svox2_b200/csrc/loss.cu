@@ -107,20 +107,23 @@ tv_grad_kernel(const int32_t* __restrict__ links, int X, int Y, int Z,
 }
 
 // tv_grad_sparse_kernel, loss_kernel.cu:178-246
-// LPC lanes cooperate on one cell (lane = channel, looping when there are more channels than
-// lanes): the cell decode and the four link loads are done once per cell instead of once per
-// (cell, channel) thread, and there is no 64-bit division on the thread index.
-template <int LPC>
-__global__ void __launch_bounds__(TV_THREADS)
-tv_grad_sparse_kernel(const int32_t* __restrict__ links, int X, int Y, int Z,
-                      const float* __restrict__ data, int64_t stride,
-                      const int32_t* __restrict__ rand_cells, int start_dim, int end_dim,
-                      float scale, int64_t n_cells, int ignore_edge, int ignore_last_z,
-                      uint8_t* __restrict__ mask_out, float* __restrict__ grad, int64_t gstride) {
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t cell = tid / LPC;
-    if (cell >= n_cells) return;
-    const int sub = (int)(tid % LPC);
+//
+// A warp owns 32 consecutive entries of rand_cells.  PROBE: lane j decodes cell j and loads its
+// four links (coalesced for the contiguous cell runs opt.py uses); cells that cannot contribute
+// (all four links empty, or the reference's early-outs) drop out by ballot, which is ~90% of a
+// run through a 10%-occupied grid.  WORK: COOP=true  - the warp sweeps the surviving cells one
+// at a time with lane = channel (coalesced 108 B rows; SH TV, 27 channels);
+// COOP=false - each lane finishes its own cell (density TV, 1 channel).
+struct TvCell {
+    int32_t l000, l001, l010, l100;
+    bool on;
+};
+
+__device__ __forceinline__ TvCell tv_probe(const int32_t* __restrict__ links, int X, int Y, int Z,
+                                           const int32_t* __restrict__ rand_cells, int64_t cell,
+                                           int64_t n_cells, int ignore_edge, int ignore_last_z) {
+    TvCell c{-1, -1, -1, -1, false};
+    if (cell >= n_cells) return c;
     const int xyz = __ldg(rand_cells + cell);
     const int z = xyz % Z;
     const int xy = xyz / Z;
@@ -128,39 +131,74 @@ tv_grad_sparse_kernel(const int32_t* __restrict__ links, int X, int Y, int Z,
     const int x = xy / Y;
     const int64_t offx = (int64_t)Y * Z;
     const int32_t* lp = links + (x * offx + (int64_t)y * Z + z);
-    const int32_t lnk000 = __ldg(lp);
-    if (ignore_edge && lnk000 == 0) return;
-    float sc[3];
-    ray_scale(X, Y, Z, sc);
+    c.l000 = __ldg(lp);
     // out-of-range neighbours read row 0, not "empty" (reference quirk)
-    const int32_t lnk001 = ((z + 1 < Z) && (!ignore_last_z || z != Z - 2)) ? __ldg(lp + 1) : 0;
-    const int32_t lnk010 = y + 1 < Y ? __ldg(lp + Z) : 0;
-    const int32_t lnk100 = x + 1 < X ? __ldg(lp + offx) : 0;
-    if (ignore_last_z && z == Z - 2) return;
-    if (lnk000 < 0 && lnk001 < 0 && lnk010 < 0 && lnk100 < 0) return;  // nothing to read or write
+    c.l001 = ((z + 1 < Z) && (!ignore_last_z || z != Z - 2)) ? __ldg(lp + 1) : 0;
+    c.l010 = y + 1 < Y ? __ldg(lp + Z) : 0;
+    c.l100 = x + 1 < X ? __ldg(lp + offx) : 0;
+    c.on = !(ignore_edge && c.l000 == 0) && !(ignore_last_z && z == Z - 2) &&
+           !(c.l000 < 0 && c.l001 < 0 && c.l010 < 0 && c.l100 < 0);
+    return c;
+}
 
-    for (int idx = start_dim + sub; idx < end_dim; idx += LPC) {
-        const float v000 = lnk000 >= 0 ? __ldg(data + (int64_t)lnk000 * stride + idx) : 0.f;
-        const float nullv = ignore_edge ? v000 : 0.f;
-        const float v001 = lnk001 >= 0 ? __ldg(data + (int64_t)lnk001 * stride + idx) : nullv;
-        const float v010 = lnk010 >= 0 ? __ldg(data + (int64_t)lnk010 * stride + idx) : nullv;
-        const float v100 = lnk100 >= 0 ? __ldg(data + (int64_t)lnk100 * stride + idx) : nullv;
-        float dx = __fsub_rn(v100, v000), dy = __fsub_rn(v010, v000), dz = __fsub_rn(v001, v000);
-        const float idelta = __fmul_rn(scale, inv_delta(dx, dy, dz));
-        dx = __fmul_rn(dx, sc[0]);
-        dy = __fmul_rn(dy, sc[1]);
-        dz = __fmul_rn(dz, sc[2]);
-        const float sm = -__fadd_rn(__fadd_rn(dx, dy), dz);
+__device__ __forceinline__ void tv_channel(const TvCell& c, int idx, const float* __restrict__ data,
+                                           int64_t stride, const float* sc, float scale,
+                                           int ignore_edge, uint8_t* __restrict__ mask_out,
+                                           float* __restrict__ grad, int64_t gstride) {
+    const float v000 = c.l000 >= 0 ? __ldg(data + (int64_t)c.l000 * stride + idx) : 0.f;
+    const float nullv = ignore_edge ? v000 : 0.f;
+    const float v001 = c.l001 >= 0 ? __ldg(data + (int64_t)c.l001 * stride + idx) : nullv;
+    const float v010 = c.l010 >= 0 ? __ldg(data + (int64_t)c.l010 * stride + idx) : nullv;
+    const float v100 = c.l100 >= 0 ? __ldg(data + (int64_t)c.l100 * stride + idx) : nullv;
+    float dx = __fsub_rn(v100, v000), dy = __fsub_rn(v010, v000), dz = __fsub_rn(v001, v000);
+    const float idelta = __fmul_rn(scale, inv_delta(dx, dy, dz));
+    dx = __fmul_rn(dx, sc[0]);
+    dy = __fmul_rn(dy, sc[1]);
+    dz = __fmul_rn(dz, sc[2]);
+    const float sm = -__fadd_rn(__fadd_rn(dx, dy), dz);
 #define MAYBE_ADD_SET(lnk, val)                                                      \
     if ((lnk) >= 0 && (val) != 0.f) {                                                \
         atomicAdd(grad + (int64_t)(lnk) * gstride + idx, __fmul_rn((val), idelta));   \
         if (mask_out) mask_out[(lnk)] = 1;                                           \
     }
-        MAYBE_ADD_SET(lnk000, sm);
-        MAYBE_ADD_SET(lnk001, dz);
-        MAYBE_ADD_SET(lnk010, dy);
-        MAYBE_ADD_SET(lnk100, dx);
+    MAYBE_ADD_SET(c.l000, sm);
+    MAYBE_ADD_SET(c.l001, dz);
+    MAYBE_ADD_SET(c.l010, dy);
+    MAYBE_ADD_SET(c.l100, dx);
 #undef MAYBE_ADD_SET
+}
+
+template <bool COOP>
+__global__ void __launch_bounds__(TV_THREADS)
+tv_grad_sparse_kernel(const int32_t* __restrict__ links, int X, int Y, int Z,
+                      const float* __restrict__ data, int64_t stride,
+                      const int32_t* __restrict__ rand_cells, int start_dim, int end_dim,
+                      float scale, int64_t n_cells, int ignore_edge, int ignore_last_z,
+                      uint8_t* __restrict__ mask_out, float* __restrict__ grad, int64_t gstride) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    if (tid - lane >= n_cells) return;  // whole warp past the end
+    const TvCell mine = tv_probe(links, X, Y, Z, rand_cells, tid, n_cells, ignore_edge, ignore_last_z);
+    float sc[3];
+    ray_scale(X, Y, Z, sc);
+    if (!COOP) {
+        if (mine.on)
+            for (int idx = start_dim; idx < end_dim; ++idx)
+                tv_channel(mine, idx, data, stride, sc, scale, ignore_edge, mask_out, grad, gstride);
+        return;
+    }
+    unsigned m = __ballot_sync(FULL, mine.on);
+    while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        TvCell c;
+        c.l000 = __shfl_sync(FULL, mine.l000, j);
+        c.l001 = __shfl_sync(FULL, mine.l001, j);
+        c.l010 = __shfl_sync(FULL, mine.l010, j);
+        c.l100 = __shfl_sync(FULL, mine.l100, j);
+        c.on = true;
+        for (int idx = start_dim + lane; idx < end_dim; idx += WARP)
+            tv_channel(c, idx, data, stride, sc, scale, ignore_edge, mask_out, grad, gstride);
     }
 }
 
@@ -283,14 +321,12 @@ extern "C" SVOX2_API int svox2_tv_grad_sparse(const int32_t* links, int32_t X, i
     const float s = scale / (float)(int)scale_cells;
     const int64_t gs = grad_stride > 0 ? grad_stride : data_stride;
     cudaStream_t st = (cudaStream_t)stream;
-#define TV_LAUNCH(LPC)                                                                          \
-    tv_grad_sparse_kernel<LPC><<<div_up(n_cells * LPC, TV_THREADS), TV_THREADS, 0, st>>>(       \
+#define TV_LAUNCH(COOP)                                                                         \
+    tv_grad_sparse_kernel<COOP><<<div_up(n_cells, TV_THREADS), TV_THREADS, 0, st>>>(            \
         links, X, Y, Z, data, data_stride, rand_cells, start_dim, end_dim, s, n_cells,          \
         ignore_edge, ignore_last_z, mask_out, grad_data, gs)
-    if (nd <= 1) TV_LAUNCH(1);
-    else if (nd <= 4) TV_LAUNCH(4);
-    else if (nd <= 16) TV_LAUNCH(16);
-    else TV_LAUNCH(32);
+    if (nd <= 2) TV_LAUNCH(false);
+    else TV_LAUNCH(true);
 #undef TV_LAUNCH
     return check_launch(__func__);
 }

@@ -64,6 +64,28 @@ __device__ __forceinline__ void lane_const_init(LaneConst& lc, int lane, int B, 
     }
 }
 
+// Tunables (A/B-tested on B200 with tools/build_variants.sh; see profiles/):
+#ifndef LB_PREFETCH_SH
+#define LB_PREFETCH_SH 2      // 0 off, 1 prefetch SH rows to L1, 2 to L2
+#endif
+#ifndef LB_PREFETCH_LINKS
+#define LB_PREFETCH_LINKS 1   // prefetch the next batch's link lines during the current batch
+#endif
+#ifndef LB_MIN_BLOCKS
+#define LB_MIN_BLOCKS 16      // __launch_bounds__ min CTAs/SM: 64-register cap, 32 warps/SM (A/B: profiles/r1_ab_variants.txt)
+#endif
+
+__device__ __forceinline__ void prefetch_line(const void* p) {
+#if LB_PREFETCH_SH == 1
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 template <bool VEC>
 __device__ __forceinline__ float4 load_quad(const float* __restrict__ p, int qi, int D) {
     if (VEC) return __ldg(reinterpret_cast<const float4*>(p));
@@ -175,6 +197,24 @@ __device__ __forceinline__ void march_pass(const GridView& g, const Opts& opt, c
             break;
         }
 
+#if LB_PREFETCH_LINKS
+        // The next batch starts at t_next: touch the link lines its candidates will probe so the
+        // probe loads of the next iteration find them in L2 (positions need not be exact here).
+        if (!done) {
+            const float ta = fmaf((float)lane, step, t_next);
+            if (ta <= ray.tmax) {
+                int nl[3];
+                float npos[3];
+                locate(ray, g, ta, nl, npos);
+                const int32_t* np = g.links + ((int64_t)nl[0] * g.offx + (int64_t)nl[1] * g.offy + nl[2]);
+                prefetch_l2(np);
+                prefetch_l2(np + g.offy);
+                prefetch_l2(np + g.offx);
+                prefetch_l2(np + g.offx + g.offy);
+            }
+        }
+#endif
+
         // ---- (3) sigma at member candidates ----
         const bool member = (members >> lane) & 1u;
         float sigma = 0.f;
@@ -190,6 +230,20 @@ __device__ __forceinline__ void march_pass(const GridView& g, const Opts& opt, c
         const float ws = (opt.last_sample_opaque && __fadd_rn(tk, step) > ray.tmax) ? 1e9f
                                                                                    : ray.world_step;
         const bool active = member && (sigma > opt.sigma_thresh);
+#if LB_PREFETCH_SH
+        // Start pulling this lane's 8 SH rows towards the SM now: the rounds below consume them
+        // one dependent round trip later, after the (serial) transmittance chain.  A 112-byte row
+        // touches at most two 128-byte lines.
+        if (active && (!BWD || ccache == nullptr)) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (lk[q] >= 0) {
+                    const float* row = g.sh + (int64_t)lk[q] * g.sh_stride;
+                    prefetch_line(row);
+                    prefetch_line(row + (D - 1));
+                }
+        }
+#endif
         const float pcnt = __fmul_rn(ws, sigma);
         unsigned act_m = __ballot_sync(FULL, active);
         float my_before = 0.f;
@@ -250,21 +304,26 @@ __device__ __forceinline__ void march_pass(const GridView& g, const Opts& opt, c
             const bool cached = BWD && has && ccache != nullptr && ord < ccap;
             float col[3] = {0.f, 0.f, 0.f};
             if (!BWD || __any_sync(FULL, has && !cached)) {
+                // Eight UNCONDITIONAL, independent 128-bit loads (all in flight together): an empty
+                // corner (or a group without a sample) reads row 0 and gets weight 0 instead of
+                // being predicated off, which would serialise the loads through a shared temp.
                 float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
-                const bool ld = has && lc.quad_on && !cached;
+                const bool ld = has && !cached;
+                const float* shq = g.sh + (lc.quad_on ? 4 * lc.qi : 0);
                 float4 v[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ld && L[q] >= 0)
-                        v[q] = load_quad<VEC>(g.sh + (int64_t)L[q] * g.sh_stride + 4 * lc.qi, lc.qi, D);
+                    const unsigned row = (ld && L[q] >= 0) ? (unsigned)L[q] : 0u;
+                    v[q] = load_quad<VEC>(shq + (size_t)row * (unsigned)g.sh_stride, lc.qi, D);
                 }
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    u.x = fmaf(wq[q], v[q].x, u.x);
-                    u.y = fmaf(wq[q], v[q].y, u.y);
-                    u.z = fmaf(wq[q], v[q].z, u.z);
-                    u.w = fmaf(wq[q], v[q].w, u.w);
+                    if (ld && L[q] >= 0) {  // predicated FMAs: a NaN in row 0 can never leak in
+                        u.x = fmaf(wq[q], v[q].x, u.x);
+                        u.y = fmaf(wq[q], v[q].y, u.y);
+                        u.z = fmaf(wq[q], v[q].z, u.z);
+                        u.w = fmaf(wq[q], v[q].w, u.w);
+                    }
                 }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
@@ -349,7 +408,7 @@ __device__ __forceinline__ void march_pass(const GridView& g, const Opts& opt, c
 }
 
 template <int MODE, bool VEC, bool FROM_CAM, bool COUNT>
-__global__ void __launch_bounds__(LB_THREADS)
+__global__ void __launch_bounds__(LB_THREADS, LB_MIN_BLOCKS)
 lattice_march_kernel(GridView g, Opts opt, MarchArgs a, GradView gr) {
     const int64_t ray_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (ray_id >= a.n_rays) return;

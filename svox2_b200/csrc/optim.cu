@@ -65,11 +65,72 @@ masked_rows_kernel(OptArgs a) {
     const int64_t my_row = row0 + lane;
     const bool on = my_row < a.rows && __ldg(a.mask + my_row) != 0;
     unsigned m = __ballot_sync(FULL, on);
-    while (m) {
-        const int r = __ffs(m) - 1;
-        m &= m - 1;
-        update_row<RMS>(a, row0 + r, lane);
+    if (a.C > WARP) {
+        while (m) {
+            const int r = __ffs(m) - 1;
+            m &= m - 1;
+            update_row<RMS>(a, row0 + r, lane);
+        }
+        return;
     }
+    // C <= 32: four touched rows in flight per iteration (12 independent loads per lane)
+    const bool chan = lane < a.C;
+    const float lr = (lane == a.C - 1) ? a.lr_last : a.lr;
+    while (m) {
+        int64_t off[4];
+        float d[4], r[4], g[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            off[k] = -1;
+            if (m) {
+                off[k] = (row0 + (__ffs(m) - 1)) * a.stride + lane;
+                m &= m - 1;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (chan && off[k] >= 0) {
+                g[k] = a.grad[off[k]];
+                d[k] = a.data[off[k]];
+                if (RMS) r[k] = a.rms[off[k]];
+            }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (chan && off[k] >= 0) {
+                if (RMS) {
+                    rmsprop_once(&d[k], &r[k], &g[k], a.beta, lr, a.eps, a.minval);
+                    a.rms[off[k]] = r[k];
+                } else {
+                    sgd_once(&d[k], &g[k], lr);
+                }
+                a.data[off[k]] = d[k];
+                a.grad[off[k]] = 0.f;
+            }
+    }
+}
+
+// bool-mask variant, C == 1 (density): four rows per thread, one 32-bit mask load
+template <bool RMS>
+__global__ void __launch_bounds__(OPT_THREADS)
+masked_scalar_kernel(OptArgs a) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t row0 = t * 4;
+    if (row0 >= a.rows) return;
+    uint32_t bits = 0;
+    if (row0 + 4 <= a.rows && (reinterpret_cast<uintptr_t>(a.mask) & 3u) == 0) {
+        bits = __ldg(reinterpret_cast<const uint32_t*>(a.mask + row0));
+    } else {
+        for (int k = 0; k < 4 && row0 + k < a.rows; ++k)
+            bits |= (uint32_t)(__ldg(a.mask + row0 + k) != 0) << (8 * k);
+    }
+    if (bits == 0) return;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if ((bits >> (8 * k)) & 0xffu) {
+            const int64_t off = (row0 + k) * a.stride;
+            if (RMS) rmsprop_once(a.data + off, a.rms + off, a.grad + off, a.beta, a.lr_last, a.eps, a.minval);
+            else sgd_once(a.data + off, a.grad + off, a.lr_last);
+        }
 }
 
 // dense / index variants and single-channel arrays: one thread per (row, channel) element
@@ -94,6 +155,10 @@ void launch(const OptArgs& a, int kind, int64_t n_index, cudaStream_t st) {
     if (kind == SVOX2_INDEXER_MASK && a.C > 1) {
         const int64_t warps = (a.rows + WARP - 1) / WARP;
         masked_rows_kernel<RMS><<<div_up(warps * WARP, OPT_THREADS), OPT_THREADS, 0, st>>>(a);
+        return;
+    }
+    if (kind == SVOX2_INDEXER_MASK && a.C == 1) {
+        masked_scalar_kernel<RMS><<<div_up((a.rows + 3) / 4, OPT_THREADS), OPT_THREADS, 0, st>>>(a);
         return;
     }
     const int64_t nrow = kind == SVOX2_INDEXER_INDEX ? n_index : a.rows;
