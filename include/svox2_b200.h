@@ -105,6 +105,12 @@ SVOX2_API int svox2_cuda_available(void);
 /* Scratch bytes the renderer entry points need for Q rays (log_transmit + accum). */
 SVOX2_API size_t svox2_render_workspace_bytes(int64_t n_rays);
 
+/* Scratch for svox2_volume_render_cuvol_fused sized for an average of `slots_per_ray` active
+ * samples per ray (record queue of the sample-queue kernels / colour cache of the single-kernel
+ * path).  Any size >= svox2_render_workspace_bytes() is legal: overflow falls back, never fails.
+ * The workspace must be 256-byte aligned. */
+SVOX2_API size_t svox2_fused_workspace_bytes(int64_t n_rays, int64_t slots_per_ray);
+
 /* volume_render_cuvol  (svox2.cpp:18, render_lerp_kernel_cuvol.cu:918-958)
  * out [Q,3].  counters may be NULL. */
 SVOX2_API int svox2_volume_render_cuvol(const svox2_grid_t* grid, const float* origins, const float* dirs,

@@ -79,6 +79,7 @@ SIGNATURES = {
     "svox2_version": (C.c_char_p, []),
     "svox2_cuda_available": (C.c_int, []),
     "svox2_render_workspace_bytes": (_SZ, [_I64]),
+    "svox2_fused_workspace_bytes": (_SZ, [_I64, _I64]),
     "svox2_volume_render_cuvol": (C.c_int, [_G, _P, _P, _I64, _O, _P, _P, _SZ, _P, _P]),
     "svox2_volume_render_cuvol_image": (C.c_int, [_G, _CAM, _O, _I32, _I32, _P, _P, _SZ, _P]),
     "svox2_volume_render_cuvol_backward": (C.c_int, [_G, _P, _P, _I64, _O, _P, _P, _GR, _P, _SZ, _P]),

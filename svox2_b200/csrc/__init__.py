@@ -336,14 +336,14 @@ def volume_render_cuvol_fused(grid, rays, opt, rgb_gt, beta_loss, sparsity_loss,
     o = _opt_struct(opt)
     Q = origins.size(0)
     with torch.cuda.device(origins.device):
-        # per-ray scalars + forward->backward colour cache: 16 B per active sample, at most one
-        # slot per lattice step along the grid diagonal (capped so the scratch stays <= 256 MB)
-        nbytes = _lib.lib().svox2_render_workspace_bytes(Q)
+        # scratch for the sample queue: up to 512 active samples per ray on average (never more
+        # than the lattice steps along the grid diagonal), capped at 1 GiB; overflow only costs speed
+        slots = 0
         if Q > 0:
             diag = sum(float(s) ** 2 for s in grid.links.shape) ** 0.5
             slots = int(diag / max(float(opt.step_size), 1e-3)) + 2
-            slots = max(0, min(slots, 4096, (256 << 20) // (16 * Q)))
-            nbytes += 16 * slots * Q
+            slots = max(64, min(slots, 512, (1 << 30) // (96 * Q)))
+        nbytes = _lib.lib().svox2_fused_workspace_bytes(Q, slots)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=origins.device)
         check(_lib.lib().svox2_volume_render_cuvol_fused(
             C.byref(g), origins.data_ptr(), dirs.data_ptr(), Q, Q if _norm_rays is None else _norm_rays,

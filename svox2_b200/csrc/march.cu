@@ -412,6 +412,7 @@ __global__ void __launch_bounds__(LB_THREADS, LB_MIN_BLOCKS)
 lattice_march_kernel(GridView g, Opts opt, MarchArgs a, GradView gr) {
     const int64_t ray_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (ray_id >= a.n_rays) return;
+    if (a.run_if != nullptr && *a.run_if == 0) return;  // fallback launch that is not needed
     const int lane = threadIdx.x & 31;
 
     float ow[3], dw[3];

@@ -25,11 +25,17 @@ struct MarchArgs {
     int64_t gsh_stride, gd_stride;          // row strides of the gradient arrays
     float4* __restrict__ ccache;            // fused: [Q, ccap] forward->backward colour cache, or NULL
     int ccap;                               // cache slots per ray (overflow samples are re-gathered)
+    const int* __restrict__ run_if;         // if set: the kernel is a no-op unless *run_if != 0
 };
 
 enum { LB_MODE_FWD = 0, LB_MODE_BWD = 1, LB_MODE_FUSED = 2 };
 
 bool march_vec_ok(const GridView& g, const GradView* gr, int64_t gsh_stride);
+// sample-queue fused path (queue_march.cu)
+size_t queue_workspace_bytes(int64_t n_rays, int64_t records);
+bool launch_queue_fused(const GridView& g, const Opts& opt, const MarchArgs& a, const GradView& gr,
+                        void* workspace, size_t workspace_bytes, const int** overflow_flag,
+                        cudaStream_t st);
 void launch_lattice_march(int mode, bool from_cam, const GridView& g, const Opts& opt,
                           const MarchArgs& a, const GradView& gr, cudaStream_t st);
 

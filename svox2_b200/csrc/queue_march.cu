@@ -1,0 +1,528 @@
+// Sample-queue fused march: the training-step renderer for small ray batches.
+//
+// Why: with 5000 rays per step a warp-per-ray kernel is ONE wave of 5000 warps whose duration is
+// the longest ray; as short rays retire the SMs drain (ncu: 22 % achieved occupancy for the
+// lattice kernel).  The expensive work -- gathering 8 SH rows per active sample and scattering
+// their gradients -- has no sequential dependence once each sample's compositing weight is
+// known, so it is taken out of the per-ray warp and run SAMPLE-parallel over a compact queue:
+//
+//   K1 trace   (warp per ray)    lattice traversal, sigma, log-transmittance chain (bit-exact,
+//                                same code path as march.cu); every active sample becomes a
+//                                96-byte record {8 links, pos, weight, logT, sigma, ws, ray};
+//                                blocks of <=32 records are bump-allocated with one atomic per
+//                                batch and chained per ray.
+//   K2 shade   (8 lanes/sample)  128-bit gathers of the 8 corner rows, colours, atomicAdd of
+//                                weight*max(colour,0) into rgb_out; colour sums kept in the record.
+//   K3 seed    (warp per ray)    MSE/beta seed from the ray's final colour, then the reference's
+//                                accum recursion over the ray's records (a warp scan per block);
+//                                leaves dL/dcolour and dL/dsigma in each record.
+//   K4 scatter (8 lanes/sample)  red.global.add.v4.f32 into grad_sh, density atomics, mask bytes.
+//
+// K2 and K4 are perfectly load balanced (grid-stride over the queue) and expose one independent
+// gather/scatter per 8 lanes.  If the queue overflows its workspace a device flag makes K2-K4
+// no-ops and the single-kernel lattice path (march.cu) redoes the batch, so correctness never
+// depends on the workspace size.
+//
+// Parity: K1 is the reference's traversal (render_lerp_kernel_cuvol.cu:56-109) -> identical sample
+// set and mask; colours/gradients are reassociated sums (float atomics), within 1e-6 relative.
+#include "common.cuh"
+#include "march.cuh"
+
+namespace svox2b {
+namespace {
+
+constexpr int TRACE_THREADS = 64;
+constexpr int SAMPLE_THREADS = 256;
+
+struct __align__(16) Record {
+    int32_t lk[8];       // corner links
+    float px, py, pz, w; // fractional position, compositing weight
+    float after, sigma, ws;
+    int32_t ray;
+    float c0, c1, c2, cgs;  // K2: colour sums (+0.5); K3: dL/dcolour (weight applied), dL/dsigma
+    int32_t blk_count, blk_next, pad0, pad1;  // valid in the first record of a block
+};
+static_assert(sizeof(Record) == 96, "record layout");
+
+struct QueueView {
+    Record* __restrict__ rec;
+    int capacity;
+    int* __restrict__ counter;    // records allocated so far
+    int* __restrict__ overflow;   // set when the queue ran out of space
+    int* __restrict__ ray_first;  // [Q] first block of each ray or -1
+    float* __restrict__ ray_logT; // [Q] forward log-transmittance (-1e3 when stopped)
+    float4* __restrict__ ray_Y;   // [Q][8] SH basis value of channels 4q..4q+3 (0 for padding)
+};
+
+__device__ __forceinline__ unsigned range_mask(int a, int b) {
+    const unsigned hi = (b >= 32) ? 0xffffffffu : ((1u << b) - 1u);
+    const unsigned lo = (a >= 32) ? 0xffffffffu : ((1u << a) - 1u);
+    return hi & ~lo;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// ---------------------------------------------------------------------------------------
+// K1: traversal -> records
+// ---------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(TRACE_THREADS, 16)
+trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv) {
+    const int64_t ray_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (ray_id >= a.n_rays) return;
+    const int lane = threadIdx.x & 31;
+    float ow[3], dw[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        ow[i] = __ldg(a.origins + ray_id * 3 + i);
+        dw[i] = __ldg(a.dirs + ray_id * 3 + i);
+    }
+    if (lane < 8) {  // per-ray basis table for the sample-parallel kernels
+        float y[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = lane * 4 + e;
+            y[e] = j < g.sh_dim ? sh_basis_k(g.basis_dim, j % g.basis_dim, dw) : 0.f;
+        }
+        qv.ray_Y[ray_id * 8 + lane] = make_float4(y[0], y[1], y[2], y[3]);
+    }
+    Ray ray;
+    ray_setup(ray, ow, dw, g, opt);
+    const float step = opt.step_size;
+    unsigned cnt[3] = {0u, 0u, 0u};
+    float lt = 0.f;
+    bool stopped = false;
+    int first_blk = -1, prev_blk = -1;
+
+    if (ray.tmin <= ray.tmax) {
+        float t0 = ray.tmin;
+        bool done = false;
+        while (!done) {
+            float tk = t0;
+#pragma unroll
+            for (int i = 0; i < 31; ++i) {
+                const float nx = __fadd_rn(tk, step);
+                tk = (i < lane) ? nx : tk;
+            }
+            const bool valid = tk <= ray.tmax;
+            int l[3];
+            float pos[3];
+            locate(ray, g, tk, l, pos);
+            const int32_t* lp = g.links + ((int64_t)l[0] * g.offx + (int64_t)l[1] * g.offy + l[2]);
+            int32_t lk[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) lk[q] = -1;
+            if (valid) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) lk[q] = __ldg(lp + corner_off(g, q));
+            }
+            const float skipd = skip_dist(ray, valid ? lk[0] : 0, l, pos);
+            const bool is_skip = valid && (skipd >= step);
+            const unsigned valid_m = __ballot_sync(FULL, valid);
+            const unsigned skip_m = __ballot_sync(FULL, is_skip);
+
+            unsigned members = 0;
+            int cur = 0;
+            float t_next = 0.f;
+            for (;;) {
+                const unsigned rem = 0xffffffffu << cur;
+                const unsigned inv = ~valid_m & rem, sk = skip_m & rem;
+                const int first_inv = inv ? __ffs(inv) - 1 : 32;
+                const int first_sk = sk ? __ffs(sk) - 1 : 32;
+                if (first_inv <= first_sk) {
+                    members |= range_mask(cur, first_inv);
+                    if (first_inv < 32) done = true;
+                    else t_next = __fadd_rn(__shfl_sync(FULL, tk, 31), step);
+                    break;
+                }
+                const int j = first_sk;
+                members |= range_mask(cur, j);
+                if (COUNT) ++cnt[0];
+                const float tn = skip_advance(__shfl_sync(FULL, tk, j), __shfl_sync(FULL, skipd, j), step);
+                const unsigned later = (j < 31) ? (0xffffffffu << (j + 1)) : 0u;
+                const unsigned eq = __ballot_sync(FULL, tk == tn) & later;
+                if (eq) {
+                    cur = __ffs(eq) - 1;
+                    continue;
+                }
+                t_next = tn;
+                if (!(tn <= ray.tmax)) done = true;
+                break;
+            }
+            if (!done) {  // next batch's link lines
+                const float ta = fmaf((float)lane, step, t_next);
+                if (ta <= ray.tmax) {
+                    int nl[3];
+                    float npos[3];
+                    locate(ray, g, ta, nl, npos);
+                    const int32_t* np = g.links + ((int64_t)nl[0] * g.offx + (int64_t)nl[1] * g.offy + nl[2]);
+                    prefetch_l2(np);
+                    prefetch_l2(np + g.offy);
+                    prefetch_l2(np + g.offx);
+                    prefetch_l2(np + g.offx + g.offy);
+                }
+            }
+            const bool member = (members >> lane) & 1u;
+            float sigma = 0.f;
+            if (member) {
+                float sv[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    sv[q] = lk[q] >= 0 ? __ldg(g.density + (int64_t)lk[q] * g.density_stride) : 0.f;
+                sigma = trilerp8(sv, pos);
+            }
+            const float ws = (opt.last_sample_opaque && __fadd_rn(tk, step) > ray.tmax) ? 1e9f
+                                                                                       : ray.world_step;
+            const bool active = member && (sigma > opt.sigma_thresh);
+            if (active) {  // pull the rows K2 will gather towards L2
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (lk[q] >= 0) {
+                        const float* row = g.sh + (int64_t)lk[q] * g.sh_stride;
+                        prefetch_l2(row);
+                        prefetch_l2(row + (g.sh_dim - 1));
+                    }
+            }
+            const float pcnt = __fmul_rn(ws, sigma);
+            unsigned act_m = __ballot_sync(FULL, active);
+            float my_before = 0.f;
+            {
+                unsigned it = act_m;
+                while (it) {
+                    const int i = __ffs(it) - 1;
+                    it &= it - 1;
+                    const float p = __shfl_sync(FULL, pcnt, i);
+                    my_before = (lane == i) ? lt : my_before;
+                    lt = __fsub_rn(lt, p);
+                    if (fexp(lt) < opt.stop_thresh) {
+                        const unsigned upto = (2u << i) - 1u;
+                        act_m &= upto;
+                        members &= upto;
+                        done = true;
+                        stopped = true;
+                        break;
+                    }
+                }
+            }
+            if (COUNT) {
+                cnt[1] += __popc(members);
+                cnt[2] += __popc(act_m);
+            }
+            const int n = __popc(act_m);
+            if (n > 0) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(qv.counter, n);
+                base = __shfl_sync(FULL, base, 0);
+                if (base + n > qv.capacity) {
+                    if (lane == 0) atomicExch(qv.overflow, 1);
+                    done = true;  // the fallback path redoes the whole batch of rays
+                } else {
+                    if ((act_m >> lane) & 1u) {
+                        const int rank = __popc(act_m & ((1u << lane) - 1u));
+                        Record* r = qv.rec + base + rank;
+                        int4* r4 = reinterpret_cast<int4*>(r);
+                        r4[0] = make_int4(lk[0], lk[1], lk[2], lk[3]);
+                        r4[1] = make_int4(lk[4], lk[5], lk[6], lk[7]);
+                        const float weight = __fmul_rn(fexp(my_before), __fsub_rn(1.f, fexp(-pcnt)));
+                        reinterpret_cast<float4*>(r)[2] = make_float4(pos[0], pos[1], pos[2], weight);
+                        r4[3] = make_int4(__float_as_int(__fsub_rn(my_before, pcnt)), __float_as_int(sigma),
+                                          __float_as_int(ws), (int)ray_id);
+                    }
+                    if (lane == 0) {  // block header and chain: always written by lane 0
+                        reinterpret_cast<int4*>(qv.rec + base)[5] = make_int4(n, -1, 0, 0);
+                        if (prev_blk >= 0) qv.rec[prev_blk].blk_next = base;
+                        else first_blk = base;
+                    }
+                    prev_blk = base;
+                }
+            }
+            t0 = t_next;
+        }
+    }
+    // forward colour starts from the background term; K2 adds the samples atomically
+    const bool hit = ray.tmin <= ray.tmax;
+    const float logT_fwd = hit ? (stopped ? -1e3f : lt) : 0.f;
+    const float bgc = hit ? fexp(logT_fwd) * opt.background_brightness : opt.background_brightness;
+    if (lane < 3) a.rgb_out[ray_id * 3 + lane] = bgc;
+    if (lane == 0) {
+        qv.ray_first[ray_id] = first_blk;
+        qv.ray_logT[ray_id] = logT_fwd;
+        if (COUNT) {
+            atomicAdd(a.counters + 0, (unsigned long long)cnt[0]);
+            atomicAdd(a.counters + 1, (unsigned long long)cnt[1]);
+            atomicAdd(a.counters + 2, (unsigned long long)cnt[2]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// helpers of the sample-parallel kernels
+// ---------------------------------------------------------------------------------------
+template <bool VEC>
+__device__ __forceinline__ float4 load_quad(const float* __restrict__ p, int qi, int D) {
+    if (VEC) return __ldg(reinterpret_cast<const float4*>(p));
+    float4 v;
+    const int j = qi * 4;
+    v.x = (j + 0 < D) ? __ldg(p + 0) : 0.f;
+    v.y = (j + 1 < D) ? __ldg(p + 1) : 0.f;
+    v.z = (j + 2 < D) ? __ldg(p + 2) : 0.f;
+    v.w = (j + 3 < D) ? __ldg(p + 3) : 0.f;
+    return v;
+}
+template <bool VEC>
+__device__ __forceinline__ void red_quad(float* __restrict__ p, int qi, int D, float a, float b,
+                                         float c, float d) {
+    if (VEC) {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b),
+                     "f"(c), "f"(d)
+                     : "memory");
+    } else {
+        const int j = qi * 4;
+        if (j + 0 < D) atomicAdd(p + 0, a);
+        if (j + 1 < D) atomicAdd(p + 1, b);
+        if (j + 2 < D) atomicAdd(p + 2, c);
+        if (j + 3 < D) atomicAdd(p + 3, d);
+    }
+}
+
+__device__ __forceinline__ void corner_weights(float px, float py, float pz, float* wq) {
+    const float ax = 1.f - px, ay = 1.f - py, az = 1.f - pz;
+    const float yz00 = ay * az, yz01 = ay * pz, yz10 = py * az, yz11 = py * pz;
+    wq[0] = yz00 * ax; wq[1] = yz01 * ax; wq[2] = yz10 * ax; wq[3] = yz11 * ax;
+    wq[4] = yz00 * px; wq[5] = yz01 * px; wq[6] = yz10 * px; wq[7] = yz11 * px;
+}
+
+// ---------------------------------------------------------------------------------------
+// K2: gather + colours, 8 lanes per sample
+// ---------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+shade_kernel(GridView g, QueueView qv, float* __restrict__ rgb_out) {
+    if (*qv.overflow) return;
+    const int n = min(*qv.counter, qv.capacity);
+    const int qi = threadIdx.x & 7;
+    const int D = g.sh_dim, B = g.basis_dim;
+    int ce[4];  // colour of each of this lane's channels (lane constant)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) ce[e] = (qi * 4 + e < D) ? (qi * 4 + e) / B : -1;
+    const float* shq = g.sh + (qi * 4 < D ? qi * 4 : 0);
+    const int groups = (gridDim.x * blockDim.x) >> 3;
+    for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; s < n; s += groups) {
+        const Record* r = qv.rec + s;
+        const int4 la = __ldcg(reinterpret_cast<const int4*>(r));
+        const int4 lb = __ldcg(reinterpret_cast<const int4*>(r) + 1);
+        const float4 pw = __ldcg(reinterpret_cast<const float4*>(r) + 2);
+        const int ray = __ldcg(&r->ray);
+        const int32_t L[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
+        float4 v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const unsigned row = L[q] >= 0 ? (unsigned)L[q] : 0u;
+            v[q] = load_quad<VEC>(shq + (size_t)row * (unsigned)g.sh_stride, qi, D);
+        }
+        const float4 Y = __ldcg(qv.ray_Y + (int64_t)ray * 8 + qi);
+        float wq[8];
+        corner_weights(pw.x, pw.y, pw.z, wq);
+        float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (L[q] >= 0) {
+                u.x = fmaf(wq[q], v[q].x, u.x);
+                u.y = fmaf(wq[q], v[q].y, u.y);
+                u.z = fmaf(wq[q], v[q].z, u.z);
+                u.w = fmaf(wq[q], v[q].w, u.w);
+            }
+        const float pr[4] = {Y.x * u.x, Y.y * u.y, Y.z * u.z, Y.w * u.w};
+        float col[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float x = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x += (ce[e] == c) ? pr[e] : 0.f;
+            x += __shfl_xor_sync(FULL, x, 1);
+            x += __shfl_xor_sync(FULL, x, 2);
+            x += __shfl_xor_sync(FULL, x, 4);
+            col[c] = x + 0.5f;
+        }
+        if (qi < 3) {
+            const float cv = qi == 0 ? col[0] : (qi == 1 ? col[1] : col[2]);
+            atomicAdd(rgb_out + (int64_t)ray * 3 + qi, pw.w * fmaxf(cv, 0.f));
+        }
+        if (qi == 0) reinterpret_cast<float4*>(qv.rec + s)[4] = make_float4(col[0], col[1], col[2], 0.f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K3: gradient seed + accum recursion per ray (cuvol.cu:248-264, 342-351, 735-747)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TRACE_THREADS)
+seed_kernel(Opts opt, MarchArgs a, QueueView qv) {
+    if (*qv.overflow) return;
+    const int64_t ray_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (ray_id >= a.n_rays) return;
+    const int lane = threadIdx.x & 31;
+    float gout[3], cc[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        cc[i] = __ldcg(a.rgb_out + ray_id * 3 + i);
+        gout[i] = (cc[i] - __ldg(a.grad_in + ray_id * 3 + i)) * a.norm_factor;
+    }
+    int blk = qv.ray_first[ray_id];
+    if (blk < 0) return;  // no active sample: nothing to scatter
+    float accum = fmaf(cc[0], gout[0], fmaf(cc[1], gout[1], cc[2] * gout[2]));
+    if (a.beta_loss > 0.f) {
+        const float transmit_in = fexp(qv.ray_logT[ray_id]);
+        accum += (float)((double)a.beta_loss *
+                         (1 - (double)transmit_in / (1 - (double)transmit_in + 1e-3)));
+    }
+    while (blk >= 0) {
+        const int count = __ldcg(&qv.rec[blk].blk_count);
+        const int next = __ldcg(&qv.rec[blk].blk_next);
+        const bool on = lane < count;
+        Record* r = qv.rec + blk + (on ? lane : 0);
+        const float4 pw = __ldcg(reinterpret_cast<const float4*>(r) + 2);
+        const float4 st = __ldcg(reinterpret_cast<const float4*>(r) + 3);
+        const float4 co = __ldcg(reinterpret_cast<const float4*>(r) + 4);
+        const float w = pw.w, after = st.x, sigma = st.y, ws = st.z;
+        const float col[3] = {co.x, co.y, co.z};
+        float gc[3], total = 0.f;
+        {
+            float tc[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float cl = fmaxf(col[c], 0.f);
+                tc[c] = cl * gout[c];
+                gc[c] = (cl == col[c]) ? w * gout[c] : 0.f;
+            }
+            total = tc[0];
+            total += tc[2];
+            total += tc[1];
+        }
+        const float wt = on ? w * total : 0.f;
+        float pre = wt;  // inclusive scan of weight*total in sample order
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const float o = __shfl_up_sync(FULL, pre, off);
+            if (lane >= off) pre += o;
+        }
+        const float my_accum = accum - pre;
+        accum -= __shfl_sync(FULL, pre, 31);
+        if (on) {
+            float cgs = ws * (total * fexp(after) - my_accum);
+            if (a.sparsity_loss > 0.f) cgs += a.sparsity_loss * (4 * sigma / (1 + 2 * (sigma * sigma)));
+            reinterpret_cast<float4*>(r)[4] = make_float4(gc[0], gc[1], gc[2], cgs);
+        }
+        blk = next;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K4: scatter, 8 lanes per sample
+// ---------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+scatter_kernel(GridView g, QueueView qv, GradView gr, int64_t gsh_stride, int64_t gd_stride) {
+    if (*qv.overflow) return;
+    const int n = min(*qv.counter, qv.capacity);
+    const int qi = threadIdx.x & 7;
+    const int D = g.sh_dim, B = g.basis_dim;
+    int ce[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) ce[e] = (qi * 4 + e < D) ? (qi * 4 + e) / B : -1;
+    const bool quad_on = qi * 4 < D;
+    const int groups = (gridDim.x * blockDim.x) >> 3;
+    for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; s < n; s += groups) {
+        const Record* r = qv.rec + s;
+        const int4 la = __ldcg(reinterpret_cast<const int4*>(r));
+        const int4 lb = __ldcg(reinterpret_cast<const int4*>(r) + 1);
+        const float4 pw = __ldcg(reinterpret_cast<const float4*>(r) + 2);
+        const float4 gg = __ldcg(reinterpret_cast<const float4*>(r) + 4);
+        const int ray = __ldcg(&r->ray);
+        const int32_t L[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
+        const float4 Y = __ldcg(qv.ray_Y + (int64_t)ray * 8 + qi);
+        float wq[8];
+        corner_weights(pw.x, pw.y, pw.z, wq);
+        const float gcs[3] = {gg.x, gg.y, gg.z};
+        const float Ye[4] = {Y.x, Y.y, Y.z, Y.w};
+        float ge[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float gsel = ce[e] == 0 ? gcs[0] : (ce[e] == 1 ? gcs[1] : (ce[e] == 2 ? gcs[2] : 0.f));
+            ge[e] = Ye[e] * gsel;
+        }
+        if (quad_on) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (L[q] >= 0)
+                    red_quad<VEC>(gr.grad_sh + (int64_t)L[q] * gsh_stride + 4 * qi, qi, D, wq[q] * ge[0],
+                                  wq[q] * ge[1], wq[q] * ge[2], wq[q] * ge[3]);
+        }
+        int32_t Lown = L[0];
+        float wown = wq[0];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) {
+            Lown = (qi == q) ? L[q] : Lown;
+            wown = (qi == q) ? wq[q] : wown;
+        }
+        if (Lown >= 0) {
+            atomicAdd(gr.grad_density + (int64_t)Lown * gd_stride, wown * gg.w);
+            if (gr.mask) gr.mask[Lown] = 1;
+        }
+    }
+}
+
+// The lattice kernel re-does the batch when the queue overflowed.
+__global__ void clear_flags_kernel(int* counter, int* overflow) {
+    *counter = 0;
+    *overflow = 0;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+size_t queue_workspace_bytes(int64_t n_rays, int64_t records) {
+    return 256 + align_up((size_t)n_rays * 4, 256) * 2 + align_up((size_t)n_rays * 8 * 16, 256) +
+           (size_t)records * sizeof(Record);
+}
+
+// Returns false if the workspace cannot hold even a minimal queue (caller uses the lattice path).
+bool launch_queue_fused(const GridView& g, const Opts& opt, const MarchArgs& a, const GradView& gr,
+                        void* workspace, size_t workspace_bytes, const int** overflow_flag,
+                        cudaStream_t st) {
+    const size_t fixed = queue_workspace_bytes(a.n_rays, 0);
+    if (!workspace || workspace_bytes < fixed + sizeof(Record) * 64 * (size_t)a.n_rays ||
+        (reinterpret_cast<uintptr_t>(workspace) & 255u))
+        return false;
+    char* p = static_cast<char*>(workspace);
+    QueueView qv;
+    qv.counter = reinterpret_cast<int*>(p);
+    qv.overflow = reinterpret_cast<int*>(p + 128);
+    p += 256;
+    qv.ray_first = reinterpret_cast<int*>(p);
+    p += align_up((size_t)a.n_rays * 4, 256);
+    qv.ray_logT = reinterpret_cast<float*>(p);
+    p += align_up((size_t)a.n_rays * 4, 256);
+    qv.ray_Y = reinterpret_cast<float4*>(p);
+    p += align_up((size_t)a.n_rays * 8 * 16, 256);
+    qv.rec = reinterpret_cast<Record*>(p);
+    const size_t cap = (workspace_bytes - fixed) / sizeof(Record);
+    qv.capacity = (int)(cap > (size_t)0x7ff00000 ? (size_t)0x7ff00000 : cap);
+    *overflow_flag = qv.overflow;
+
+    clear_flags_kernel<<<1, 1, 0, st>>>(qv.counter, qv.overflow);
+    const unsigned ray_blocks = div_up(a.n_rays * WARP, TRACE_THREADS);
+    if (a.counters) trace_kernel<true><<<ray_blocks, TRACE_THREADS, 0, st>>>(g, opt, a, qv);
+    else trace_kernel<false><<<ray_blocks, TRACE_THREADS, 0, st>>>(g, opt, a, qv);
+    const bool vec = march_vec_ok(g, &gr, a.gsh_stride);
+    const unsigned sblocks = 148 * 8;  // persistent grid-stride: 8 CTAs of 256 threads per SM
+    if (vec) shade_kernel<true><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, a.rgb_out);
+    else shade_kernel<false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, a.rgb_out);
+    seed_kernel<<<ray_blocks, TRACE_THREADS, 0, st>>>(opt, a, qv);
+    if (vec) scatter_kernel<true><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride);
+    else scatter_kernel<false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride);
+    return true;
+}
+
+}  // namespace svox2b

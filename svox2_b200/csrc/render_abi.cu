@@ -19,6 +19,15 @@ bool use_v1() {
     return v == 1;
 }
 
+// SVOX2_B200_MARCH=lattice forces the single-kernel fused path (A/B and debugging)
+bool use_queue() {
+    static const int v = [] {
+        const char* e = std::getenv("SVOX2_B200_MARCH");
+        return (e && std::strcmp(e, "lattice") == 0) ? 0 : 1;
+    }();
+    return v == 1;
+}
+
 int validate_rays(const float* origins, const float* dirs, int64_t n, const char* who) {
     if (n < 0 || (n > 0 && (!origins || !dirs))) {
         set_error("%s: rays must be non-null [Q,3] float32 device arrays", who);
@@ -115,6 +124,14 @@ int run_bwd(const GridView& g, const Opts& opt, const MarchArgs& a, const GradVi
 extern "C" SVOX2_API size_t svox2_render_workspace_bytes(int64_t n_rays) {
     const int64_t padded = ((n_rays + 63) / 64) * 64;
     return (size_t)padded * 2 * sizeof(float) + 256;
+}
+
+extern "C" SVOX2_API size_t svox2_fused_workspace_bytes(int64_t n_rays, int64_t slots_per_ray) {
+    if (n_rays < 0) n_rays = 0;
+    if (slots_per_ray < 0) slots_per_ray = 0;
+    const size_t lattice = svox2_render_workspace_bytes(n_rays) + 16 * (size_t)slots_per_ray * (size_t)n_rays;
+    const size_t queue = queue_workspace_bytes(n_rays, slots_per_ray * n_rays);
+    return lattice > queue ? lattice : queue;
 }
 
 extern "C" SVOX2_API int svox2_volume_render_cuvol(const svox2_grid_t* grid, const float* origins,
@@ -229,6 +246,18 @@ extern "C" SVOX2_API int svox2_volume_render_cuvol_fused(
     a.fused_seed = 1;
     a.counters = reinterpret_cast<unsigned long long*>(counters);
 
+    if (!use_bg && !use_v1() && use_queue()) {
+        // sample-queue path (queue_march.cu): trace -> shade -> seed -> scatter; the lattice
+        // kernel is enqueued behind it as a conditional fallback for a queue overflow.
+        const int* overflow = nullptr;
+        if (launch_queue_fused(g, *opt, a, gr, workspace, workspace_bytes, &overflow, st)) {
+            MarchArgs fb = a;
+            fb.counters = nullptr;
+            fb.run_if = overflow;
+            launch_lattice_march(LB_MODE_FUSED, false, g, *opt, fb, gr, st);
+            return check_launch(__func__);
+        }
+    }
     if (!use_bg && !use_v1()) {
         // single launch: forward pass, gradient seed and backward pass inside one warp per ray.
         // Whatever workspace lies beyond the per-ray scalars is used as the forward->backward
