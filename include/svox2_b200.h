@@ -203,6 +203,15 @@ SVOX2_API int svox2_tv_grad_sparse(const int32_t* links, int32_t X, int32_t Y, i
                          int32_t start_dim, int32_t end_dim, float scale, int32_t ignore_edge,
                          int32_t ignore_last_z, float ndc_coeffx, float ndc_coeffy,
                          float* grad_data, int64_t grad_stride, svox2_stream_t stream);
+/* Same as svox2_tv_grad_sparse for the contiguous wrapped cell run [cell_start, cell_start+n_cells)
+ * mod X*Y*Z that SparseGrid._get_rand_cells(contiguous=True) builds (svox2.py:2230-2237), without
+ * materialising the index tensor. */
+SVOX2_API int svox2_tv_grad_sparse_run(const int32_t* links, int32_t X, int32_t Y, int32_t Z,
+                             const float* data, int64_t data_stride, int64_t cell_start,
+                             int64_t n_cells, int64_t scale_cells, uint8_t* mask_out,
+                             int32_t start_dim, int32_t end_dim, float scale, int32_t ignore_edge,
+                             int32_t ignore_last_z, float* grad_data, int64_t grad_stride,
+                             svox2_stream_t stream);
 SVOX2_API int svox2_msi_tv_grad_sparse(const int32_t* background_links, int32_t reso, const float* msi,
                              int32_t nlayers, int32_t nchannels, const int32_t* rand_cells,
                              int64_t n_cells, int64_t scale_cells, uint8_t* mask_out, float scale,

@@ -26,7 +26,7 @@ __all__ = [
     "volume_render_sigma_thresh", "volume_render_nvol", "volume_render_nvol_backward",
     "volume_render_nvol_fused", "volume_render_svox1", "volume_render_svox1_backward",
     "volume_render_svox1_fused", "dilate", "accel_dist_prop", "grid_weight_render", "tv",
-    "tv_grad", "tv_grad_sparse", "msi_tv_grad_sparse", "lumisphere_tv_grad_sparse",
+    "tv_grad", "tv_grad_sparse", "tv_grad_sparse_run", "msi_tv_grad_sparse", "lumisphere_tv_grad_sparse",
     "rmsprop_step", "sgd_step",
 ]
 
@@ -484,6 +484,22 @@ def tv_grad_sparse(links, data, rand_cells, mask_out, start_dim, end_dim, scale,
             rand_cells.size(0), int(_scale_cells), mask_ptr, int(start_dim), int(end_dim),
             float(scale), int(bool(ignore_edge)), int(bool(ignore_last_z)), float(ndc_coeffx),
             float(ndc_coeffy), grad_data.data_ptr(), _row_stride(grad_data), _stream()))
+
+
+def tv_grad_sparse_run(links, data, cell_start, n_cells, mask_out, start_dim, end_dim, scale,
+                       ignore_edge, ignore_last_z, grad_data, _scale_cells=0):
+    """Extension: tv_grad_sparse over the contiguous wrapped cell run [cell_start, cell_start+n_cells)
+    without an index tensor (what inplace_tv_grad(contiguous=True) needs every step)."""
+    X, Y, Z = _tv_common(links, data)
+    _check_rows(grad_data, "grad_data")
+    _check_input(mask_out, "mask_out")
+    mask_ptr = mask_out.data_ptr() if (mask_out.dim() > 0 and mask_out.numel() > 0) else None
+    with torch.cuda.device(data.device):
+        check(_lib.lib().svox2_tv_grad_sparse_run(
+            links.data_ptr(), X, Y, Z, data.data_ptr(), _row_stride(data), int(cell_start),
+            int(n_cells), int(_scale_cells), mask_ptr, int(start_dim), int(end_dim), float(scale),
+            int(bool(ignore_edge)), int(bool(ignore_last_z)), grad_data.data_ptr(),
+            _row_stride(grad_data), _stream()))
 
 
 def msi_tv_grad_sparse(links, msi, rand_cells, mask_out, scale, scale_last, grad_msi,

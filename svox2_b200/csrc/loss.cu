@@ -120,11 +120,15 @@ struct TvCell {
 };
 
 __device__ __forceinline__ TvCell tv_probe(const int32_t* __restrict__ links, int X, int Y, int Z,
-                                           const int32_t* __restrict__ rand_cells, int64_t cell,
-                                           int64_t n_cells, int ignore_edge, int ignore_last_z) {
+                                           const int32_t* __restrict__ rand_cells,
+                                           int64_t cell_start, int64_t cell, int64_t n_cells,
+                                           int ignore_edge, int ignore_last_z) {
     TvCell c{-1, -1, -1, -1, false};
     if (cell >= n_cells) return c;
-    const int xyz = __ldg(rand_cells + cell);
+    // rand_cells == NULL: the contiguous wrapped run [cell_start, cell_start + n_cells) that
+    // SparseGrid._get_rand_cells(contiguous=True) would materialise (svox2.py:2230-2237)
+    const int xyz = rand_cells ? __ldg(rand_cells + cell)
+                               : (int)((cell_start + cell) % ((int64_t)X * Y * Z));
     const int z = xyz % Z;
     const int xy = xyz / Z;
     const int y = xy % Y;
@@ -172,13 +176,13 @@ template <bool COOP>
 __global__ void __launch_bounds__(TV_THREADS)
 tv_grad_sparse_kernel(const int32_t* __restrict__ links, int X, int Y, int Z,
                       const float* __restrict__ data, int64_t stride,
-                      const int32_t* __restrict__ rand_cells, int start_dim, int end_dim,
-                      float scale, int64_t n_cells, int ignore_edge, int ignore_last_z,
+                      const int32_t* __restrict__ rand_cells, int64_t cell_start, int start_dim,
+                      int end_dim, float scale, int64_t n_cells, int ignore_edge, int ignore_last_z,
                       uint8_t* __restrict__ mask_out, float* __restrict__ grad, int64_t gstride) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     if (tid - lane >= n_cells) return;  // whole warp past the end
-    const TvCell mine = tv_probe(links, X, Y, Z, rand_cells, tid, n_cells, ignore_edge, ignore_last_z);
+    const TvCell mine = tv_probe(links, X, Y, Z, rand_cells, cell_start, tid, n_cells, ignore_edge, ignore_last_z);
     float sc[3];
     ray_scale(X, Y, Z, sc);
     if (!COOP) {
@@ -304,17 +308,17 @@ extern "C" SVOX2_API int svox2_tv_grad(const int32_t* links, int32_t X, int32_t 
     return check_launch(__func__);
 }
 
-extern "C" SVOX2_API int svox2_tv_grad_sparse(const int32_t* links, int32_t X, int32_t Y, int32_t Z,
-                                    const float* data, int64_t data_stride,
-                                    const int32_t* rand_cells, int64_t n_cells,
-                                    int64_t scale_cells, uint8_t* mask_out, int32_t start_dim,
-                                    int32_t end_dim, float scale, int32_t ignore_edge,
-                                    int32_t ignore_last_z, float ndc_coeffx, float ndc_coeffy,
-                                    float* grad_data, int64_t grad_stride, svox2_stream_t stream) {
-    (void)ndc_coeffx; (void)ndc_coeffy;
-    if (int e = check_tv_args(links, X, Y, Z, data, data_stride, start_dim, end_dim, __func__)) return e;
-    SVOX2_REQUIRE(grad_data, "grad_data must not be null");
-    SVOX2_REQUIRE(n_cells >= 0 && (n_cells == 0 || rand_cells), "rand_cells must not be null");
+static int tv_grad_sparse_impl(const int32_t* links, int32_t X, int32_t Y, int32_t Z,
+                               const float* data, int64_t data_stride, const int32_t* rand_cells,
+                               int64_t cell_start, int64_t n_cells, int64_t scale_cells,
+                               uint8_t* mask_out, int32_t start_dim, int32_t end_dim, float scale,
+                               int32_t ignore_edge, int32_t ignore_last_z, float* grad_data,
+                               int64_t grad_stride, svox2_stream_t stream, const char* who) {
+    if (int e = check_tv_args(links, X, Y, Z, data, data_stride, start_dim, end_dim, who)) return e;
+    if (!grad_data) {
+        set_error("%s: grad_data must not be null", who);
+        return SVOX2_ERR_INVALID;
+    }
     if (n_cells == 0) return SVOX2_OK;
     if (scale_cells <= 0) scale_cells = n_cells;
     const int nd = end_dim - start_dim;
@@ -323,12 +327,39 @@ extern "C" SVOX2_API int svox2_tv_grad_sparse(const int32_t* links, int32_t X, i
     cudaStream_t st = (cudaStream_t)stream;
 #define TV_LAUNCH(COOP)                                                                         \
     tv_grad_sparse_kernel<COOP><<<div_up(n_cells, TV_THREADS), TV_THREADS, 0, st>>>(            \
-        links, X, Y, Z, data, data_stride, rand_cells, start_dim, end_dim, s, n_cells,          \
-        ignore_edge, ignore_last_z, mask_out, grad_data, gs)
+        links, X, Y, Z, data, data_stride, rand_cells, cell_start, start_dim, end_dim, s,       \
+        n_cells, ignore_edge, ignore_last_z, mask_out, grad_data, gs)
     if (nd <= 2) TV_LAUNCH(false);
     else TV_LAUNCH(true);
 #undef TV_LAUNCH
-    return check_launch(__func__);
+    return check_launch(who);
+}
+
+extern "C" SVOX2_API int svox2_tv_grad_sparse(const int32_t* links, int32_t X, int32_t Y, int32_t Z,
+                                    const float* data, int64_t data_stride,
+                                    const int32_t* rand_cells, int64_t n_cells,
+                                    int64_t scale_cells, uint8_t* mask_out, int32_t start_dim,
+                                    int32_t end_dim, float scale, int32_t ignore_edge,
+                                    int32_t ignore_last_z, float ndc_coeffx, float ndc_coeffy,
+                                    float* grad_data, int64_t grad_stride, svox2_stream_t stream) {
+    (void)ndc_coeffx; (void)ndc_coeffy;
+    SVOX2_REQUIRE(n_cells >= 0 && (n_cells == 0 || rand_cells), "rand_cells must not be null");
+    return tv_grad_sparse_impl(links, X, Y, Z, data, data_stride, rand_cells, 0, n_cells, scale_cells,
+                               mask_out, start_dim, end_dim, scale, ignore_edge, ignore_last_z,
+                               grad_data, grad_stride, stream, __func__);
+}
+
+extern "C" SVOX2_API int svox2_tv_grad_sparse_run(const int32_t* links, int32_t X, int32_t Y, int32_t Z,
+                                        const float* data, int64_t data_stride,
+                                        int64_t cell_start, int64_t n_cells, int64_t scale_cells,
+                                        uint8_t* mask_out, int32_t start_dim, int32_t end_dim,
+                                        float scale, int32_t ignore_edge, int32_t ignore_last_z,
+                                        float* grad_data, int64_t grad_stride,
+                                        svox2_stream_t stream) {
+    SVOX2_REQUIRE(n_cells >= 0 && cell_start >= 0, "bad cell run");
+    return tv_grad_sparse_impl(links, X, Y, Z, data, data_stride, nullptr, cell_start, n_cells,
+                               scale_cells, mask_out, start_dim, end_dim, scale, ignore_edge,
+                               ignore_last_z, grad_data, grad_stride, stream, __func__);
 }
 
 extern "C" SVOX2_API int svox2_msi_tv_grad_sparse(const int32_t* background_links, int32_t reso,

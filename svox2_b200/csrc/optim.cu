@@ -11,7 +11,11 @@
 namespace svox2b {
 namespace {
 
+#ifndef OPT_ROWS_IN_FLIGHT
+#define OPT_ROWS_IN_FLIGHT 4
+#endif
 constexpr int OPT_THREADS = 256;
+constexpr int RIF = OPT_ROWS_IN_FLIGHT;
 
 // rmsprop_once, optim_kernel.cu:15-25
 __device__ __forceinline__ void rmsprop_once(float* __restrict__ d, float* __restrict__ r,
@@ -77,10 +81,10 @@ masked_rows_kernel(OptArgs a) {
     const bool chan = lane < a.C;
     const float lr = (lane == a.C - 1) ? a.lr_last : a.lr;
     while (m) {
-        int64_t off[4];
-        float d[4], r[4], g[4];
+        int64_t off[RIF];
+        float d[RIF], r[RIF], g[RIF];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < RIF; ++k) {
             off[k] = -1;
             if (m) {
                 off[k] = (row0 + (__ffs(m) - 1)) * a.stride + lane;
@@ -88,14 +92,14 @@ masked_rows_kernel(OptArgs a) {
             }
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < RIF; ++k)
             if (chan && off[k] >= 0) {
                 g[k] = a.grad[off[k]];
                 d[k] = a.data[off[k]];
                 if (RMS) r[k] = a.rms[off[k]];
             }
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < RIF; ++k)
             if (chan && off[k] >= 0) {
                 if (RMS) {
                     rmsprop_once(&d[k], &r[k], &g[k], a.beta, lr, a.eps, a.minval);

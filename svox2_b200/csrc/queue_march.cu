@@ -31,6 +31,14 @@
 namespace svox2b {
 namespace {
 
+// Tunables (A/B on B200, profiles/r1_ab_variants.txt)
+#ifndef QM_PREFETCH_SH
+#define QM_PREFETCH_SH 0   // prefetching SH rows from K1 only evicts them again before K2 runs
+#endif
+#ifndef QM_SAMPLE_CTAS
+#define QM_SAMPLE_CTAS 8   // persistent CTAs per SM for the sample-parallel kernels
+#endif
+
 constexpr int TRACE_THREADS = 64;
 constexpr int SAMPLE_THREADS = 256;
 
@@ -175,6 +183,7 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv) {
             const float ws = (opt.last_sample_opaque && __fadd_rn(tk, step) > ray.tmax) ? 1e9f
                                                                                        : ray.world_step;
             const bool active = member && (sigma > opt.sigma_thresh);
+#if QM_PREFETCH_SH
             if (active) {  // pull the rows K2 will gather towards L2
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
@@ -184,6 +193,7 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv) {
                         prefetch_l2(row + (g.sh_dim - 1));
                     }
             }
+#endif
             const float pcnt = __fmul_rn(ws, sigma);
             unsigned act_m = __ballot_sync(FULL, active);
             float my_before = 0.f;
@@ -516,7 +526,7 @@ bool launch_queue_fused(const GridView& g, const Opts& opt, const MarchArgs& a, 
     if (a.counters) trace_kernel<true><<<ray_blocks, TRACE_THREADS, 0, st>>>(g, opt, a, qv);
     else trace_kernel<false><<<ray_blocks, TRACE_THREADS, 0, st>>>(g, opt, a, qv);
     const bool vec = march_vec_ok(g, &gr, a.gsh_stride);
-    const unsigned sblocks = 148 * 8;  // persistent grid-stride: 8 CTAs of 256 threads per SM
+    const unsigned sblocks = 148 * QM_SAMPLE_CTAS;  // persistent grid-stride CTAs of 256 threads
     if (vec) shade_kernel<true><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, a.rgb_out);
     else shade_kernel<false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, a.rgb_out);
     seed_kernel<<<ray_blocks, TRACE_THREADS, 0, st>>>(opt, a, qv);

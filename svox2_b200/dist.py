@@ -66,15 +66,14 @@ class ShardedTrainer:
         # march fwd + march bwd + 2 TV + 2 optimiser kernels
         self.kernels_per_step = 2 + (lambda_tv > 0) + (lambda_tv_sh > 0) + 2
 
-    def _tv_cells(self):
-        """This rank's slice of the step's contiguous cell run (drawn with numpy's global RNG,
-        which must be seeded identically on every rank) and the global cell count."""
-        cells = self.grid._get_rand_cells(self.tv_sparsity)
-        n = cells.numel()
+    def _tv_run(self):
+        """This rank's slice (start, count) of the step's contiguous wrapped cell run (drawn with
+        numpy's global RNG, which must be seeded identically on every rank) and the global count."""
+        start, n = self.grid._draw_cell_run(self.tv_sparsity)
         if self.world_size == 1:
-            return cells, n
+            return (start, n), n
         b, e = shard_range(n, self.world_size, self.rank)
-        return cells[b:e].contiguous(), n
+        return (start + b, e - b), n
 
     def step(self, rays, rgb_gt: torch.Tensor, global_batch: Optional[int] = None,
              lr_sigma: Optional[float] = None, lr_sh: Optional[float] = None):
@@ -82,12 +81,12 @@ class ShardedTrainer:
         rgb = g.volume_render_fused(rays, rgb_gt, beta_loss=self.beta_loss,
                                     sparsity_loss=self.sparsity_loss, _norm_rays=global_batch)
         if self.lambda_tv > 0.0:
-            cells, n = self._tv_cells()
-            g.inplace_tv_grad(g.density_data.grad, scaling=self.lambda_tv, _rand_cells=cells,
+            run, n = self._tv_run()
+            g.inplace_tv_grad(g.density_data.grad, scaling=self.lambda_tv, _cell_run=run,
                               _scale_cells=n)
         if self.lambda_tv_sh > 0.0:
-            cells, n = self._tv_cells()
-            g.inplace_tv_color_grad(g.sh_data.grad, scaling=self.lambda_tv_sh, _rand_cells=cells,
+            run, n = self._tv_run()
+            g.inplace_tv_color_grad(g.sh_data.grad, scaling=self.lambda_tv_sh, _cell_run=run,
                                     _scale_cells=n)
         if self.world_size > 1:
             g.sparse_grad_indexer, g.sparse_sh_grad_indexer = exchange_sparse_grads(

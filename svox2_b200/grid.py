@@ -741,10 +741,18 @@ class SparseGrid(nn.Module):
     def inplace_tv_grad(self, grad: torch.Tensor, scaling: float = 1.0, sparse_frac: float = 0.01,
                         logalpha: bool = False, logalpha_delta: float = 2.0,
                         ndc_coeffs: Tuple[float, float] = (-1.0, -1.0), contiguous: bool = True,
-                        _rand_cells=None, _scale_cells: int = 0):
+                        _rand_cells=None, _scale_cells: int = 0, _cell_run=None):
         """Add the density TV gradient (x ``scaling``) into ``grad`` (svox2.py:1731-1766)."""
         assert self.density_data.is_cuda and grad.is_cuda, "CUDA is required for total variation"
         assert not logalpha, "No longer supported"
+        run = _cell_run if _cell_run is not None else (
+            self._draw_cell_run(sparse_frac) if (contiguous and _rand_cells is None) else None)
+        if run is not None:  # contiguous wrapped run: no index tensor, same cells as the reference
+            if run[1] > 0:
+                _C.tv_grad_sparse_run(self.links, self.density_data, run[0], run[1],
+                                      self._get_sparse_grad_indexer(), 0, 1, scaling, False,
+                                      self.opt.last_sample_opaque, grad, _scale_cells=_scale_cells)
+            return
         cells = _rand_cells if _rand_cells is not None else \
             self._get_rand_cells(sparse_frac, contiguous=contiguous)
         if cells is not None:
@@ -763,11 +771,21 @@ class SparseGrid(nn.Module):
                               sparse_frac: float = 0.01, logalpha: bool = False,
                               logalpha_delta: float = 2.0,
                               ndc_coeffs: Tuple[float, float] = (-1.0, -1.0),
-                              contiguous: bool = True, _rand_cells=None, _scale_cells: int = 0):
+                              contiguous: bool = True, _rand_cells=None, _scale_cells: int = 0,
+                              _cell_run=None):
         """Add the SH TV gradient (x ``scaling``) into ``grad`` (svox2.py:1768-1820)."""
         assert self.sh_data.is_cuda and grad.is_cuda, "CUDA is required for total variation"
         assert not logalpha, "No longer supported"
+        self._ensure_layout()
         start_dim, end_dim = self._dim_range(start_dim, end_dim)
+        run = _cell_run if _cell_run is not None else (
+            self._draw_cell_run(sparse_frac) if (contiguous and _rand_cells is None) else None)
+        if run is not None:
+            if run[1] > 0:
+                _C.tv_grad_sparse_run(self.links, self.sh_data, run[0], run[1],
+                                      self._get_sparse_sh_grad_indexer(), start_dim, end_dim, scaling,
+                                      True, False, grad, _scale_cells=_scale_cells)
+            return
         cells = _rand_cells if _rand_cells is not None else \
             self._get_rand_cells(sparse_frac, contiguous=contiguous)
         if cells is not None:
@@ -920,6 +938,16 @@ class SparseGrid(nn.Module):
             n = self.links.size(0) * self.links.size(1) * self.links.size(2)
             return self._cell_run(n, max(int(sparse_frac * n), 1), contiguous)
         return None
+
+    def _draw_cell_run(self, sparse_frac: float):
+        """(start, count) of the contiguous wrapped cell run ``_get_rand_cells`` would return;
+        consumes numpy's global RNG exactly like the reference.  None when sparse_frac >= 1."""
+        if sparse_frac >= 1.0:
+            return None
+        assert self.sparse_grad_indexer is None or self.sparse_grad_indexer.dtype == torch.bool, \
+            "please call sparse loss after rendering and before gradient updates"
+        n = self.links.size(0) * self.links.size(1) * self.links.size(2)
+        return int(np.random.randint(0, n)), max(int(sparse_frac * n), 1)
 
     def _get_rand_cells_background(self, sparse_frac: float, contiguous: bool = True):
         assert self.use_background, "Can only use sparse background loss if using background"

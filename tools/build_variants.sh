@@ -8,9 +8,9 @@ mkdir -p build/variants
 for spec in "$@"; do
   name="${spec%%:*}"; flags="${spec#*:}"
   odir="build/variants/$name"; mkdir -p "$odir"
-  for f in abi render march render_abi misc loss optim; do
-    if [ "$f" = march ]; then extra="$flags"; else extra=""; fi
-    if [ "$f" != march ] && [ -f "build/$f.o" ]; then cp "build/$f.o" "$odir/$f.o"; continue; fi
+  for f in abi render march queue_march render_abi misc loss optim; do
+    case "$f" in march|queue_march|optim|loss) extra="$flags";; *) extra="";; esac
+    if [ -z "$extra" ] && [ -f "build/$f.o" ]; then cp "build/$f.o" "$odir/$f.o"; continue; fi
     /usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a \
       -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr -Xptxas -v $extra \
       -c "$f.cu" -o "$odir/$f.o" 2> "$odir/$f.ptxas.log"
