@@ -118,6 +118,44 @@ def build_rays(n_total, device, seed=20200823):
 # ----------------------------------------------------------------------------------------------
 # helpers
 # ----------------------------------------------------------------------------------------------
+N_CAMS = 8
+CAM_KW = dict(fx=1111.11, width=800, height=800)
+
+
+def bench_cameras(device, seed=5):
+    """N_CAMS OpenCV-convention c2w matrices on the r=2.687 upper hemisphere, looking at 0."""
+    gen = torch.Generator().manual_seed(seed)
+    zc = 0.15 + 0.7 * torch.rand(N_CAMS, generator=gen)
+    phi = torch.rand(N_CAMS, generator=gen) * 2 * math.pi
+    rxy = torch.sqrt(1 - zc * zc)
+    pos = torch.stack([rxy * torch.cos(phi), rxy * torch.sin(phi), zc], -1).double() * 2.687
+    fwd = -pos / pos.norm(dim=-1, keepdim=True)
+    up = torch.tensor([0.0, 0.0, 1.0], dtype=torch.float64).expand_as(fwd)
+    right = torch.cross(fwd, up, dim=-1)
+    right = right / right.norm(dim=-1, keepdim=True)
+    down = torch.cross(fwd, right, dim=-1)
+    c2w = torch.eye(4, dtype=torch.float64).repeat(N_CAMS, 1, 1)
+    c2w[:, :3, :3] = torch.stack([right, down, fwd], dim=-1)
+    c2w[:, :3, 3] = pos
+    return [m.float().to(device).contiguous() for m in c2w]
+
+
+def time_images(render, cams, reps=3):
+    """ms per image (CUDA events), after one warm-up pass over the cameras."""
+    with torch.no_grad():
+        for c in cams:
+            render(c)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            for c in cams:
+                render(c)
+        e1.record()
+        torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / (reps * len(cams))
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
@@ -300,10 +338,22 @@ def run_ours(args):
     grid.density_data.grad.zero_()
     grid.sh_data.grad.zero_()
 
-    times = torch.tensor([ms, ms_e2e, ms_fused], dtype=torch.float64, device=dev)
+    # second half of the headline metric: whole-image render, 800x800 test cameras
+    cams = bench_cameras(dev)
+    ms_img = time_images(lambda c: grid.volume_render_image(sv.Camera(c, **CAM_KW)), cams)
+
+    phase_ms = None
+    if world > 1:   # untimed extra steps with per-phase CUDA events (rank 0 reports its own)
+        trainer.profile = True
+        for i in range(min(args.steps, 10)):
+            step(*batches[i % POOL])
+        phase_ms = {k: round(v, 4) for k, v in trainer.phase_times_ms().items()}
+        trainer.profile = False
+
+    times = torch.tensor([ms, ms_e2e, ms_fused, ms_img], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, ms_fused = times.tolist()
+    ms, ms_e2e, ms_fused, ms_img = times.tolist()
 
     if rank != 0:
         if world > 1:
@@ -335,11 +385,18 @@ def run_ours(args):
                 "ms_per_step": ms_e2e / args.steps, "last_loss": loss_val},
         "gpu_launches": trainer.kernels_per_step * args.steps,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "march_fwd_kernel + march_bwd_kernel (fused call)",
+        "roofline": {"bound": "hbm", "kernel": "fused call: trace + shade + seed + scatter kernels",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes,
                      "ms_per_launch": ms_fused, "traffic": None},
     }
+    line["render"] = {"value": world * 0.64 / (ms_img * 1e-3), "unit": "MPix/s",
+                      "ms_per_image": ms_img, "what": "volume_render_image, 800x800, fx 1111.11, "
+                      f"{N_CAMS} hemisphere cameras per GPU (images sharded over GPUs)"}
+    if world > 1:
+        line["exchange"] = {"rows_per_step": trainer.exchanged_rows,
+                            "bytes_all_reduced_per_step": trainer.exchanged_rows * 28 * 4,
+                            "phase_ms": phase_ms}
     if args.cpu_baseline:
         line["cpu_baseline"] = cpu_port_baseline(sc, grid, batches[0], budget_rays=args.cpu_rays)
     if args.ref_cuda:
@@ -429,8 +486,10 @@ def reference_cuda_baseline(sc, grid, batches, args, gq):
     e1.record()
     torch.cuda.synchronize()
     ms_f = e0.elapsed_time(e1) / args.steps
+    ms_img = time_images(lambda c: rg.volume_render_image(ref.Camera(c, **CAM_KW)),
+                         bench_cameras(dev))
     return {"value": BATCH / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms,
-            "ms_fused_call": ms_f, "what": "sxyu/svox2 CUDA extension (TORCH_CUDA_ARCH_LIST=10.0), "
+            "ms_fused_call": ms_f, "render_mpix_s": 0.64 / (ms_img * 1e-3), "ms_per_image": ms_img, "what": "sxyu/svox2 CUDA extension (TORCH_CUDA_ARCH_LIST=10.0), "
             "same grid/rays/step on this GPU, 1 GPU"}
 
 

@@ -569,3 +569,47 @@ def sgd_step(data, grad, indexer, lr, lr_last):
         check(_lib.lib().svox2_sgd_step(
             data.data_ptr(), grad.data_ptr(), data.size(0), data.size(1), _row_stride(data), kind,
             mask, index, n_index, float(lr), float(lr_last), _stream()))
+
+
+# ---- multi-GPU gradient exchange helpers (extension) -------------------------
+def packed_row_floats(sh_channels: int) -> int:
+    """Floats per packed exchange row: SH channels + 1 density slot, padded to a multiple of 4."""
+    return (sh_channels + 1 + 3) // 4 * 4
+
+
+def pack_grad_rows(grad_sh, grad_density, rows, packed):
+    """packed[i] = [grad_sh[rows[i]], grad_density[rows[i]], 0...]; zeroes what it gathered."""
+    _check_rows(grad_sh, "grad_sh")
+    _check_rows(grad_density, "grad_density")
+    _check_rows(packed, "packed")
+    _check_cuda(rows, "rows", torch.int64, 1)
+    if not rows.is_contiguous() or packed.size(0) != rows.numel():
+        _fail("rows must be contiguous and match packed.size(0)")
+    with torch.cuda.device(grad_sh.device):
+        check(_lib.lib().svox2_pack_grad_rows(
+            grad_sh.data_ptr(), _row_stride(grad_sh), grad_sh.size(1), grad_density.data_ptr(),
+            _row_stride(grad_density), rows.data_ptr(), rows.numel(), packed.data_ptr(),
+            _row_stride(packed), _stream()))
+
+
+def rmsprop_step_packed(sh_data, sh_rms, density_data, density_rms, rows, packed, mask_sh,
+                        mask_density, beta, lr_sh, lr_density, epsilon, minval_sh=-1e9,
+                        minval_density=-1e9):
+    """Masked RMSProp on density + SH of the listed rows, gradients from the packed buffer."""
+    for t, n in ((sh_data, "sh_data"), (sh_rms, "sh_rms"), (density_data, "density_data"),
+                 (density_rms, "density_rms"), (packed, "packed")):
+        _check_rows(t, n)
+    _check_cuda(rows, "rows", torch.int64, 1)
+    for m, n in ((mask_sh, "mask_sh"), (mask_density, "mask_density")):
+        _check_cuda(m, n)
+        if m.dtype not in (torch.bool, torch.uint8) or m.numel() != sh_data.size(0) or not m.is_contiguous():
+            _fail(f"{n} must be a contiguous bool/uint8 tensor with one entry per row")
+    if _row_stride(sh_data) != _row_stride(sh_rms) or _row_stride(density_data) != _row_stride(density_rms):
+        _fail("data and rms must share one layout")
+    with torch.cuda.device(sh_data.device):
+        check(_lib.lib().svox2_rmsprop_step_packed(
+            sh_data.data_ptr(), sh_rms.data_ptr(), _row_stride(sh_data), sh_data.size(1),
+            density_data.data_ptr(), density_rms.data_ptr(), _row_stride(density_data),
+            rows.data_ptr(), rows.numel(), packed.data_ptr(), _row_stride(packed),
+            mask_sh.data_ptr(), mask_density.data_ptr(), float(beta), float(lr_sh),
+            float(lr_density), float(epsilon), float(minval_sh), float(minval_density), _stream()))

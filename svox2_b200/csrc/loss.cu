@@ -206,6 +206,102 @@ tv_grad_sparse_kernel(const int32_t* __restrict__ links, int X, int Y, int Z,
     }
 }
 
+// Vector form of the COOP sweep for 16-byte-aligned padded rows: lane = one float4 of a row, so a
+// 27-channel cell takes 7 lanes, a warp finishes 4 surviving cells per pass and keeps TV_VEC_PASSES
+// passes (32 independent 128-bit loads) in flight.  The scalar sweep walked a warp's surviving
+// cells one by one -- up to 32 dependent load->atomic round trips in the warps that cross a blob.
+// Per-element arithmetic is unchanged; channels whose value is exactly 0 add 0.0f (the reference
+// skips them) and a link's mask byte is set iff one of its channels is non-zero.
+#ifndef TV_USE_VEC
+#define TV_USE_VEC 1
+#endif
+#ifndef TV_VEC_PASSES
+#define TV_VEC_PASSES 2
+#endif
+__global__ void __launch_bounds__(TV_THREADS)
+tv_grad_sparse_vec_kernel(const int32_t* __restrict__ links, int X, int Y, int Z,
+                          const float* __restrict__ data, int64_t stride,
+                          const int32_t* __restrict__ rand_cells, int64_t cell_start, int start_dim,
+                          int end_dim, float scale, int64_t n_cells, int ignore_edge,
+                          int ignore_last_z, uint8_t* __restrict__ mask_out,
+                          float* __restrict__ grad, int64_t gstride, int qpr) {
+    constexpr int U = TV_VEC_PASSES;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    if (tid - lane >= n_cells) return;
+    const TvCell mine = tv_probe(links, X, Y, Z, rand_cells, cell_start, tid, n_cells, ignore_edge, ignore_last_z);
+    float sc[3];
+    ray_scale(X, Y, Z, sc);
+    const int cpp = WARP / qpr;  // cells per pass
+    const int grp = lane / qpr;
+    const int ch0 = start_dim + (lane - grp * qpr) * 4;
+    const bool lane_on = grp < cpp;
+    bool ok[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) ok[e] = ch0 + e < end_dim;
+    unsigned m = __ballot_sync(FULL, mine.on);
+    while (m) {
+        int32_t l[U][4];
+        bool on[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned p = lane_on ? __fns(m, 0, grp + 1 + u * cpp) : 0xffffffffu;
+            on[u] = p < 32u;
+            const int src = on[u] ? (int)p : 0;
+            l[u][0] = __shfl_sync(FULL, mine.l000, src);
+            l[u][1] = __shfl_sync(FULL, mine.l001, src);
+            l[u][2] = __shfl_sync(FULL, mine.l010, src);
+            l[u][3] = __shfl_sync(FULL, mine.l100, src);
+        }
+        {
+            const unsigned p = __fns(m, 0, U * cpp);
+            m = p < 32u ? (m & ~((2u << p) - 1u)) : 0u;
+        }
+        float4 v[U][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (on[u] && l[u][k] >= 0)
+                    v[u][k] = __ldg(reinterpret_cast<const float4*>(data + (int64_t)l[u][k] * stride + ch0));
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!on[u]) continue;
+            float out[4][4];  // [link][element]
+            bool any[4] = {false, false, false, false};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float v000 = l[u][0] >= 0 ? reinterpret_cast<const float*>(&v[u][0])[e] : 0.f;
+                const float nullv = ignore_edge ? v000 : 0.f;
+                const float v001 = l[u][1] >= 0 ? reinterpret_cast<const float*>(&v[u][1])[e] : nullv;
+                const float v010 = l[u][2] >= 0 ? reinterpret_cast<const float*>(&v[u][2])[e] : nullv;
+                const float v100 = l[u][3] >= 0 ? reinterpret_cast<const float*>(&v[u][3])[e] : nullv;
+                float dx = __fsub_rn(v100, v000), dy = __fsub_rn(v010, v000), dz = __fsub_rn(v001, v000);
+                const float idelta = __fmul_rn(scale, inv_delta(dx, dy, dz));
+                dx = __fmul_rn(dx, sc[0]);
+                dy = __fmul_rn(dy, sc[1]);
+                dz = __fmul_rn(dz, sc[2]);
+                const float val[4] = {-__fadd_rn(__fadd_rn(dx, dy), dz), dz, dy, dx};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool nz = ok[e] && val[k] != 0.f;
+                    out[k][e] = nz ? __fmul_rn(val[k], idelta) : 0.f;
+                    any[k] = any[k] || nz;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (l[u][k] >= 0 && any[k]) {
+                    float* gp = grad + (int64_t)l[u][k] * gstride + ch0;
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gp),
+                                 "f"(out[k][0]), "f"(out[k][1]), "f"(out[k][2]), "f"(out[k][3])
+                                 : "memory");
+                    if (mask_out) mask_out[l[u][k]] = 1;
+                }
+        }
+    }
+}
+
 // msi_tv_grad_sparse_kernel, loss_kernel.cu:248-333
 __global__ void __launch_bounds__(TV_THREADS)
 msi_tv_grad_sparse_kernel(const int32_t* __restrict__ links, int reso,
@@ -329,7 +425,14 @@ static int tv_grad_sparse_impl(const int32_t* links, int32_t X, int32_t Y, int32
     tv_grad_sparse_kernel<COOP><<<div_up(n_cells, TV_THREADS), TV_THREADS, 0, st>>>(            \
         links, X, Y, Z, data, data_stride, rand_cells, cell_start, start_dim, end_dim, s,       \
         n_cells, ignore_edge, ignore_last_z, mask_out, grad_data, gs)
+    const int qpr = (nd + 3) / 4;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(data) | reinterpret_cast<uintptr_t>(grad_data);
     if (nd <= 2) TV_LAUNCH(false);
+    else if (TV_USE_VEC && qpr <= WARP && start_dim % 4 == 0 && data_stride % 4 == 0 && gs % 4 == 0 &&
+             start_dim + qpr * 4 <= data_stride && start_dim + qpr * 4 <= gs && (al & 15u) == 0)
+        tv_grad_sparse_vec_kernel<<<div_up(n_cells, TV_THREADS), TV_THREADS, 0, st>>>(
+            links, X, Y, Z, data, data_stride, rand_cells, cell_start, start_dim, end_dim, s,
+            n_cells, ignore_edge, ignore_last_z, mask_out, grad_data, gs, qpr);
     else TV_LAUNCH(true);
 #undef TV_LAUNCH
     return check_launch(who);

@@ -14,7 +14,10 @@ namespace {
 #ifndef OPT_ROWS_IN_FLIGHT
 #define OPT_ROWS_IN_FLIGHT 4
 #endif
-constexpr int OPT_THREADS = 256;
+#ifndef OPT_THREADS_N
+#define OPT_THREADS_N 64
+#endif
+constexpr int OPT_THREADS = OPT_THREADS_N;
 constexpr int RIF = OPT_ROWS_IN_FLIGHT;
 
 // rmsprop_once, optim_kernel.cu:15-25
@@ -113,6 +116,126 @@ masked_rows_kernel(OptArgs a) {
     }
 }
 
+// bool-mask variant on 16-byte-aligned padded rows (the layout SparseGrid keeps sh_data / sh_rms /
+// grad in): lane = one float4 of a row, so a 27-channel row takes 7 lanes and a warp updates
+// 4 touched rows per pass, OPT_VEC_PASSES passes in flight.  Persistent warps stride over the
+// 32-row chunks, which keeps every resident warp busy (the one-chunk-per-warp kernel spent most
+// of its 52 k blocks on chunks with nothing to do) and cuts the instruction count ~4x (the
+// scalar kernel was issue-bound: IEEE sqrt + divide per element).
+#ifndef OPT_VEC_PASSES
+#define OPT_VEC_PASSES 2
+#endif
+#ifndef OPT_USE_VEC
+#define OPT_USE_VEC 1
+#endif
+#ifndef OPT_VEC_BLOCKS
+#define OPT_VEC_BLOCKS 16
+#endif
+#ifndef OPT_SUPER_N
+#define OPT_SUPER_N 512
+#endif
+#ifndef OPT_VEC_GRID_CAP
+#define OPT_VEC_GRID_CAP 0   // persistent CTAs per SM (0: one CTA per 8 super-chunks, not capped)
+#endif
+constexpr int OPT_SUPER = OPT_SUPER_N;  // rows scanned per warp step
+template <bool RMS>
+__global__ void __launch_bounds__(OPT_THREADS, OPT_VEC_BLOCKS)
+masked_rows_vec_kernel(OptArgs a, int qpr) {
+    constexpr int U = OPT_VEC_PASSES;
+    const int lane = threadIdx.x & 31;
+    const int rpp = WARP / qpr;            // rows per pass
+    const int grp = lane / qpr;
+    const int ch0 = (lane - grp * qpr) * 4;
+    const bool lane_on = grp < rpp;
+    float lr4[4];
+    bool ok[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        ok[e] = ch0 + e < a.C;
+        lr4[e] = (ch0 + e == a.C - 1) ? a.lr_last : a.lr;
+    }
+    // a warp scans 512 mask bytes per step (one 128-bit load per lane): the scan is a chain of
+    // dependent global loads per warp, so it must be short
+    const int64_t nsuper = (a.rows + OPT_SUPER - 1) / OPT_SUPER;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const bool mask_al = (reinterpret_cast<uintptr_t>(a.mask) & 15u) == 0;
+    for (int64_t sc = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; sc < nsuper; sc += nwarps) {
+#if OPT_SUPER_N == 32
+        const int64_t my_row = sc * OPT_SUPER + lane;
+        const uint32_t h = (my_row < a.rows && __ldg(a.mask + my_row) != 0) ? 1u : 0u;
+        const unsigned m32 = __ballot_sync(FULL, h != 0u);
+        if (m32 == 0u) continue;
+#else
+        const int64_t base = sc * OPT_SUPER + lane * 16;
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (mask_al && base + 16 <= a.rows) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(a.mask + base));
+            w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+        } else {
+            for (int k = 0; k < 16 && base + k < a.rows; ++k)
+                w[k >> 2] |= (uint32_t)(__ldg(a.mask + base + k) != 0) << (8 * (k & 3));
+        }
+        if (!__any_sync(FULL, (w[0] | w[1] | w[2] | w[3]) != 0u)) continue;
+        // 16 bytes -> 16 bits, then two lanes' halves make the ballot of one 32-row chunk
+        uint32_t h = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t nz = __vcmpne4(w[i], 0u) & 0x01010101u;
+            h |= (((nz * 0x01020408u) >> 24) & 0xfu) << (4 * i);
+        }
+#endif
+#pragma unroll 1
+        for (int c = 0; c < OPT_SUPER / WARP; ++c) {
+#if OPT_SUPER_N == 32
+        unsigned m = m32;
+#else
+        unsigned m = __shfl_sync(FULL, h, 2 * c) | (__shfl_sync(FULL, h, 2 * c + 1) << 16);
+#endif
+        const int64_t row0 = sc * OPT_SUPER + c * WARP;
+        while (m) {
+            // pop the next U*rpp touched rows in address order; group g of pass u keeps row g + u*rpp
+            int sel[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) sel[u] = -1;
+            for (int i = 0; i < U * rpp && m; ++i) {
+                const int bit = __ffs(m) - 1;
+                m &= m - 1;
+#pragma unroll
+                for (int u = 0; u < U; ++u) sel[u] = (i == grp + u * rpp) ? bit : sel[u];
+            }
+            int64_t off[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                off[u] = (lane_on && sel[u] >= 0) ? (row0 + sel[u]) * a.stride + ch0 : -1;
+            float4 g[U], d[U], r[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (off[u] >= 0) {
+                    g[u] = *reinterpret_cast<const float4*>(a.grad + off[u]);
+                    d[u] = *reinterpret_cast<const float4*>(a.data + off[u]);
+                    if (RMS) r[u] = *reinterpret_cast<const float4*>(a.rms + off[u]);
+                }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (off[u] >= 0) {
+                    float* gv = reinterpret_cast<float*>(&g[u]);
+                    float* dv = reinterpret_cast<float*>(&d[u]);
+                    float* rv = reinterpret_cast<float*>(&r[u]);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (ok[e]) {  // padding floats keep their values
+                            if (RMS) rmsprop_once(dv + e, rv + e, gv + e, a.beta, lr4[e], a.eps, a.minval);
+                            else sgd_once(dv + e, gv + e, lr4[e]);
+                        }
+                    if (RMS) *reinterpret_cast<float4*>(a.rms + off[u]) = r[u];
+                    *reinterpret_cast<float4*>(a.data + off[u]) = d[u];
+                    *reinterpret_cast<float4*>(a.grad + off[u]) = g[u];
+                }
+        }
+        }
+    }
+}
+
 // bool-mask variant, C == 1 (density): four rows per thread, one 32-bit mask load
 template <bool RMS>
 __global__ void __launch_bounds__(OPT_THREADS)
@@ -157,6 +280,17 @@ elementwise_kernel(OptArgs a, int64_t Q) {
 template <bool RMS>
 void launch(const OptArgs& a, int kind, int64_t n_index, cudaStream_t st) {
     if (kind == SVOX2_INDEXER_MASK && a.C > 1) {
+        const int qpr = (a.C + 3) / 4;
+        const uintptr_t al = reinterpret_cast<uintptr_t>(a.data) | reinterpret_cast<uintptr_t>(a.grad) |
+                             (RMS ? reinterpret_cast<uintptr_t>(a.rms) : 0);
+        if (OPT_USE_VEC && qpr <= WARP && a.stride % 4 == 0 && a.stride >= qpr * 4 && (al & 15u) == 0) {
+            const int64_t supers = (a.rows + OPT_SUPER - 1) / OPT_SUPER;
+            const int64_t want = div_up(supers * WARP, OPT_THREADS);
+            const int64_t cap = OPT_VEC_GRID_CAP > 0 ? 148 * OPT_VEC_GRID_CAP : want;
+            const unsigned blocks = (unsigned)(want < cap ? want : cap);
+            masked_rows_vec_kernel<RMS><<<blocks, OPT_THREADS, 0, st>>>(a, qpr);
+            return;
+        }
         const int64_t warps = (a.rows + WARP - 1) / WARP;
         masked_rows_kernel<RMS><<<div_up(warps * WARP, OPT_THREADS), OPT_THREADS, 0, st>>>(a);
         return;

@@ -39,6 +39,16 @@ namespace {
 #define QM_SAMPLE_CTAS 8   // persistent CTAs per SM for the sample-parallel kernels
 #endif
 
+#ifndef QM_GATHER_AHEAD
+#define QM_GATHER_AHEAD 3  // bit 0: K2, bit 1: K4 prefetch the rows of the group's NEXT record to L2
+#endif
+#ifndef QM_TRACE_PIPE
+#define QM_TRACE_PIPE 0    // K1: issue the next round's link loads before this round's density loads
+#endif
+#ifndef QM_TRACE_BLOCKS
+#define QM_TRACE_BLOCKS 16
+#endif
+
 constexpr int TRACE_THREADS = 64;
 constexpr int SAMPLE_THREADS = 256;
 
@@ -75,7 +85,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 // K1: traversal -> records
 // ---------------------------------------------------------------------------------------
 template <bool COUNT>
-__global__ void __launch_bounds__(TRACE_THREADS, 16)
+__global__ void __launch_bounds__(TRACE_THREADS, QM_TRACE_BLOCKS)
 trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv) {
     const int64_t ray_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (ray_id >= a.n_rays) return;
@@ -106,25 +116,38 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv) {
     if (ray.tmin <= ray.tmax) {
         float t0 = ray.tmin;
         bool done = false;
-        while (!done) {
-            float tk = t0;
+        // one round = 32 lattice candidates t0 + lane*step (sequential adds, bit-exact)
+        float tk;
+        bool valid;
+        int l[3];
+        float pos[3];
+        int32_t lk[8];
+        auto load_round = [&](float t_first, float& tk_o, bool& valid_o, int* l_o, float* pos_o,
+                              int32_t* lk_o) {
+            float t = t_first;
 #pragma unroll
             for (int i = 0; i < 31; ++i) {
-                const float nx = __fadd_rn(tk, step);
-                tk = (i < lane) ? nx : tk;
+                const float nx = __fadd_rn(t, step);
+                t = (i < lane) ? nx : t;
             }
-            const bool valid = tk <= ray.tmax;
-            int l[3];
-            float pos[3];
-            locate(ray, g, tk, l, pos);
-            const int32_t* lp = g.links + ((int64_t)l[0] * g.offx + (int64_t)l[1] * g.offy + l[2]);
-            int32_t lk[8];
+            tk_o = t;
+            valid_o = t <= ray.tmax;
+            locate(ray, g, t, l_o, pos_o);
+            const int32_t* lp = g.links + ((int64_t)l_o[0] * g.offx + (int64_t)l_o[1] * g.offy + l_o[2]);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) lk[q] = -1;
-            if (valid) {
+            for (int q = 0; q < 8; ++q) lk_o[q] = -1;
+            if (valid_o) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) lk[q] = __ldg(lp + corner_off(g, q));
+                for (int q = 0; q < 8; ++q) lk_o[q] = __ldg(lp + corner_off(g, q));
             }
+        };
+#if QM_TRACE_PIPE
+        load_round(t0, tk, valid, l, pos, lk);
+#endif
+        while (!done) {
+#if !QM_TRACE_PIPE
+            load_round(t0, tk, valid, l, pos, lk);
+#endif
             const float skipd = skip_dist(ray, valid ? lk[0] : 0, l, pos);
             const bool is_skip = valid && (skipd >= step);
             const unsigned valid_m = __ballot_sync(FULL, valid);
@@ -158,6 +181,32 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv) {
                 if (!(tn <= ray.tmax)) done = true;
                 break;
             }
+#if QM_TRACE_PIPE
+            // this round's samples keep their own copies; the next round's link loads are issued
+            // now and stay in flight under the density gathers and the transmittance chain
+            const float tk_c = tk;
+            float pos_c[3] = {pos[0], pos[1], pos[2]};
+            int32_t lk_c[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) lk_c[q] = lk[q];
+            if (!done) {
+                load_round(t_next, tk, valid, l, pos, lk);
+                const float ta = fmaf((float)(lane + 32), step, t_next);
+                if (ta <= ray.tmax) {
+                    int nl[3];
+                    float npos[3];
+                    locate(ray, g, ta, nl, npos);
+                    const int32_t* np = g.links + ((int64_t)nl[0] * g.offx + (int64_t)nl[1] * g.offy + nl[2]);
+                    prefetch_l2(np);
+                    prefetch_l2(np + g.offy);
+                    prefetch_l2(np + g.offx);
+                    prefetch_l2(np + g.offx + g.offy);
+                }
+            }
+#define TK tk_c
+#define POS pos_c
+#define LK lk_c
+#else
             if (!done) {  // next batch's link lines
                 const float ta = fmaf((float)lane, step, t_next);
                 if (ta <= ray.tmax) {
@@ -171,24 +220,28 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv) {
                     prefetch_l2(np + g.offx + g.offy);
                 }
             }
+#define TK tk
+#define POS pos
+#define LK lk
+#endif
             const bool member = (members >> lane) & 1u;
             float sigma = 0.f;
             if (member) {
                 float sv[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
-                    sv[q] = lk[q] >= 0 ? __ldg(g.density + (int64_t)lk[q] * g.density_stride) : 0.f;
-                sigma = trilerp8(sv, pos);
+                    sv[q] = LK[q] >= 0 ? __ldg(g.density + (int64_t)LK[q] * g.density_stride) : 0.f;
+                sigma = trilerp8(sv, POS);
             }
-            const float ws = (opt.last_sample_opaque && __fadd_rn(tk, step) > ray.tmax) ? 1e9f
+            const float ws = (opt.last_sample_opaque && __fadd_rn(TK, step) > ray.tmax) ? 1e9f
                                                                                        : ray.world_step;
             const bool active = member && (sigma > opt.sigma_thresh);
 #if QM_PREFETCH_SH
             if (active) {  // pull the rows K2 will gather towards L2
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
-                    if (lk[q] >= 0) {
-                        const float* row = g.sh + (int64_t)lk[q] * g.sh_stride;
+                    if (LK[q] >= 0) {
+                        const float* row = g.sh + (int64_t)LK[q] * g.sh_stride;
                         prefetch_l2(row);
                         prefetch_l2(row + (g.sh_dim - 1));
                     }
@@ -232,10 +285,10 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv) {
                         const int rank = __popc(act_m & ((1u << lane) - 1u));
                         Record* r = qv.rec + base + rank;
                         int4* r4 = reinterpret_cast<int4*>(r);
-                        r4[0] = make_int4(lk[0], lk[1], lk[2], lk[3]);
-                        r4[1] = make_int4(lk[4], lk[5], lk[6], lk[7]);
+                        r4[0] = make_int4(LK[0], LK[1], LK[2], LK[3]);
+                        r4[1] = make_int4(LK[4], LK[5], LK[6], LK[7]);
                         const float weight = __fmul_rn(fexp(my_before), __fsub_rn(1.f, fexp(-pcnt)));
-                        reinterpret_cast<float4*>(r)[2] = make_float4(pos[0], pos[1], pos[2], weight);
+                        reinterpret_cast<float4*>(r)[2] = make_float4(POS[0], POS[1], POS[2], weight);
                         r4[3] = make_int4(__float_as_int(__fsub_rn(my_before, pcnt)), __float_as_int(sigma),
                                           __float_as_int(ws), (int)ray_id);
                     }
@@ -249,6 +302,9 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv) {
             }
             t0 = t_next;
         }
+#undef TK
+#undef POS
+#undef LK
     }
     // forward colour starts from the background term; K2 adds the samples atomically
     const bool hit = ray.tmin <= ray.tmax;
@@ -320,6 +376,16 @@ shade_kernel(GridView g, QueueView qv, float* __restrict__ rgb_out) {
     const int groups = (gridDim.x * blockDim.x) >> 3;
     for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; s < n; s += groups) {
         const Record* r = qv.rec + s;
+#if QM_GATHER_AHEAD & 1
+        if (s + groups < n) {  // lane q of the group pulls corner q of the next record
+            const int32_t ln = __ldcg(&qv.rec[s + groups].lk[qi]);
+            if (ln >= 0) {
+                const float* row = g.sh + (size_t)ln * (unsigned)g.sh_stride;
+                prefetch_l2(row);
+                prefetch_l2(row + (D - 1));
+            }
+        }
+#endif
         const int4 la = __ldcg(reinterpret_cast<const int4*>(r));
         const int4 lb = __ldcg(reinterpret_cast<const int4*>(r) + 1);
         const float4 pw = __ldcg(reinterpret_cast<const float4*>(r) + 2);
@@ -444,6 +510,17 @@ scatter_kernel(GridView g, QueueView qv, GradView gr, int64_t gsh_stride, int64_
     const int groups = (gridDim.x * blockDim.x) >> 3;
     for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; s < n; s += groups) {
         const Record* r = qv.rec + s;
+#if QM_GATHER_AHEAD & 2
+        if (s + groups < n) {
+            const int32_t ln = __ldcg(&qv.rec[s + groups].lk[qi]);
+            if (ln >= 0) {
+                const float* row = gr.grad_sh + (int64_t)ln * gsh_stride;
+                prefetch_l2(row);
+                prefetch_l2(row + (D - 1));
+                prefetch_l2(gr.grad_density + (int64_t)ln * gd_stride);
+            }
+        }
+#endif
         const int4 la = __ldcg(reinterpret_cast<const int4*>(r));
         const int4 lb = __ldcg(reinterpret_cast<const int4*>(r) + 1);
         const float4 pw = __ldcg(reinterpret_cast<const float4*>(r) + 2);

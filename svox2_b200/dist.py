@@ -64,7 +64,11 @@ class ShardedTrainer:
         self.tv_sparsity, self.rms_beta = tv_sparsity, rms_beta
         self.beta_loss, self.sparsity_loss = beta_loss, sparsity_loss
         # march fwd + march bwd + 2 TV + 2 optimiser kernels
-        self.kernels_per_step = 2 + (lambda_tv > 0) + (lambda_tv_sh > 0) + 2
+        # clear + trace + shade + seed + scatter + (conditional) lattice fallback, 2 TV, then
+        # 2 optimiser kernels (1 GPU) or pack + packed optimiser (multi-GPU)
+        self.kernels_per_step = 6 + (lambda_tv > 0) + (lambda_tv_sh > 0) + 2
+        self.profile, self._events, self.exchanged_rows = False, [], 0
+        self._packed = None
 
     def _tv_run(self):
         """This rank's slice (start, count) of the step's contiguous wrapped cell run (drawn with
@@ -88,10 +92,65 @@ class ShardedTrainer:
             run, n = self._tv_run()
             g.inplace_tv_color_grad(g.sh_data.grad, scaling=self.lambda_tv_sh, _cell_run=run,
                                     _scale_cells=n)
+        lr_sigma = self.lr_sigma if lr_sigma is None else lr_sigma
+        lr_sh = self.lr_sh if lr_sh is None else lr_sh
+        if self.world_size > 1 and g.sh_data.is_cuda:
+            self._exchange_and_step_packed(lr_sigma, lr_sh)
+            return rgb
         if self.world_size > 1:
             g.sparse_grad_indexer, g.sparse_sh_grad_indexer = exchange_sparse_grads(
                 g.density_data.grad, g.sh_data.grad, g.sparse_grad_indexer,
                 g.sparse_sh_grad_indexer, group=self.group)
-        g.optim_density_step(self.lr_sigma if lr_sigma is None else lr_sigma, beta=self.rms_beta)
-        g.optim_sh_step(self.lr_sh if lr_sh is None else lr_sh, beta=self.rms_beta)
+        g.optim_density_step(lr_sigma, beta=self.rms_beta)
+        g.optim_sh_step(lr_sh, beta=self.rms_beta)
         return rgb
+
+    def _exchange_and_step_packed(self, lr_sigma: float, lr_sh: float):
+        """CUDA path of the exchange: OR the masks, pack the union's rows ([rows, 28] = 27 SH
+        gradients + the density gradient) with one kernel, ONE NCCL all-reduce, then a single
+        masked RMSProp kernel that reads the reduced gradients from the packed buffer (no unpack
+        pass).  Same result as exchange_sparse_grads + the two optimiser steps."""
+        from . import csrc as _C
+        g = self.grid
+        mark = self._mark
+        mark("local")
+        g._ensure_layout()
+        masks = torch.stack([g.sparse_grad_indexer, g.sparse_sh_grad_indexer]).view(torch.uint8)
+        dist.all_reduce(masks, op=dist.ReduceOp.MAX, group=self.group)
+        mark("mask_allreduce")
+        rows = torch.nonzero(masks[0] | masks[1]).flatten()     # sorted; one host sync
+        mark("row_list")
+        D = g.sh_data.size(1)
+        # persistent, geometrically grown buffer: a fresh several-hundred-MB tensor per step would
+        # miss the caching allocator (the NCCL stream still holds the previous one) and cudaMalloc
+        if self._packed is None or self._packed.size(0) < rows.numel():
+            self._packed = None
+            self._packed = torch.empty((int(rows.numel() * 1.25) + 1024, _C.packed_row_floats(D)),
+                                       dtype=torch.float32, device=g.sh_data.device)
+        packed = self._packed[:rows.numel()]
+        _C.pack_grad_rows(g.sh_data.grad, g.density_data.grad, rows, packed)
+        mark("pack")
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.group)
+        mark("grad_allreduce")
+        g._ensure_rms()
+        _C.rmsprop_step_packed(g.sh_data.data, g.sh_rms, g.density_data.data, g.density_rms, rows,
+                               packed, masks[1], masks[0], self.rms_beta, lr_sh, lr_sigma, 1e-8)
+        mark("optimiser")
+        self.exchanged_rows = rows.numel()
+        g.sparse_grad_indexer, g.sparse_sh_grad_indexer = masks[0].view(torch.bool), masks[1].view(torch.bool)
+
+    # ---- optional phase timing (CUDA events; enable with trainer.profile = True) -------------
+    def _mark(self, name):
+        if self.profile:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._events.append((name, ev))
+
+    def phase_times_ms(self):
+        """Mean milliseconds per phase since profiling was enabled ("local" = march + TV)."""
+        torch.cuda.synchronize()
+        out, n = {}, {}
+        for (_, e0), (name, e1) in zip(self._events[:-1], self._events[1:]):
+            out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
+            n[name] = n.get(name, 0) + 1
+        return {k: out[k] / n[k] for k in out}

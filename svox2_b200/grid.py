@@ -852,6 +852,18 @@ class SparseGrid(nn.Module):
         else:
             raise NotImplementedError(f"Unsupported optimizer {optim}")
 
+    def _ensure_rms(self):
+        """Create the RMSProp state of density / SH in the parameters' layout (optimisers that
+        do not go through _step, e.g. the packed multi-GPU step)."""
+        for name, rms_name in (("density_data", "density_rms"), ("sh_data", "sh_rms")):
+            p, rms = getattr(self, name), getattr(self, rms_name)
+            if rms is None or rms.shape != p.data.shape or rms.stride() != p.data.stride():
+                old = rms if (rms is not None and rms.shape == p.data.shape) else None
+                rms = self._zeros_same_layout(p.data)
+                if old is not None:
+                    rms.copy_(old)
+                setattr(self, rms_name, rms)
+
     def optim_density_step(self, lr: float, beta: float = 0.9, epsilon: float = 1e-8,
                            optim: str = "rmsprop"):
         """RMSProp / SGD step on density restricted to the sparse mask; zeroes the grads it used."""

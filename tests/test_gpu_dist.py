@@ -25,7 +25,7 @@ def _worker(rank, world, port, out):
     import svox2_b200 as sv
     from svox2_b200.dist import ShardedTrainer
     from gpu_helpers import make_grid, set_opt, t
-    from scenes import make_scene, rel_err
+    from scenes import frac_bad, make_scene
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -51,17 +51,28 @@ def _worker(rank, world, port, out):
         rgb = tr.step(sv.Rays(t(sc["origins"][b:e], dev), t(sc["dirs"][b:e], dev)), t(sc["rgb_gt"][b:e], dev),
                       global_batch=B)
         torch.cuda.synchronize()
-        ok = (rgb - rgb1[b:e]).abs().max().item() < 1e-5
+        m = {"rgb": (rgb - rgb1[b:e]).abs().max().item()}
+        ok = m["rgb"] < 1e-5
         # after the optimiser: parameters of the sharded replica == single-GPU parameters
-        ok = ok and rel_err(grid.density_data.detach().cpu().numpy(), ref.density_data.detach().cpu().numpy()) < 1e-4
+        # (first-step RMSProp moves by ~lr*sign(g): a gradient that cancels to ~0 may flip sign with
+        # the atomic order, on one GPU as much as on two, hence a fraction and not a max norm)
+        m["density"] = frac_bad(grid.density_data.detach().cpu().numpy(), ref.density_data.detach().cpu().numpy())
+        ok = ok and m["density"] < 1e-3
         dsh = (grid.sh_data.detach() - ref.sh_data.detach()).abs()
-        ok = ok and torch.quantile(dsh.flatten()[:2000000], 0.999).item() < 1e-4
+        m["sh_q999"] = torch.quantile(dsh.flatten()[:2000000], 0.999).item()
+        ok = ok and m["sh_q999"] < 1e-4
+        m["masks"] = bool(torch.equal(grid.sparse_grad_indexer, ref.sparse_grad_indexer) and
+                          torch.equal(grid.sparse_sh_grad_indexer, ref.sparse_sh_grad_indexer))
+        ok = ok and m["masks"]
+        m["grads_zeroed"] = float(grid.sh_data.grad.abs().max().item() + grid.density_data.grad.abs().max().item())
+        ok = ok and m["grads_zeroed"] == 0.0
         # replicas bit-identical across ranks
         mine = grid.sh_data.detach().contiguous()
         gathered = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(gathered, mine)
-        ok = ok and all(torch.equal(gathered[0], g) for g in gathered)
-        out[rank] = bool(ok)
+        m["replicas_equal"] = all(torch.equal(gathered[0], g) for g in gathered)
+        ok = ok and m["replicas_equal"]
+        out[rank] = (bool(ok), m)
     finally:
         dist.destroy_process_group()
 
@@ -79,4 +90,5 @@ def test_two_gpu_step_equals_single_gpu_step():
     for p in procs:
         p.join(300)
         assert p.exitcode == 0
-    assert dict(out) == {0: True, 1: True}
+    res = dict(out)
+    assert all(res[r][0] for r in range(2)), res
