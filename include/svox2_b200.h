@@ -233,11 +233,11 @@ SVOX2_API int svox2_sgd_step(float* data, float* grad, int64_t rows, int32_t n_c
 
 /* Multi-GPU gradient exchange (no reference counterpart).
  * svox2_pack_grad_rows: packed[i, 0:C] = grad_sh[rows[i], 0:C], packed[i, C] = grad_density[rows[i]],
- *   remaining floats of the packed row 0; the gathered gradient elements are zeroed (the packed
- *   optimiser never reads them again).  rows is a sorted int64 list identical on every rank.
+ *   remaining floats of the packed row 0.  rows is a sorted int64 list identical on every rank.
  * svox2_rmsprop_step_packed: the masked RMSProp of svox2_rmsprop_step (optim_kernel.cu:15-25) for
  *   density (if mask_density[row]) and SH (if mask_sh[row]) of every listed row, gradients read
- *   from the all-reduced packed buffer.
+ *   from the all-reduced packed buffer; if grad_sh/grad_density are given, those rows of the
+ *   local gradient arrays are zeroed (as svox2_rmsprop_step zeroes the gradients it consumed).
  * Both require 16-byte aligned SH rows padded to a multiple of 4 floats. */
 SVOX2_API int svox2_pack_grad_rows(float* grad_sh, int64_t grad_sh_stride, int32_t sh_channels,
                          float* grad_density, int64_t grad_density_stride, const int64_t* rows,
@@ -246,8 +246,9 @@ SVOX2_API int svox2_rmsprop_step_packed(float* sh_data, float* sh_rms, int64_t s
                          int32_t sh_channels, float* density_data, float* density_rms,
                          int64_t density_stride, const int64_t* rows, int64_t n_sel,
                          const float* packed, int64_t pack_stride, const uint8_t* mask_sh,
-                         const uint8_t* mask_density, float beta, float lr_sh, float lr_density,
-                         float epsilon, float minval_sh, float minval_density,
+                         const uint8_t* mask_density, float* grad_sh, int64_t grad_sh_stride,
+                         float* grad_density, int64_t grad_density_stride, float beta,
+                         float lr_sh, float lr_density, float epsilon, float minval_sh, float minval_density,
                          svox2_stream_t stream);
 
 #ifdef __cplusplus

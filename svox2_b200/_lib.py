@@ -105,7 +105,7 @@ SIGNATURES = {
     "svox2_sgd_step": (C.c_int, [_P, _P, _I64, _I32, _I64, _I32, _P, _P, _I64, _F, _F, _P]),
     "svox2_pack_grad_rows": (C.c_int, [_P, _I64, _I32, _P, _I64, _P, _I64, _P, _I64, _P]),
     "svox2_rmsprop_step_packed": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _I64, _P, _I64, _P, _I64, _P, _P,
-                                            _F, _F, _F, _F, _F, _F, _P]),
+                                            _P, _I64, _P, _I64, _F, _F, _F, _F, _F, _F, _P]),
 }
 
 _lib = None

@@ -578,7 +578,7 @@ def packed_row_floats(sh_channels: int) -> int:
 
 
 def pack_grad_rows(grad_sh, grad_density, rows, packed):
-    """packed[i] = [grad_sh[rows[i]], grad_density[rows[i]], 0...]; zeroes what it gathered."""
+    """packed[i] = [grad_sh[rows[i]], grad_density[rows[i]], 0...]."""
     _check_rows(grad_sh, "grad_sh")
     _check_rows(grad_density, "grad_density")
     _check_rows(packed, "packed")
@@ -594,8 +594,14 @@ def pack_grad_rows(grad_sh, grad_density, rows, packed):
 
 def rmsprop_step_packed(sh_data, sh_rms, density_data, density_rms, rows, packed, mask_sh,
                         mask_density, beta, lr_sh, lr_density, epsilon, minval_sh=-1e9,
-                        minval_density=-1e9):
-    """Masked RMSProp on density + SH of the listed rows, gradients from the packed buffer."""
+                        minval_density=-1e9, grad_sh=None, grad_density=None):
+    """Masked RMSProp on density + SH of the listed rows, gradients from the packed buffer;
+    zeroes those rows of grad_sh / grad_density (the local gradients that were packed)."""
+    if (grad_sh is None) != (grad_density is None):
+        _fail("grad_sh and grad_density go together")
+    if grad_sh is not None:
+        _check_rows(grad_sh, "grad_sh")
+        _check_rows(grad_density, "grad_density")
     for t, n in ((sh_data, "sh_data"), (sh_rms, "sh_rms"), (density_data, "density_data"),
                  (density_rms, "density_rms"), (packed, "packed")):
         _check_rows(t, n)
@@ -611,5 +617,7 @@ def rmsprop_step_packed(sh_data, sh_rms, density_data, density_rms, rows, packed
             sh_data.data_ptr(), sh_rms.data_ptr(), _row_stride(sh_data), sh_data.size(1),
             density_data.data_ptr(), density_rms.data_ptr(), _row_stride(density_data),
             rows.data_ptr(), rows.numel(), packed.data_ptr(), _row_stride(packed),
-            mask_sh.data_ptr(), mask_density.data_ptr(), float(beta), float(lr_sh),
+            mask_sh.data_ptr(), mask_density.data_ptr(), _ptr(grad_sh),
+            0 if grad_sh is None else _row_stride(grad_sh), _ptr(grad_density),
+            0 if grad_density is None else _row_stride(grad_density), float(beta), float(lr_sh),
             float(lr_density), float(epsilon), float(minval_sh), float(minval_density), _stream()))

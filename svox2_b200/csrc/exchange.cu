@@ -14,6 +14,9 @@ namespace svox2b {
 namespace {
 
 constexpr int EX_THREADS = 128;
+#ifndef EX_ZERO_IN_PACK
+#define EX_ZERO_IN_PACK 0  // 1: the pack kernel zeroes what it gathers; 0: the packed optimiser does
+#endif
 
 struct PackArgs {
     float* __restrict__ grad_sh;
@@ -43,7 +46,9 @@ pack_rows_kernel(PackArgs a) {
         if (ch0 < a.C) {  // quads past the SH channels hold only the density slot / padding
             float4* src = reinterpret_cast<float4*>(a.grad_sh + row * a.gsh_stride + ch0);
             v = *src;
+#if EX_ZERO_IN_PACK
             *src = make_float4(0.f, 0.f, 0.f, 0.f);
+#endif
         }
         float* ve = reinterpret_cast<float*>(&v);
 #pragma unroll
@@ -51,7 +56,9 @@ pack_rows_kernel(PackArgs a) {
             if (ch0 + e == a.C) {
                 float* d = a.grad_density + row * a.gd_stride;
                 ve[e] = *d;
+#if EX_ZERO_IN_PACK
                 *d = 0.f;
+#endif
             } else if (ch0 + e > a.C) {
                 ve[e] = 0.f;
             }
@@ -74,6 +81,10 @@ struct PackedOptArgs {
     int64_t pack_stride;
     const uint8_t* __restrict__ mask_sh;
     const uint8_t* __restrict__ mask_density;
+    float* __restrict__ grad_sh;       // zeroed for every listed row (may be NULL)
+    int64_t gsh_stride;
+    float* __restrict__ grad_density;
+    int64_t gd_stride;
     float beta, lr_sh, lr_density, eps, minval_sh, minval_density;
 };
 
@@ -99,6 +110,11 @@ rmsprop_packed_kernel(PackedOptArgs a) {
         const int64_t row = __ldg(a.rows + i);
         const bool on_sh = __ldg(a.mask_sh + row) != 0 && ch0 < a.C;
         const bool on_den = __ldg(a.mask_density + row) != 0 && ch0 <= a.C && a.C < ch0 + 4;
+        if (a.grad_sh) {  // the local gradients of this row are consumed: zero them for the next step
+            if (ch0 < a.C)
+                *reinterpret_cast<float4*>(a.grad_sh + row * a.gsh_stride + ch0) = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ch0 <= a.C && a.C < ch0 + 4) a.grad_density[row * a.gd_stride] = 0.f;
+        }
         if (!on_sh && !on_den) continue;
         const float4 g = __ldg(reinterpret_cast<const float4*>(a.packed + i * a.pack_stride + ch0));
         const float* ge = reinterpret_cast<const float*>(&g);
@@ -166,6 +182,7 @@ extern "C" SVOX2_API int svox2_rmsprop_step_packed(
     float* sh_data, float* sh_rms, int64_t sh_stride, int32_t sh_channels, float* density_data,
     float* density_rms, int64_t density_stride, const int64_t* rows, int64_t n_sel,
     const float* packed, int64_t pack_stride, const uint8_t* mask_sh, const uint8_t* mask_density,
+    float* grad_sh, int64_t grad_sh_stride, float* grad_density, int64_t grad_density_stride,
     float beta, float lr_sh, float lr_density, float epsilon, float minval_sh, float minval_density,
     svox2_stream_t stream) {
     SVOX2_REQUIRE(n_sel >= 0, "n_sel must be >= 0");
@@ -180,9 +197,13 @@ extern "C" SVOX2_API int svox2_rmsprop_step_packed(
                       aligned16(sh_data) && aligned16(sh_rms) && aligned16(packed),
                   "sh_data/sh_rms/packed need 16-byte aligned rows padded to a multiple of 4 floats");
     SVOX2_REQUIRE(density_stride >= 1, "bad density stride");
+    SVOX2_REQUIRE(!grad_sh || (grad_density && aligned16(grad_sh) && grad_sh_stride % 4 == 0 &&
+                               grad_sh_stride >= ((sh_channels + 3) / 4) * 4 &&
+                               grad_density_stride >= 1),
+                  "grad_sh/grad_density (optional, zeroed) need the same padded layout");
     PackedOptArgs a{sh_data,     sh_rms,  sh_stride, sh_channels, density_data,
                     density_rms, density_stride, rows, n_sel, packed, pack_stride, mask_sh,
-                    mask_density, beta, lr_sh, lr_density, epsilon, minval_sh, minval_density};
+                    mask_density, grad_sh, grad_sh_stride, grad_density, grad_density_stride, beta, lr_sh, lr_density, epsilon, minval_sh, minval_density};
     const int rpp = WARP / (int)(pack_stride / 4);
     rmsprop_packed_kernel<<<ex_blocks(n_sel, rpp), EX_THREADS, 0, (cudaStream_t)stream>>>(a);
     return check_launch(__func__);

@@ -134,7 +134,8 @@ class ShardedTrainer:
         mark("grad_allreduce")
         g._ensure_rms()
         _C.rmsprop_step_packed(g.sh_data.data, g.sh_rms, g.density_data.data, g.density_rms, rows,
-                               packed, masks[1], masks[0], self.rms_beta, lr_sh, lr_sigma, 1e-8)
+                               packed, masks[1], masks[0], self.rms_beta, lr_sh, lr_sigma, 1e-8,
+                               grad_sh=g.sh_data.grad, grad_density=g.density_data.grad)
         mark("optimiser")
         self.exchanged_rows = rows.numel()
         g.sparse_grad_indexer, g.sparse_sh_grad_indexer = masks[0].view(torch.bool), masks[1].view(torch.bool)
