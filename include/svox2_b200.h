@@ -251,6 +251,30 @@ SVOX2_API int svox2_rmsprop_step_packed(float* sh_data, float* sh_rms, int64_t s
                          float lr_sh, float lr_density, float epsilon, float minval_sh, float minval_density,
                          svox2_stream_t stream);
 
+/* Slab mode: the grid is sharded over GPUs by x-range of cells [x_lo, x_hi) (no reference
+ * counterpart).  Every rank traverses ALL rays of the global batch, so the sample
+ * lattice is the reference's (render_lerp_kernel_cuvol.cu:56-109), but gathers / records only the
+ * samples whose cell lies in its slab.  Between the three calls the ranks exchange per-ray scalars:
+ *   svox2_slab_trace    -> logT_local[Q]   (this slab's sum of -sigma*delta)
+ *   ... all-gather, lt_in[Q] = log-transmittance at slab entry along each ray ...
+ *   svox2_slab_shade    -> rgb_partial[Q,3] (+=, caller zeroes), stopped[Q] (=1 where the stop
+ *                          threshold fired; caller zeroes)
+ *   ... all-gather, total colour -> gout[Q,3] = dL/d(rgb), accum_start[Q] = the reference's
+ *       `accum` (cuvol.cu:248-264) at slab entry ...
+ *   svox2_slab_backward -> gradients / mask of this slab's samples.
+ * The workspace (svox2_fused_workspace_bytes) carries the sample records between the calls. */
+SVOX2_API int svox2_slab_trace(const svox2_grid_t* grid, const float* origins, const float* dirs,
+                     int64_t n_rays, const svox2_render_opts_t* opt, int32_t x_lo, int32_t x_hi,
+                     float* logT_local, void* workspace, size_t workspace_bytes,
+                     svox2_stream_t stream);
+SVOX2_API int svox2_slab_shade(const svox2_grid_t* grid, int64_t n_rays, const svox2_render_opts_t* opt,
+                     const float* lt_in, float* rgb_partial, float* stopped, void* workspace,
+                     size_t workspace_bytes, svox2_stream_t stream);
+SVOX2_API int svox2_slab_backward(const svox2_grid_t* grid, int64_t n_rays,
+                     const svox2_render_opts_t* opt, const float* lt_in, const float* gout,
+                     const float* accum_start, float sparsity_loss, const svox2_grads_t* grads,
+                     void* workspace, size_t workspace_bytes, svox2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -621,3 +621,52 @@ def rmsprop_step_packed(sh_data, sh_rms, density_data, density_rms, rows, packed
             0 if grad_sh is None else _row_stride(grad_sh), _ptr(grad_density),
             0 if grad_density is None else _row_stride(grad_density), float(beta), float(lr_sh),
             float(lr_density), float(epsilon), float(minval_sh), float(minval_density), _stream()))
+
+
+# ---- slab mode (grid sharded over GPUs by x-range of cells; svox2_b200/slab.py) --------------
+def slab_workspace(n_rays: int, slots_per_ray: int, device):
+    """Sample-record scratch shared by slab_trace / slab_shade / slab_backward."""
+    nbytes = _lib.lib().svox2_fused_workspace_bytes(n_rays, max(int(slots_per_ray), 64))
+    return torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+
+def slab_overflowed(workspace) -> bool:
+    """True if the last slab_trace ran out of record space (host sync)."""
+    return bool(workspace[128:132].view(torch.int32).item())
+
+
+def slab_trace(grid, rays, opt, x_lo, x_hi, logT_local, workspace):
+    g = _grid_struct(grid)
+    origins, dirs = _rays(rays)
+    o = _opt_struct(opt)
+    _check_input(logT_local, "logT_local", torch.float32, 1)
+    with torch.cuda.device(origins.device):
+        check(_lib.lib().svox2_slab_trace(
+            C.byref(g), origins.data_ptr(), dirs.data_ptr(), origins.size(0), C.byref(o), int(x_lo),
+            int(x_hi), logT_local.data_ptr(), workspace.data_ptr(), workspace.numel(), _stream()))
+
+
+def slab_shade(grid, n_rays, opt, lt_in, rgb_partial, stopped, workspace):
+    g = _grid_struct(grid)
+    o = _opt_struct(opt)
+    _check_input(lt_in, "lt_in", torch.float32, 1)
+    _check_input(rgb_partial, "rgb_partial", torch.float32, 2)
+    _check_input(stopped, "stopped", torch.float32, 1)
+    with torch.cuda.device(lt_in.device):
+        check(_lib.lib().svox2_slab_shade(
+            C.byref(g), int(n_rays), C.byref(o), lt_in.data_ptr(), rgb_partial.data_ptr(),
+            stopped.data_ptr(), workspace.data_ptr(), workspace.numel(), _stream()))
+
+
+def slab_backward(grid, n_rays, opt, lt_in, gout, accum_start, sparsity_loss, grads, workspace):
+    g = _grid_struct(grid)
+    o = _opt_struct(opt)
+    gr, _ = _grads_struct(grads, grid)
+    _check_input(lt_in, "lt_in", torch.float32, 1)
+    _check_input(gout, "gout", torch.float32, 2)
+    _check_input(accum_start, "accum_start", torch.float32, 1)
+    with torch.cuda.device(lt_in.device):
+        check(_lib.lib().svox2_slab_backward(
+            C.byref(g), int(n_rays), C.byref(o), lt_in.data_ptr(), gout.data_ptr(),
+            accum_start.data_ptr(), float(sparsity_loss), C.byref(gr), workspace.data_ptr(),
+            workspace.numel(), _stream()))

@@ -36,6 +36,16 @@ size_t queue_workspace_bytes(int64_t n_rays, int64_t records);
 bool launch_queue_fused(const GridView& g, const Opts& opt, const MarchArgs& a, const GradView& gr,
                         void* workspace, size_t workspace_bytes, const int** overflow_flag,
                         cudaStream_t st);
+// slab mode (grid sharded by x-range over GPUs): trace | exchange | shade | exchange | backward
+bool launch_slab_trace(const GridView& g, const Opts& opt, const MarchArgs& a, void* workspace,
+                       size_t workspace_bytes, int x_lo, int x_hi, float* logT_local,
+                       cudaStream_t st);
+bool launch_slab_shade(const GridView& g, const Opts& opt, int64_t n_rays, void* workspace,
+                       size_t workspace_bytes, const float* lt_in, float* rgb_partial,
+                       float* stopped, cudaStream_t st);
+bool launch_slab_backward(const GridView& g, const Opts& opt, const MarchArgs& a, const GradView& gr,
+                          void* workspace, size_t workspace_bytes, const float* lt_in,
+                          const float* gout, const float* accum_start, cudaStream_t st);
 void launch_lattice_march(int mode, bool from_cam, const GridView& g, const Opts& opt,
                           const MarchArgs& a, const GradView& gr, cudaStream_t st);
 

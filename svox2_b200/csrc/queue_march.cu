@@ -72,6 +72,20 @@ struct QueueView {
     float4* __restrict__ ray_Y;   // [Q][8] SH basis value of channels 4q..4q+3 (0 for padding)
 };
 
+// Slab mode (grid sharded over GPUs by x-range of cells, slab.py): the ray is traversed in full so
+// that the sample lattice is the reference's, but only samples whose cell lies in [x_lo, x_hi)
+// are gathered / recorded; transmittance is accumulated from 0 and shifted by the other slabs'
+// contribution (lt_in) once that is known.
+struct SlabView {
+    int x_lo, x_hi;
+    float* __restrict__ logT_local;        // K1 out: [Q] sum of -sigma*delta over this slab's samples
+    const float* __restrict__ lt_in;       // K2-K4 in: [Q] log-transmittance at slab entry
+    const float* __restrict__ gout;        // K3 in: [Q,3] dL/d(rgb) of the whole ray
+    const float* __restrict__ accum_start; // K3 in: [Q] the reference's accum at slab entry
+    float* __restrict__ stopped;           // K2 out: [Q] set to 1 where the stop threshold fired
+    float stop_thresh;
+};
+
 __device__ __forceinline__ unsigned range_mask(int a, int b) {
     const unsigned hi = (b >= 32) ? 0xffffffffu : ((1u << b) - 1u);
     const unsigned lo = (a >= 32) ? 0xffffffffu : ((1u << a) - 1u);
@@ -84,9 +98,10 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 // ---------------------------------------------------------------------------------------
 // K1: traversal -> records
 // ---------------------------------------------------------------------------------------
-template <bool COUNT>
+static_assert(!QM_TRACE_PIPE, "slab mode reads l[] after the pipelined reload");
+template <bool COUNT, bool SLAB>
 __global__ void __launch_bounds__(TRACE_THREADS, QM_TRACE_BLOCKS)
-trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv) {
+trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
     const int64_t ray_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (ray_id >= a.n_rays) return;
     const int lane = threadIdx.x & 31;
@@ -113,7 +128,23 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv) {
     bool stopped = false;
     int first_blk = -1, prev_blk = -1;
 
-    if (ray.tmin <= ray.tmax) {
+    // slab mode: t-interval in which the x coordinate can fall into the slab (one cell of margin;
+    // the outermost slabs are open-ended because locate() clamps)
+    bool takes_part = ray.tmin <= ray.tmax;
+    float t_exit = 3.0e38f;
+    if (SLAB && takes_part) {
+        const float lo = sl.x_lo <= 0 ? -3.0e38f : (float)(sl.x_lo - 1);
+        const float hi = sl.x_hi >= g.size[0] - 1 ? 3.0e38f : (float)(sl.x_hi + 1);
+        if (ray.d[0] == 0.f) {
+            takes_part = ray.o[0] >= lo && ray.o[0] <= hi;
+        } else {
+            const float ta = (lo - ray.o[0]) * ray.invd[0], tb = (hi - ray.o[0]) * ray.invd[0];
+            t_exit = fmaxf(ta, tb);
+            takes_part = t_exit >= ray.tmin && fminf(ta, tb) <= ray.tmax;
+        }
+    }
+
+    if (takes_part) {
         float t0 = ray.tmin;
         bool done = false;
         // one round = 32 lattice candidates t0 + lane*step (sequential adds, bit-exact)
@@ -145,6 +176,7 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv) {
         load_round(t0, tk, valid, l, pos, lk);
 #endif
         while (!done) {
+            if (SLAB && t0 > t_exit) break;  // past the slab: nothing left for this rank
 #if !QM_TRACE_PIPE
             load_round(t0, tk, valid, l, pos, lk);
 #endif
@@ -224,6 +256,7 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv) {
 #define POS pos
 #define LK lk
 #endif
+            if (SLAB) members &= __ballot_sync(FULL, l[0] >= sl.x_lo && l[0] < sl.x_hi);
             const bool member = (members >> lane) & 1u;
             float sigma = 0.f;
             if (member) {
@@ -287,7 +320,9 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv) {
                         int4* r4 = reinterpret_cast<int4*>(r);
                         r4[0] = make_int4(LK[0], LK[1], LK[2], LK[3]);
                         r4[1] = make_int4(LK[4], LK[5], LK[6], LK[7]);
-                        const float weight = __fmul_rn(fexp(my_before), __fsub_rn(1.f, fexp(-pcnt)));
+                        // slab mode keeps the local log-transmittance; K2 makes the weight
+                        const float weight = SLAB ? my_before
+                                                  : __fmul_rn(fexp(my_before), __fsub_rn(1.f, fexp(-pcnt)));
                         reinterpret_cast<float4*>(r)[2] = make_float4(POS[0], POS[1], POS[2], weight);
                         r4[3] = make_int4(__float_as_int(__fsub_rn(my_before, pcnt)), __float_as_int(sigma),
                                           __float_as_int(ws), (int)ray_id);
@@ -309,8 +344,12 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv) {
     // forward colour starts from the background term; K2 adds the samples atomically
     const bool hit = ray.tmin <= ray.tmax;
     const float logT_fwd = hit ? (stopped ? -1e3f : lt) : 0.f;
-    const float bgc = hit ? fexp(logT_fwd) * opt.background_brightness : opt.background_brightness;
-    if (lane < 3) a.rgb_out[ray_id * 3 + lane] = bgc;
+    if (SLAB) {
+        if (lane == 0) sl.logT_local[ray_id] = lt;
+    } else {
+        const float bgc = hit ? fexp(logT_fwd) * opt.background_brightness : opt.background_brightness;
+        if (lane < 3) a.rgb_out[ray_id * 3 + lane] = bgc;
+    }
     if (lane == 0) {
         qv.ray_first[ray_id] = first_blk;
         qv.ray_logT[ray_id] = logT_fwd;
@@ -362,9 +401,9 @@ __device__ __forceinline__ void corner_weights(float px, float py, float pz, flo
 // ---------------------------------------------------------------------------------------
 // K2: gather + colours, 8 lanes per sample
 // ---------------------------------------------------------------------------------------
-template <bool VEC>
+template <bool VEC, bool SLAB>
 __global__ void __launch_bounds__(SAMPLE_THREADS)
-shade_kernel(GridView g, QueueView qv, float* __restrict__ rgb_out) {
+shade_kernel(GridView g, QueueView qv, float* __restrict__ rgb_out, SlabView sl) {
     if (*qv.overflow) return;
     const int n = min(*qv.counter, qv.capacity);
     const int qi = threadIdx.x & 7;
@@ -373,6 +412,7 @@ shade_kernel(GridView g, QueueView qv, float* __restrict__ rgb_out) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) ce[e] = (qi * 4 + e < D) ? (qi * 4 + e) / B : -1;
     const float* shq = g.sh + (qi * 4 < D ? qi * 4 : 0);
+    const unsigned gmask = 0xffu << (threadIdx.x & 24);  // the 8 lanes that share a sample
     const int groups = (gridDim.x * blockDim.x) >> 3;
     for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; s < n; s += groups) {
         const Record* r = qv.rec + s;
@@ -388,8 +428,25 @@ shade_kernel(GridView g, QueueView qv, float* __restrict__ rgb_out) {
 #endif
         const int4 la = __ldcg(reinterpret_cast<const int4*>(r));
         const int4 lb = __ldcg(reinterpret_cast<const int4*>(r) + 1);
-        const float4 pw = __ldcg(reinterpret_cast<const float4*>(r) + 2);
+        float4 pw = __ldcg(reinterpret_cast<const float4*>(r) + 2);
         const int ray = __ldcg(&r->ray);
+        if (SLAB) {
+            // pw.w is the slab-local log-transmittance before the sample (cuvol.cu:170-178 with the
+            // entry value added); a sample behind the stop threshold is dead for K3 / K4 too
+            const float4 st = __ldcg(reinterpret_cast<const float4*>(r) + 3);
+            const float lt_in = __ldg(sl.lt_in + ray);
+            const float before = __fadd_rn(lt_in, pw.w);
+            if (fexp(before) < sl.stop_thresh) {
+                if (qi == 0) qv.rec[s].w = -1.f;
+                continue;
+            }
+            const float pcnt = __fmul_rn(st.z, st.y);
+            pw.w = __fmul_rn(fexp(before), __fsub_rn(1.f, fexp(-pcnt)));
+            if (qi == 0) {
+                qv.rec[s].w = pw.w;
+                if (fexp(__fadd_rn(lt_in, st.x)) < sl.stop_thresh) sl.stopped[ray] = 1.f;
+            }
+        }
         const int32_t L[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
         float4 v[8];
 #pragma unroll
@@ -416,9 +473,9 @@ shade_kernel(GridView g, QueueView qv, float* __restrict__ rgb_out) {
             float x = 0.f;
 #pragma unroll
             for (int e = 0; e < 4; ++e) x += (ce[e] == c) ? pr[e] : 0.f;
-            x += __shfl_xor_sync(FULL, x, 1);
-            x += __shfl_xor_sync(FULL, x, 2);
-            x += __shfl_xor_sync(FULL, x, 4);
+            x += __shfl_xor_sync(gmask, x, 1);
+            x += __shfl_xor_sync(gmask, x, 2);
+            x += __shfl_xor_sync(gmask, x, 4);
             col[c] = x + 0.5f;
         }
         if (qi < 3) {
@@ -432,8 +489,9 @@ shade_kernel(GridView g, QueueView qv, float* __restrict__ rgb_out) {
 // ---------------------------------------------------------------------------------------
 // K3: gradient seed + accum recursion per ray (cuvol.cu:248-264, 342-351, 735-747)
 // ---------------------------------------------------------------------------------------
+template <bool SLAB>
 __global__ void __launch_bounds__(TRACE_THREADS)
-seed_kernel(Opts opt, MarchArgs a, QueueView qv) {
+seed_kernel(Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
     if (*qv.overflow) return;
     const int64_t ray_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (ray_id >= a.n_rays) return;
@@ -441,13 +499,20 @@ seed_kernel(Opts opt, MarchArgs a, QueueView qv) {
     float gout[3], cc[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        cc[i] = __ldcg(a.rgb_out + ray_id * 3 + i);
-        gout[i] = (cc[i] - __ldg(a.grad_in + ray_id * 3 + i)) * a.norm_factor;
+        if (SLAB) {
+            gout[i] = __ldg(sl.gout + ray_id * 3 + i);
+            cc[i] = 0.f;
+        } else {
+            cc[i] = __ldcg(a.rgb_out + ray_id * 3 + i);
+            gout[i] = (cc[i] - __ldg(a.grad_in + ray_id * 3 + i)) * a.norm_factor;
+        }
     }
     int blk = qv.ray_first[ray_id];
     if (blk < 0) return;  // no active sample: nothing to scatter
     float accum = fmaf(cc[0], gout[0], fmaf(cc[1], gout[1], cc[2] * gout[2]));
-    if (a.beta_loss > 0.f) {
+    const float lt_in = SLAB ? __ldg(sl.lt_in + ray_id) : 0.f;
+    if (SLAB) accum = __ldg(sl.accum_start + ray_id);  // seed and beta term of the whole ray
+    if (!SLAB && a.beta_loss > 0.f) {
         const float transmit_in = fexp(qv.ray_logT[ray_id]);
         accum += (float)((double)a.beta_loss *
                          (1 - (double)transmit_in / (1 - (double)transmit_in + 1e-3)));
@@ -455,12 +520,13 @@ seed_kernel(Opts opt, MarchArgs a, QueueView qv) {
     while (blk >= 0) {
         const int count = __ldcg(&qv.rec[blk].blk_count);
         const int next = __ldcg(&qv.rec[blk].blk_next);
-        const bool on = lane < count;
+        bool on = lane < count;
         Record* r = qv.rec + blk + (on ? lane : 0);
         const float4 pw = __ldcg(reinterpret_cast<const float4*>(r) + 2);
         const float4 st = __ldcg(reinterpret_cast<const float4*>(r) + 3);
         const float4 co = __ldcg(reinterpret_cast<const float4*>(r) + 4);
-        const float w = pw.w, after = st.x, sigma = st.y, ws = st.z;
+        if (SLAB) on = on && pw.w >= 0.f;  // dead: behind the stop threshold
+        const float w = pw.w, after = SLAB ? __fadd_rn(lt_in, st.x) : st.x, sigma = st.y, ws = st.z;
         const float col[3] = {co.x, co.y, co.z};
         float gc[3], total = 0.f;
         {
@@ -496,7 +562,7 @@ seed_kernel(Opts opt, MarchArgs a, QueueView qv) {
 // ---------------------------------------------------------------------------------------
 // K4: scatter, 8 lanes per sample
 // ---------------------------------------------------------------------------------------
-template <bool VEC>
+template <bool VEC, bool SLAB>
 __global__ void __launch_bounds__(SAMPLE_THREADS)
 scatter_kernel(GridView g, QueueView qv, GradView gr, int64_t gsh_stride, int64_t gd_stride) {
     if (*qv.overflow) return;
@@ -526,6 +592,7 @@ scatter_kernel(GridView g, QueueView qv, GradView gr, int64_t gsh_stride, int64_
         const float4 pw = __ldcg(reinterpret_cast<const float4*>(r) + 2);
         const float4 gg = __ldcg(reinterpret_cast<const float4*>(r) + 4);
         const int ray = __ldcg(&r->ray);
+        if (SLAB && pw.w < 0.f) continue;  // dead sample
         const int32_t L[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
         const float4 Y = __ldcg(qv.ray_Y + (int64_t)ray * 8 + qi);
         float wq[8];
@@ -574,41 +641,100 @@ size_t queue_workspace_bytes(int64_t n_rays, int64_t records) {
            (size_t)records * sizeof(Record);
 }
 
-// Returns false if the workspace cannot hold even a minimal queue (caller uses the lattice path).
-bool launch_queue_fused(const GridView& g, const Opts& opt, const MarchArgs& a, const GradView& gr,
-                        void* workspace, size_t workspace_bytes, const int** overflow_flag,
-                        cudaStream_t st) {
-    const size_t fixed = queue_workspace_bytes(a.n_rays, 0);
-    if (!workspace || workspace_bytes < fixed + sizeof(Record) * 64 * (size_t)a.n_rays ||
+// Carves the workspace; false if it cannot hold even a minimal queue.
+static bool carve_queue(void* workspace, size_t workspace_bytes, int64_t n_rays, QueueView& qv) {
+    const size_t fixed = queue_workspace_bytes(n_rays, 0);
+    if (!workspace || workspace_bytes < fixed + sizeof(Record) * 64 * (size_t)n_rays ||
         (reinterpret_cast<uintptr_t>(workspace) & 255u))
         return false;
     char* p = static_cast<char*>(workspace);
-    QueueView qv;
     qv.counter = reinterpret_cast<int*>(p);
     qv.overflow = reinterpret_cast<int*>(p + 128);
     p += 256;
     qv.ray_first = reinterpret_cast<int*>(p);
-    p += align_up((size_t)a.n_rays * 4, 256);
+    p += align_up((size_t)n_rays * 4, 256);
     qv.ray_logT = reinterpret_cast<float*>(p);
-    p += align_up((size_t)a.n_rays * 4, 256);
+    p += align_up((size_t)n_rays * 4, 256);
     qv.ray_Y = reinterpret_cast<float4*>(p);
-    p += align_up((size_t)a.n_rays * 8 * 16, 256);
+    p += align_up((size_t)n_rays * 8 * 16, 256);
     qv.rec = reinterpret_cast<Record*>(p);
     const size_t cap = (workspace_bytes - fixed) / sizeof(Record);
     qv.capacity = (int)(cap > (size_t)0x7ff00000 ? (size_t)0x7ff00000 : cap);
+    return true;
+}
+
+// Returns false if the workspace is too small (caller uses the lattice path).
+bool launch_queue_fused(const GridView& g, const Opts& opt, const MarchArgs& a, const GradView& gr,
+                        void* workspace, size_t workspace_bytes, const int** overflow_flag,
+                        cudaStream_t st) {
+    QueueView qv;
+    if (!carve_queue(workspace, workspace_bytes, a.n_rays, qv)) return false;
     *overflow_flag = qv.overflow;
+    const SlabView none{};
 
     clear_flags_kernel<<<1, 1, 0, st>>>(qv.counter, qv.overflow);
     const unsigned ray_blocks = div_up(a.n_rays * WARP, TRACE_THREADS);
-    if (a.counters) trace_kernel<true><<<ray_blocks, TRACE_THREADS, 0, st>>>(g, opt, a, qv);
-    else trace_kernel<false><<<ray_blocks, TRACE_THREADS, 0, st>>>(g, opt, a, qv);
+    if (a.counters) trace_kernel<true, false><<<ray_blocks, TRACE_THREADS, 0, st>>>(g, opt, a, qv, none);
+    else trace_kernel<false, false><<<ray_blocks, TRACE_THREADS, 0, st>>>(g, opt, a, qv, none);
     const bool vec = march_vec_ok(g, &gr, a.gsh_stride);
     const unsigned sblocks = 148 * QM_SAMPLE_CTAS;  // persistent grid-stride CTAs of 256 threads
-    if (vec) shade_kernel<true><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, a.rgb_out);
-    else shade_kernel<false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, a.rgb_out);
-    seed_kernel<<<ray_blocks, TRACE_THREADS, 0, st>>>(opt, a, qv);
-    if (vec) scatter_kernel<true><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride);
-    else scatter_kernel<false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride);
+    if (vec) shade_kernel<true, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, a.rgb_out, none);
+    else shade_kernel<false, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, a.rgb_out, none);
+    seed_kernel<false><<<ray_blocks, TRACE_THREADS, 0, st>>>(opt, a, qv, none);
+    if (vec) scatter_kernel<true, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride);
+    else scatter_kernel<false, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride);
+    return true;
+}
+
+// ---- slab mode: the three phases between which the ranks exchange per-ray scalars -----------
+bool launch_slab_trace(const GridView& g, const Opts& opt, const MarchArgs& a, void* workspace,
+                       size_t workspace_bytes, int x_lo, int x_hi, float* logT_local,
+                       cudaStream_t st) {
+    QueueView qv;
+    if (!carve_queue(workspace, workspace_bytes, a.n_rays, qv)) return false;
+    SlabView sl{};
+    sl.x_lo = x_lo;
+    sl.x_hi = x_hi;
+    sl.logT_local = logT_local;
+    clear_flags_kernel<<<1, 1, 0, st>>>(qv.counter, qv.overflow);
+    trace_kernel<false, true><<<div_up(a.n_rays * WARP, TRACE_THREADS), TRACE_THREADS, 0, st>>>(
+        g, opt, a, qv, sl);
+    return true;
+}
+
+bool launch_slab_shade(const GridView& g, const Opts& opt, int64_t n_rays, void* workspace,
+                       size_t workspace_bytes, const float* lt_in, float* rgb_partial,
+                       float* stopped, cudaStream_t st) {
+    QueueView qv;
+    if (!carve_queue(workspace, workspace_bytes, n_rays, qv)) return false;
+    SlabView sl{};
+    sl.lt_in = lt_in;
+    sl.stopped = stopped;
+    sl.stop_thresh = opt.stop_thresh;
+    const unsigned sblocks = 148 * QM_SAMPLE_CTAS;
+    if (march_vec_ok(g, nullptr, 0))
+        shade_kernel<true, true><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, rgb_partial, sl);
+    else
+        shade_kernel<false, true><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, rgb_partial, sl);
+    return true;
+}
+
+bool launch_slab_backward(const GridView& g, const Opts& opt, const MarchArgs& a, const GradView& gr,
+                          void* workspace, size_t workspace_bytes, const float* lt_in,
+                          const float* gout, const float* accum_start, cudaStream_t st) {
+    QueueView qv;
+    if (!carve_queue(workspace, workspace_bytes, a.n_rays, qv)) return false;
+    SlabView sl{};
+    sl.lt_in = lt_in;
+    sl.gout = gout;
+    sl.accum_start = accum_start;
+    sl.stop_thresh = opt.stop_thresh;
+    seed_kernel<true><<<div_up(a.n_rays * WARP, TRACE_THREADS), TRACE_THREADS, 0, st>>>(opt, a, qv, sl);
+    const unsigned sblocks = 148 * QM_SAMPLE_CTAS;
+    if (march_vec_ok(g, &gr, a.gsh_stride))
+        scatter_kernel<true, true><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride);
+    else
+        scatter_kernel<false, true><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride);
     return true;
 }
 

@@ -322,3 +322,61 @@ extern "C" SVOX2_API int svox2_volume_render_sigma_thresh(const svox2_grid_t* gr
                  (cudaStream_t)stream);
     return check_launch(__func__);
 }
+
+// ---- slab mode (grid sharded over GPUs by x-range; host side: svox2_b200/slab.py) -------------
+extern "C" SVOX2_API int svox2_slab_trace(const svox2_grid_t* grid, const float* origins,
+                                          const float* dirs, int64_t n_rays,
+                                          const svox2_render_opts_t* opt, int32_t x_lo, int32_t x_hi,
+                                          float* logT_local, void* workspace,
+                                          size_t workspace_bytes, svox2_stream_t stream) {
+    if (int e = validate_grid(grid, __func__)) return e;
+    if (int e = validate_rays(origins, dirs, n_rays, __func__)) return e;
+    if (int e = validate_opt(opt, __func__)) return e;
+    SVOX2_REQUIRE(0 <= x_lo && x_lo <= x_hi && x_hi <= grid->size[0], "bad slab range");
+    SVOX2_REQUIRE(grid->background_nlayers == 0, "slab mode does not support an MSI background");
+    SVOX2_REQUIRE(logT_local || n_rays == 0, "logT_local must not be null");
+    if (n_rays == 0) return SVOX2_OK;
+    const GridView g = make_grid_view(grid);
+    MarchArgs a = base_args(origins, dirs, n_rays);
+    SVOX2_REQUIRE(launch_slab_trace(g, *opt, a, workspace, workspace_bytes, x_lo, x_hi, logT_local,
+                                    (cudaStream_t)stream),
+                  "workspace too small or not 256-byte aligned (svox2_fused_workspace_bytes)");
+    return check_launch(__func__);
+}
+
+extern "C" SVOX2_API int svox2_slab_shade(const svox2_grid_t* grid, int64_t n_rays,
+                                          const svox2_render_opts_t* opt, const float* lt_in,
+                                          float* rgb_partial, float* stopped, void* workspace,
+                                          size_t workspace_bytes, svox2_stream_t stream) {
+    if (int e = validate_grid(grid, __func__)) return e;
+    if (int e = validate_opt(opt, __func__)) return e;
+    SVOX2_REQUIRE((lt_in && rgb_partial && stopped) || n_rays == 0, "null argument");
+    if (n_rays == 0) return SVOX2_OK;
+    const GridView g = make_grid_view(grid);
+    SVOX2_REQUIRE(launch_slab_shade(g, *opt, n_rays, workspace, workspace_bytes, lt_in, rgb_partial,
+                                    stopped, (cudaStream_t)stream),
+                  "workspace too small or not 256-byte aligned (svox2_fused_workspace_bytes)");
+    return check_launch(__func__);
+}
+
+extern "C" SVOX2_API int svox2_slab_backward(const svox2_grid_t* grid, int64_t n_rays,
+                                             const svox2_render_opts_t* opt, const float* lt_in,
+                                             const float* gout, const float* accum_start,
+                                             float sparsity_loss, const svox2_grads_t* grads,
+                                             void* workspace, size_t workspace_bytes,
+                                             svox2_stream_t stream) {
+    if (int e = validate_grid(grid, __func__)) return e;
+    if (int e = validate_opt(opt, __func__)) return e;
+    if (int e = validate_grads(grads, __func__)) return e;
+    SVOX2_REQUIRE((lt_in && gout && accum_start) || n_rays == 0, "null argument");
+    if (n_rays == 0) return SVOX2_OK;
+    const GridView g = make_grid_view(grid);
+    const GradView gr = make_grad_view(grads);
+    MarchArgs a = base_args(nullptr, nullptr, n_rays);
+    set_grad_strides(a, grid, grads);
+    a.sparsity_loss = sparsity_loss;
+    SVOX2_REQUIRE(launch_slab_backward(g, *opt, a, gr, workspace, workspace_bytes, lt_in, gout,
+                                       accum_start, (cudaStream_t)stream),
+                  "workspace too small or not 256-byte aligned (svox2_fused_workspace_bytes)");
+    return check_launch(__func__);
+}
