@@ -226,6 +226,7 @@ def run_ours(args):
     import svox2_b200 as sv
     from svox2_b200 import csrc as C
     from svox2_b200.dist import ShardedTrainer
+    from svox2_b200.slab import SlabTrainer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -255,14 +256,23 @@ def run_ours(args):
                         for i in range(0, POOL * gq, 50000)])
         ggen = torch.Generator(device=dev).manual_seed(99)
         gt = (gt + 0.02 * torch.randn(gt.shape, generator=ggen, device=dev)).clamp_(0, 1)
+    slab = world > 1 and args.dist == "slab"
+    # this rank's BATCH rays of every pooled global batch (kernel-only timing, counters)
     sl = [slice(b * gq + rank * BATCH, b * gq + (rank + 1) * BATCH) for b in range(POOL)]
-    batches = [(origins[s].contiguous(), dirs[s].contiguous(), gt[s].contiguous()) for s in sl]
+    own = [(origins[s].contiguous(), dirs[s].contiguous(), gt[s].contiguous()) for s in sl]
+    if slab:    # grid sharded by x-slabs: every rank takes the whole global batch
+        gsl = [slice(b * gq, (b + 1) * gq) for b in range(POOL)]
+        batches = [(origins[s].contiguous(), dirs[s].contiguous(), gt[s].contiguous()) for s in gsl]
+        trainer = SlabTrainer(grid, world_size=world, rank=rank, **SYN)
+    else:       # rays sharded, grid replicated
+        batches = own
+        trainer = ShardedTrainer(grid, world_size=world, rank=rank, **SYN)
     host = [tuple(x.cpu().pin_memory() for x in b) for b in batches]
-
-    trainer = ShardedTrainer(grid, world_size=world, rank=rank, **SYN)
     np.random.seed(1234)
 
     def step(o, d, g):
+        if slab:
+            return trainer.step(sv.Rays(o, d), g)
         return trainer.step(sv.Rays(o, d), g, global_batch=gq)
 
     def barrier():
@@ -273,7 +283,7 @@ def run_ours(args):
 
     # counts of the roofline model, one counting pass per pooled batch (untimed)
     counters = torch.zeros(4, dtype=torch.int64, device=dev)
-    for o, d, g in batches:
+    for o, d, g in own:
         C.volume_render_cuvol(grid._to_cpp(), sv.Rays(o, d)._to_cpp(), grid.opt._to_cpp(),
                               _counters=counters)
     torch.cuda.synchronize()
@@ -308,23 +318,33 @@ def run_ours(args):
     ms_e2e = t0.elapsed_time(t1)
     clocks = sampler.stop() if sampler else None
 
+    phase_ms = None
+    if world > 1:   # untimed extra steps with per-phase CUDA events (rank 0 reports its own)
+        trainer.profile = True
+        for i in range(min(args.steps, 10)):
+            step(*batches[i % POOL])
+        phase_ms = {k: round(v, 4) for k, v in trainer.phase_times_ms().items()}
+        trainer.profile = False
+    if slab:
+        trainer.gather_params()     # re-replicate before the single-GPU style measurements
+
     # dominant kernels alone: the fused fwd+bwd march pair
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     spec, ropt = grid._to_cpp(), grid.opt._to_cpp()
     holder = C.GridOutputGrads()
     holder.grad_density_out, holder.grad_sh_out = grid.density_data.grad, grid.sh_data.grad
     holder.mask_out = torch.zeros(sc["n_rows"], dtype=torch.bool, device=dev)
-    rgb_out = torch.zeros_like(batches[0][2])
-    rspecs = [sv.Rays(o, d)._to_cpp() for o, d, _ in batches]
+    rgb_out = torch.zeros_like(own[0][2])
+    rspecs = [sv.Rays(o, d)._to_cpp() for o, d, _ in own]
     for i in range(3):
-        C.volume_render_cuvol_fused(spec, rspecs[i % POOL], ropt, batches[i % POOL][2], 0.0, 0.0,
+        C.volume_render_cuvol_fused(spec, rspecs[i % POOL], ropt, own[i % POOL][2], 0.0, 0.0,
                                     rgb_out, holder, _norm_rays=gq)
     torch.cuda.synchronize()
     if args.profile:
         torch.cuda.profiler.start()     # ncu --profile-from-start off captures from here
     k0.record()
     for i in range(args.steps):
-        C.volume_render_cuvol_fused(spec, rspecs[i % POOL], ropt, batches[i % POOL][2], 0.0, 0.0,
+        C.volume_render_cuvol_fused(spec, rspecs[i % POOL], ropt, own[i % POOL][2], 0.0, 0.0,
                                     rgb_out, holder, _norm_rays=gq)
     k1.record()
     torch.cuda.synchronize()
@@ -341,14 +361,6 @@ def run_ours(args):
     # second half of the headline metric: whole-image render, 800x800 test cameras
     cams = bench_cameras(dev)
     ms_img = time_images(lambda c: grid.volume_render_image(sv.Camera(c, **CAM_KW)), cams)
-
-    phase_ms = None
-    if world > 1:   # untimed extra steps with per-phase CUDA events (rank 0 reports its own)
-        trainer.profile = True
-        for i in range(min(args.steps, 10)):
-            step(*batches[i % POOL])
-        phase_ms = {k: round(v, 4) for k, v in trainer.phase_times_ms().items()}
-        trainer.profile = False
 
     times = torch.tensor([ms, ms_e2e, ms_fused, ms_img], dtype=torch.float64, device=dev)
     if world > 1:
@@ -375,13 +387,15 @@ def run_ours(args):
             "occupancy": round(sc["occupancy"], 4), "rays_per_gpu": BATCH, "global_batch": gq,
             "step": "volume_render_fused + tv_grad_sparse(sigma,sh) + rmsprop(sigma,sh)",
             "l2": "inputs larger than L2 (grid+grads+rms >> 126 MB); 8 distinct ray batches cycled",
-            "parallelism": f"ray-sharded x{world}, replicated grid" +
-                           (", masked packed grad all-reduce (NCCL)" if world > 1 else ""),
+            "parallelism": (f"grid sharded into {world} x-slabs, every rank traverses the global "
+                            "batch; per-ray scalar all-gathers + halo planes (NCCL)") if slab else
+                           (f"ray-sharded x{world}, replicated grid" +
+                            (", masked packed grad all-reduce (NCCL)" if world > 1 else "")),
             "samples_per_ray": {"skip": cnt[0] / BATCH, "visited": cnt[1] / BATCH,
                                 "active": cnt[2] / BATCH},
         },
         "e2e": {"value": gq * args.steps / (ms_e2e * 1e-3), "unit": "rays/s",
-                "h2d_bytes_per_step": 3 * BATCH * 3 * 4, "d2h_bytes_per_step": 4,
+                "h2d_bytes_per_step": 3 * batches[0][0].size(0) * 3 * 4, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps, "last_loss": loss_val},
         "gpu_launches": trainer.kernels_per_step * args.steps,
         "clocks": clocks,
@@ -393,8 +407,13 @@ def run_ours(args):
     line["render"] = {"value": world * 0.64 / (ms_img * 1e-3), "unit": "MPix/s",
                       "ms_per_image": ms_img, "what": "volume_render_image, 800x800, fx 1111.11, "
                       f"{N_CAMS} hemisphere cameras per GPU (images sharded over GPUs)"}
-    if world > 1:
-        line["exchange"] = {"rows_per_step": trainer.exchanged_rows,
+    if slab:
+        halo = sum(h.numel() for h in (trainer.halo_left, trainer.halo_right) if h is not None)
+        line["exchange"] = {"mode": "slab", "slab_bounds": trainer.bounds,
+                            "bytes_all_gathered_per_step": gq * 20 * world,
+                            "halo_rows_rank0": halo, "phase_ms": phase_ms}
+    elif world > 1:
+        line["exchange"] = {"mode": "rays", "rows_per_step": trainer.exchanged_rows,
                             "bytes_all_reduced_per_step": trainer.exchanged_rows * 28 * 4,
                             "phase_ms": phase_ms}
     if args.cpu_baseline:
@@ -602,6 +621,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
+    ap.add_argument("--dist", default="slab", choices=["slab", "rays"],
+                    help="multi-GPU decomposition: grid sharded by x-slabs (default) or rays "
+                         "sharded over a replicated grid with a packed gradient all-reduce")
     ap.add_argument("--cpu-rays", type=int, default=2048, help="bounded CPU sample (rays)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-ref-cuda", dest="ref_cuda", action="store_false")

@@ -233,7 +233,8 @@ SVOX2_API int svox2_sgd_step(float* data, float* grad, int64_t rows, int32_t n_c
 
 /* Multi-GPU gradient exchange (no reference counterpart).
  * svox2_pack_grad_rows: packed[i, 0:C] = grad_sh[rows[i], 0:C], packed[i, C] = grad_density[rows[i]],
- *   remaining floats of the packed row 0.  rows is a sorted int64 list identical on every rank.
+ *   then (optional) mask_a[rows[i]], mask_b[rows[i]] as 0/1 floats, remaining floats 0.
+ *   rows is an int64 list identical on every rank that takes part.
  * svox2_rmsprop_step_packed: the masked RMSProp of svox2_rmsprop_step (optim_kernel.cu:15-25) for
  *   density (if mask_density[row]) and SH (if mask_sh[row]) of every listed row, gradients read
  *   from the all-reduced packed buffer; if grad_sh/grad_density are given, those rows of the
@@ -241,7 +242,15 @@ SVOX2_API int svox2_sgd_step(float* data, float* grad, int64_t rows, int32_t n_c
  * Both require 16-byte aligned SH rows padded to a multiple of 4 floats. */
 SVOX2_API int svox2_pack_grad_rows(float* grad_sh, int64_t grad_sh_stride, int32_t sh_channels,
                          float* grad_density, int64_t grad_density_stride, const int64_t* rows,
-                         int64_t n_sel, float* packed, int64_t pack_stride, svox2_stream_t stream);
+                         int64_t n_sel, float* packed, int64_t pack_stride,
+                         const uint8_t* mask_a, const uint8_t* mask_b, svox2_stream_t stream);
+/* svox2_unpack_rows: the inverse of svox2_pack_grad_rows for any pair of [rows, stride] arrays:
+ *   dst[rows[i]] = packed[i] (add == 0) or += packed[i] (add != 0); mask_a/mask_b (optional) are
+ *   OR-ed with the flags packed behind the density slot (mask_a/mask_b of svox2_pack_grad_rows). */
+SVOX2_API int svox2_unpack_rows(const float* packed, int64_t pack_stride, const int64_t* rows,
+                         int64_t n_sel, float* dst_sh, int64_t dst_sh_stride, int32_t sh_channels,
+                         float* dst_density, int64_t dst_density_stride, int32_t add,
+                         uint8_t* mask_a, uint8_t* mask_b, svox2_stream_t stream);
 SVOX2_API int svox2_rmsprop_step_packed(float* sh_data, float* sh_rms, int64_t sh_stride,
                          int32_t sh_channels, float* density_data, float* density_rms,
                          int64_t density_stride, const int64_t* rows, int64_t n_sel,
@@ -257,8 +266,8 @@ SVOX2_API int svox2_rmsprop_step_packed(float* sh_data, float* sh_rms, int64_t s
  * samples whose cell lies in its slab.  Between the three calls the ranks exchange per-ray scalars:
  *   svox2_slab_trace    -> logT_local[Q]   (this slab's sum of -sigma*delta)
  *   ... all-gather, lt_in[Q] = log-transmittance at slab entry along each ray ...
- *   svox2_slab_shade    -> rgb_partial[Q,3] (+=, caller zeroes), stopped[Q] (=1 where the stop
- *                          threshold fired; caller zeroes)
+ *   svox2_slab_shade    -> part[Q,4] (caller zeroes): .xyz += this slab's colour, .w = 1 where the
+ *                          stop threshold fired
  *   ... all-gather, total colour -> gout[Q,3] = dL/d(rgb), accum_start[Q] = the reference's
  *       `accum` (cuvol.cu:248-264) at slab entry ...
  *   svox2_slab_backward -> gradients / mask of this slab's samples.
@@ -268,12 +277,23 @@ SVOX2_API int svox2_slab_trace(const svox2_grid_t* grid, const float* origins, c
                      float* logT_local, void* workspace, size_t workspace_bytes,
                      svox2_stream_t stream);
 SVOX2_API int svox2_slab_shade(const svox2_grid_t* grid, int64_t n_rays, const svox2_render_opts_t* opt,
-                     const float* lt_in, float* rgb_partial, float* stopped, void* workspace,
-                     size_t workspace_bytes, svox2_stream_t stream);
+                     const float* lt_in, float* part, void* workspace, size_t workspace_bytes,
+                     svox2_stream_t stream);
 SVOX2_API int svox2_slab_backward(const svox2_grid_t* grid, int64_t n_rays,
                      const svox2_render_opts_t* opt, const float* lt_in, const float* gout,
                      const float* accum_start, float sparsity_loss, const svox2_grads_t* grads,
                      void* workspace, size_t workspace_bytes, svox2_stream_t stream);
+
+/* per-ray glue between the slab calls (one thread per ray; all arrays of the all-gathers are
+ * [n_slabs, Q(, 4)]): lt_in = prefix of logT over the slabs before `rank` in ray order;
+ * combine = total colour (+ background term unless stopped), gout = (rgb - rgb_gt) * 2/(3Q),
+ * accum_start = rgb.gout (+ beta term) - sum over earlier slabs of gout.rgb_partial. */
+SVOX2_API int svox2_slab_prefix(const float* logT_all, const float* dirs, int64_t n_rays,
+                     int32_t n_slabs, int32_t rank, float* lt_in, svox2_stream_t stream);
+SVOX2_API int svox2_slab_combine(const float* part_all, const float* logT_all, const float* dirs,
+                     const float* rgb_gt, int64_t n_rays, int32_t n_slabs, int32_t rank,
+                     float background_brightness, float beta_loss, float* rgb, float* gout,
+                     float* accum_start, svox2_stream_t stream);
 
 #ifdef __cplusplus
 }

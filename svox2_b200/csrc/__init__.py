@@ -577,8 +577,9 @@ def packed_row_floats(sh_channels: int) -> int:
     return (sh_channels + 1 + 3) // 4 * 4
 
 
-def pack_grad_rows(grad_sh, grad_density, rows, packed):
-    """packed[i] = [grad_sh[rows[i]], grad_density[rows[i]], 0...]."""
+def pack_grad_rows(grad_sh, grad_density, rows, packed, mask_a=None, mask_b=None):
+    """packed[i] = [grad_sh[rows[i]], grad_density[rows[i]], mask_a[rows[i]], mask_b[rows[i]], 0...]
+    (any pair of [N, C] / [N, 1] arrays in the padded layout, e.g. the parameters themselves)."""
     _check_rows(grad_sh, "grad_sh")
     _check_rows(grad_density, "grad_density")
     _check_rows(packed, "packed")
@@ -589,7 +590,49 @@ def pack_grad_rows(grad_sh, grad_density, rows, packed):
         check(_lib.lib().svox2_pack_grad_rows(
             grad_sh.data_ptr(), _row_stride(grad_sh), grad_sh.size(1), grad_density.data_ptr(),
             _row_stride(grad_density), rows.data_ptr(), rows.numel(), packed.data_ptr(),
-            _row_stride(packed), _stream()))
+            _row_stride(packed), _ptr(mask_a), _ptr(mask_b), _stream()))
+
+
+def unpack_rows(packed, rows, dst_sh, dst_density, add, mask_a=None, mask_b=None):
+    """dst[rows[i]] (+)= packed[i]; mask_a / mask_b |= the flags packed by pack_grad_rows."""
+    _check_rows(packed, "packed")
+    _check_rows(dst_sh, "dst_sh")
+    _check_rows(dst_density, "dst_density")
+    _check_cuda(rows, "rows", torch.int64, 1)
+    if not rows.is_contiguous() or packed.size(0) != rows.numel():
+        _fail("rows must be contiguous and match packed.size(0)")
+    with torch.cuda.device(dst_sh.device):
+        check(_lib.lib().svox2_unpack_rows(
+            packed.data_ptr(), _row_stride(packed), rows.data_ptr(), rows.numel(), dst_sh.data_ptr(),
+            _row_stride(dst_sh), dst_sh.size(1), dst_density.data_ptr(), _row_stride(dst_density),
+            1 if add else 0, _ptr(mask_a), _ptr(mask_b), _stream()))
+
+
+def slab_prefix(logT_all, dirs, rank, lt_in):
+    """lt_in[q] = sum of logT_all[j, q] over the slabs ray q crosses before slab `rank`."""
+    _check_input(logT_all, "logT_all", torch.float32, 2)
+    _check_input(dirs, "dirs", torch.float32, 2)
+    _check_input(lt_in, "lt_in", torch.float32, 1)
+    with torch.cuda.device(dirs.device):
+        check(_lib.lib().svox2_slab_prefix(logT_all.data_ptr(), dirs.data_ptr(), dirs.size(0),
+                                           logT_all.size(0), int(rank), lt_in.data_ptr(), _stream()))
+
+
+def slab_combine(part_all, logT_all, dirs, rgb_gt, rank, background_brightness, beta_loss, rgb, gout,
+                 accum_start):
+    """Total colour, dL/d(rgb) and the reference's accum at slab entry from the gathered partials."""
+    _check_input(part_all, "part_all", torch.float32, 3)
+    _check_input(logT_all, "logT_all", torch.float32, 2)
+    for t_, n_ in ((dirs, "dirs"), (rgb_gt, "rgb_gt"), (rgb, "rgb"), (gout, "gout")):
+        _check_input(t_, n_, torch.float32, 2)
+    _check_input(accum_start, "accum_start", torch.float32, 1)
+    if part_all.size(2) != 4:
+        _fail("part_all must be [slabs, Q, 4]")
+    with torch.cuda.device(dirs.device):
+        check(_lib.lib().svox2_slab_combine(
+            part_all.data_ptr(), logT_all.data_ptr(), dirs.data_ptr(), rgb_gt.data_ptr(), dirs.size(0),
+            part_all.size(0), int(rank), float(background_brightness), float(beta_loss),
+            rgb.data_ptr(), gout.data_ptr(), accum_start.data_ptr(), _stream()))
 
 
 def rmsprop_step_packed(sh_data, sh_rms, density_data, density_rms, rows, packed, mask_sh,
@@ -646,16 +689,18 @@ def slab_trace(grid, rays, opt, x_lo, x_hi, logT_local, workspace):
             int(x_hi), logT_local.data_ptr(), workspace.data_ptr(), workspace.numel(), _stream()))
 
 
-def slab_shade(grid, n_rays, opt, lt_in, rgb_partial, stopped, workspace):
+def slab_shade(grid, n_rays, opt, lt_in, part, workspace):
+    """part [Q,4] (zeroed by the caller): .xyz += colour of this slab's samples, .w = stop flag."""
     g = _grid_struct(grid)
     o = _opt_struct(opt)
     _check_input(lt_in, "lt_in", torch.float32, 1)
-    _check_input(rgb_partial, "rgb_partial", torch.float32, 2)
-    _check_input(stopped, "stopped", torch.float32, 1)
+    _check_input(part, "part", torch.float32, 2)
+    if part.size(1) != 4:
+        _fail("part must be [Q, 4]")
     with torch.cuda.device(lt_in.device):
         check(_lib.lib().svox2_slab_shade(
-            C.byref(g), int(n_rays), C.byref(o), lt_in.data_ptr(), rgb_partial.data_ptr(),
-            stopped.data_ptr(), workspace.data_ptr(), workspace.numel(), _stream()))
+            C.byref(g), int(n_rays), C.byref(o), lt_in.data_ptr(), part.data_ptr(),
+            workspace.data_ptr(), workspace.numel(), _stream()))
 
 
 def slab_backward(grid, n_rays, opt, lt_in, gout, accum_start, sparsity_loss, grads, workspace):

@@ -41,8 +41,7 @@ bool launch_slab_trace(const GridView& g, const Opts& opt, const MarchArgs& a, v
                        size_t workspace_bytes, int x_lo, int x_hi, float* logT_local,
                        cudaStream_t st);
 bool launch_slab_shade(const GridView& g, const Opts& opt, int64_t n_rays, void* workspace,
-                       size_t workspace_bytes, const float* lt_in, float* rgb_partial,
-                       float* stopped, cudaStream_t st);
+                       size_t workspace_bytes, const float* lt_in, float* part, cudaStream_t st);
 bool launch_slab_backward(const GridView& g, const Opts& opt, const MarchArgs& a, const GradView& gr,
                           void* workspace, size_t workspace_bytes, const float* lt_in,
                           const float* gout, const float* accum_start, cudaStream_t st);

@@ -82,7 +82,7 @@ struct SlabView {
     const float* __restrict__ lt_in;       // K2-K4 in: [Q] log-transmittance at slab entry
     const float* __restrict__ gout;        // K3 in: [Q,3] dL/d(rgb) of the whole ray
     const float* __restrict__ accum_start; // K3 in: [Q] the reference's accum at slab entry
-    float* __restrict__ stopped;           // K2 out: [Q] set to 1 where the stop threshold fired
+    float* __restrict__ stopped;           // K2 out: stride 4 (the .w of the [Q,4] partials): 1 where the stop fired
     float stop_thresh;
 };
 
@@ -444,7 +444,7 @@ shade_kernel(GridView g, QueueView qv, float* __restrict__ rgb_out, SlabView sl)
             pw.w = __fmul_rn(fexp(before), __fsub_rn(1.f, fexp(-pcnt)));
             if (qi == 0) {
                 qv.rec[s].w = pw.w;
-                if (fexp(__fadd_rn(lt_in, st.x)) < sl.stop_thresh) sl.stopped[ray] = 1.f;
+                if (fexp(__fadd_rn(lt_in, st.x)) < sl.stop_thresh) sl.stopped[(int64_t)ray * 4] = 1.f;
             }
         }
         const int32_t L[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
@@ -480,7 +480,7 @@ shade_kernel(GridView g, QueueView qv, float* __restrict__ rgb_out, SlabView sl)
         }
         if (qi < 3) {
             const float cv = qi == 0 ? col[0] : (qi == 1 ? col[1] : col[2]);
-            atomicAdd(rgb_out + (int64_t)ray * 3 + qi, pw.w * fmaxf(cv, 0.f));
+            atomicAdd(rgb_out + (int64_t)ray * (SLAB ? 4 : 3) + qi, pw.w * fmaxf(cv, 0.f));
         }
         if (qi == 0) reinterpret_cast<float4*>(qv.rec + s)[4] = make_float4(col[0], col[1], col[2], 0.f);
     }
@@ -703,19 +703,19 @@ bool launch_slab_trace(const GridView& g, const Opts& opt, const MarchArgs& a, v
 }
 
 bool launch_slab_shade(const GridView& g, const Opts& opt, int64_t n_rays, void* workspace,
-                       size_t workspace_bytes, const float* lt_in, float* rgb_partial,
-                       float* stopped, cudaStream_t st) {
+                       size_t workspace_bytes, const float* lt_in, float* part,
+                       cudaStream_t st) {
     QueueView qv;
     if (!carve_queue(workspace, workspace_bytes, n_rays, qv)) return false;
     SlabView sl{};
     sl.lt_in = lt_in;
-    sl.stopped = stopped;
+    sl.stopped = part + 3;
     sl.stop_thresh = opt.stop_thresh;
     const unsigned sblocks = 148 * QM_SAMPLE_CTAS;
     if (march_vec_ok(g, nullptr, 0))
-        shade_kernel<true, true><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, rgb_partial, sl);
+        shade_kernel<true, true><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, part, sl);
     else
-        shade_kernel<false, true><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, rgb_partial, sl);
+        shade_kernel<false, true><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, part, sl);
     return true;
 }
 

@@ -346,15 +346,15 @@ extern "C" SVOX2_API int svox2_slab_trace(const svox2_grid_t* grid, const float*
 
 extern "C" SVOX2_API int svox2_slab_shade(const svox2_grid_t* grid, int64_t n_rays,
                                           const svox2_render_opts_t* opt, const float* lt_in,
-                                          float* rgb_partial, float* stopped, void* workspace,
-                                          size_t workspace_bytes, svox2_stream_t stream) {
+                                          float* part, void* workspace, size_t workspace_bytes,
+                                          svox2_stream_t stream) {
     if (int e = validate_grid(grid, __func__)) return e;
     if (int e = validate_opt(opt, __func__)) return e;
-    SVOX2_REQUIRE((lt_in && rgb_partial && stopped) || n_rays == 0, "null argument");
+    SVOX2_REQUIRE((lt_in && part) || n_rays == 0, "null argument");
     if (n_rays == 0) return SVOX2_OK;
     const GridView g = make_grid_view(grid);
-    SVOX2_REQUIRE(launch_slab_shade(g, *opt, n_rays, workspace, workspace_bytes, lt_in, rgb_partial,
-                                    stopped, (cudaStream_t)stream),
+    SVOX2_REQUIRE(launch_slab_shade(g, *opt, n_rays, workspace, workspace_bytes, lt_in, part,
+                                    (cudaStream_t)stream),
                   "workspace too small or not 256-byte aligned (svox2_fused_workspace_bytes)");
     return check_launch(__func__);
 }

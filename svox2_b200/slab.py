@@ -12,9 +12,10 @@ back-propagates only the samples inside its slab.  Per step the ranks exchange p
                                           in the order the ray crosses them, i.e. by sign of d_x)
   B. all-gather of rgb_partial[Q,3(+1)] -> total colour, dL/d(rgb), and the value of the
                                           reference's `accum` (cuvol.cu:248-264) at slab entry
-  C. halo: samples in the last cell plane of a slab touch the first voxel plane of the next one;
-     those gradient rows go to their owner (one P2P message per boundary), and the owner returns
-     the updated parameters of that plane after its optimiser step.
+  C. halo: samples in the last cell plane of a slab interpolate from the first voxel plane of the
+     next one.  That plane is CO-OWNED: the two neighbours swap the gradients / mask bits they
+     accumulated for it (one P2P message each way per boundary) and both apply the identical
+     update, so no parameters ever travel.
 
 16 B per ray per rank instead of 110 B per touched row: the exchange no longer scales with the
 grid.  TV and RMSProp run on the owned rows only.  Everything outside a rank's slab (+ halo
@@ -69,13 +70,16 @@ class SlabTrainer:
         self.own_mask = torch.zeros(grid.density_data.size(0), dtype=torch.bool, device=dev)
         own = links[self.x_lo:self.x_hi].reshape(-1)
         self.own_mask[own[own >= 0].long()] = True
-        # halo planes: first voxel plane of the right neighbour / my own first plane
+        # boundary planes, co-owned: first voxel plane of the right neighbour / my own first plane
         self.halo_right = self._plane_rows(self.x_hi) if rank < world_size - 1 else None
         self.halo_left = self._plane_rows(self.x_lo) if rank > 0 else None
+        self.excl_mask = self.own_mask.clone()          # exclusive ownership (gather_params)
+        if self.halo_right is not None:
+            self.own_mask[self.halo_right] = True
         self._ws = None
         self._steps = 0
-        # clear + trace, shade, seed + scatter, TV x2, optimiser x2
-        self.kernels_per_step = 2 + 1 + 2 + (lambda_tv > 0) + (lambda_tv_sh > 0) + 2
+        # clear + trace, prefix, shade, combine, seed + scatter, TV x2, halo pack/unpack, optimiser x2
+        self.kernels_per_step = 2 + 1 + 1 + 1 + 2 + (lambda_tv > 0) + (lambda_tv_sh > 0) + 2 + 2
         self.profile, self._events = False, []
 
     def _plane_rows(self, x: int) -> torch.Tensor:
@@ -98,15 +102,6 @@ class SlabTrainer:
         out = torch.empty((self.world_size,) + tuple(t.shape), dtype=t.dtype, device=t.device)
         dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
         return out
-
-    def _before(self, per_slab: torch.Tensor, forward: torch.Tensor) -> torch.Tensor:
-        """Sum of per_slab[j] over the slabs a ray crosses BEFORE this rank's: j < rank for rays
-        with d_x >= 0, j > rank otherwise.  per_slab [G,Q], forward [Q] bool."""
-        k = self.rank
-        zero = torch.zeros_like(per_slab[0])
-        lo = per_slab[:k].sum(0) if k > 0 else zero
-        hi = per_slab[k + 1:].sum(0) if k + 1 < self.world_size else zero
-        return torch.where(forward, lo, hi)
 
     def _tv_runs(self):
         """This rank's part of the step's wrapped contiguous cell run (x-major linear index)."""
@@ -156,31 +151,20 @@ class SlabTrainer:
         _C.slab_trace(spec, rspec, ropt, self.x_lo, self.x_hi, logT_local, ws)
         self._mark("trace")
         logT_all = self._gather(logT_local)                                   # exchange A
-        forward = rays.dirs[:, 0] >= 0
-        lt_in = self._before(logT_all, forward).contiguous()
+        lt_in = torch.empty(Q, dtype=torch.float32, device=dev)
+        _C.slab_prefix(logT_all, rays.dirs, self.rank, lt_in)
         self._mark("exchange_a")
 
         # 2. colours of this slab's samples
-        part = torch.zeros((Q, 4), dtype=torch.float32, device=dev)          # rgb, stopped flag
-        rgb_part, stopped = part[:, :3], part[:, 3]
-        rgb_local = torch.zeros((Q, 3), dtype=torch.float32, device=dev)
-        stop_local = torch.zeros(Q, dtype=torch.float32, device=dev)
-        _C.slab_shade(spec, Q, ropt, lt_in, rgb_local, stop_local, ws)
-        rgb_part.copy_(rgb_local)
-        stopped.copy_(stop_local)
+        part = torch.zeros((Q, 4), dtype=torch.float32, device=dev)          # rgb, stop flag
+        _C.slab_shade(spec, Q, ropt, lt_in, part, ws)
         self._mark("shade")
         part_all = self._gather(part)                                         # exchange B
-        rgb_all = part_all[:, :, :3]
-        stopped_any = part_all[:, :, 3].sum(0) > 0
-        logT_total = torch.where(stopped_any, torch.full_like(lt_in, -1e3), logT_all.sum(0))
-        rgb = rgb_all.sum(0) + (torch.exp(logT_total) * g.opt.background_brightness).unsqueeze(-1)
-        gout = ((rgb - rgb_gt) * (2.0 / (3 * Q))).contiguous()                # cuvol.cu:736
-        accum0 = (rgb * gout).sum(-1)
-        if self.beta_loss > 0.0:                                             # cuvol.cu:248-256
-            T = torch.exp(logT_total).double()
-            accum0 = accum0 + ((self.beta_loss / Q) * (1 - T / (1 - T + 1e-3))).float()
-        dots = (rgb_all * gout.unsqueeze(0)).sum(-1)                          # [G,Q]
-        accum_start = (accum0 - self._before(dots, forward)).contiguous()
+        rgb = torch.empty((Q, 3), dtype=torch.float32, device=dev)
+        gout = torch.empty((Q, 3), dtype=torch.float32, device=dev)
+        accum_start = torch.empty(Q, dtype=torch.float32, device=dev)
+        _C.slab_combine(part_all, logT_all, rays.dirs, rgb_gt, self.rank,
+                        g.opt.background_brightness, self.beta_loss, rgb, gout, accum_start)
         self._mark("exchange_b")
 
         # 3. gradients of this slab's samples, TV on the owned cells
@@ -204,7 +188,8 @@ class SlabTrainer:
                                         _scale_cells=n)
         self._mark("tv")
 
-        # 4. halo gradients to their owner, optimiser on the owned rows, halo parameters back
+        # 4. boundary planes: both neighbours add each other's gradients (a + b == b + a, so the
+        #    two copies of a co-owned plane stay bit-identical), then RMSProp on the owned rows
         self._halo_grads()
         g.sparse_grad_indexer &= self.own_mask
         g.sparse_sh_grad_indexer &= self.own_mask
@@ -212,8 +197,6 @@ class SlabTrainer:
         g.optim_density_step(self.lr_sigma if lr_sigma is None else lr_sigma, beta=self.rms_beta)
         g.optim_sh_step(self.lr_sh if lr_sh is None else lr_sh, beta=self.rms_beta)
         self._mark("optimiser")
-        self._halo_params()
-        self._mark("halo_params")
 
         if self._steps % 256 == 0 and _C.slab_overflowed(ws):
             raise RuntimeError("SlabTrainer: sample-record workspace overflowed")
@@ -221,59 +204,30 @@ class SlabTrainer:
         return rgb
 
     def _halo_grads(self):
-        """Send the gradients / mask bits this rank produced for the right neighbour's first voxel
-        plane, add what the left neighbour produced for mine."""
+        """The first voxel plane of every slab is co-owned with the left neighbour (its last cell
+        plane interpolates from it).  Both sides send what they accumulated for the plane --
+        gradients and mask bits, packed 32 floats per row -- and add what they receive."""
         if self.world_size == 1:
             return
         g = self.grid
         gsh, gd = g.sh_data.grad, g.density_data.grad
-        D = gsh.size(1)
-        ops, recv = [], None
-        if self.halo_right is not None:
-            r = self.halo_right
-            send = torch.empty((r.numel(), D + 3), dtype=torch.float32, device=gsh.device)
-            send[:, :D] = gsh[r]
-            send[:, D] = gd[r, 0]
-            send[:, D + 1] = g.sparse_grad_indexer[r].float()
-            send[:, D + 2] = g.sparse_sh_grad_indexer[r].float()
-            gsh[r] = 0.0                      # not mine: never reaches my optimiser
-            gd[r] = 0.0
-            ops.append(dist.P2POp(dist.isend, send, self.rank + 1, group=self.group))
-        if self.halo_left is not None:
-            recv = torch.empty((self.halo_left.numel(), D + 3), dtype=torch.float32, device=gsh.device)
-            ops.append(dist.P2POp(dist.irecv, recv, self.rank - 1, group=self.group))
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-        if recv is not None:
-            r = self.halo_left
-            gsh[r] += recv[:, :D]
-            gd[r, 0] += recv[:, D]
-            g.sparse_grad_indexer[r] |= recv[:, D + 1] > 0
-            g.sparse_sh_grad_indexer[r] |= recv[:, D + 2] > 0
-
-    def _halo_params(self):
-        """Owner -> left neighbour: updated parameters of my first voxel plane."""
-        if self.world_size == 1:
-            return
-        g = self.grid
-        sh, den = g.sh_data.data, g.density_data.data
-        D = sh.size(1)
-        ops, recv = [], None
-        if self.halo_left is not None:
-            r = self.halo_left
-            send = torch.empty((r.numel(), D + 1), dtype=torch.float32, device=sh.device)
-            send[:, :D] = sh[r]
-            send[:, D] = den[r, 0]
-            ops.append(dist.P2POp(dist.isend, send, self.rank - 1, group=self.group))
-        if self.halo_right is not None:
-            recv = torch.empty((self.halo_right.numel(), D + 1), dtype=torch.float32, device=sh.device)
-            ops.append(dist.P2POp(dist.irecv, recv, self.rank + 1, group=self.group))
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-        if recv is not None:
-            r = self.halo_right
-            sh[r] = recv[:, :D]
-            den[r, 0] = recv[:, D]
+        md, msh = g.sparse_grad_indexer, g.sparse_sh_grad_indexer
+        width = _C.packed_row_floats(gsh.size(1) + 2)
+        ops, todo = [], []
+        for rows, peer in ((self.halo_right, self.rank + 1), (self.halo_left, self.rank - 1)):
+            if rows is None or rows.numel() == 0:
+                continue
+            send = torch.empty((rows.numel(), width), dtype=torch.float32, device=gsh.device)
+            recv = torch.empty_like(send)
+            _C.pack_grad_rows(gsh, gd, rows, send, mask_a=md, mask_b=msh)
+            ops.append(dist.P2POp(dist.isend, send, peer, group=self.group))
+            ops.append(dist.P2POp(dist.irecv, recv, peer, group=self.group))
+            todo.append((rows, recv))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for rows, recv in todo:
+            _C.unpack_rows(recv, rows, gsh, gd, True, mask_a=md, mask_b=msh)
 
     def gather_params(self):
         """Re-replicate: every rank receives the owners' density / SH rows (one-off, e.g. before
@@ -282,7 +236,7 @@ class SlabTrainer:
             return
         g = self.grid
         for p in (g.density_data.data, g.sh_data.data):
-            p.mul_(self.own_mask.unsqueeze(-1).to(p.dtype))
+            p.mul_(self.excl_mask.unsqueeze(-1).to(p.dtype))
             # padded SH rows: reduce the whole [N, row_stride] storage behind the [:, :27] view
             flat = p if p.is_contiguous() else p.as_strided((p.size(0), p.stride(0)), (p.stride(0), 1))
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
