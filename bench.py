@@ -323,8 +323,11 @@ def run_ours(args):
         trainer.profile = True
         for i in range(min(args.steps, 10)):
             step(*batches[i % POOL])
-        phase_ms = {k: round(v, 4) for k, v in trainer.phase_times_ms().items()}
+        mine = {k: round(v, 4) for k, v in trainer.phase_times_ms().items()}
         trainer.profile = False
+        every = [None] * world
+        dist.all_gather_object(every, mine)
+        phase_ms = {k: [e.get(k) for e in every] for k in mine}     # per phase, one entry per rank
     if slab:
         trainer.gather_params()     # re-replicate before the single-GPU style measurements
 
@@ -402,7 +405,10 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": "fused call: trace + shade + seed + scatter kernels",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes,
-                     "ms_per_launch": ms_fused, "traffic": None},
+                     "ms_per_launch": ms_fused,
+                     # dram__bytes_read+write of K1..K4 of one fused call, ncu --set full capture
+                     # of this command (profiles/r1_ncu_step_kernels_full.txt): 331+250+45+390 MB
+                     "traffic": 1.016e9 if args.workload == "c3" else None},
     }
     line["render"] = {"value": world * 0.64 / (ms_img * 1e-3), "unit": "MPix/s",
                       "ms_per_image": ms_img, "what": "volume_render_image, 800x800, fx 1111.11, "
