@@ -111,3 +111,40 @@ def test_cabi_argument_errors_are_reported_not_printed():
     assert b"non-null" in lib.svox2_last_error()
     with pytest.raises(_lib.Svox2Error):
         _lib.check(st)
+
+
+@pytest.mark.parametrize("background", [False, True])
+def test_checkpoint_interop_with_reference(ref_svox2, tmp_path, background):
+    """ckpt.npz written by this package loads in the unmodified reference and vice versa
+    (svox2.py:1526-1628): f32 density, f16 SH, int32 links, MSI arrays, radius/center."""
+    kw = dict(reso=[10, 8, 12], basis_dim=4, use_sphere_bound=True, device="cpu", radius=[1.0, 0.8, 1.2],
+              center=[0.1, 0.0, -0.2])
+    if background:
+        kw.update(background_nlayers=4, background_reso=8)
+    ours = sv.SparseGrid(**kw)
+    with torch.no_grad():
+        ours.density_data[:] = torch.rand_like(ours.density_data)
+        ours.sh_data[:] = torch.randn_like(ours.sh_data)
+        if background:
+            ours.background_data[:] = torch.rand_like(ours.background_data)
+    p1 = str(tmp_path / "ours.npz")
+    ours.save(p1)
+    theirs = ref_svox2.SparseGrid.load(p1, device="cpu")
+    assert torch.equal(theirs.links, ours.links)
+    assert torch.equal(theirs.density_data.data, ours.density_data.data)
+    assert torch.equal(theirs.sh_data.data, ours.sh_data.data.half().float())
+    assert torch.allclose(theirs.radius, ours.radius) and torch.allclose(theirs.center, ours.center)
+    if background:
+        assert torch.equal(theirs.background_data.data, ours.background_data.data)
+        assert torch.equal(theirs.background_links, ours.background_links)
+    # and back: the reference's own file through our loader, bit-identical arrays
+    p2 = str(tmp_path / "theirs.npz")
+    theirs.save(p2)
+    back = sv.SparseGrid.load(p2, device="cpu")
+    z1, z2 = np.load(p1), np.load(p2)
+    assert sorted(z1.files) == sorted(z2.files)
+    for k in z1.files:
+        assert z1[k].dtype == z2[k].dtype and np.array_equal(z1[k], z2[k]), k
+    assert torch.equal(back.links, ours.links) and back.basis_dim == ours.basis_dim
+    assert torch.equal(back.sh_data.data, theirs.sh_data.data)
+    assert back.use_background == background

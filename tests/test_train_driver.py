@@ -1,0 +1,53 @@
+"""Training driver (svox2_b200/train.py; reference: opt/opt.py + opt/util/util.py)."""
+import json
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from svox2_b200 import train as T
+
+
+def test_expon_lr_matches_reference_schedule():
+    # values of the reference's get_expon_lr_func (util.py:78-111) for opt.py's default schedules
+    steps = (0, 100, 7500, 15000, 128000, 300000)
+    sigma = [0.30000000000000004, 0.6094505465080994, 17.581539900773915, 20.43770751712794,
+             1.134247457728419, 0.05000000000000001]
+    sh = [0.010000000000000004, 0.009969642562331182, 0.00796102706029178, 0.006337795185469799,
+          0.0002041139288460212, 4.999999999999999e-06]
+    f = T.expon_lr(3e1, 5e-2, 15000, 1e-2, 250000)
+    g = T.expon_lr(1e-2, 5e-6, 0, 1e-2, 250000)
+    assert np.allclose([f(s) for s in steps], sigma, rtol=1e-12)
+    assert np.allclose([g(s) for s in steps], sh, rtol=1e-12)
+    assert T.expon_lr(0.0, 0.0)(10) == 0.0 and f(-1) == 0.0
+
+
+def test_config_reads_reference_json(tmp_path):
+    p = tmp_path / "syn.json"
+    p.write_text(json.dumps({"reso": "[[256, 256, 256], [512, 512, 512]]", "upsamp_every": 38400,
+                             "lr_sigma": 3e1, "lr_sh": 1e-2, "lambda_tv": 1e-5, "lambda_tv_sh": 1e-3,
+                             "unknown_key": 1}))
+    c = T.TrainConfig.from_json(str(p), n_iters=10)
+    assert c.reso_list() == [[256] * 3, [512] * 3] and c.upsamp_every == 38400 and c.n_iters == 10
+    assert T.TrainConfig(reso="[64, [32, 48, 64]]").reso_list() == [[64, 64, 64], [32, 48, 64]]
+
+
+@pytest.mark.gpu
+def test_training_run_with_upsampling_fits_the_scene():
+    dev = torch.device("cuda:0")
+    data = T.synthetic_dataset(dev, n_images=20, width=80, height=80, reso=48)
+    train = T.PosedImages(data.c2w[:16], data.images[:16], data.fx, data.width, data.height)
+    test = T.PosedImages(data.c2w[16:], data.images[16:], data.fx, data.width, data.height)
+    cfg = T.TrainConfig(reso="[[32,32,32],[64,64,64]]", upsamp_every=200, n_iters=500, batch_size=4096,
+                        lr_sigma_delay_steps=100, print_every=50, weight_thresh=0.0005 * 64)
+    logs = []
+    tr = T.Trainer(cfg, train, test, log=logs.append)
+    before = tr.eval_psnr()
+    tr.run()
+    after = tr.eval_psnr()
+    assert tr.step_id == 500 and tr.reso_id == 1
+    assert list(tr.grid.links.shape) == [64, 64, 64]
+    assert tr.lambda_tv == 0.0                      # tv_early_only: TV off after the first upsample
+    assert any("upsampled" in m for m in logs)
+    assert after > before + 8.0 and after > 18.0, (before, after, logs[-3:])
