@@ -267,6 +267,7 @@ def run_ours(args):
     else:       # rays sharded, grid replicated
         batches = own
         trainer = ShardedTrainer(grid, world_size=world, rank=rank, **SYN)
+    # e2e inputs in pinned host memory (one stacked buffer / F.mse_loss were measured SLOWER)
     host = [tuple(x.cpu().pin_memory() for x in b) for b in batches]
     np.random.seed(1234)
 
@@ -308,9 +309,7 @@ def run_ours(args):
     t0.record()
     loss_val = 0.0
     for i in range(args.steps):
-        ho, hd, hg = host[i % POOL]
-        o, d, g = (ho.to(dev, non_blocking=True), hd.to(dev, non_blocking=True),
-                   hg.to(dev, non_blocking=True))
+        o, d, g = (x.to(dev, non_blocking=True) for x in host[i % POOL])
         rgb = step(o, d, g)
         loss_val = torch.mean((rgb - g) ** 2).item()         # opt.py:505-508 (host sync per step)
     t1.record()
@@ -422,9 +421,9 @@ def run_ours(args):
         line["exchange"] = {"mode": "rays", "rows_per_step": trainer.exchanged_rows,
                             "bytes_all_reduced_per_step": trainer.exchanged_rows * 28 * 4,
                             "phase_ms": phase_ms}
-    if args.cpu_baseline:
+    if args.cpu_baseline and world == 1:        # reported baselines: rank 0 at N=1 only
         line["cpu_baseline"] = cpu_port_baseline(sc, grid, batches[0], budget_rays=args.cpu_rays)
-    if args.ref_cuda:
+    if args.ref_cuda and world == 1:
         line["ref_cuda"] = reference_cuda_baseline(sc, grid, batches, args, gq)
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -550,16 +549,41 @@ def run_reference(args):
     import ctypes as CT
     gc, cnt = g.c(), og._Counts()
 
+    # the rest of the step (opt.py:593-603): sparse TV on a contiguous cell run and masked RMSProp,
+    # cell count scaled to the ray sample so that the per-ray cost is that of a whole step
+    X, Y, Z = links.shape
+    total_cells = X * Y * Z
+    n_tv = max(int(SYN["tv_sparsity"] * total_cells * sample / BATCH), 1)
+    drms = np.zeros_like(g.density)
+    shrms = np.zeros_like(g.sh)
+    L = og.lib()
+
+    def tv_cells():
+        start = int(rng.integers(0, total_cells))
+        return np.ascontiguousarray((np.arange(start, start + n_tv, dtype=np.int64) % total_cells)
+                                    .astype(np.int32))
+
     def one(i):
         s = (i % POOL) * gq
         o = np.ascontiguousarray(origins[s:s + sample].numpy())
         d = np.ascontiguousarray(dirs[s:s + sample].numpy())
         gt = rng.uniform(0, 1, o.shape).astype(np.float32)
         rgb = np.zeros_like(o)
-        og.lib().og_volume_render_fused(CT.byref(gc), CT.byref(opt), og._ptr(o), og._ptr(d),
-                                        CT.c_int64(sample), CT.c_int64(sample), og._ptr(gt),
-                                        CT.c_float(0.0), CT.c_float(0.0), og._ptr(rgb), og._ptr(gd),
-                                        og._ptr(gsh), None, og._ptr(mask), None, CT.byref(cnt))
+        L.og_volume_render_fused(CT.byref(gc), CT.byref(opt), og._ptr(o), og._ptr(d),
+                                 CT.c_int64(sample), CT.c_int64(sample), og._ptr(gt),
+                                 CT.c_float(0.0), CT.c_float(0.0), og._ptr(rgb), og._ptr(gd),
+                                 og._ptr(gsh), None, og._ptr(mask), None, CT.byref(cnt))
+        for data, ch, grad, lam in ((g.density, 1, gd, SYN["lambda_tv"]), (g.sh, g.sh.shape[1], gsh, SYN["lambda_tv_sh"])):
+            cells = tv_cells()
+            L.og_tv_grad_sparse(og._ptr(links), X, Y, Z, og._ptr(data), ch, og._ptr(cells),
+                                CT.c_int64(n_tv), og._ptr(mask), 0, ch, CT.c_float(lam), 0, 0,
+                                og._ptr(grad))
+        for data, rms, ch, grad, lr in ((g.density, drms, 1, gd, SYN["lr_sigma"]),
+                                        (g.sh, shrms, g.sh.shape[1], gsh, SYN["lr_sh"])):
+            L.og_rmsprop_step(og._ptr(data), og._ptr(rms), og._ptr(grad), CT.c_int64(mask.shape[0]), ch,
+                              1, og._ptr(mask), None, CT.c_int64(0), CT.c_float(SYN["rms_beta"]),
+                              CT.c_float(lr), CT.c_float(1e-8), CT.c_float(-1e9), CT.c_float(lr))
+        mask[:] = 0
 
     for i in range(min(args.warmup, 1)):
         one(i)
@@ -576,7 +600,8 @@ def run_reference(args):
         "config": {"workload": sc["name"], "reso": sc["reso"], "stored_voxels": sc["n_rows"],
                    "rays_per_step": sample},
         "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} rays of each pooled batch per step, fused fwd+bwd march "
+                         "sample": f"{sample} rays of each pooled batch per step: fused fwd+bwd march + "
+                                   f"sparse TV on {n_tv} cells x2 + masked RMSProp x2 "
                                    f"(oracle C port of the reference algorithm, {cores} pthreads)"},
         "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }

@@ -1091,14 +1091,24 @@ void og_tv_grad(const int32_t* links, int32_t X, int32_t Y, int32_t Z, const flo
             }
 }
 
-void og_tv_grad_sparse(const int32_t* links, int32_t X, int32_t Y, int32_t Z,
-                       const float* data, int32_t ddim, const int32_t* rand_cells,
-                       int64_t n_cells, uint8_t* mask, int32_t start_dim, int32_t end_dim,
-                       float scale, int32_t ignore_edge, int32_t ignore_last_z, float* grad) {
+typedef struct {
+    const int32_t* links; int32_t X, Y, Z; const float* data; int32_t ddim;
+    const int32_t* rand_cells; uint8_t* mask; int32_t start_dim, end_dim; float s;
+    int32_t ignore_edge, ignore_last_z; float* grad;
+} tvs_ctx_t;
+
+static void tvs_range(int64_t begin, int64_t end, void* vctx) {
+    const tvs_ctx_t* c = (const tvs_ctx_t*)vctx;
+    const int32_t* links = c->links;
+    const int32_t X = c->X, Y = c->Y, Z = c->Z, ddim = c->ddim;
+    const float* data = c->data;
+    float* grad = c->grad;
+    uint8_t* mask = c->mask;
+    const int32_t ignore_edge = c->ignore_edge, ignore_last_z = c->ignore_last_z;
+    const float s = c->s;
     const float sc[3] = {(float)X * (1.f / 256.f), (float)Y * (1.f / 256.f), (float)Z * (1.f / 256.f)};
-    const float s = scale / (float)(int)n_cells;
-    for (int64_t i = 0; i < n_cells; ++i) {
-        const int xyz = rand_cells[i];
+    for (int64_t i = begin; i < end; ++i) {
+        const int xyz = c->rand_cells[i];
         const int z = xyz % Z;
         const int xy = xyz / Z;
         const int y = xy % Y;
@@ -1111,7 +1121,7 @@ void og_tv_grad_sparse(const int32_t* links, int32_t X, int32_t Y, int32_t Z,
         const int32_t lnk010 = y + 1 < Y ? lp[offy] : 0;
         const int32_t lnk100 = x + 1 < X ? lp[offx] : 0;
         if (ignore_last_z && z == Z - 2) continue;
-        for (int idx = start_dim; idx < end_dim; ++idx) {
+        for (int idx = c->start_dim; idx < c->end_dim; ++idx) {
             const float v000 = lnk000 >= 0 ? data[(int64_t)lnk000 * ddim + idx] : 0.f;
             const float nullv = ignore_edge ? v000 : 0.f;
             const float v001 = lnk001 >= 0 ? data[(int64_t)lnk001 * ddim + idx] : nullv;
@@ -1121,10 +1131,10 @@ void og_tv_grad_sparse(const int32_t* links, int32_t X, int32_t Y, int32_t Z,
             const float idelta = s * (float)(1.0 / sqrt((double)(1e-9f + dx * dx + dy * dy + dz * dz)));
             dx *= sc[0]; dy *= sc[1]; dz *= sc[2];
             const float sm = -(dx + dy + dz);
-#define MAYBE_ADD_SET(lnk, val)                                   \
-    if ((lnk) >= 0 && (val) != 0.f) {                             \
-        grad[(int64_t)(lnk) * ddim + idx] += (val) * idelta;      \
-        if (mask) mask[(lnk)] = 1;                                \
+#define MAYBE_ADD_SET(lnk, val)                                          \
+    if ((lnk) >= 0 && (val) != 0.f) {                                    \
+        add_float(&grad[(int64_t)(lnk) * ddim + idx], (val) * idelta);   \
+        if (mask) mask[(lnk)] = 1;                                       \
     }
             MAYBE_ADD_SET(lnk000, sm);
             MAYBE_ADD_SET(lnk001, dz);
@@ -1133,6 +1143,16 @@ void og_tv_grad_sparse(const int32_t* links, int32_t X, int32_t Y, int32_t Z,
 #undef MAYBE_ADD_SET
         }
     }
+}
+
+/* tv_grad_sparse_kernel, loss_kernel.cu:178-246; cells are independent -> parallel_for */
+void og_tv_grad_sparse(const int32_t* links, int32_t X, int32_t Y, int32_t Z,
+                       const float* data, int32_t ddim, const int32_t* rand_cells,
+                       int64_t n_cells, uint8_t* mask, int32_t start_dim, int32_t end_dim,
+                       float scale, int32_t ignore_edge, int32_t ignore_last_z, float* grad) {
+    tvs_ctx_t c = {links, X, Y, Z, data, ddim, rand_cells, mask, start_dim, end_dim,
+                   scale / (float)(int)n_cells, ignore_edge, ignore_last_z, grad};
+    parallel_for(n_cells, tvs_range, &c);
 }
 #undef LNK
 
@@ -1195,26 +1215,31 @@ static inline void rmsprop_once(float* d, float* r, float* gp, float beta, float
     *gp = 0.f;
 }
 
+typedef struct {
+    float* data; float* rms; float* grad; int32_t C; int32_t kind; const uint8_t* mask;
+    const int64_t* index; float beta, lr, eps, minval, lr_last;
+} opt_ctx_t;
+
+static void rmsprop_range(int64_t begin, int64_t end, void* vctx) {
+    const opt_ctx_t* c = (const opt_ctx_t*)vctx;
+    for (int64_t k = begin; k < end; ++k) {
+        if (c->kind == 1 && !c->mask[k]) continue;
+        const int64_t r = c->kind == 2 ? c->index[k] : k;
+        for (int ch = 0; ch < c->C; ++ch) {
+            const int64_t off = r * c->C + ch;
+            rmsprop_once(c->data + off, c->rms + off, c->grad + off, c->beta,
+                         ch == c->C - 1 ? c->lr_last : c->lr, c->eps, c->minval);
+        }
+    }
+}
+
 void og_rmsprop_step(float* data, float* rms, float* grad, int64_t rows, int32_t C,
                      int32_t indexer_kind, const uint8_t* mask, const int64_t* index,
                      int64_t n_index, float beta, float lr, float eps, float minval,
                      float lr_last) {
     if (lr_last < 0.f) lr_last = lr;
-    if (indexer_kind == 2) {
-        for (int64_t k = 0; k < n_index; ++k)
-            for (int c = 0; c < C; ++c) {
-                const int64_t off = index[k] * C + c;
-                rmsprop_once(data + off, rms + off, grad + off, beta, c == C - 1 ? lr_last : lr, eps, minval);
-            }
-        return;
-    }
-    for (int64_t r = 0; r < rows; ++r) {
-        if (indexer_kind == 1 && !mask[r]) continue;
-        for (int c = 0; c < C; ++c) {
-            const int64_t off = r * C + c;
-            rmsprop_once(data + off, rms + off, grad + off, beta, c == C - 1 ? lr_last : lr, eps, minval);
-        }
-    }
+    opt_ctx_t c = {data, rms, grad, C, indexer_kind, mask, index, beta, lr, eps, minval, lr_last};
+    parallel_for(indexer_kind == 2 ? n_index : rows, rmsprop_range, &c);
 }
 
 void og_sgd_step(float* data, float* grad, int64_t rows, int32_t C, int32_t indexer_kind,
