@@ -71,6 +71,12 @@ __device__ __forceinline__ void lane_const_init(LaneConst& lc, int lane, int B, 
 #ifndef LB_PREFETCH_LINKS
 #define LB_PREFETCH_LINKS 1   // prefetch the next batch's link lines during the current batch
 #endif
+#ifndef LB_MIN_BLOCKS_FWD
+#define LB_MIN_BLOCKS_FWD 16  // forward-only instantiations (image rendering is issue-bound)
+#endif
+#ifndef LB_IMAGE_TILES
+#define LB_IMAGE_TILES 1   // image rendering: warps are mapped to pixels in 2-D tiles
+#endif
 #ifndef LB_MIN_BLOCKS
 #define LB_MIN_BLOCKS 16      // __launch_bounds__ min CTAs/SM: 64-register cap, 32 warps/SM (A/B: profiles/r1_ab_variants.txt)
 #endif
@@ -248,6 +254,8 @@ __device__ __forceinline__ void march_pass(const GridView& g, const Opts& opt, c
         unsigned act_m = __ballot_sync(FULL, active);
         float my_before = 0.f;
         {
+            // the subtraction chain is the only sequential part (bit-exact running sum); the
+            // exp / threshold test of every sample runs in parallel afterwards
             unsigned it = act_m;
             while (it) {
                 const int i = __ffs(it) - 1;
@@ -255,14 +263,18 @@ __device__ __forceinline__ void march_pass(const GridView& g, const Opts& opt, c
                 const float p = __shfl_sync(FULL, pcnt, i);
                 my_before = (lane == i) ? lt : my_before;
                 lt = __fsub_rn(lt, p);
-                if (fexp(lt) < opt.stop_thresh) {  // cuvol.cu:103-106 / :367-369
-                    const unsigned upto = (2u << i) - 1u;
-                    act_m &= upto;
-                    members &= upto;
-                    done = true;
-                    po.stopped = true;
-                    break;
-                }
+            }
+            const float aft = __fsub_rn(my_before, pcnt);
+            const unsigned tm = __ballot_sync(  // cuvol.cu:103-106 / :367-369
+                FULL, ((act_m >> lane) & 1u) && fexp(aft) < opt.stop_thresh);
+            if (tm) {
+                const int sidx = __ffs(tm) - 1;
+                const unsigned upto = (2u << sidx) - 1u;
+                act_m &= upto;
+                members &= upto;
+                done = true;
+                po.stopped = true;
+                lt = __shfl_sync(FULL, aft, sidx);
             }
         }
         if (COUNT) {
@@ -408,19 +420,35 @@ __device__ __forceinline__ void march_pass(const GridView& g, const Opts& opt, c
 }
 
 template <int MODE, bool VEC, bool FROM_CAM, bool COUNT>
-__global__ void __launch_bounds__(LB_THREADS, LB_MIN_BLOCKS)
+__global__ void __launch_bounds__(LB_THREADS, MODE == 0 ? LB_MIN_BLOCKS_FWD : LB_MIN_BLOCKS)
 lattice_march_kernel(GridView g, Opts opt, MarchArgs a, GradView gr) {
-    const int64_t ray_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (ray_id >= a.n_rays) return;
-    if (a.run_if != nullptr && *a.run_if == 0) return;  // fallback launch that is not needed
+    int64_t ray_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
 
     float ow[3], dw[3];
     if (FROM_CAM) {
+#if LB_IMAGE_TILES
+        // warp -> pixel in 64x64 super-tiles of 8x8 tiles: the ~4700 warps resident on the GPU at
+        // any time cover a compact patch of the image (their rays cross the same voxels -> L2/L1
+        // reuse) instead of a 6-pixel-high strip
+        const int W = a.cam.width, rows = (int)(a.n_rays / W);
+        const int supers_x = (W + 63) >> 6;
+        const int64_t s = ray_id >> 12;
+        const int r = (int)(ray_id & 4095);
+        const int ix = (int)(s % supers_x) * 64 + ((r >> 6) & 7) * 8 + (r & 7);
+        const int iyl = (int)(s / supers_x) * 64 + (r >> 9) * 8 + ((r >> 3) & 7);
+        if (ix >= W || iyl >= rows) return;
+        ray_id = (int64_t)iyl * W + ix;
+        cam2world_ray<false>(ix, iyl + a.row_begin, a.cam, dw, ow);
+#else
+        if (ray_id >= a.n_rays) return;
         const int ix = (int)(ray_id % a.cam.width);
         const int iy = (int)(ray_id / a.cam.width) + a.row_begin;
         cam2world_ray<false>(ix, iy, a.cam, dw, ow);
+#endif
     } else {
+        if (ray_id >= a.n_rays) return;
+        if (a.run_if != nullptr && *a.run_if == 0) return;  // fallback launch that is not needed
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             ow[i] = __ldg(a.origins + ray_id * 3 + i);
@@ -519,7 +547,14 @@ lattice_march_kernel(GridView g, Opts opt, MarchArgs a, GradView gr) {
 template <int MODE, bool VEC, bool FROM_CAM>
 void launch_mode(const GridView& g, const Opts& opt, const MarchArgs& a, const GradView& gr,
                  cudaStream_t st) {
-    const unsigned blocks = div_up(a.n_rays * WARP, LB_THREADS);
+    int64_t warps = a.n_rays;
+#if LB_IMAGE_TILES
+    if (FROM_CAM) {  // padded to whole 64x64 super-tiles; out-of-image warps exit at once
+        const int64_t W = a.cam.width, rows = a.n_rays / W;
+        warps = ((W + 63) / 64) * ((rows + 63) / 64) * 4096;
+    }
+#endif
+    const unsigned blocks = div_up(warps * WARP, LB_THREADS);
     if (a.counters)
         lattice_march_kernel<MODE, VEC, FROM_CAM, true><<<blocks, LB_THREADS, 0, st>>>(g, opt, a, gr);
     else

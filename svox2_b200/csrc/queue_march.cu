@@ -287,6 +287,8 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
             unsigned act_m = __ballot_sync(FULL, active);
             float my_before = 0.f;
             {
+                // the subtraction chain is the only sequential part (bit-exact running sum); the
+                // exp / threshold test of every sample runs in parallel afterwards
                 unsigned it = act_m;
                 while (it) {
                     const int i = __ffs(it) - 1;
@@ -294,14 +296,18 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
                     const float p = __shfl_sync(FULL, pcnt, i);
                     my_before = (lane == i) ? lt : my_before;
                     lt = __fsub_rn(lt, p);
-                    if (fexp(lt) < opt.stop_thresh) {
-                        const unsigned upto = (2u << i) - 1u;
-                        act_m &= upto;
-                        members &= upto;
-                        done = true;
-                        stopped = true;
-                        break;
-                    }
+                }
+                const float aft = __fsub_rn(my_before, pcnt);
+                const unsigned tm = __ballot_sync(  // cuvol.cu:103-106 / :367-369
+                    FULL, ((act_m >> lane) & 1u) && fexp(aft) < opt.stop_thresh);
+                if (tm) {
+                    const int sidx = __ffs(tm) - 1;
+                    const unsigned upto = (2u << sidx) - 1u;
+                    act_m &= upto;
+                    members &= upto;
+                    done = true;
+                    stopped = true;
+                    lt = __shfl_sync(FULL, aft, sidx);
                 }
             }
             if (COUNT) {
