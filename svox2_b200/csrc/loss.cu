@@ -228,8 +228,24 @@ tv_grad_sparse_vec_kernel(const int32_t* __restrict__ links, int X, int Y, int Z
     constexpr int U = TV_VEC_PASSES;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    if (tid - lane >= n_cells) return;
+    // PROBE, then the block pools its surviving cells in shared memory: blobs are contiguous in
+    // the cell run, so without pooling one warp of a block would sweep 32 cells while its
+    // neighbours idle
+    __shared__ int4 s_cell[TV_THREADS];
+    __shared__ int s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
     const TvCell mine = tv_probe(links, X, Y, Z, rand_cells, cell_start, tid, n_cells, ignore_edge, ignore_last_z);
+    {
+        const unsigned m = __ballot_sync(FULL, mine.on);
+        int base = 0;
+        if (lane == 0 && m) base = atomicAdd(&s_n, __popc(m));
+        base = __shfl_sync(FULL, base, 0);
+        if (mine.on)
+            s_cell[base + __popc(m & ((1u << lane) - 1u))] = make_int4(mine.l000, mine.l001, mine.l010, mine.l100);
+    }
+    __syncthreads();
+    const int n_live = s_n;
     float sc[3];
     ray_scale(X, Y, Z, sc);
     const int cpp = WARP / qpr;  // cells per pass
@@ -239,23 +255,16 @@ tv_grad_sparse_vec_kernel(const int32_t* __restrict__ links, int X, int Y, int Z
     bool ok[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) ok[e] = ch0 + e < end_dim;
-    unsigned m = __ballot_sync(FULL, mine.on);
-    while (m) {
+    const int per_round = U * cpp;
+    for (int i0 = (threadIdx.x >> 5) * per_round; i0 < n_live; i0 += (TV_THREADS / WARP) * per_round) {
         int32_t l[U][4];
         bool on[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const unsigned p = lane_on ? __fns(m, 0, grp + 1 + u * cpp) : 0xffffffffu;
-            on[u] = p < 32u;
-            const int src = on[u] ? (int)p : 0;
-            l[u][0] = __shfl_sync(FULL, mine.l000, src);
-            l[u][1] = __shfl_sync(FULL, mine.l001, src);
-            l[u][2] = __shfl_sync(FULL, mine.l010, src);
-            l[u][3] = __shfl_sync(FULL, mine.l100, src);
-        }
-        {
-            const unsigned p = __fns(m, 0, U * cpp);
-            m = p < 32u ? (m & ~((2u << p) - 1u)) : 0u;
+            const int i = i0 + u * cpp + grp;
+            on[u] = lane_on && i < n_live;
+            const int4 c = s_cell[on[u] ? i : 0];
+            l[u][0] = c.x; l[u][1] = c.y; l[u][2] = c.z; l[u][3] = c.w;
         }
         float4 v[U][4];
 #pragma unroll
