@@ -57,8 +57,13 @@ class ShardedTrainer:
     def __init__(self, grid, world_size: int = 1, rank: int = 0, lr_sigma: float = 30.0,
                  lr_sh: float = 1e-2, lambda_tv: float = 1e-5, lambda_tv_sh: float = 1e-3,
                  tv_sparsity: float = 0.01, rms_beta: float = 0.95, beta_loss: float = 0.0,
-                 sparsity_loss: float = 0.0, group=None):
+                 sparsity_loss: float = 0.0, group=None, lr_sigma_bg: float = 3e0,
+                 lr_color_bg: float = 1e-1, lambda_tv_background_sigma: float = 0.0,
+                 lambda_tv_background_color: float = 0.0, tv_background_sparsity: float = 0.01):
         self.grid, self.world_size, self.rank, self.group = grid, world_size, rank, group
+        self.lr_sigma_bg, self.lr_color_bg = lr_sigma_bg, lr_color_bg
+        self.lambda_tv_bg_sigma, self.lambda_tv_bg_color = lambda_tv_background_sigma, lambda_tv_background_color
+        self.tv_background_sparsity = tv_background_sparsity
         self.lr_sigma, self.lr_sh = lr_sigma, lr_sh
         self.lambda_tv, self.lambda_tv_sh = lambda_tv, lambda_tv_sh
         self.tv_sparsity, self.rms_beta = tv_sparsity, rms_beta
@@ -94,6 +99,8 @@ class ShardedTrainer:
                                     _scale_cells=n)
         lr_sigma = self.lr_sigma if lr_sigma is None else lr_sigma
         lr_sh = self.lr_sh if lr_sh is None else lr_sh
+        if g.use_background:
+            self._background_step()
         if self.world_size > 1 and g.sh_data.is_cuda:
             self._exchange_and_step_packed(lr_sigma, lr_sh)
             return rgb
@@ -104,6 +111,30 @@ class ShardedTrainer:
         g.optim_density_step(lr_sigma, beta=self.rms_beta)
         g.optim_sh_step(lr_sh, beta=self.rms_beta)
         return rgb
+
+    def _background_step(self):
+        """MSI background (opt.py:566-603): sparse TV on this rank's share of the drawn cells, sum of
+        the masked gradient rows over ranks, identical masked RMSProp on every rank."""
+        g = self.grid
+        grad = g.background_data.grad
+        if self.lambda_tv_bg_sigma > 0.0 or self.lambda_tv_bg_color > 0.0:
+            cells = g._get_rand_cells_background(self.tv_background_sparsity, contiguous=True)
+            n = cells.numel()
+            if self.world_size > 1:
+                b, e = shard_range(n, self.world_size, self.rank)
+                cells = cells[b:e].contiguous()
+            g.inplace_tv_background_grad(grad, scaling=self.lambda_tv_bg_color,
+                                         scaling_density=self.lambda_tv_bg_sigma, _rand_cells=cells,
+                                         _scale_cells=n)
+        if self.world_size > 1:
+            mask = g.sparse_background_indexer.view(torch.uint8)
+            dist.all_reduce(mask, op=dist.ReduceOp.MAX, group=self.group)
+            idx = torch.nonzero(mask.view(-1)).flatten()
+            flat = grad.view(-1, grad.size(-1))
+            packed = flat[idx]
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.group)
+            flat[idx] = packed
+        g.optim_background_step(self.lr_sigma_bg, self.lr_color_bg, beta=self.rms_beta)
 
     def _exchange_and_step_packed(self, lr_sigma: float, lr_sh: float):
         """CUDA path of the exchange: OR the masks, pack the union's rows ([rows, 28] = 27 SH

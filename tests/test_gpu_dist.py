@@ -18,7 +18,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, bg=False):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     import torch.distributed as dist
@@ -33,21 +33,23 @@ def _worker(rank, world, port, out):
     dev = f"cuda:{rank}"
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
     try:
-        sc = make_scene(reso=48, basis_dim=9, seed=41, n_rays=4096)
+        sc = make_scene(reso=48, basis_dim=9, seed=41, n_rays=4096, bg=(16, 8) if bg else None,
+                        inside=bg)
         B = sc["origins"].shape[0]
         opts = dict(sigma_thresh=1e-8, stop_thresh=1e-7)
+        kw = dict(lambda_tv_background_sigma=1e-3, lambda_tv_background_color=1e-3, beta_loss=1e-3) if bg else {}
         # single-GPU reference on the full batch (every rank computes it on its own device)
         ref = make_grid(sv, sc, dev)
         set_opt(ref, **opts)
         np.random.seed(7)
-        tr1 = ShardedTrainer(ref, world_size=1, rank=0)
+        tr1 = ShardedTrainer(ref, world_size=1, rank=0, **kw)
         rgb1 = tr1.step(sv.Rays(t(sc["origins"], dev), t(sc["dirs"], dev)), t(sc["rgb_gt"], dev), global_batch=B)
         # sharded: this rank marches its contiguous slice
         grid = make_grid(sv, sc, dev)
         set_opt(grid, **opts)
         np.random.seed(7)
         b, e = rank * B // world, (rank + 1) * B // world
-        tr = ShardedTrainer(grid, world_size=world, rank=rank)
+        tr = ShardedTrainer(grid, world_size=world, rank=rank, **kw)
         rgb = tr.step(sv.Rays(t(sc["origins"][b:e], dev), t(sc["dirs"][b:e], dev)), t(sc["rgb_gt"][b:e], dev),
                       global_batch=B)
         torch.cuda.synchronize()
@@ -64,6 +66,12 @@ def _worker(rank, world, port, out):
         m["masks"] = bool(torch.equal(grid.sparse_grad_indexer, ref.sparse_grad_indexer) and
                           torch.equal(grid.sparse_sh_grad_indexer, ref.sparse_sh_grad_indexer))
         ok = ok and m["masks"]
+        if bg:
+            m["background"] = frac_bad(grid.background_data.detach().cpu().numpy(),
+                                       ref.background_data.detach().cpu().numpy())
+            ok = ok and m["background"] < 1e-3
+            m["bg_mask"] = bool(torch.equal(grid.sparse_background_indexer, ref.sparse_background_indexer))
+            ok = ok and m["bg_mask"]
         m["grads_zeroed"] = float(grid.sh_data.grad.abs().max().item() + grid.density_data.grad.abs().max().item())
         ok = ok and m["grads_zeroed"] == 0.0
         # replicas bit-identical across ranks
@@ -77,14 +85,15 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_two_gpu_step_equals_single_gpu_step():
+@pytest.mark.parametrize("bg", [False, True])
+def test_two_gpu_step_equals_single_gpu_step(bg):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     out = ctx.Manager().dict()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out, bg)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
