@@ -328,7 +328,8 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
 
     phase_ms = None
-    if world > 1:   # untimed extra steps with per-phase CUDA events (rank 0 reports its own)
+    if world > 1:   # untimed extra steps with per-phase CUDA events, one entry per rank
+        barrier()
         trainer.profile = True
         for i in range(min(args.steps, 10)):
             step(*batches[i % POOL])
@@ -417,8 +418,8 @@ def run_ours(args):
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes,
                      "ms_per_launch": ms_fused,
                      # dram__bytes_read+write of K1..K4 of one fused call, ncu --set full capture
-                     # of this command (profiles/r1_ncu_step_kernels_full.txt): 331+250+45+390 MB
-                     "traffic": 1.016e9 if args.workload == "c3" else None},
+                     # of this command (profiles/r1_ncu_step_kernels_full.txt): 335+252+45+419 MB
+                     "traffic": 1.051e9 if args.workload == "c3" else None},
     }
     line["render"] = {"value": world * 0.64 / (ms_img * 1e-3), "unit": "MPix/s",
                       "ms_per_image": ms_img, "what": "volume_render_image, 800x800, fx 1111.11, "
