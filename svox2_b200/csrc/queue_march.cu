@@ -45,9 +45,6 @@ namespace {
 #ifndef QM_SCATTER_SPAN
 #define QM_SCATTER_SPAN 1  // K4 walks contiguous record runs and merges same-cell samples
 #endif
-#ifndef QM_TRACE_PIPE
-#define QM_TRACE_PIPE 0    // K1: issue the next round's link loads before this round's density loads
-#endif
 #ifndef QM_TRACE_BLOCKS
 #define QM_TRACE_BLOCKS 16
 #endif
@@ -101,7 +98,6 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 // ---------------------------------------------------------------------------------------
 // K1: traversal -> records
 // ---------------------------------------------------------------------------------------
-static_assert(!QM_TRACE_PIPE, "slab mode reads l[] after the pipelined reload");
 template <bool COUNT, bool SLAB>
 __global__ void __launch_bounds__(TRACE_THREADS, QM_TRACE_BLOCKS)
 trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
@@ -175,14 +171,9 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
                 for (int q = 0; q < 8; ++q) lk_o[q] = __ldg(lp + corner_off(g, q));
             }
         };
-#if QM_TRACE_PIPE
-        load_round(t0, tk, valid, l, pos, lk);
-#endif
         while (!done) {
             if (SLAB && t0 > t_exit) break;  // past the slab: nothing left for this rank
-#if !QM_TRACE_PIPE
             load_round(t0, tk, valid, l, pos, lk);
-#endif
             const float skipd = skip_dist(ray, valid ? lk[0] : 0, l, pos);
             const bool is_skip = valid && (skipd >= step);
             const unsigned valid_m = __ballot_sync(FULL, valid);
@@ -216,32 +207,6 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
                 if (!(tn <= ray.tmax)) done = true;
                 break;
             }
-#if QM_TRACE_PIPE
-            // this round's samples keep their own copies; the next round's link loads are issued
-            // now and stay in flight under the density gathers and the transmittance chain
-            const float tk_c = tk;
-            float pos_c[3] = {pos[0], pos[1], pos[2]};
-            int32_t lk_c[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) lk_c[q] = lk[q];
-            if (!done) {
-                load_round(t_next, tk, valid, l, pos, lk);
-                const float ta = fmaf((float)(lane + 32), step, t_next);
-                if (ta <= ray.tmax) {
-                    int nl[3];
-                    float npos[3];
-                    locate(ray, g, ta, nl, npos);
-                    const int32_t* np = g.links + ((int64_t)nl[0] * g.offx + (int64_t)nl[1] * g.offy + nl[2]);
-                    prefetch_l2(np);
-                    prefetch_l2(np + g.offy);
-                    prefetch_l2(np + g.offx);
-                    prefetch_l2(np + g.offx + g.offy);
-                }
-            }
-#define TK tk_c
-#define POS pos_c
-#define LK lk_c
-#else
             if (!done) {  // next batch's link lines
                 const float ta = fmaf((float)lane, step, t_next);
                 if (ta <= ray.tmax) {
@@ -255,10 +220,6 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
                     prefetch_l2(np + g.offx + g.offy);
                 }
             }
-#define TK tk
-#define POS pos
-#define LK lk
-#endif
             if (SLAB) members &= __ballot_sync(FULL, l[0] >= sl.x_lo && l[0] < sl.x_hi);
             const bool member = (members >> lane) & 1u;
             float sigma = 0.f;
@@ -266,18 +227,18 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
                 float sv[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
-                    sv[q] = LK[q] >= 0 ? __ldg(g.density + (int64_t)LK[q] * g.density_stride) : 0.f;
-                sigma = trilerp8(sv, POS);
+                    sv[q] = lk[q] >= 0 ? __ldg(g.density + (int64_t)lk[q] * g.density_stride) : 0.f;
+                sigma = trilerp8(sv, pos);
             }
-            const float ws = (opt.last_sample_opaque && __fadd_rn(TK, step) > ray.tmax) ? 1e9f
+            const float ws = (opt.last_sample_opaque && __fadd_rn(tk, step) > ray.tmax) ? 1e9f
                                                                                        : ray.world_step;
             const bool active = member && (sigma > opt.sigma_thresh);
 #if QM_PREFETCH_SH
             if (active) {  // pull the rows K2 will gather towards L2
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
-                    if (LK[q] >= 0) {
-                        const float* row = g.sh + (int64_t)LK[q] * g.sh_stride;
+                    if (lk[q] >= 0) {
+                        const float* row = g.sh + (int64_t)lk[q] * g.sh_stride;
                         prefetch_l2(row);
                         prefetch_l2(row + (g.sh_dim - 1));
                     }
@@ -327,12 +288,12 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
                         const int rank = __popc(act_m & ((1u << lane) - 1u));
                         Record* r = qv.rec + base + rank;
                         int4* r4 = reinterpret_cast<int4*>(r);
-                        r4[0] = make_int4(LK[0], LK[1], LK[2], LK[3]);
-                        r4[1] = make_int4(LK[4], LK[5], LK[6], LK[7]);
+                        r4[0] = make_int4(lk[0], lk[1], lk[2], lk[3]);
+                        r4[1] = make_int4(lk[4], lk[5], lk[6], lk[7]);
                         // slab mode keeps the local log-transmittance; K2 makes the weight
                         const float weight = SLAB ? my_before
                                                   : __fmul_rn(fexp(my_before), __fsub_rn(1.f, fexp(-pcnt)));
-                        reinterpret_cast<float4*>(r)[2] = make_float4(POS[0], POS[1], POS[2], weight);
+                        reinterpret_cast<float4*>(r)[2] = make_float4(pos[0], pos[1], pos[2], weight);
                         r4[3] = make_int4(__float_as_int(__fsub_rn(my_before, pcnt)), __float_as_int(sigma),
                                           __float_as_int(ws), (int)ray_id);
                     }
@@ -346,9 +307,6 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
             }
             t0 = t_next;
         }
-#undef TK
-#undef POS
-#undef LK
     }
     // forward colour starts from the background term; K2 adds the samples atomically
     const bool hit = ray.tmin <= ray.tmax;

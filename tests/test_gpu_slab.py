@@ -130,3 +130,54 @@ def test_two_gpu_slab_step_equals_single_gpu_step():
         assert p.exitcode == 0
     res = dict(out)
     assert all(res[r][0] for r in range(2)), res
+
+
+def _train_worker(rank, world, port, out):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import torch.distributed as dist
+    from svox2_b200 import train as T
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        data = T.synthetic_dataset(dev, n_images=20, width=80, height=80, reso=48)
+        train = T.PosedImages(data.c2w[:16], data.images[:16], data.fx, data.width, data.height)
+        test = T.PosedImages(data.c2w[16:], data.images[16:], data.fx, data.width, data.height)
+        cfg = T.TrainConfig(reso="[[32,32,32],[64,64,64]]", upsamp_every=100, n_iters=250, batch_size=2048,
+                            lr_sigma_delay_steps=100, print_every=1000, weight_thresh=0.0005 * 64)
+        single = T.Trainer(cfg, train, test, log=lambda m: None)      # same global batch on one GPU
+        single.cfg = T.dataclasses.replace(cfg, batch_size=2048 * world)
+        single.run()
+        want = single.eval_psnr()
+        tr = T.Trainer(cfg, train, test, world_size=world, rank=rank, dist_mode="slab", log=lambda m: None)
+        tr.run()
+        got = tr.eval_psnr()
+        same_reso = list(tr.grid.links.shape) == list(single.grid.links.shape) == [64, 64, 64]
+        out[rank] = (bool(same_reso and tr.reso_id == 1 and abs(got - want) < 1.0 and got > 15.0),
+                     dict(single=want, slab=got, voxels=(single.grid.density_data.size(0),
+                                                         tr.grid.density_data.size(0))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_slab_training_run_with_upsampling_matches_single_gpu():
+    """The driver (LR schedule, shuffled pool, upsample with gather + re-partition) on 2 slabs
+    reaches the PSNR of the same run on one GPU."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(600)
+        assert p.exitcode == 0
+    res = dict(out)
+    assert all(res[r][0] for r in range(2)), res

@@ -113,6 +113,33 @@ def test_cabi_argument_errors_are_reported_not_printed():
         _lib.check(st)
 
 
+def test_cabi_extension_entry_points_validate_their_arguments():
+    """The multi-GPU / slab extensions reject bad arguments before touching the GPU."""
+    lib = _lib.lib()
+    buf = (ctypes.c_float * 64)()
+    rows = (ctypes.c_int64 * 2)(0, 1)
+    p = ctypes.addressof
+    # pack: stride not a multiple of 4, stride too small for the mask flags, null pointers
+    assert lib.svox2_pack_grad_rows(p(buf), 28, 27, p(buf), 1, p(rows), 2, p(buf), 30, None, None, None) == 1
+    assert b"pack_stride" in lib.svox2_last_error()
+    assert lib.svox2_pack_grad_rows(p(buf), 28, 27, p(buf), 1, p(rows), 2, p(buf), 28, p(buf), None, None) == 1
+    assert lib.svox2_pack_grad_rows(None, 28, 27, None, 1, p(rows), 2, p(buf), 28, None, None, None) == 1
+    assert lib.svox2_pack_grad_rows(None, 28, 27, None, 1, None, 0, None, 28, None, None, None) == 0   # empty: ok
+    assert lib.svox2_unpack_rows(p(buf), 28, p(rows), 2, p(buf), 27, 27, p(buf), 1, 1, None, None, None) == 1
+    assert b"padded" in lib.svox2_last_error()
+    assert lib.svox2_rmsprop_step_packed(None, None, 28, 27, None, None, 1, p(rows), 2, p(buf), 28, None,
+                                         None, None, 0, None, 0, 0.9, 0.1, 0.1, 1e-8, -1e9, -1e9, None) == 1
+    # slab: range outside the grid, rank outside the slab count
+    g = _lib.GridT()
+    o = _lib.RenderOptsT()
+    assert lib.svox2_slab_trace(ctypes.byref(g), None, None, 0, ctypes.byref(o), 0, 4, None, None, 0, None) == 1
+    assert lib.svox2_slab_prefix(p(buf), p(buf), 4, 2, 2, p(buf), None) == 1
+    assert b"slab" in lib.svox2_last_error()
+    assert lib.svox2_slab_combine(p(buf), p(buf), p(buf), p(buf), 4, 0, 0, 1.0, 0.0, p(buf), p(buf),
+                                  p(buf), None) == 1
+    assert lib.svox2_slab_prefix(None, None, 0, 1, 0, None, None) == 0                                 # empty: ok
+
+
 @pytest.mark.parametrize("background", [False, True])
 def test_checkpoint_interop_with_reference(ref_svox2, tmp_path, background):
     """ckpt.npz written by this package loads in the unmodified reference and vice versa
