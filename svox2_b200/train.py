@@ -6,10 +6,12 @@ device-resident shuffled ray pool (util.py:178-190 keeps it on the host), fused 
 Differences by design: the per-step MSE is accumulated on the device and read every
 ``print_every`` steps instead of ``.item()`` per step (opt.py:505-508), and the step itself is a
 ``ShardedTrainer`` / ``SlabTrainer`` call, so the same driver runs on 1..8 GPUs (one process per
-GPU, ``torchrun``).  Dataset loaders are out of scope: ``synthetic_dataset``
-renders posed images of a hidden analytic scene with this package's own renderer.
+GPU, ``torchrun``).  Data: ``load_nerf_synthetic`` reads a NeRF-synthetic (Blender) scene
+directory; without one, ``synthetic_dataset`` renders posed images of a hidden analytic scene with
+this package's own renderer (no dataset ships with the image).
 
     python -m svox2_b200.train --reso "[[64,64,64],[128,128,128]]" --n_iters 600
+    python -m svox2_b200.train --config opt/configs/syn.json --data_dir <nerf_synthetic/lego>
 """
 import argparse
 import dataclasses
@@ -179,6 +181,33 @@ def synthetic_dataset(device, n_images: int = 24, width: int = 100, height: int 
     return PosedImages(c2w, imgs.clamp(0, 1), fx, width, height)
 
 
+def load_nerf_synthetic(root: str, split: str, device, scene_scale: float = 2.0 / 3.0,
+                        white_bkgd: bool = True, n_images: Optional[int] = None) -> PosedImages:
+    """NeRF-synthetic (Blender) scene directory -> PosedImages (behaviour of
+    opt/util/nerf_dataset.py:14-120): ``transforms_<split>.json`` + ``<split>/<name>.png``,
+    OpenGL -> OpenCV camera convention (c2w @ diag(1,-1,-1,1)), translations scaled by
+    ``scene_scale``, RGBA composited over white, focal = W / (2 tan(camera_angle_x / 2))."""
+    import os
+    from PIL import Image
+    with open(os.path.join(root, f"transforms_{split}.json")) as f:
+        meta = json.load(f)
+    flip = torch.diag(torch.tensor([1.0, -1.0, -1.0, 1.0]))
+    c2w, imgs = [], []
+    for frame in meta["frames"][:n_images]:
+        path = os.path.join(root, split, os.path.basename(frame["file_path"]) + ".png")
+        im = torch.from_numpy(np.asarray(Image.open(path), dtype=np.uint8).copy()).float() / 255.0
+        if im.size(-1) == 4:
+            im = im[..., :3] * im[..., 3:] + (1.0 - im[..., 3:]) if white_bkgd else im[..., :3]
+        m = torch.tensor(frame["transform_matrix"], dtype=torch.float32) @ flip
+        m[:3, 3] *= scene_scale
+        c2w.append(m)
+        imgs.append(im)
+    images = torch.stack(imgs).to(device)
+    h, w = images.shape[1:3]
+    fx = float(0.5 * w / math.tan(0.5 * meta["camera_angle_x"]))
+    return PosedImages(torch.stack(c2w).to(device), images, fx, w, h)
+
+
 class Trainer:
     """One process of the training job.  ``dist_mode``: "slab" (grid sharded) or "rays"."""
 
@@ -300,6 +329,9 @@ def main():
     ap.add_argument("--config", default=None, help="JSON with TrainConfig fields (e.g. opt/configs/syn.json)")
     ap.add_argument("--dist", default="slab", choices=["slab", "rays"])
     ap.add_argument("--save", default=None, help="write ckpt.npz here at the end")
+    ap.add_argument("--data_dir", default=None,
+                    help="NeRF-synthetic scene directory (transforms_train.json ...); default: a "
+                         "synthetic posed-image set rendered on the fly")
     for f in dataclasses.fields(TrainConfig):
         ap.add_argument(f"--{f.name}", type=type(f.default), default=None)
     args = ap.parse_args()
@@ -314,9 +346,13 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    data = synthetic_dataset(dev, n_images=28)
-    test = PosedImages(data.c2w[24:], data.images[24:], data.fx, data.width, data.height)
-    train = PosedImages(data.c2w[:24], data.images[:24], data.fx, data.width, data.height)
+    if args.data_dir:
+        train = load_nerf_synthetic(args.data_dir, "train", dev)
+        test = load_nerf_synthetic(args.data_dir, "test", dev, n_images=10)
+    else:
+        data = synthetic_dataset(dev, n_images=28)
+        test = PosedImages(data.c2w[24:], data.images[24:], data.fx, data.width, data.height)
+        train = PosedImages(data.c2w[:24], data.images[:24], data.fx, data.width, data.height)
     tr = Trainer(cfg, train, test, world_size=world, rank=rank, dist_mode=args.dist)
     tr.run()
     psnr = tr.eval_psnr()

@@ -33,6 +33,27 @@ def test_config_reads_reference_json(tmp_path):
     assert T.TrainConfig(reso="[64, [32, 48, 64]]").reso_list() == [[64, 64, 64], [32, 48, 64]]
 
 
+def test_nerf_synthetic_loader_conventions(tmp_path):
+    """transforms json + RGBA pngs -> OpenCV c2w, scaled translation, white compositing, focal."""
+    from PIL import Image
+    (tmp_path / "train").mkdir()
+    rgba = np.zeros((6, 8, 4), np.uint8)
+    rgba[..., 0] = 255            # opaque red on the left half, transparent on the right
+    rgba[:, :4, 3] = 255
+    Image.fromarray(rgba).save(tmp_path / "train" / "r_0.png")
+    m = np.eye(4)
+    m[:3, 3] = [3.0, 0.0, 1.5]
+    (tmp_path / "transforms_train.json").write_text(json.dumps(
+        {"camera_angle_x": 0.6911, "frames": [{"file_path": "./train/r_0", "transform_matrix": m.tolist()}]}))
+    d = T.load_nerf_synthetic(str(tmp_path), "train", "cpu")
+    assert d.images.shape == (1, 6, 8, 3) and (d.width, d.height) == (8, 6)
+    assert torch.allclose(d.images[0, 0, 0], torch.tensor([1.0, 0.0, 0.0]))      # opaque red
+    assert torch.allclose(d.images[0, 0, 7], torch.tensor([1.0, 1.0, 1.0]))      # transparent -> white
+    assert torch.allclose(d.c2w[0, :3, 3], torch.tensor([2.0, 0.0, 1.0]))        # scene_scale 2/3
+    assert torch.allclose(torch.diagonal(d.c2w[0])[:3], torch.tensor([1.0, -1.0, -1.0]))   # GL -> CV
+    assert abs(d.fx - 0.5 * 8 / math.tan(0.5 * 0.6911)) < 1e-5
+
+
 @pytest.mark.gpu
 def test_training_run_with_upsampling_fits_the_scene():
     dev = torch.device("cuda:0")
