@@ -51,9 +51,7 @@ void launch_lattice_march(int mode, bool from_cam, const GridView& g, const Opts
 }  // namespace svox2b
 
 namespace svox2b {
-// launchers defined in render.cu (v1 march kernels, MSI background, depth)
-void launch_v1_fwd(bool from_cam, const GridView& g, const Opts& opt, const MarchArgs& a, cudaStream_t st);
-void launch_v1_bwd(const GridView& g, const Opts& opt, const MarchArgs& a, const GradView& gr, cudaStream_t st);
+// launchers defined in render.cu (MSI background, depth)
 void launch_bg_fwd(bool from_cam, const GridView& g, const Opts& opt, const MarchArgs& a,
                    const float* logT, cudaStream_t st);
 void launch_bg_bwd(const GridView& g, const Opts& opt, const MarchArgs& a, const float* color_cache,

@@ -1,11 +1,5 @@
-// Ray-march kernels: forward, backward, fused seed, whole-image, MSI background, depth.
-//
-// Warp-per-ray march.  Lanes 0..7 own the eight corner links / sigma values of the current
-// cell (one LDG each instead of eight redundant broadcasts per lane), lane j < 3*basis_dim
-// owns SH channel j for the colour gather and the gradient scatter.  The traversal
-// (t lattice, skipping, sigma, log-transmittance) is bit-exact with the reference:
-//   forward   render_lerp_kernel_cuvol.cu:30-120, 611-690
-//   backward  render_lerp_kernel_cuvol.cu:227-383, 692-773
+// MSI background (one thread per ray) and depth kernels (warp per ray); the foreground march
+// lives in march.cu / queue_march.cu.  Traversal bit-exact with the reference:
 //   MSI       render_lerp_kernel_cuvol.cu:386-607, 775-860
 //   depth     render_lerp_kernel_cuvol.cu:122-225, 862-902
 #include "common.cuh"
@@ -13,28 +7,10 @@
 
 namespace svox2b {
 
-namespace v1 {
+namespace aux {
 
 constexpr int MARCH_THREADS = 128;
 constexpr int BG_THREADS = 128;
-
-// Sum over each group of B consecutive lanes, valid in the group's first lane.
-__device__ __forceinline__ float seg_sum(float x, int k, int B) {
-#pragma unroll
-    for (int off = 1; off < 16; off <<= 1) {
-        const float o = __shfl_down_sync(FULL, x, off);
-        if (k + off < B) x += o;
-    }
-    return x;
-}
-
-__device__ __forceinline__ float corner_w(const float* pos, int c, float g) {
-    // (ay*az) * ((1-px)*g), the association used by render_util.cuh:102-119
-    const float wx = (c & 4) ? pos[0] : 1.f - pos[0];
-    const float wy = (c & 2) ? pos[1] : 1.f - pos[1];
-    const float wz = (c & 1) ? pos[2] : 1.f - pos[2];
-    return (wy * wz) * (wx * g);
-}
 
 struct RaySource {
     const float* __restrict__ origins;
@@ -55,214 +31,6 @@ __device__ __forceinline__ void load_ray(const RaySource& src, int64_t ray_id, f
             o[i] = __ldg(src.origins + ray_id * 3 + i);
             d[i] = __ldg(src.dirs + ray_id * 3 + i);
         }
-    }
-}
-
-// ---------------------------------------------------------------------------------------
-// forward march
-// ---------------------------------------------------------------------------------------
-template <bool FROM_CAM, bool COUNT>
-__global__ void __launch_bounds__(MARCH_THREADS)
-march_fwd_kernel(GridView g, Opts opt, RaySource src, int64_t n_rays, float* __restrict__ out,
-                 float* __restrict__ logT_out, unsigned long long* __restrict__ counters) {
-    const int64_t ray_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (ray_id >= n_rays) return;
-    const int lane = threadIdx.x & 31;
-    const int B = g.basis_dim, D = g.sh_dim;
-    const int k = lane % B, cgrp = lane / B;
-    const bool chan_lane = lane < D;
-
-    float ow[3], dw[3];
-    load_ray<FROM_CAM>(src, ray_id, ow, dw);
-    const float Yk = sh_basis_k(B, k, dw);  // raw input direction (cuvol.cu:632-635)
-    Ray ray;
-    ray_setup(ray, ow, dw, g, opt);
-
-    const bool has_bg = g.bg_nlayers > 0;
-    float outv = 0.f, logT = 0.f;
-    unsigned n_skip = 0, n_vis = 0, n_act = 0;
-
-    if (ray.tmin <= ray.tmax) {
-        float t = ray.tmin;
-        while (t <= ray.tmax) {
-            int l[3];
-            float pos[3];
-            locate(ray, g, t, l, pos);
-            const int64_t base = (int64_t)l[0] * g.offx + (int64_t)l[1] * g.offy + l[2];
-            int32_t mylink = -1;
-            if (lane < 8) mylink = __ldg(g.links + base + corner_off(g, lane));
-            const int32_t link0 = __shfl_sync(FULL, mylink, 0);
-            const float skip = skip_dist(ray, link0, l, pos);
-            if (skip >= opt.step_size) {
-                t = skip_advance(t, skip, opt.step_size);
-                if (COUNT) ++n_skip;
-                continue;
-            }
-            float myv = 0.f;
-            if (lane < 8 && mylink >= 0) myv = __ldg(g.density + (int64_t)mylink * g.density_stride);
-            const float sigma = trilerp_lanes(myv, pos);
-            if (COUNT) ++n_vis;
-            if (opt.last_sample_opaque && __fadd_rn(t, opt.step_size) > ray.tmax)
-                ray.world_step = 1e9f;
-            if (sigma > opt.sigma_thresh) {
-                if (COUNT) ++n_act;
-                float v[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int32_t lk = __shfl_sync(FULL, mylink, c);
-                    v[c] = (chan_lane && lk >= 0) ? __ldg(g.sh + (int64_t)lk * g.sh_stride + lane) : 0.f;
-                }
-                const float total = seg_sum(trilerp8(v, pos) * Yk, k, B);
-                const float pcnt = __fmul_rn(ray.world_step, sigma);
-                const float weight = __fmul_rn(fexp(logT), __fsub_rn(1.f, fexp(-pcnt)));
-                logT = __fsub_rn(logT, pcnt);
-                outv = fmaf(weight, fmaxf(total + 0.5f, 0.f), outv);
-                if (fexp(logT) < opt.stop_thresh) {
-                    logT = -1e3f;
-                    break;
-                }
-            }
-            t = __fadd_rn(t, opt.step_size);
-        }
-        if (!has_bg) outv = fmaf(fexp(logT), opt.background_brightness, outv);
-    } else {
-        outv = has_bg ? 0.f : opt.background_brightness;
-        logT = 0.f;
-    }
-    if (chan_lane && k == 0) out[ray_id * 3 + cgrp] = outv;
-    if (lane == 0) {
-        if (logT_out) logT_out[ray_id] = logT;
-        if (COUNT) {
-            atomicAdd(counters + 0, (unsigned long long)n_skip);
-            atomicAdd(counters + 1, (unsigned long long)n_vis);
-            atomicAdd(counters + 2, (unsigned long long)n_act);
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------
-// backward march (re-materialises the samples)
-// ---------------------------------------------------------------------------------------
-struct BwdArgs {
-    const float* __restrict__ grad_in;      // grad_out [Q,3], or rgb_gt when fused
-    const float* __restrict__ color_cache;  // [Q,3]
-    const float* __restrict__ logT_in;      // forward log-transmittance (beta loss) or NULL
-    float* __restrict__ accum_out;          // [Q] or NULL (MSI hand-over)
-    float* __restrict__ logT_out;           // [Q] or NULL
-    float beta_loss;                        // already divided by norm_rays
-    float sparsity_loss;
-    float norm_factor;                      // 2/(3*norm_rays)
-    int fused;
-};
-
-__global__ void __launch_bounds__(MARCH_THREADS)
-march_bwd_kernel(GridView g, Opts opt, const float* __restrict__ origins,
-                 const float* __restrict__ dirs, int64_t n_rays, BwdArgs a, GradView gr) {
-    const int64_t ray_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (ray_id >= n_rays) return;
-    const int lane = threadIdx.x & 31;
-    const int B = g.basis_dim, D = g.sh_dim;
-    const int k = lane % B, cgrp = lane / B;
-    const bool chan_lane = lane < D;
-
-    float ow[3], dw[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        ow[i] = __ldg(origins + ray_id * 3 + i);
-        dw[i] = __ldg(dirs + ray_id * 3 + i);
-    }
-    const float Yk = sh_basis_k(B, k, dw);
-    Ray ray;
-    ray_setup(ray, ow, dw, g, opt);
-
-    float gout[3], cc[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        cc[i] = __ldg(a.color_cache + ray_id * 3 + i);
-        const float gi = __ldg(a.grad_in + ray_id * 3 + i);
-        gout[i] = a.fused ? (cc[i] - gi) * a.norm_factor : gi;  // cuvol.cu:735-747
-    }
-    float accum = fmaf(cc[0], gout[0], fmaf(cc[1], gout[1], cc[2] * gout[2]));
-    float beta_loss = a.beta_loss;
-    float logT = 0.f;
-
-    if (ray.tmin <= ray.tmax) {
-        if (beta_loss > 0.f) {  // cuvol.cu:259-264
-            const float transmit_in = fexp(a.logT_in ? a.logT_in[ray_id] : 0.f);
-            beta_loss = (float)((double)beta_loss *
-                                (1 - (double)transmit_in / (1 - (double)transmit_in + 1e-3)));
-            accum += beta_loss;
-        }
-        const float my_gout = cgrp == 0 ? gout[0] : (cgrp == 1 ? gout[1] : gout[2]);
-        float t = ray.tmin;
-        while (t <= ray.tmax) {
-            int l[3];
-            float pos[3];
-            locate(ray, g, t, l, pos);
-            const int64_t base = (int64_t)l[0] * g.offx + (int64_t)l[1] * g.offy + l[2];
-            int32_t mylink = -1;
-            if (lane < 8) mylink = __ldg(g.links + base + corner_off(g, lane));
-            const int32_t link0 = __shfl_sync(FULL, mylink, 0);
-            const float skip = skip_dist(ray, link0, l, pos);
-            if (skip >= opt.step_size) {
-                t = skip_advance(t, skip, opt.step_size);
-                continue;
-            }
-            float myv = 0.f;
-            if (lane < 8 && mylink >= 0) myv = __ldg(g.density + (int64_t)mylink * g.density_stride);
-            const float sigma = trilerp_lanes(myv, pos);
-            if (opt.last_sample_opaque && __fadd_rn(t, opt.step_size) > ray.tmax)
-                ray.world_step = 1e9f;
-            if (sigma > opt.sigma_thresh) {
-                int32_t lk[8];
-                float v[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    lk[c] = __shfl_sync(FULL, mylink, c);
-                    v[c] = (chan_lane && lk[c] >= 0) ? __ldg(g.sh + (int64_t)lk[c] * g.sh_stride + lane) : 0.f;
-                }
-                const float lct = seg_sum(trilerp8(v, pos) * Yk, k, B) + 0.5f;
-                const float pcnt = __fmul_rn(ray.world_step, sigma);
-                const float weight = __fmul_rn(fexp(logT), __fsub_rn(1.f, fexp(-pcnt)));
-                logT = __fsub_rn(logT, pcnt);
-
-                const float c0 = __shfl_sync(FULL, lct, 0);
-                const float c1 = __shfl_sync(FULL, lct, B);
-                const float c2 = __shfl_sync(FULL, lct, 2 * B);
-                float total_color = fmaxf(c0, 0.f) * gout[0];
-                total_color += fmaxf(c2, 0.f) * gout[2];
-                total_color += fmaxf(c1, 0.f) * gout[1];
-                const float my_c = cgrp == 0 ? c0 : (cgrp == 1 ? c1 : c2);
-                const float in01 = (fmaxf(my_c, 0.f) == my_c) ? 1.f : 0.f;
-                const float grad_common = weight * in01 * my_gout;
-                const float curr_grad_color = Yk * grad_common;
-
-                accum -= weight * total_color;
-                float curr_grad_sigma = ray.world_step * (total_color * fexp(logT) - accum);
-                if (a.sparsity_loss > 0.f)
-                    curr_grad_sigma += a.sparsity_loss * (4 * sigma / (1 + 2 * (sigma * sigma)));
-
-                if (chan_lane) {
-#pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        if (lk[c] >= 0)
-                            atomicAdd(gr.grad_sh + (int64_t)lk[c] * g.sh_stride + lane,
-                                      corner_w(pos, c, curr_grad_color));
-                }
-                if (lane < 8 && mylink >= 0) {
-                    atomicAdd(gr.grad_density + (int64_t)mylink * g.density_stride,
-                              corner_w(pos, lane, curr_grad_sigma));
-                    if (gr.mask) gr.mask[mylink] = 1;
-                }
-                if (fexp(logT) < opt.stop_thresh) break;
-            }
-            t = __fadd_rn(t, opt.step_size);
-        }
-        accum -= beta_loss;  // "cancel beta loss out in case of background", cuvol.cu:375-377
-    }
-    if (lane == 0) {
-        if (a.accum_out) a.accum_out[ray_id] = accum;
-        if (a.logT_out) a.logT_out[ray_id] = logT;
     }
 }
 
@@ -551,49 +319,15 @@ depth_kernel(GridView g, Opts opt, const float* __restrict__ origins,
     out[ray_id] = outv;
 }
 
-}  // namespace v1
+}  // namespace aux
 
 // ---------------------------------------------------------------------------------------
 // host launchers used by render_abi.cu
 // ---------------------------------------------------------------------------------------
-using namespace v1;
+using namespace aux;
 
 static RaySource make_source(const MarchArgs& a) {
     return RaySource{a.origins, a.dirs, a.cam, a.row_begin};
-}
-
-// v1 (warp-per-ray, lane-per-channel) march kernels: kept as a debugging / A-B reference for the
-// lattice-batch kernel; selected with SVOX2_B200_MARCH=v1.  Gradient strides must equal the
-// data strides on this path.
-void launch_v1_fwd(bool from_cam, const GridView& g, const Opts& opt, const MarchArgs& a,
-                   cudaStream_t st) {
-    const unsigned blocks = div_up(a.n_rays * WARP, MARCH_THREADS);
-    const RaySource src = make_source(a);
-    if (from_cam)
-        march_fwd_kernel<true, false><<<blocks, MARCH_THREADS, 0, st>>>(g, opt, src, a.n_rays, a.rgb_out,
-                                                                       a.logT_out, nullptr);
-    else if (a.counters)
-        march_fwd_kernel<false, true><<<blocks, MARCH_THREADS, 0, st>>>(g, opt, src, a.n_rays, a.rgb_out,
-                                                                       a.logT_out, a.counters);
-    else
-        march_fwd_kernel<false, false><<<blocks, MARCH_THREADS, 0, st>>>(g, opt, src, a.n_rays, a.rgb_out,
-                                                                        a.logT_out, nullptr);
-}
-
-void launch_v1_bwd(const GridView& g, const Opts& opt, const MarchArgs& a, const GradView& gr,
-                   cudaStream_t st) {
-    BwdArgs b{};
-    b.grad_in = a.grad_in;
-    b.color_cache = a.color_cache;
-    b.logT_in = a.logT_in;
-    b.accum_out = a.accum_out;
-    b.logT_out = a.logT_out;
-    b.beta_loss = a.beta_loss;
-    b.sparsity_loss = a.sparsity_loss;
-    b.norm_factor = a.norm_factor;
-    b.fused = a.fused_seed;
-    march_bwd_kernel<<<div_up(a.n_rays * WARP, MARCH_THREADS), MARCH_THREADS, 0, st>>>(
-        g, opt, a.origins, a.dirs, a.n_rays, b, gr);
 }
 
 void launch_bg_fwd(bool from_cam, const GridView& g, const Opts& opt, const MarchArgs& a,

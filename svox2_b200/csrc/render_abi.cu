@@ -11,14 +11,6 @@ using namespace svox2b;
 
 namespace {
 
-bool use_v1() {
-    static const int v = [] {
-        const char* e = std::getenv("SVOX2_B200_MARCH");
-        return (e && std::strcmp(e, "v1") == 0) ? 1 : 0;
-    }();
-    return v == 1;
-}
-
 // SVOX2_B200_MARCH=lattice forces the single-kernel fused path (A/B and debugging)
 bool use_queue() {
     static const int v = [] {
@@ -101,21 +93,12 @@ void set_grad_strides(MarchArgs& a, const svox2_grid_t* grid, const svox2_grads_
 }
 
 void run_fwd(bool from_cam, const GridView& g, const Opts& opt, const MarchArgs& a, cudaStream_t st) {
-    if (use_v1()) launch_v1_fwd(from_cam, g, opt, a, st);
-    else launch_lattice_march(LB_MODE_FWD, from_cam, g, opt, a, GradView{}, st);
+    launch_lattice_march(LB_MODE_FWD, from_cam, g, opt, a, GradView{}, st);
 }
 
 int run_bwd(const GridView& g, const Opts& opt, const MarchArgs& a, const GradView& gr,
             cudaStream_t st, const char* who) {
-    if (use_v1()) {
-        if (a.gsh_stride != g.sh_stride || a.gd_stride != g.density_stride) {
-            set_error("%s: SVOX2_B200_MARCH=v1 needs gradient strides equal to the data strides", who);
-            return SVOX2_ERR_INVALID;
-        }
-        launch_v1_bwd(g, opt, a, gr, st);
-    } else {
-        launch_lattice_march(LB_MODE_BWD, false, g, opt, a, gr, st);
-    }
+    launch_lattice_march(LB_MODE_BWD, false, g, opt, a, gr, st);
     return SVOX2_OK;
 }
 
@@ -246,7 +229,7 @@ extern "C" SVOX2_API int svox2_volume_render_cuvol_fused(
     a.fused_seed = 1;
     a.counters = reinterpret_cast<unsigned long long*>(counters);
 
-    if (!use_bg && !use_v1() && use_queue()) {
+    if (!use_bg && use_queue()) {
         // sample-queue path (queue_march.cu): trace -> shade -> seed -> scatter; the lattice
         // kernel is enqueued behind it as a conditional fallback for a queue overflow.
         const int* overflow = nullptr;
@@ -258,7 +241,7 @@ extern "C" SVOX2_API int svox2_volume_render_cuvol_fused(
             return check_launch(__func__);
         }
     }
-    if (!use_bg && !use_v1()) {
+    if (!use_bg) {
         // single launch: forward pass, gradient seed and backward pass inside one warp per ray.
         // Whatever workspace lies beyond the per-ray scalars is used as the forward->backward
         // colour cache (16 B per active sample); samples beyond a ray's share are re-gathered.
