@@ -284,6 +284,15 @@ SVOX2_API int svox2_slab_backward(const svox2_grid_t* grid, int64_t n_rays,
                      const float* accum_start, float sparsity_loss, const svox2_grads_t* grads,
                      void* workspace, size_t workspace_bytes, svox2_stream_t stream);
 
+/* svox2_peer_store: copies [src, src+n_bytes) to base_p + dst_offset_bytes for every p, where
+ * base_p are n_peers device pointers mapped into this process (symmetric / peer memory over
+ * NVLink).  One launch = this rank's contribution to an all-gather; the caller provides the
+ * cross-GPU barrier before the gathered buffer is read. */
+#define SVOX2_MAX_PEERS 16
+SVOX2_API int svox2_peer_store(const uint64_t* peer_base_ptrs, int32_t n_peers,
+                     int64_t dst_offset_bytes, const void* src, int64_t n_bytes,
+                     svox2_stream_t stream);
+
 /* per-ray glue between the slab calls (one thread per ray; all arrays of the all-gathers are
  * [n_slabs, Q(, 4)]): lt_in = prefix of logT over the slabs before `rank` in ray order;
  * combine = total colour (+ background term unless stopped), gout = (rgb - rgb_gt) * 2/(3Q),

@@ -108,6 +108,7 @@ SIGNATURES = {
     "svox2_slab_backward": (C.c_int, [_G, _I64, _O, _P, _P, _P, _F, _GR, _P, _SZ, _P]),
     "svox2_pack_grad_rows": (C.c_int, [_P, _I64, _I32, _P, _I64, _P, _I64, _P, _I64, _P, _P, _P]),
     "svox2_unpack_rows": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I32, _P, _I64, _I32, _P, _P, _P]),
+    "svox2_peer_store": (C.c_int, [_P, _I32, _I64, _P, _I64, _P]),
     "svox2_slab_prefix": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P]),
     "svox2_slab_combine": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _F, _F, _P, _P, _P, _P]),
     "svox2_rmsprop_step_packed": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _I64, _P, _I64, _P, _I64, _P, _P,

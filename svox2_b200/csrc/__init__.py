@@ -715,3 +715,13 @@ def slab_backward(grid, n_rays, opt, lt_in, gout, accum_start, sparsity_loss, gr
             C.byref(g), int(n_rays), C.byref(o), lt_in.data_ptr(), gout.data_ptr(),
             accum_start.data_ptr(), float(sparsity_loss), C.byref(gr), workspace.data_ptr(),
             workspace.numel(), _stream()))
+
+
+def peer_store(peer_ptrs, dst_offset_bytes, src):
+    """src -> (base + dst_offset_bytes) of every peer buffer (list of device pointers mapped into
+    this process, e.g. torch symmetric memory ``buffer_ptrs``); one launch, NVLink P2P stores."""
+    _check_input(src, "src")
+    arr = (C.c_uint64 * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+    with torch.cuda.device(src.device):
+        check(_lib.lib().svox2_peer_store(C.addressof(arr), len(peer_ptrs), int(dst_offset_bytes),
+                                          src.data_ptr(), src.numel() * src.element_size(), _stream()))

@@ -179,6 +179,26 @@ __global__ void slab_combine_kernel(const float* __restrict__ part_all /*[G,Q,4]
     accum_start[q] = accum;
 }
 
+// ---- peer stores over NVLink (symmetric memory): all-gather without a collective library ------
+// Every rank owns a buffer of identical layout; the base pointers of all ranks' buffers are mapped
+// into every process (torch symmetric memory).  One launch copies this rank's slice into the same
+// slot of EVERY rank's buffer with plain 128-bit stores (NVLink P2P writes); a device-side barrier
+// (the caller's) then makes the gathered array readable everywhere.  20 B per ray per rank: the
+// cost is two kernel launches, not a collective.
+struct PeerPtrs {
+    float* base[SVOX2_MAX_PEERS];
+    int n;
+};
+
+__global__ void __launch_bounds__(256)
+peer_store_kernel(PeerPtrs peers, int64_t dst_off4, const float4* __restrict__ src, int64_t n4) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = __ldg(src + i);
+        for (int p = 0; p < peers.n; ++p) reinterpret_cast<float4*>(peers.base[p])[dst_off4 + i] = v;
+    }
+}
+
 struct PackedOptArgs {
     float* __restrict__ sh_data;
     float* __restrict__ sh_rms;
@@ -372,5 +392,27 @@ extern "C" SVOX2_API int svox2_slab_combine(const float* part_all, const float* 
     slab_combine_kernel<<<div_up(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(
         part_all, logT_all, dirs, rgb_gt, n_rays, n_slabs, rank, background_brightness,
         2.f / (float)(3 * (int)n_rays), beta_loss / (float)n_rays, rgb, gout, accum_start);
+    return check_launch(__func__);
+}
+
+extern "C" SVOX2_API int svox2_peer_store(const uint64_t* peer_base_ptrs, int32_t n_peers,
+                                          int64_t dst_offset_bytes, const void* src, int64_t n_bytes,
+                                          svox2_stream_t stream) {
+    SVOX2_REQUIRE(n_bytes >= 0 && n_peers >= 0 && n_peers <= SVOX2_MAX_PEERS, "bad peer count / size");
+    if (n_bytes == 0 || n_peers == 0) return SVOX2_OK;
+    SVOX2_REQUIRE(peer_base_ptrs && src, "null argument");
+    SVOX2_REQUIRE(n_bytes % 16 == 0 && dst_offset_bytes % 16 == 0 && dst_offset_bytes >= 0 &&
+                      aligned16(src),
+                  "sizes, offsets and src must be 16-byte aligned");
+    PeerPtrs peers;
+    peers.n = n_peers;
+    for (int p = 0; p < n_peers; ++p) {
+        SVOX2_REQUIRE(peer_base_ptrs[p] != 0 && peer_base_ptrs[p] % 16 == 0, "bad peer pointer");
+        peers.base[p] = reinterpret_cast<float*>(peer_base_ptrs[p]);
+    }
+    const int64_t n4 = n_bytes / 16;
+    const int64_t want = (n4 + 255) / 256;
+    peer_store_kernel<<<(unsigned)(want < 148 * 4 ? want : 148 * 4), 256, 0, (cudaStream_t)stream>>>(
+        peers, dst_offset_bytes / 16, static_cast<const float4*>(src), n4);
     return check_launch(__func__);
 }

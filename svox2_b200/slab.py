@@ -26,6 +26,8 @@ per-slab partial sums instead of one sequential sum (~1e-7 relative), covered by
 """
 from typing import List, Optional
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -45,6 +47,50 @@ def balanced_slabs(links: torch.Tensor, world_size: int) -> List[int]:
         bounds.append(min(max(b, bounds[-1] + 1), X - (world_size - k)))
     bounds.append(X)
     return bounds
+
+
+class PeerMemory:
+    """One symmetric buffer per rank, all of them mapped into every process (torch symmetric
+    memory over NVLink).  Exchanges become: a kernel that stores into the peers' buffers, a
+    device-side barrier, a kernel that reads the local buffer -- no collective library call.
+
+    Layout (floats; identical on every rank): A [G,Q] | B [G,Q,4] | halo packets received from the
+    left neighbour [H,32] | from the right neighbour [H,32]."""
+
+    WIDTH = 32
+
+    def __init__(self, group, world_size: int, rank: int, device, n_rays: int, halo_rows: int):
+        import torch.distributed._symmetric_memory as symm
+        G, Q = world_size, n_rays
+        self.world_size, self.rank, self.n_rays = G, rank, Q
+        self.off_a, self.off_b = 0, G * Q
+        self.off_hl = self.off_b + G * Q * 4
+        self.off_hr = self.off_hl + halo_rows * self.WIDTH
+        total = self.off_hr + halo_rows * self.WIDTH
+        self.buf = symm.empty(total, dtype=torch.float32, device=device)
+        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.buf.zero_()
+        torch.cuda.synchronize()
+        self.hdl.barrier(channel=0)
+
+    def all_gather(self, local: torch.Tensor, region: str) -> torch.Tensor:
+        """local [Q] (region "a") or [Q,4] (region "b") -> [G,Q(,4)] of every rank."""
+        G, Q = self.world_size, self.n_rays
+        off, per = (self.off_a, Q) if region == "a" else (self.off_b, Q * 4)
+        _C.peer_store(self.ptrs, (off + self.rank * per) * 4, local)
+        self.hdl.barrier(channel=1 if region == "a" else 2)
+        view = self.buf[off:off + G * per]
+        return view.view(G, Q) if region == "a" else view.view(G, Q, 4)
+
+    def neighbour_inbox(self, peer: int, from_left: bool, rows: int) -> torch.Tensor:
+        """The [rows,32] region of ``peer``'s buffer that receives packets from its left / right."""
+        off = self.off_hl if from_left else self.off_hr
+        return self.hdl.get_buffer(peer, (rows, self.WIDTH), torch.float32, off)
+
+    def inbox(self, from_left: bool, rows: int) -> torch.Tensor:
+        off = self.off_hl if from_left else self.off_hr
+        return self.buf[off:off + rows * self.WIDTH].view(rows, self.WIDTH)
 
 
 class SlabTrainer:
@@ -77,6 +123,8 @@ class SlabTrainer:
         if self.halo_right is not None:
             self.own_mask[self.halo_right] = True
         self._ws = None
+        self._peer = None          # PeerMemory for the current batch size, False if unavailable
+        self.use_peer_memory = os.environ.get("SVOX2_B200_PEER", "1") != "0"
         self._steps = 0
         # clear + trace, prefix, shade, combine, seed + scatter, TV x2, halo pack/unpack, optimiser x2
         self.kernels_per_step = 2 + 1 + 1 + 1 + 2 + (lambda_tv > 0) + (lambda_tv_sh > 0) + 2 + 2
@@ -95,10 +143,30 @@ class SlabTrainer:
             self._ws = ((n_rays, slots), _C.slab_workspace(n_rays, slots, g.links.device))
         return self._ws[1]
 
-    def _gather(self, t: torch.Tensor) -> torch.Tensor:
+    def _peer_memory(self, n_rays: int):
+        """Symmetric-memory exchange buffers for this batch size, or None (-> NCCL collectives)."""
+        if self.world_size == 1 or not self.use_peer_memory or n_rays % 4 != 0:
+            return None
+        if self._peer is None or (self._peer is not False and self._peer.n_rays != n_rays):
+            try:
+                halo = torch.tensor([max([h.numel() for h in (self.halo_left, self.halo_right)
+                                          if h is not None] + [1])], device=self.grid.links.device)
+                dist.all_reduce(halo, op=dist.ReduceOp.MAX, group=self.group)
+                self._peer = PeerMemory(self.group, self.world_size, self.rank,
+                                        self.grid.links.device, n_rays, int(halo.item()))
+            except Exception as e:      # no symmetric-memory support on this system / build
+                if self.rank == 0:
+                    print(f"SlabTrainer: peer memory unavailable ({type(e).__name__}: {e}); using NCCL")
+                self._peer = False
+        return self._peer or None
+
+    def _gather(self, t: torch.Tensor, region: str) -> torch.Tensor:
         """[G, *t.shape]: t of every rank (this rank's own row is t itself)."""
         if self.world_size == 1:
             return t.unsqueeze(0)
+        peer = self._peer_memory(t.size(0))
+        if peer is not None:
+            return peer.all_gather(t, region)
         out = torch.empty((self.world_size,) + tuple(t.shape), dtype=t.dtype, device=t.device)
         dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
         return out
@@ -150,7 +218,7 @@ class SlabTrainer:
         logT_local = torch.empty(Q, dtype=torch.float32, device=dev)
         _C.slab_trace(spec, rspec, ropt, self.x_lo, self.x_hi, logT_local, ws)
         self._mark("trace")
-        logT_all = self._gather(logT_local)                                   # exchange A
+        logT_all = self._gather(logT_local, "a")                                 # exchange A
         lt_in = torch.empty(Q, dtype=torch.float32, device=dev)
         _C.slab_prefix(logT_all, rays.dirs, self.rank, lt_in)
         self._mark("exchange_a")
@@ -159,7 +227,7 @@ class SlabTrainer:
         part = torch.zeros((Q, 4), dtype=torch.float32, device=dev)          # rgb, stop flag
         _C.slab_shade(spec, Q, ropt, lt_in, part, ws)
         self._mark("shade")
-        part_all = self._gather(part)                                         # exchange B
+        part_all = self._gather(part, "b")                                       # exchange B
         rgb = torch.empty((Q, 3), dtype=torch.float32, device=dev)
         gout = torch.empty((Q, 3), dtype=torch.float32, device=dev)
         accum_start = torch.empty(Q, dtype=torch.float32, device=dev)
@@ -213,6 +281,25 @@ class SlabTrainer:
         gsh, gd = g.sh_data.grad, g.density_data.grad
         md, msh = g.sparse_grad_indexer, g.sparse_sh_grad_indexer
         width = _C.packed_row_floats(gsh.size(1) + 2)
+        peer = self._peer if (self._peer not in (None, False)) else None
+        if peer is not None and width == peer.WIDTH:
+            # pack straight into the neighbour's inbox (NVLink stores), barrier, add my inbox
+            if self.halo_right is not None and self.halo_right.numel():
+                _C.pack_grad_rows(gsh, gd, self.halo_right,
+                                  peer.neighbour_inbox(self.rank + 1, True, self.halo_right.numel()),
+                                  mask_a=md, mask_b=msh)
+            if self.halo_left is not None and self.halo_left.numel():
+                _C.pack_grad_rows(gsh, gd, self.halo_left,
+                                  peer.neighbour_inbox(self.rank - 1, False, self.halo_left.numel()),
+                                  mask_a=md, mask_b=msh)
+            peer.hdl.barrier(channel=3)
+            if self.halo_left is not None and self.halo_left.numel():
+                _C.unpack_rows(peer.inbox(True, self.halo_left.numel()), self.halo_left, gsh, gd, True,
+                               mask_a=md, mask_b=msh)
+            if self.halo_right is not None and self.halo_right.numel():
+                _C.unpack_rows(peer.inbox(False, self.halo_right.numel()), self.halo_right, gsh, gd, True,
+                               mask_a=md, mask_b=msh)
+            return
         ops, todo = [], []
         for rows, peer in ((self.halo_right, self.rank + 1), (self.halo_left, self.rank - 1)):
             if rows is None or rows.numel() == 0:
