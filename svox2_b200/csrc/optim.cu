@@ -131,13 +131,10 @@ masked_rows_kernel(OptArgs a) {
 #ifndef OPT_VEC_BLOCKS
 #define OPT_VEC_BLOCKS 16
 #endif
-#ifndef OPT_SUPER_N
-#define OPT_SUPER_N 512
-#endif
 #ifndef OPT_VEC_GRID_CAP
 #define OPT_VEC_GRID_CAP 0   // persistent CTAs per SM (0: one CTA per 8 super-chunks, not capped)
 #endif
-constexpr int OPT_SUPER = OPT_SUPER_N;  // rows scanned per warp step
+constexpr int OPT_SUPER = 512;  // rows scanned per warp step
 template <bool RMS>
 __global__ void __launch_bounds__(OPT_THREADS, OPT_VEC_BLOCKS)
 masked_rows_vec_kernel(OptArgs a, int qpr) {
@@ -160,12 +157,6 @@ masked_rows_vec_kernel(OptArgs a, int qpr) {
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const bool mask_al = (reinterpret_cast<uintptr_t>(a.mask) & 15u) == 0;
     for (int64_t sc = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; sc < nsuper; sc += nwarps) {
-#if OPT_SUPER_N == 32
-        const int64_t my_row = sc * OPT_SUPER + lane;
-        const uint32_t h = (my_row < a.rows && __ldg(a.mask + my_row) != 0) ? 1u : 0u;
-        const unsigned m32 = __ballot_sync(FULL, h != 0u);
-        if (m32 == 0u) continue;
-#else
         const int64_t base = sc * OPT_SUPER + lane * 16;
         uint32_t w[4] = {0u, 0u, 0u, 0u};
         if (mask_al && base + 16 <= a.rows) {
@@ -183,14 +174,9 @@ masked_rows_vec_kernel(OptArgs a, int qpr) {
             const uint32_t nz = __vcmpne4(w[i], 0u) & 0x01010101u;
             h |= (((nz * 0x01020408u) >> 24) & 0xfu) << (4 * i);
         }
-#endif
 #pragma unroll 1
         for (int c = 0; c < OPT_SUPER / WARP; ++c) {
-#if OPT_SUPER_N == 32
-        unsigned m = m32;
-#else
         unsigned m = __shfl_sync(FULL, h, 2 * c) | (__shfl_sync(FULL, h, 2 * c + 1) << 16);
-#endif
         const int64_t row0 = sc * OPT_SUPER + c * WARP;
         while (m) {
             // pop the next U*rpp touched rows in address order; group g of pass u keeps row g + u*rpp

@@ -16,10 +16,12 @@
 //   K3 seed    (warp per ray)    MSE/beta seed from the ray's final colour, then the reference's
 //                                accum recursion over the ray's records (a warp scan per block);
 //                                leaves dL/dcolour and dL/dsigma in each record.
-//   K4 scatter (8 lanes/sample)  red.global.add.v4.f32 into grad_sh, density atomics, mask bytes.
+//   K4 scatter (8 lanes/run)     each 8-lane group walks a contiguous run of records, merges
+//                                consecutive samples that share a cell, then red.global.add.v4.f32
+//                                into grad_sh, density atomics, mask bytes.
 //
-// K2 and K4 are perfectly load balanced (grid-stride over the queue) and expose one independent
-// gather/scatter per 8 lanes.  If the queue overflows its workspace a device flag makes K2-K4
+// K2 and K4 are load balanced over the queue (equal record counts per group) and expose one
+// independent gather/scatter per 8 lanes.  If the queue overflows its workspace a device flag makes K2-K4
 // no-ops and the single-kernel lattice path (march.cu) redoes the batch, so correctness never
 // depends on the workspace size.
 //
@@ -32,18 +34,12 @@ namespace svox2b {
 namespace {
 
 // Tunables (A/B on B200, profiles/r1_ab_variants.txt)
-#ifndef QM_PREFETCH_SH
-#define QM_PREFETCH_SH 0   // prefetching SH rows from K1 only evicts them again before K2 runs
-#endif
 #ifndef QM_SAMPLE_CTAS
 #define QM_SAMPLE_CTAS 16  // persistent CTAs per SM for the sample-parallel kernels
 #endif
 
 #ifndef QM_GATHER_AHEAD
-#define QM_GATHER_AHEAD 3  // bit 0: K2, bit 1: K4 prefetch the rows of the group's NEXT record to L2
-#endif
-#ifndef QM_SCATTER_SPAN
-#define QM_SCATTER_SPAN 1  // K4 walks contiguous record runs and merges same-cell samples
+#define QM_GATHER_AHEAD 1  // K2 prefetches the rows of the group's NEXT record to L2
 #endif
 #ifndef QM_TRACE_BLOCKS
 #define QM_TRACE_BLOCKS 16
@@ -233,17 +229,6 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
             const float ws = (opt.last_sample_opaque && __fadd_rn(tk, step) > ray.tmax) ? 1e9f
                                                                                        : ray.world_step;
             const bool active = member && (sigma > opt.sigma_thresh);
-#if QM_PREFETCH_SH
-            if (active) {  // pull the rows K2 will gather towards L2
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    if (lk[q] >= 0) {
-                        const float* row = g.sh + (int64_t)lk[q] * g.sh_stride;
-                        prefetch_l2(row);
-                        prefetch_l2(row + (g.sh_dim - 1));
-                    }
-            }
-#endif
             const float pcnt = __fmul_rn(ws, sigma);
             unsigned act_m = __ballot_sync(FULL, active);
             float my_before = 0.f;
@@ -527,79 +512,15 @@ seed_kernel(Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
 }
 
 // ---------------------------------------------------------------------------------------
-// K4: scatter, 8 lanes per sample
+// K4: scatter, 8 lanes per contiguous run of records
 // ---------------------------------------------------------------------------------------
-template <bool VEC, bool SLAB>
-__global__ void __launch_bounds__(SAMPLE_THREADS)
-scatter_kernel(GridView g, QueueView qv, GradView gr, int64_t gsh_stride, int64_t gd_stride) {
-    if (*qv.overflow) return;
-    const int n = min(*qv.counter, qv.capacity);
-    const int qi = threadIdx.x & 7;
-    const int D = g.sh_dim, B = g.basis_dim;
-    int ce[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) ce[e] = (qi * 4 + e < D) ? (qi * 4 + e) / B : -1;
-    const bool quad_on = qi * 4 < D;
-    const int groups = (gridDim.x * blockDim.x) >> 3;
-    for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; s < n; s += groups) {
-        const Record* r = qv.rec + s;
-#if QM_GATHER_AHEAD & 2
-        if (s + groups < n) {
-            const int32_t ln = __ldcg(&qv.rec[s + groups].lk[qi]);
-            if (ln >= 0) {
-                const float* row = gr.grad_sh + (int64_t)ln * gsh_stride;
-                prefetch_l2(row);
-                prefetch_l2(row + (D - 1));
-                prefetch_l2(gr.grad_density + (int64_t)ln * gd_stride);
-            }
-        }
-#endif
-        const int4 la = __ldcg(reinterpret_cast<const int4*>(r));
-        const int4 lb = __ldcg(reinterpret_cast<const int4*>(r) + 1);
-        const float4 pw = __ldcg(reinterpret_cast<const float4*>(r) + 2);
-        const float4 gg = __ldcg(reinterpret_cast<const float4*>(r) + 4);
-        const int ray = __ldcg(&r->ray);
-        if (SLAB && pw.w < 0.f) continue;  // dead sample
-        const int32_t L[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
-        const float4 Y = __ldcg(qv.ray_Y + (int64_t)ray * 8 + qi);
-        float wq[8];
-        corner_weights(pw.x, pw.y, pw.z, wq);
-        const float gcs[3] = {gg.x, gg.y, gg.z};
-        const float Ye[4] = {Y.x, Y.y, Y.z, Y.w};
-        float ge[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float gsel = ce[e] == 0 ? gcs[0] : (ce[e] == 1 ? gcs[1] : (ce[e] == 2 ? gcs[2] : 0.f));
-            ge[e] = Ye[e] * gsel;
-        }
-        if (quad_on) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-                if (L[q] >= 0)
-                    red_quad<VEC>(gr.grad_sh + (int64_t)L[q] * gsh_stride + 4 * qi, qi, D, wq[q] * ge[0],
-                                  wq[q] * ge[1], wq[q] * ge[2], wq[q] * ge[3]);
-        }
-        int32_t Lown = L[0];
-        float wown = wq[0];
-#pragma unroll
-        for (int q = 1; q < 8; ++q) {
-            Lown = (qi == q) ? L[q] : Lown;
-            wown = (qi == q) ? wq[q] : wown;
-        }
-        if (Lown >= 0) {
-            atomicAdd(gr.grad_density + (int64_t)Lown * gd_stride, wown * gg.w);
-            if (gr.mask) gr.mask[Lown] = 1;
-        }
-    }
-}
-
-// K4, span form: every 8-lane group walks a CONTIGUOUS run of records (consecutive samples of a
+// Every 8-lane group walks a CONTIGUOUS run of records (consecutive samples of a
 // ray lie next to each other in the queue) and keeps the gradient of the current cell in
 // registers; consecutive samples that fall into the same cell (~35 % at step 0.5) are merged
 // before the REDs leave the SM.  The basis table of the ray is re-read only when the ray changes.
 template <bool VEC, bool SLAB>
 __global__ void __launch_bounds__(SAMPLE_THREADS)
-scatter_span_kernel(GridView g, QueueView qv, GradView gr, int64_t gsh_stride, int64_t gd_stride) {
+scatter_kernel(GridView g, QueueView qv, GradView gr, int64_t gsh_stride, int64_t gd_stride) {
     if (*qv.overflow) return;
     const int n = min(*qv.counter, qv.capacity);
     const int qi = threadIdx.x & 7;
@@ -748,13 +669,8 @@ bool launch_queue_fused(const GridView& g, const Opts& opt, const MarchArgs& a, 
     if (vec) shade_kernel<true, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, a.rgb_out, none);
     else shade_kernel<false, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, a.rgb_out, none);
     seed_kernel<false><<<ray_blocks, TRACE_THREADS, 0, st>>>(opt, a, qv, none);
-#if QM_SCATTER_SPAN
-    if (vec) scatter_span_kernel<true, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride);
-    else scatter_span_kernel<false, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride);
-#else
     if (vec) scatter_kernel<true, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride);
     else scatter_kernel<false, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride);
-#endif
     return true;
 }
 
@@ -803,17 +719,10 @@ bool launch_slab_backward(const GridView& g, const Opts& opt, const MarchArgs& a
     sl.stop_thresh = opt.stop_thresh;
     seed_kernel<true><<<div_up(a.n_rays * WARP, TRACE_THREADS), TRACE_THREADS, 0, st>>>(opt, a, qv, sl);
     const unsigned sblocks = 148 * QM_SAMPLE_CTAS;
-#if QM_SCATTER_SPAN
-    if (march_vec_ok(g, &gr, a.gsh_stride))
-        scatter_span_kernel<true, true><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride);
-    else
-        scatter_span_kernel<false, true><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride);
-#else
     if (march_vec_ok(g, &gr, a.gsh_stride))
         scatter_kernel<true, true><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride);
     else
         scatter_kernel<false, true><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride);
-#endif
     return true;
 }
 
