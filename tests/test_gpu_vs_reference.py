@@ -8,7 +8,7 @@ import torch
 
 import svox2_b200 as sv
 from gpu_helpers import make_grid, set_opt, t
-from scenes import make_scene, rel_err
+from scenes import frac_bad, make_scene, rel_err
 from test_gpu_parity import CASES, OPTS, SCENES, _cam
 
 pytestmark = pytest.mark.gpu
@@ -214,3 +214,36 @@ def test_train_steps_vs_reference_cuda(ref_svox2):
     ds = (ours.sh_data - ref.sh_data).abs().flatten()
     assert torch.quantile(dd[:1000000], 0.999).item() < 1e-2 * ref.density_data.abs().max().item()
     assert torch.quantile(ds[:1000000], 0.999).item() < 1e-2 * ref.sh_data.abs().max().item()
+
+
+def test_config_c1_vs_reference_pytorch_cpu_renderer(ref_svox2):
+    """BASELINE.json configs[0]: SparseGrid 128^3 dense, basis_dim 9, the reference's pure-PyTorch
+    lerp renderer + autograd on CPU (volume_render(use_kernel=False)) vs our CUDA path on the same
+    grid and rays: colours and the MSE gradients (a ray subset keeps the CPU side to seconds)."""
+    gen = torch.Generator().manual_seed(1234)
+    ref = ref_svox2.SparseGrid(reso=128, basis_dim=9, use_z_order=False, use_sphere_bound=False, device="cpu")
+    with torch.no_grad():
+        ref.sh_data[:] = torch.randn(ref.sh_data.shape, generator=gen) * 0.1
+        ref.sh_data[:, ::9] = 0.5
+        ref.density_data[:] = torch.rand(ref.density_data.shape, generator=gen) * 2
+    ours = sv.SparseGrid(reso=128, basis_dim=9, use_z_order=False, use_sphere_bound=False, device="cuda")
+    assert torch.equal(ours.links.cpu(), ref.links)
+    with torch.no_grad():
+        ours.sh_data.data.copy_(ref.sh_data.data.cuda())
+        ours.density_data.data.copy_(ref.density_data.data.cuda())
+    for g in (ref, ours):
+        g.opt.step_size, g.opt.sigma_thresh, g.opt.stop_thresh, g.opt.background_brightness = 0.5, 1e-8, 1e-7, 1.0
+    n = 192
+    v = torch.nn.functional.normalize(torch.randn(n, 3, generator=gen), dim=-1)
+    origins = v * 2.687
+    dirs = torch.nn.functional.normalize(torch.rand(n, 3, generator=gen) - 0.5 - origins, dim=-1)
+    gt = torch.rand(n, 3, generator=gen)
+    rgb_r = ref.volume_render(ref_svox2.Rays(origins, dirs), use_kernel=False)
+    torch.nn.functional.mse_loss(rgb_r, gt).backward()
+    rgb_o = ours.volume_render_fused(sv.Rays(origins.cuda(), dirs.cuda()), gt.cuda())
+    assert (rgb_o.cpu() - rgb_r.detach()).abs().max().item() < 1e-4
+    gd_r, gsh_r = ref.density_data.grad.numpy(), ref.sh_data.grad.numpy()
+    assert frac_bad(ours.density_data.grad.cpu().numpy(), gd_r) < 1e-4
+    assert frac_bad(ours.sh_data.grad.cpu().numpy(), gsh_r) < 1e-4
+    touched = torch.from_numpy((np.abs(gsh_r).sum(1) > 0) | (np.abs(gd_r[:, 0]) > 0))
+    assert not bool((touched & ~ours.sparse_grad_indexer.cpu()).any())
