@@ -175,3 +175,34 @@ def test_checkpoint_interop_with_reference(ref_svox2, tmp_path, background):
     assert torch.equal(back.links, ours.links) and back.basis_dim == ours.basis_dim
     assert torch.equal(back.sh_data.data, theirs.sh_data.data)
     assert back.use_background == background
+
+
+def test_slab_partition_host_logic():
+    """SlabTrainer's partition of rows, halo planes and the TV cell run (no GPU work involved)."""
+    from svox2_b200.slab import SlabTrainer, balanced_slabs
+    g = sv.SparseGrid(reso=[24, 10, 12], basis_dim=1, use_sphere_bound=True, device="cpu")
+    N = g.density_data.size(0)
+    for G in (1, 2, 3, 5):
+        bounds = balanced_slabs(g.links, G)
+        assert bounds[0] == 0 and bounds[-1] == 24 and all(bounds[i] < bounds[i + 1] for i in range(G))
+        trainers = [SlabTrainer(g, world_size=G, rank=r, bounds=bounds) for r in range(G)]
+        excl = torch.stack([t_.excl_mask for t_ in trainers]).sum(0)
+        assert torch.equal(excl, torch.ones(N, dtype=excl.dtype))           # every row has one owner
+        for r in range(G - 1):                                               # neighbours agree on the plane
+            assert torch.equal(trainers[r].halo_right, trainers[r + 1].halo_left)
+            co_owned = trainers[r].own_mask & trainers[r + 1].own_mask
+            assert int(co_owned.sum()) == trainers[r].halo_right.numel()
+        assert trainers[0].halo_left is None and trainers[-1].halo_right is None
+        # the wrapped TV run is split without gaps or overlaps
+        total = 24 * 10 * 12
+        for seed in range(4):
+            cells = []
+            for t_ in trainers:
+                np.random.seed(seed)
+                runs, n = t_._tv_runs()
+                for a, c in runs:
+                    cells.append(np.arange(a, a + c))
+            np.random.seed(seed)
+            start, n = g._draw_cell_run(trainers[0].tv_sparsity)
+            want = np.sort((start + np.arange(n)) % total)
+            assert np.array_equal(np.sort(np.concatenate(cells)), want)
