@@ -445,36 +445,78 @@ def run_ours(args):
 # ----------------------------------------------------------------------------------------------
 # baselines
 # ----------------------------------------------------------------------------------------------
-def cpu_port_baseline(sc, grid, batch, budget_rays=1024):
-    """The oracle (a C port of the reference algorithm) timed on the host cores on a bounded
-    sample of the SAME workload: the first `budget_rays` rays of batch 0, fused fwd+bwd."""
-    import oracle as og
-    links = grid.links.cpu().numpy()
-    g = og.Grid(links, sc["density"].cpu().numpy(), sc["sh"].cpu().numpy(),
-                (grid._offset * grid._grid_size() - 0.5).numpy(),
-                (grid._scaling * grid._grid_size()).numpy())
-    opt = og.make_opt(**RENDER)
-    o, d, gt = (x[:budget_rays].cpu().numpy() for x in batch)
-    cores = os.cpu_count() or 1
-    og.set_num_threads(cores)
-    og.set_accum_float(True)
-    gd = np.zeros(g.density.shape[0], np.float32)
-    gsh = np.zeros(g.sh.shape, np.float32)
-    mask = np.zeros(g.density.shape[0], np.uint8)
-    rgb = np.zeros((o.shape[0], 3), np.float32)
-    import ctypes as CT
-    gc, cnt = g.c(), og._Counts()
+class CpuPortStep:
+    """One train step of the reference ALGORITHM on the host cores: the oracle's C port (pthreads
+    over rays / cells / rows) of the fused fwd+bwd march, the sparse TV on a contiguous cell run
+    and the masked RMSProp, on `sample` rays.  The TV cell count is scaled by sample/BATCH so
+    that the per-ray cost is that of a whole step (opt.py:474-603)."""
+
+    def __init__(self, sc, links, sample):
+        import ctypes as CT
+        import oracle as og
+        self.og, self.CT, self.sample = og, CT, sample
+        gsz = float(sc["reso"])
+        self.links = np.ascontiguousarray(links, np.int32)
+        self.g = og.Grid(self.links, sc["density"].cpu().numpy(), sc["sh"].cpu().numpy(),
+                         np.full(3, 0.5 * gsz - 0.5, np.float32), np.full(3, 0.5 * gsz, np.float32))
+        self.opt = og.make_opt(**RENDER)
+        self.cores = os.cpu_count() or 1
+        og.set_num_threads(self.cores)
+        og.set_accum_float(True)
+        n = self.g.density.shape[0]
+        self.gd, self.gsh = np.zeros(n, np.float32), np.zeros(self.g.sh.shape, np.float32)
+        self.drms, self.shrms = np.zeros_like(self.g.density), np.zeros_like(self.g.sh)
+        self.mask = np.zeros(n, np.uint8)
+        self.rng = np.random.default_rng(0)
+        self.total_cells = int(np.prod(self.links.shape))
+        self.n_tv = max(int(SYN["tv_sparsity"] * self.total_cells * sample / BATCH), 1)
+        self.gc, self.cnt = self.g.c(), og._Counts()
+
+    def __call__(self, o, d, gt):
+        og, CT, L, g = self.og, self.CT, self.og.lib(), self.g
+        X, Y, Z = self.links.shape
+        rgb = np.zeros_like(o)
+        L.og_volume_render_fused(CT.byref(self.gc), CT.byref(self.opt), og._ptr(o), og._ptr(d),
+                                 CT.c_int64(o.shape[0]), CT.c_int64(o.shape[0]), og._ptr(gt),
+                                 CT.c_float(0.0), CT.c_float(0.0), og._ptr(rgb), og._ptr(self.gd),
+                                 og._ptr(self.gsh), None, og._ptr(self.mask), None, CT.byref(self.cnt))
+        for data, ch, grad, lam in ((g.density, 1, self.gd, SYN["lambda_tv"]),
+                                    (g.sh, g.sh.shape[1], self.gsh, SYN["lambda_tv_sh"])):
+            start = int(self.rng.integers(0, self.total_cells))
+            cells = np.ascontiguousarray((np.arange(start, start + self.n_tv, dtype=np.int64)
+                                          % self.total_cells).astype(np.int32))
+            L.og_tv_grad_sparse(og._ptr(self.links), X, Y, Z, og._ptr(data), ch, og._ptr(cells),
+                                CT.c_int64(self.n_tv), og._ptr(self.mask), 0, ch, CT.c_float(lam), 0, 0,
+                                og._ptr(grad))
+        for data, rms, ch, grad, lr in ((g.density, self.drms, 1, self.gd, SYN["lr_sigma"]),
+                                        (g.sh, self.shrms, g.sh.shape[1], self.gsh, SYN["lr_sh"])):
+            L.og_rmsprop_step(og._ptr(data), og._ptr(rms), og._ptr(grad), CT.c_int64(self.mask.shape[0]),
+                              ch, 1, og._ptr(self.mask), None, CT.c_int64(0), CT.c_float(SYN["rms_beta"]),
+                              CT.c_float(lr), CT.c_float(1e-8), CT.c_float(-1e9), CT.c_float(lr))
+        self.mask[:] = 0
+
+    def close(self):
+        self.og.set_num_threads(1)
+        self.og.set_accum_float(False)
+
+    def describe(self):
+        return (f"fused fwd+bwd march + sparse TV on {self.n_tv} cells x2 + masked RMSProp x2, oracle C "
+                f"port of the reference algorithm, {self.cores} pthreads")
+
+
+def cpu_port_baseline(sc, grid, batch, budget_rays=1024, reps=3):
+    """cpu_baseline of the N=1 line: CpuPortStep on the first `budget_rays` rays of batch 0."""
+    step = CpuPortStep(sc, grid.links.cpu().numpy(), budget_rays)
+    o, d, gt = (np.ascontiguousarray(x[:budget_rays].cpu().numpy()) for x in batch)
+    step(o, d, gt)                                   # warm-up (page faults of the 1.4 GB arrays)
     t = time.perf_counter()
-    og.lib().og_volume_render_fused(CT.byref(gc), CT.byref(opt), og._ptr(o), og._ptr(d),
-                                    CT.c_int64(o.shape[0]), CT.c_int64(o.shape[0]), og._ptr(gt),
-                                    CT.c_float(0.0), CT.c_float(0.0), og._ptr(rgb), og._ptr(gd),
-                                    og._ptr(gsh), None, og._ptr(mask), None, CT.byref(cnt))
-    dt = time.perf_counter() - t
-    og.set_num_threads(1)
-    og.set_accum_float(False)
-    return {"value": o.shape[0] / dt, "unit": "rays/s", "cores": cores, "kind": "port",
-            "sample": f"first {o.shape[0]} rays of batch 0, fused fwd+bwd march only "
-                      f"(no TV/optimiser), oracle C port, {cores} pthreads, {dt:.2f} s"}
+    for _ in range(reps):
+        step(o, d, gt)
+    dt = (time.perf_counter() - t) / reps
+    step.close()
+    return {"value": o.shape[0] / dt, "unit": "rays/s", "cores": step.cores, "kind": "port",
+            "sample": f"first {o.shape[0]} rays of batch 0, one whole step: {step.describe()}, "
+                      f"{dt:.2f} s per step"}
 
 
 def reference_cuda_baseline(sc, grid, batches, args, gq):
@@ -542,60 +584,19 @@ def run_reference(args):
     dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
     sc = build_scene(args.workload, dev)
     import oracle as og
-    links = og.accel_dist_prop(sc["links"].cpu().numpy())
-    gsz = float(sc["reso"])
-    g = og.Grid(links, sc["density"].cpu().numpy(), sc["sh"].cpu().numpy(),
-                np.full(3, 0.5 * gsz - 0.5, np.float32), np.full(3, 0.5 * gsz, np.float32))
-    opt = og.make_opt(**RENDER)
     world = args.gpus
     gq = BATCH * world
     origins, dirs = build_rays(POOL * gq, "cpu")
     sample = args.cpu_rays
-    cores = os.cpu_count() or 1
-    og.set_num_threads(cores)
-    og.set_accum_float(True)
-    gd = np.zeros(g.density.shape[0], np.float32)
-    gsh = np.zeros(g.sh.shape, np.float32)
-    mask = np.zeros(g.density.shape[0], np.uint8)
-    rng = np.random.default_rng(0)
-    import ctypes as CT
-    gc, cnt = g.c(), og._Counts()
-
-    # the rest of the step (opt.py:593-603): sparse TV on a contiguous cell run and masked RMSProp,
-    # cell count scaled to the ray sample so that the per-ray cost is that of a whole step
-    X, Y, Z = links.shape
-    total_cells = X * Y * Z
-    n_tv = max(int(SYN["tv_sparsity"] * total_cells * sample / BATCH), 1)
-    drms = np.zeros_like(g.density)
-    shrms = np.zeros_like(g.sh)
-    L = og.lib()
-
-    def tv_cells():
-        start = int(rng.integers(0, total_cells))
-        return np.ascontiguousarray((np.arange(start, start + n_tv, dtype=np.int64) % total_cells)
-                                    .astype(np.int32))
+    step = CpuPortStep(sc, og.accel_dist_prop(sc["links"].cpu().numpy()), sample)
+    cores, n_tv = step.cores, step.n_tv
+    rng = np.random.default_rng(1)
 
     def one(i):
         s = (i % POOL) * gq
         o = np.ascontiguousarray(origins[s:s + sample].numpy())
         d = np.ascontiguousarray(dirs[s:s + sample].numpy())
-        gt = rng.uniform(0, 1, o.shape).astype(np.float32)
-        rgb = np.zeros_like(o)
-        L.og_volume_render_fused(CT.byref(gc), CT.byref(opt), og._ptr(o), og._ptr(d),
-                                 CT.c_int64(sample), CT.c_int64(sample), og._ptr(gt),
-                                 CT.c_float(0.0), CT.c_float(0.0), og._ptr(rgb), og._ptr(gd),
-                                 og._ptr(gsh), None, og._ptr(mask), None, CT.byref(cnt))
-        for data, ch, grad, lam in ((g.density, 1, gd, SYN["lambda_tv"]), (g.sh, g.sh.shape[1], gsh, SYN["lambda_tv_sh"])):
-            cells = tv_cells()
-            L.og_tv_grad_sparse(og._ptr(links), X, Y, Z, og._ptr(data), ch, og._ptr(cells),
-                                CT.c_int64(n_tv), og._ptr(mask), 0, ch, CT.c_float(lam), 0, 0,
-                                og._ptr(grad))
-        for data, rms, ch, grad, lr in ((g.density, drms, 1, gd, SYN["lr_sigma"]),
-                                        (g.sh, shrms, g.sh.shape[1], gsh, SYN["lr_sh"])):
-            L.og_rmsprop_step(og._ptr(data), og._ptr(rms), og._ptr(grad), CT.c_int64(mask.shape[0]), ch,
-                              1, og._ptr(mask), None, CT.c_int64(0), CT.c_float(SYN["rms_beta"]),
-                              CT.c_float(lr), CT.c_float(1e-8), CT.c_float(-1e9), CT.c_float(lr))
-        mask[:] = 0
+        step(o, d, rng.uniform(0, 1, o.shape).astype(np.float32))
 
     for i in range(min(args.warmup, 1)):
         one(i)
