@@ -157,14 +157,18 @@ def time_images(render, cams, reps=3):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons, sampled every 20 ms in a side process.  nvidia-smi
+    needs ~0.1 s before its first line, longer than a short timed region, so it is started before
+    the warm-up; `mark()` brackets the timed region on the host clock and only samples whose
+    receive time falls inside are reported (all samples under load as a fallback, flagged)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.proc = None
-        self.lines = []
+        self.lines = []          # (host receive time, line)
+        self.t0 = self.t1 = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
@@ -177,7 +181,14 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark(self):
+        """Call right after the synchronising barrier at the start and at the end of the region."""
+        if self.t0 is None:
+            self.t0 = time.perf_counter()
+        else:
+            self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
@@ -187,23 +198,34 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            p = [x.strip() for x in ln.split(",")]
-            if len(p) < 6:
-                continue
-            try:
-                sm.append(float(p[0]))
-                mx.append(float(p[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, p[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
+
+        def digest(lines):
+            sm, mx, reasons = [], [], set()
+            for _, ln in lines:
+                p = [x.strip() for x in ln.split(",")]
+                if len(p) < 6:
+                    continue
+                try:
+                    sm.append(float(p[0]))
+                    mx.append(float(p[1]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, p[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            return sm, mx, reasons
+
+        inside = [x for x in self.lines if self.t0 is not None and self.t1 is not None and
+                  self.t0 <= x[0] <= self.t1 + 0.02]
+        sm, mx, reasons = digest(inside)
+        window = "timed region"
+        if not sm:      # region shorter than the sampling period: everything sampled under load
+            sm, mx, reasons = digest(self.lines)
+            window = "warm-up + timed region"
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def peaks():
@@ -290,10 +312,12 @@ def run_ours(args):
     torch.cuda.synchronize()
     cnt = [c / POOL for c in counters.cpu().tolist()]
 
+    sampler = ClockSampler(local) if rank == 0 else None
     for i in range(args.warmup):
         step(*batches[i % POOL])
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
@@ -325,6 +349,8 @@ def run_ours(args):
     t1.record()
     barrier()
     ms_e2e = t0.elapsed_time(t1)
+    if sampler:
+        sampler.mark()
     clocks = sampler.stop() if sampler else None
 
     phase_ms = None
@@ -661,8 +687,8 @@ def reference_pytorch_c1(n_rays):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
     ap.add_argument("--dist", default="slab", choices=["slab", "rays"],
