@@ -71,6 +71,9 @@ __device__ __forceinline__ void lane_const_init(LaneConst& lc, int lane, int B, 
 #ifndef LB_PREFETCH_LINKS
 #define LB_PREFETCH_LINKS 1   // prefetch the next batch's link lines during the current batch
 #endif
+#ifndef LB_LINKS_TWO_PHASE
+#define LB_LINKS_TWO_PHASE 1
+#endif
 #ifndef LB_MIN_BLOCKS_FWD
 #define LB_MIN_BLOCKS_FWD 16  // forward-only instantiations (image rendering is issue-bound)
 #endif
@@ -158,6 +161,22 @@ __device__ __forceinline__ void march_pass(const GridView& g, const Opts& opt, c
         float pos[3];
         locate(ray, g, tk, l, pos);
         const int32_t* lp = g.links + ((int64_t)l[0] * g.offx + (int64_t)l[1] * g.offy + l[2]);
+#if LB_LINKS_TWO_PHASE
+        // probe first (corner 0 decides skipping); a candidate in empty space stops there and
+        // leaves its other three link sectors alone (they would be 7/8 of the traffic of the
+        // ~17 rounds per ray that end in a skip); only non-skipping candidates pay the second trip
+        int32_t lk[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) lk[q] = -1;
+        if (valid) lk[0] = __ldg(lp);
+        const int32_t probe = valid ? lk[0] : 0;
+        const float skipd = skip_dist(ray, probe, l, pos);
+        const bool is_skip = valid && (skipd >= step);
+        if (valid && !is_skip) {
+#pragma unroll
+            for (int q = 1; q < 8; ++q) lk[q] = __ldg(lp + corner_off(g, q));
+        }
+#else
         // all 8 corner links at once: the probe (corner 0) decides skipping, the other 7 are
         // needed one dependent round trip later if the candidate turns out to be a sample
         int32_t lk[8];
@@ -170,6 +189,7 @@ __device__ __forceinline__ void march_pass(const GridView& g, const Opts& opt, c
         const int32_t probe = valid ? lk[0] : 0;
         const float skipd = skip_dist(ray, probe, l, pos);
         const bool is_skip = valid && (skipd >= step);
+#endif
         const unsigned valid_m = __ballot_sync(FULL, valid);
         const unsigned skip_m = __ballot_sync(FULL, is_skip);
 
