@@ -55,7 +55,7 @@ class PeerMemory:
     device-side barrier, a kernel that reads the local buffer -- no collective library call.
 
     Layout (floats; identical on every rank): A [G,Q] | B [G,Q,4] | halo packets received from the
-    left neighbour [H,32] | from the right neighbour [H,32]."""
+    left neighbour [H,32] | from the right neighbour [H,32] | row-0 packets [G,32]."""
 
     WIDTH = 32
 
@@ -66,7 +66,8 @@ class PeerMemory:
         self.off_a, self.off_b = 0, G * Q
         self.off_hl = self.off_b + G * Q * 4
         self.off_hr = self.off_hl + halo_rows * self.WIDTH
-        total = self.off_hr + halo_rows * self.WIDTH
+        self.off_z = self.off_hr + halo_rows * self.WIDTH      # [G, 32]: row-0 packets (see _row0_*)
+        total = self.off_z + G * self.WIDTH
         self.buf = symm.empty(total, dtype=torch.float32, device=device)
         self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
@@ -122,6 +123,10 @@ class SlabTrainer:
         self.excl_mask = self.own_mask.clone()          # exclusive ownership (gather_params)
         if self.halo_right is not None:
             self.own_mask[self.halo_right] = True
+        # Reference quirk: TV cells on the grid faces read row 0 for their out-of-range
+        # neighbour and add gradient / mask bits to it.  Such cells lie in every slab, row 0 in one.
+        self._row0 = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._holds_row0 = bool(self.own_mask[0].item()) if self.own_mask.numel() else True
         self._ws = None
         self._peer = None          # PeerMemory for the current batch size, False if unavailable
         self.use_peer_memory = os.environ.get("SVOX2_B200_PEER", "1") != "0"
@@ -282,7 +287,14 @@ class SlabTrainer:
         md, msh = g.sparse_grad_indexer, g.sparse_sh_grad_indexer
         width = _C.packed_row_floats(gsh.size(1) + 2)
         peer = self._peer if (self._peer not in (None, False)) else None
+        # row 0: ranks that do not hold it publish (and clear) what their face cells added to it
+        z = torch.zeros((1, width), dtype=torch.float32, device=gsh.device)
+        if not self._holds_row0:
+            _C.pack_grad_rows(gsh, gd, self._row0, z, mask_a=md, mask_b=msh)
+            gsh[0] = 0.0
+            gd[0] = 0.0
         if peer is not None and width == peer.WIDTH:
+            _C.peer_store(peer.ptrs, (peer.off_z + self.rank * width) * 4, z)
             # pack straight into the neighbour's inbox (NVLink stores), barrier, add my inbox
             if self.halo_right is not None and self.halo_right.numel():
                 _C.pack_grad_rows(gsh, gd, self.halo_right,
@@ -299,7 +311,13 @@ class SlabTrainer:
             if self.halo_right is not None and self.halo_right.numel():
                 _C.unpack_rows(peer.inbox(False, self.halo_right.numel()), self.halo_right, gsh, gd, True,
                                mask_a=md, mask_b=msh)
+            if self._holds_row0:
+                zs = peer.buf[peer.off_z:peer.off_z + self.world_size * width].view(self.world_size, width)
+                _C.unpack_rows(zs.sum(0, keepdim=True), self._row0, gsh, gd, True, mask_a=md, mask_b=msh)
             return
+        dist.all_reduce(z, op=dist.ReduceOp.SUM, group=self.group)
+        if self._holds_row0:
+            _C.unpack_rows(z, self._row0, gsh, gd, True, mask_a=md, mask_b=msh)
         ops, todo = [], []
         for rows, peer in ((self.halo_right, self.rank + 1), (self.halo_left, self.rank - 1)):
             if rows is None or rows.numel() == 0:

@@ -115,21 +115,22 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_two_gpu_slab_step_equals_single_gpu_step():
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+@pytest.mark.parametrize("world", [2, 4])
+def test_multi_gpu_slab_step_equals_single_gpu_step(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs (run under gpurun --gpus {world})")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     out = ctx.Manager().dict()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
         p.join(300)
         assert p.exitcode == 0
     res = dict(out)
-    assert all(res[r][0] for r in range(2)), res
+    assert all(res[r][0] for r in range(world)), res
 
 
 def _train_worker(rank, world, port, out):
