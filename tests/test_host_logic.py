@@ -206,3 +206,40 @@ def test_slab_partition_host_logic():
             start, n = g._draw_cell_run(trainers[0].tv_sparsity)
             want = np.sort((start + np.arange(n)) % total)
             assert np.array_equal(np.sort(np.concatenate(cells)), want)
+
+
+def test_slab_compositing_algebra():
+    """The identities svox2_slab_prefix / svox2_slab_combine rely on, in numpy:
+    compositing a ray slab by slab with the entry log-transmittance added equals the sequential
+    march, and the reference's backward `accum` (cuvol.cu:248-264) at a slab's first sample is
+    rgb.gout minus gout.rgb_partial of the slabs crossed before it."""
+    rng = np.random.default_rng(0)
+    n, G = 40, 4
+    p = rng.uniform(0.0, 0.3, n)                      # sigma * delta per sample
+    col = rng.uniform(0.0, 1.0, (n, 3))               # clamped sample colours
+    cuts = [0, 9, 17, 31, n]                          # samples of slab k: cuts[k]..cuts[k+1]
+    bg, gt = 1.0, rng.uniform(0, 1, 3)
+    # sequential (reference) forward
+    lt, rgb, w = 0.0, np.zeros(3), np.zeros(n)
+    for i in range(n):
+        w[i] = np.exp(lt) * (1 - np.exp(-p[i]))
+        rgb += w[i] * col[i]
+        lt -= p[i]
+    rgb_seq = rgb + np.exp(lt) * bg
+    # slab-wise forward
+    logT = np.array([-p[cuts[k]:cuts[k + 1]].sum() for k in range(G)])
+    lt_in = np.concatenate([[0.0], np.cumsum(logT)[:-1]])
+    part = np.zeros((G, 3))
+    for k in range(G):
+        local = 0.0
+        for i in range(cuts[k], cuts[k + 1]):
+            part[k] += np.exp(lt_in[k] + local) * (1 - np.exp(-p[i])) * col[i]
+            local -= p[i]
+    rgb_slab = part.sum(0) + np.exp(logT.sum()) * bg
+    assert np.allclose(rgb_slab, rgb_seq, rtol=1e-12)
+    # backward: accum before sample i = rgb.gout - sum_{j<i} w_j (col_j . gout)
+    gout = (rgb_seq - gt) * (2.0 / 3.0)
+    accum = rgb_seq @ gout - np.concatenate([[0.0], np.cumsum(w * (col @ gout))[:-1]])
+    for k in range(G):
+        start = rgb_seq @ gout - sum(part[j] @ gout for j in range(k))
+        assert np.isclose(start, accum[cuts[k]], rtol=1e-10)
