@@ -28,6 +28,7 @@
 // ~1e-6 relative.
 #include "common.cuh"
 #include "march.cuh"
+#include "traverse.cuh"
 
 namespace svox2b {
 namespace {
@@ -36,11 +37,6 @@ constexpr int LB_THREADS = 64;  // 2 rays per CTA: fine-grained tail balance at 
 
 enum { MODE_FWD = 0, MODE_BWD = 1, MODE_FUSED = 2 };
 
-__device__ __forceinline__ unsigned range_mask(int a, int b) {  // bits a .. b-1, 0 <= a <= b <= 32
-    const unsigned hi = (b >= 32) ? 0xffffffffu : ((1u << b) - 1u);
-    const unsigned lo = (a >= 32) ? 0xffffffffu : ((1u << a) - 1u);
-    return hi & ~lo;
-}
 
 // Per-lane constants of the quad mapping: lane i of each 8-lane group owns channels 4i..4i+3.
 struct LaneConst {
@@ -90,9 +86,6 @@ __device__ __forceinline__ void prefetch_line(const void* p) {
 #else
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 #endif
-}
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 template <bool VEC>
@@ -149,108 +142,23 @@ __device__ __forceinline__ void march_pass(const GridView& g, const Opts& opt, c
     po.stopped = false;
 
     while (!done) {
-        // ---- (1) lattice candidates: lane k holds t_0 advanced by k sequential steps ----
-        float tk = t0;
-#pragma unroll
-        for (int i = 0; i < 31; ++i) {
-            const float nx = __fadd_rn(tk, step);
-            tk = (i < lane) ? nx : tk;
-        }
-        const bool valid = tk <= ray.tmax;
-        int l[3];
-        float pos[3];
-        locate(ray, g, tk, l, pos);
-        const int32_t* lp = g.links + ((int64_t)l[0] * g.offx + (int64_t)l[1] * g.offy + l[2]);
-#if LB_LINKS_TWO_PHASE
-        // probe first (corner 0 decides skipping); a candidate in empty space stops there and
-        // leaves its other three link sectors alone (they would be 7/8 of the traffic of the
-        // ~17 rounds per ray that end in a skip); only non-skipping candidates pay the second trip
-        int32_t lk[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) lk[q] = -1;
-        if (valid) lk[0] = __ldg(lp);
-        const int32_t probe = valid ? lk[0] : 0;
-        const float skipd = skip_dist(ray, probe, l, pos);
-        const bool is_skip = valid && (skipd >= step);
-        if (valid && !is_skip) {
-#pragma unroll
-            for (int q = 1; q < 8; ++q) lk[q] = __ldg(lp + corner_off(g, q));
-        }
-#else
-        // all 8 corner links at once: the probe (corner 0) decides skipping, the other 7 are
-        // needed one dependent round trip later if the candidate turns out to be a sample
-        int32_t lk[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) lk[q] = -1;
-        if (valid) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) lk[q] = __ldg(lp + corner_off(g, q));
-        }
-        const int32_t probe = valid ? lk[0] : 0;
-        const float skipd = skip_dist(ray, probe, l, pos);
-        const bool is_skip = valid && (skipd >= step);
-#endif
-        const unsigned valid_m = __ballot_sync(FULL, valid);
-        const unsigned skip_m = __ballot_sync(FULL, is_skip);
-
-        // ---- (2) which candidates are on the reference's sample lattice (warp-uniform) ----
-        unsigned members = 0;
-        int cur = 0;
+        // ---- (1)+(2) lattice candidates and which of them are samples (traverse.cuh) ----
+        Candidates c;
+        load_candidates<LB_LINKS_TWO_PHASE != 0>(ray, g, t0, step, lane, c);
         float t_next = 0.f;
-        for (;;) {
-            const unsigned rem = 0xffffffffu << cur;
-            const unsigned inv = ~valid_m & rem, sk = skip_m & rem;
-            const int first_inv = inv ? __ffs(inv) - 1 : 32;
-            const int first_sk = sk ? __ffs(sk) - 1 : 32;
-            if (first_inv <= first_sk) {  // ray leaves [tmin,tmax] (or batch exhausted) first
-                members |= range_mask(cur, first_inv);
-                if (first_inv < 32) done = true;
-                else t_next = __fadd_rn(__shfl_sync(FULL, tk, 31), step);
-                break;
-            }
-            const int j = first_sk;  // lane j skips empty space
-            members |= range_mask(cur, j);
-            if (COUNT) ++cnt[0];
-            const float tn = skip_advance(__shfl_sync(FULL, tk, j), __shfl_sync(FULL, skipd, j), step);
-            const unsigned later = (j < 31) ? (0xffffffffu << (j + 1)) : 0u;
-            const unsigned eq = __ballot_sync(FULL, tk == tn) & later;
-            if (eq) {  // landed exactly on a later candidate of this batch: keep going there
-                cur = __ffs(eq) - 1;
-                continue;
-            }
-            t_next = tn;
-            if (!(tn <= ray.tmax)) done = true;
-            break;
-        }
-
+        unsigned n_skips = 0;
+        unsigned members = resolve_lattice(ray, c, step, t_next, done, n_skips);
+        if (COUNT) cnt[0] += n_skips;
 #if LB_PREFETCH_LINKS
-        // The next batch starts at t_next: touch the link lines its candidates will probe so the
-        // probe loads of the next iteration find them in L2 (positions need not be exact here).
-        if (!done) {
-            const float ta = fmaf((float)lane, step, t_next);
-            if (ta <= ray.tmax) {
-                int nl[3];
-                float npos[3];
-                locate(ray, g, ta, nl, npos);
-                const int32_t* np = g.links + ((int64_t)nl[0] * g.offx + (int64_t)nl[1] * g.offy + nl[2]);
-                prefetch_l2(np);
-                prefetch_l2(np + g.offy);
-                prefetch_l2(np + g.offx);
-                prefetch_l2(np + g.offx + g.offy);
-            }
-        }
+        if (!done) prefetch_next_links(ray, g, t_next, step, lane);
 #endif
 
         // ---- (3) sigma at member candidates ----
         const bool member = (members >> lane) & 1u;
-        float sigma = 0.f;
-        if (member) {
-            float sv[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-                sv[q] = lk[q] >= 0 ? __ldg(g.density + (int64_t)lk[q] * g.density_stride) : 0.f;
-            sigma = trilerp8(sv, pos);
-        }
+        const float sigma = member_sigma(g, c, member);
+        const float tk = c.tk;
+        const int32_t (&lk)[8] = c.lk;
+        const float (&pos)[3] = c.pos;
 
         // ---- (4) log-transmittance chain + stop test, replayed in sample order ----
         const float ws = (opt.last_sample_opaque && __fadd_rn(tk, step) > ray.tmax) ? 1e9f
@@ -263,40 +171,17 @@ __device__ __forceinline__ void march_pass(const GridView& g, const Opts& opt, c
         if (active && (!BWD || ccache == nullptr)) {
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-                if (lk[q] >= 0) {
-                    const float* row = g.sh + (int64_t)lk[q] * g.sh_stride;
+                if (c.lk[q] >= 0) {
+                    const float* row = g.sh + (int64_t)c.lk[q] * g.sh_stride;
                     prefetch_line(row);
                     prefetch_line(row + (D - 1));
                 }
         }
 #endif
         const float pcnt = __fmul_rn(ws, sigma);
-        unsigned act_m = __ballot_sync(FULL, active);
-        float my_before = 0.f;
-        {
-            // the subtraction chain is the only sequential part (bit-exact running sum); the
-            // exp / threshold test of every sample runs in parallel afterwards
-            unsigned it = act_m;
-            while (it) {
-                const int i = __ffs(it) - 1;
-                it &= it - 1;
-                const float p = __shfl_sync(FULL, pcnt, i);
-                my_before = (lane == i) ? lt : my_before;
-                lt = __fsub_rn(lt, p);
-            }
-            const float aft = __fsub_rn(my_before, pcnt);
-            const unsigned tm = __ballot_sync(  // cuvol.cu:103-106 / :367-369
-                FULL, ((act_m >> lane) & 1u) && fexp(aft) < opt.stop_thresh);
-            if (tm) {
-                const int sidx = __ffs(tm) - 1;
-                const unsigned upto = (2u << sidx) - 1u;
-                act_m &= upto;
-                members &= upto;
-                done = true;
-                po.stopped = true;
-                lt = __shfl_sync(FULL, aft, sidx);
-            }
-        }
+        float my_before;
+        unsigned act_m = transmittance_chain(active, pcnt, opt.stop_thresh, lane, lt, members, done,
+                                             po.stopped, my_before);
         if (COUNT) {
             cnt[1] += __popc(members);
             cnt[2] += __popc(act_m);

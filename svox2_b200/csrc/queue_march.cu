@@ -29,6 +29,7 @@
 // set and mask; colours/gradients are reassociated sums (float atomics), within 1e-6 relative.
 #include "common.cuh"
 #include "march.cuh"
+#include "traverse.cuh"
 
 namespace svox2b {
 namespace {
@@ -82,14 +83,6 @@ struct SlabView {
     float stop_thresh;
 };
 
-__device__ __forceinline__ unsigned range_mask(int a, int b) {
-    const unsigned hi = (b >= 32) ? 0xffffffffu : ((1u << b) - 1u);
-    const unsigned lo = (a >= 32) ? 0xffffffffu : ((1u << a) - 1u);
-    return hi & ~lo;
-}
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
 
 // ---------------------------------------------------------------------------------------
 // K1: traversal -> records
@@ -142,120 +135,29 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
     if (takes_part) {
         float t0 = ray.tmin;
         bool done = false;
-        // one round = 32 lattice candidates t0 + lane*step (sequential adds, bit-exact)
-        float tk;
-        bool valid;
-        int l[3];
-        float pos[3];
-        int32_t lk[8];
-        auto load_round = [&](float t_first, float& tk_o, bool& valid_o, int* l_o, float* pos_o,
-                              int32_t* lk_o) {
-            float t = t_first;
-#pragma unroll
-            for (int i = 0; i < 31; ++i) {
-                const float nx = __fadd_rn(t, step);
-                t = (i < lane) ? nx : t;
-            }
-            tk_o = t;
-            valid_o = t <= ray.tmax;
-            locate(ray, g, t, l_o, pos_o);
-            const int32_t* lp = g.links + ((int64_t)l_o[0] * g.offx + (int64_t)l_o[1] * g.offy + l_o[2]);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) lk_o[q] = -1;
-            if (valid_o) {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) lk_o[q] = __ldg(lp + corner_off(g, q));
-            }
-        };
         while (!done) {
             if (SLAB && t0 > t_exit) break;  // past the slab: nothing left for this rank
-            load_round(t0, tk, valid, l, pos, lk);
-            const float skipd = skip_dist(ray, valid ? lk[0] : 0, l, pos);
-            const bool is_skip = valid && (skipd >= step);
-            const unsigned valid_m = __ballot_sync(FULL, valid);
-            const unsigned skip_m = __ballot_sync(FULL, is_skip);
-
-            unsigned members = 0;
-            int cur = 0;
+            // one round = 32 lattice candidates t0 + lane*step (traverse.cuh)
+            Candidates c;
+            load_candidates<false>(ray, g, t0, step, lane, c);
             float t_next = 0.f;
-            for (;;) {
-                const unsigned rem = 0xffffffffu << cur;
-                const unsigned inv = ~valid_m & rem, sk = skip_m & rem;
-                const int first_inv = inv ? __ffs(inv) - 1 : 32;
-                const int first_sk = sk ? __ffs(sk) - 1 : 32;
-                if (first_inv <= first_sk) {
-                    members |= range_mask(cur, first_inv);
-                    if (first_inv < 32) done = true;
-                    else t_next = __fadd_rn(__shfl_sync(FULL, tk, 31), step);
-                    break;
-                }
-                const int j = first_sk;
-                members |= range_mask(cur, j);
-                if (COUNT) ++cnt[0];
-                const float tn = skip_advance(__shfl_sync(FULL, tk, j), __shfl_sync(FULL, skipd, j), step);
-                const unsigned later = (j < 31) ? (0xffffffffu << (j + 1)) : 0u;
-                const unsigned eq = __ballot_sync(FULL, tk == tn) & later;
-                if (eq) {
-                    cur = __ffs(eq) - 1;
-                    continue;
-                }
-                t_next = tn;
-                if (!(tn <= ray.tmax)) done = true;
-                break;
-            }
-            if (!done) {  // next batch's link lines
-                const float ta = fmaf((float)lane, step, t_next);
-                if (ta <= ray.tmax) {
-                    int nl[3];
-                    float npos[3];
-                    locate(ray, g, ta, nl, npos);
-                    const int32_t* np = g.links + ((int64_t)nl[0] * g.offx + (int64_t)nl[1] * g.offy + nl[2]);
-                    prefetch_l2(np);
-                    prefetch_l2(np + g.offy);
-                    prefetch_l2(np + g.offx);
-                    prefetch_l2(np + g.offx + g.offy);
-                }
-            }
-            if (SLAB) members &= __ballot_sync(FULL, l[0] >= sl.x_lo && l[0] < sl.x_hi);
+            unsigned n_skips = 0;
+            unsigned members = resolve_lattice(ray, c, step, t_next, done, n_skips);
+            if (COUNT) cnt[0] += n_skips;
+            if (!done) prefetch_next_links(ray, g, t_next, step, lane);
+            if (SLAB) members &= __ballot_sync(FULL, c.l[0] >= sl.x_lo && c.l[0] < sl.x_hi);
             const bool member = (members >> lane) & 1u;
-            float sigma = 0.f;
-            if (member) {
-                float sv[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    sv[q] = lk[q] >= 0 ? __ldg(g.density + (int64_t)lk[q] * g.density_stride) : 0.f;
-                sigma = trilerp8(sv, pos);
-            }
+            const float sigma = member_sigma(g, c, member);
+            const float tk = c.tk;
+            const int32_t (&lk)[8] = c.lk;
+            const float (&pos)[3] = c.pos;
             const float ws = (opt.last_sample_opaque && __fadd_rn(tk, step) > ray.tmax) ? 1e9f
                                                                                        : ray.world_step;
             const bool active = member && (sigma > opt.sigma_thresh);
             const float pcnt = __fmul_rn(ws, sigma);
-            unsigned act_m = __ballot_sync(FULL, active);
-            float my_before = 0.f;
-            {
-                // the subtraction chain is the only sequential part (bit-exact running sum); the
-                // exp / threshold test of every sample runs in parallel afterwards
-                unsigned it = act_m;
-                while (it) {
-                    const int i = __ffs(it) - 1;
-                    it &= it - 1;
-                    const float p = __shfl_sync(FULL, pcnt, i);
-                    my_before = (lane == i) ? lt : my_before;
-                    lt = __fsub_rn(lt, p);
-                }
-                const float aft = __fsub_rn(my_before, pcnt);
-                const unsigned tm = __ballot_sync(  // cuvol.cu:103-106 / :367-369
-                    FULL, ((act_m >> lane) & 1u) && fexp(aft) < opt.stop_thresh);
-                if (tm) {
-                    const int sidx = __ffs(tm) - 1;
-                    const unsigned upto = (2u << sidx) - 1u;
-                    act_m &= upto;
-                    members &= upto;
-                    done = true;
-                    stopped = true;
-                    lt = __shfl_sync(FULL, aft, sidx);
-                }
-            }
+            float my_before;
+            unsigned act_m = transmittance_chain(active, pcnt, opt.stop_thresh, lane, lt, members, done,
+                                                 stopped, my_before);
             if (COUNT) {
                 cnt[1] += __popc(members);
                 cnt[2] += __popc(act_m);
