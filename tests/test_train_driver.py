@@ -72,3 +72,26 @@ def test_training_run_with_upsampling_fits_the_scene():
     assert tr.lambda_tv == 0.0                      # tv_early_only: TV off after the first upsample
     assert any("upsampled" in m for m in logs)
     assert after > before + 8.0 and after > 18.0, (before, after, logs[-3:])
+
+
+def test_ray_pool_is_deterministic_across_ranks_and_covers_every_pixel():
+    """Every rank builds the pool from the same seed, so the per-epoch permutation -- and with it
+    the split of a global batch over ranks -- is identical without any communication."""
+    c2w = T.hemisphere_cameras(3, 2.687, "cpu", seed=1)
+    # cameras look at the origin: the optical axis (3rd column) is -position / |position|
+    pos = c2w[:, :3, 3]
+    assert torch.allclose(c2w[:, :3, 2], -pos / pos.norm(dim=-1, keepdim=True), atol=1e-6)
+    assert torch.allclose(pos.norm(dim=-1), torch.full((3,), 2.687), atol=1e-5)
+    imgs = torch.arange(3 * 4 * 5 * 3, dtype=torch.float32).view(3, 4, 5, 3)
+    data = T.PosedImages(c2w, imgs, fx=6.0, width=5, height=4)
+    a, b = T.RayPool(data, seed=7), T.RayPool(data, seed=7)
+    assert len(a) == 3 * 4 * 5
+    for _ in range(2):                                   # two epochs
+        assert torch.equal(a.rgb, b.rgb) and torch.equal(a.origins, b.origins) and torch.equal(a.dirs, b.dirs)
+        assert torch.equal(torch.sort(a.rgb[:, 0])[0], imgs.view(-1, 3)[:, 0])      # a permutation
+        a.shuffle()
+        b.shuffle()
+    rays, gt = a.batch(10, 25)
+    assert rays.origins.shape == (15, 3) and gt.shape == (15, 3)
+    assert torch.allclose(rays.dirs.norm(dim=-1), torch.ones(15), atol=1e-5)
+    assert not torch.equal(T.RayPool(data, seed=8).rgb, T.RayPool(data, seed=7).rgb)
