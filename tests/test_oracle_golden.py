@@ -85,3 +85,36 @@ def test_optimizers_match_formula():
     assert np.array_equal(d3, d2) and np.array_equal(r3, r2) and np.array_equal(g3, g2)
     d4, g4 = og.sgd_step(data, grad, None, 0.1, -1.0)
     assert np.allclose(d4, data - 0.1 * grad, rtol=1e-6) and (g4 == 0).all()
+
+
+def test_oracle_matches_the_reference_pytorch_renderer_live(ref_svox2):
+    """Not a stored vector: the unmodified reference (oracle/_ref, pure-PyTorch path + autograd) and the
+    C oracle on a fresh tiny case, forward colours and all gradients (guards against stale fixtures)."""
+    import torch
+    import torch.nn.functional as F
+    gen = torch.Generator().manual_seed(77)
+    grid = ref_svox2.SparseGrid(reso=[9, 8, 10], radius=[1.0, 0.9, 1.1], center=[0.05, 0.0, -0.05],
+                                basis_dim=4, use_z_order=False, use_sphere_bound=True, device="cpu")
+    N = grid.density_data.shape[0]
+    with torch.no_grad():
+        grid.sh_data[:] = torch.randn(N, 12, generator=gen) * 0.3
+        grid.sh_data[:, ::4] += 0.3
+        grid.density_data[:] = torch.rand(N, 1, generator=gen) * 4.0
+    grid.opt.step_size, grid.opt.background_brightness = 0.41, 0.7
+    grid.opt.sigma_thresh = grid.opt.stop_thresh = 0.0
+    n = 24
+    v = F.normalize(torch.randn(n, 3, generator=gen), dim=-1)
+    origins = v * 2.6 + torch.tensor([0.05, 0.0, -0.05])
+    dirs = F.normalize((torch.rand(n, 3, generator=gen) - 0.5) * 0.9 - v * 2.6, dim=-1)
+    gt = torch.rand(n, 3, generator=gen)
+    rgb = grid.volume_render(ref_svox2.Rays(origins, dirs), use_kernel=False)
+    F.mse_loss(rgb, gt).backward()
+    gsz = torch.tensor(grid.links.shape, dtype=torch.float32)
+    og_grid = og.Grid(grid.links.numpy(), grid.density_data.detach().numpy(), grid.sh_data.detach().numpy(),
+                      (grid._offset * gsz - 0.5).numpy(), (grid._scaling * gsz).numpy())
+    opt = og.make_opt(background_brightness=0.7, step_size=0.41, sigma_thresh=0.0, stop_thresh=0.0)
+    out = og.volume_render_fused(og_grid, opt, origins.numpy(), dirs.numpy(), gt.numpy())
+    assert np.abs(out["rgb"] - rgb.detach().numpy()).max() < 5e-6
+    gd, gsh = grid.density_data.grad.numpy().reshape(-1), grid.sh_data.grad.numpy()
+    assert np.abs(out["grad_density"] - gd).max() <= 1e-4 * np.abs(gd).max()
+    assert np.abs(out["grad_sh"] - gsh).max() <= 1e-4 * np.abs(gsh).max()
