@@ -670,12 +670,16 @@ def rmsprop_step_packed(sh_data, sh_rms, density_data, density_rms, rows, packed
 def slab_workspace(n_rays: int, slots_per_ray: int, device):
     """Sample-record scratch shared by slab_trace / slab_shade / slab_backward."""
     nbytes = _lib.lib().svox2_fused_workspace_bytes(n_rays, max(int(slots_per_ray), 64))
-    return torch.empty(nbytes, dtype=torch.uint8, device=device)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    ws[:256].zero_()        # queue header: counter, overflow flag, sticky overflow count
+    return ws
 
 
 def slab_overflowed(workspace) -> bool:
-    """True if the last slab_trace ran out of record space (host sync)."""
-    return bool(workspace[128:132].view(torch.int32).item())
+    """True if the last slab_trace, or any earlier one on this workspace since it was created,
+    ran out of record space (host sync)."""
+    hdr = workspace[:256].view(torch.int32)
+    return bool((hdr[32] != 0).item() or (hdr[48] != 0).item())
 
 
 def slab_trace(grid, rays, opt, x_lo, x_hi, logT_local, workspace):

@@ -64,6 +64,7 @@ struct QueueView {
     int capacity;
     int* __restrict__ counter;    // records allocated so far
     int* __restrict__ overflow;   // set when the queue ran out of space
+    int* __restrict__ sticky;     // batches that overflowed before the current one (slab mode)
     int* __restrict__ ray_first;  // [Q] first block of each ray or -1
     float* __restrict__ ray_logT; // [Q] forward log-transmittance (-1e3 when stopped)
     float4* __restrict__ ray_Y;   // [Q][8] SH basis value of channels 4q..4q+3 (0 for padding)
@@ -516,8 +517,12 @@ scatter_kernel(GridView g, QueueView qv, GradView gr, int64_t gsh_stride, int64_
     if (have) flush();
 }
 
-// The lattice kernel re-does the batch when the queue overflowed.
-__global__ void clear_flags_kernel(int* counter, int* overflow) {
+// Resets the queue for a new batch.  The overflow flag of the PREVIOUS batch that used this
+// workspace is folded into a sticky count first (header offset 192), so that callers that keep a
+// workspace across steps and have no fallback (slab mode) can detect a dropped step at any later
+// sync point.  (The single-GPU fused call re-does an overflowed batch with the lattice kernel.)
+__global__ void clear_flags_kernel(int* counter, int* overflow, int* sticky) {
+    if (*overflow) *sticky = (*sticky < 0 ? 0 : *sticky) + 1;
     *counter = 0;
     *overflow = 0;
 }
@@ -540,6 +545,7 @@ static bool carve_queue(void* workspace, size_t workspace_bytes, int64_t n_rays,
     char* p = static_cast<char*>(workspace);
     qv.counter = reinterpret_cast<int*>(p);
     qv.overflow = reinterpret_cast<int*>(p + 128);
+    qv.sticky = reinterpret_cast<int*>(p + 192);
     p += 256;
     qv.ray_first = reinterpret_cast<int*>(p);
     p += align_up((size_t)n_rays * 4, 256);
@@ -562,7 +568,7 @@ bool launch_queue_fused(const GridView& g, const Opts& opt, const MarchArgs& a, 
     *overflow_flag = qv.overflow;
     const SlabView none{};
 
-    clear_flags_kernel<<<1, 1, 0, st>>>(qv.counter, qv.overflow);
+    clear_flags_kernel<<<1, 1, 0, st>>>(qv.counter, qv.overflow, qv.sticky);
     const unsigned ray_blocks = div_up(a.n_rays * WARP, TRACE_THREADS);
     if (a.counters) trace_kernel<true, false><<<ray_blocks, TRACE_THREADS, 0, st>>>(g, opt, a, qv, none);
     else trace_kernel<false, false><<<ray_blocks, TRACE_THREADS, 0, st>>>(g, opt, a, qv, none);
@@ -586,7 +592,7 @@ bool launch_slab_trace(const GridView& g, const Opts& opt, const MarchArgs& a, v
     sl.x_lo = x_lo;
     sl.x_hi = x_hi;
     sl.logT_local = logT_local;
-    clear_flags_kernel<<<1, 1, 0, st>>>(qv.counter, qv.overflow);
+    clear_flags_kernel<<<1, 1, 0, st>>>(qv.counter, qv.overflow, qv.sticky);
     trace_kernel<false, true><<<div_up(a.n_rays * WARP, TRACE_THREADS), TRACE_THREADS, 0, st>>>(
         g, opt, a, qv, sl);
     return true;

@@ -68,6 +68,10 @@ class ShardedTrainer:
         self.lambda_tv, self.lambda_tv_sh = lambda_tv, lambda_tv_sh
         self.tv_sparsity, self.rms_beta = tv_sparsity, rms_beta
         self.beta_loss, self.sparsity_loss = beta_loss, sparsity_loss
+        if tv_sparsity >= 1.0 and world_size > 1 and (lambda_tv > 0.0 or lambda_tv_sh > 0.0):
+            # sparse_frac >= 1 selects the dense TV kernel and a dense optimiser step in the
+            # reference (svox2.py:1760-1766): there is no sparse mask to exchange then
+            raise ValueError("ShardedTrainer with world_size > 1 needs tv_sparsity < 1")
         # march fwd + march bwd + 2 TV + 2 optimiser kernels
         # clear + trace + shade + seed + scatter + (conditional) lattice fallback, 2 TV, then
         # 2 optimiser kernels (1 GPU) or pack + packed optimiser (multi-GPU)
@@ -89,14 +93,21 @@ class ShardedTrainer:
         g = self.grid
         rgb = g.volume_render_fused(rays, rgb_gt, beta_loss=self.beta_loss,
                                     sparsity_loss=self.sparsity_loss, _norm_rays=global_batch)
-        if self.lambda_tv > 0.0:
-            run, n = self._tv_run()
-            g.inplace_tv_grad(g.density_data.grad, scaling=self.lambda_tv, _cell_run=run,
-                              _scale_cells=n)
-        if self.lambda_tv_sh > 0.0:
-            run, n = self._tv_run()
-            g.inplace_tv_color_grad(g.sh_data.grad, scaling=self.lambda_tv_sh, _cell_run=run,
-                                    _scale_cells=n)
+        if self.tv_sparsity >= 1.0:     # single GPU: the reference's dense TV + dense step
+            if self.lambda_tv > 0.0:
+                g.inplace_tv_grad(g.density_data.grad, scaling=self.lambda_tv, sparse_frac=self.tv_sparsity)
+            if self.lambda_tv_sh > 0.0:
+                g.inplace_tv_color_grad(g.sh_data.grad, scaling=self.lambda_tv_sh,
+                                        sparse_frac=self.tv_sparsity)
+        else:
+            if self.lambda_tv > 0.0:
+                run, n = self._tv_run()
+                g.inplace_tv_grad(g.density_data.grad, scaling=self.lambda_tv, _cell_run=run,
+                                  _scale_cells=n)
+            if self.lambda_tv_sh > 0.0:
+                run, n = self._tv_run()
+                g.inplace_tv_color_grad(g.sh_data.grad, scaling=self.lambda_tv_sh, _cell_run=run,
+                                        _scale_cells=n)
         lr_sigma = self.lr_sigma if lr_sigma is None else lr_sigma
         lr_sh = self.lr_sh if lr_sh is None else lr_sh
         if g.use_background:

@@ -55,7 +55,8 @@ class PeerMemory:
     device-side barrier, a kernel that reads the local buffer -- no collective library call.
 
     Layout (floats; identical on every rank): A [G,Q] | B [G,Q,4] | halo packets received from the
-    left neighbour [H,32] | from the right neighbour [H,32] | row-0 packets [G,32]."""
+    left neighbour [H,32] | from the right neighbour [H,32] | row-0 gradient packets [G,32] |
+    row-0 parameters published by its owner [32]."""
 
     WIDTH = 32
 
@@ -67,7 +68,8 @@ class PeerMemory:
         self.off_hl = self.off_b + G * Q * 4
         self.off_hr = self.off_hl + halo_rows * self.WIDTH
         self.off_z = self.off_hr + halo_rows * self.WIDTH      # [G, 32]: row-0 packets (see _row0_*)
-        total = self.off_z + G * self.WIDTH
+        self.off_p = self.off_z + G * self.WIDTH               # [32]: row-0 parameters (see _publish_row0)
+        total = self.off_p + self.WIDTH
         self.buf = symm.empty(total, dtype=torch.float32, device=device)
         self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
@@ -104,6 +106,10 @@ class SlabTrainer:
                  tv_sparsity: float = 0.01, rms_beta: float = 0.95, beta_loss: float = 0.0,
                  sparsity_loss: float = 0.0, group=None, bounds: Optional[List[int]] = None):
         assert not grid.use_background, "slab mode does not support an MSI background"
+        if tv_sparsity >= 1.0 and (lambda_tv > 0.0 or lambda_tv_sh > 0.0):
+            # the reference switches to the dense TV kernel and a dense optimiser step there
+            # (svox2.py:1760-1766); the slab step is built on the sparse contiguous cell run
+            raise ValueError("SlabTrainer needs tv_sparsity < 1 (sparse contiguous TV run)")
         self.grid, self.world_size, self.rank, self.group = grid, world_size, rank, group
         self.lr_sigma, self.lr_sh = lr_sigma, lr_sh
         self.lambda_tv, self.lambda_tv_sh = lambda_tv, lambda_tv_sh
@@ -127,7 +133,15 @@ class SlabTrainer:
         # neighbour and add gradient / mask bits to it.  Such cells lie in every slab, row 0 in one.
         self._row0 = torch.zeros(1, dtype=torch.int64, device=dev)
         self._holds_row0 = bool(self.own_mask[0].item()) if self.own_mask.numel() else True
+        # its exclusive owner (known to every rank from the replicated links) publishes the updated
+        # parameters of row 0 after each step, so that the face cells of the other slabs keep
+        # reading the value the single-GPU step would read
+        at = (links == 0).nonzero()
+        x0 = int(at[0, 0].item()) if at.numel() else 0
+        self._row0_owner = max(k for k in range(world_size) if self.bounds[k] <= x0)
+        self._row0_pending = False      # a published row 0 waits in the peer buffer
         self._ws = None
+        self.slots_per_ray = None  # record slots per ray of the workspace (None: min(diagonal, 512))
         self._peer = None          # PeerMemory for the current batch size, False if unavailable
         self.use_peer_memory = os.environ.get("SVOX2_B200_PEER", "1") != "0"
         self._steps = 0
@@ -144,6 +158,8 @@ class SlabTrainer:
         g = self.grid
         diag = sum(float(s) ** 2 for s in g.links.shape) ** 0.5
         slots = max(64, min(int(diag / max(float(g.opt.step_size), 1e-3)) + 2, 512))
+        if self.slots_per_ray is not None:
+            slots = max(64, int(self.slots_per_ray))
         if self._ws is None or self._ws[0] != (n_rays, slots):
             self._ws = ((n_rays, slots), _C.slab_workspace(n_rays, slots, g.links.device))
         return self._ws[1]
@@ -224,6 +240,7 @@ class SlabTrainer:
         _C.slab_trace(spec, rspec, ropt, self.x_lo, self.x_hi, logT_local, ws)
         self._mark("trace")
         logT_all = self._gather(logT_local, "a")                                 # exchange A
+        self._refresh_row0()            # the barrier of exchange A made the owner's store visible
         lt_in = torch.empty(Q, dtype=torch.float32, device=dev)
         _C.slab_prefix(logT_all, rays.dirs, self.rank, lt_in)
         self._mark("exchange_a")
@@ -269,12 +286,55 @@ class SlabTrainer:
         self._mark("halo_grads")
         g.optim_density_step(self.lr_sigma if lr_sigma is None else lr_sigma, beta=self.rms_beta)
         g.optim_sh_step(self.lr_sh if lr_sh is None else lr_sh, beta=self.rms_beta)
+        self._publish_row0()
         self._mark("optimiser")
 
-        if self._steps % 256 == 0 and _C.slab_overflowed(ws):
-            raise RuntimeError("SlabTrainer: sample-record workspace overflowed")
+        if self._steps % 256 == 0:
+            self.check_overflow()
         self._steps += 1
         return rgb
+
+    def check_overflow(self):
+        """Raise if any step since the last check ran out of sample-record space (its colours and
+        gradients were dropped).  The trace kernel keeps a sticky count in the workspace, so the
+        check can be made at any host sync point (every 256 steps, logging, gather_params)."""
+        if self._ws is not None and _C.slab_overflowed(self._ws[1]):
+            raise RuntimeError(
+                "SlabTrainer: the sample-record workspace overflowed in at least one step since "
+                "the last check (those steps contributed no colour / gradient); raise "
+                "SlabTrainer.slots_per_ray")
+
+    def _publish_row0(self):
+        """Row-0 parameters -> every rank (reference quirk B5: TV face cells read row 0 wherever
+        they are).  Peer memory: the owner stores [sh, density] of row 0 into every rank's buffer;
+        readers pick it up behind the next step's first barrier.  NCCL: one tiny broadcast."""
+        if self.world_size == 1:
+            return
+        g = self.grid
+        width = _C.packed_row_floats(g.sh_data.size(1) + 2)
+        peer = self._peer if (self._peer not in (None, False)) else None
+        z = torch.empty((1, width), dtype=torch.float32, device=g.sh_data.device)
+        if self.rank == self._row0_owner:       # the pack kernel writes every float of the packet
+            _C.pack_grad_rows(g.sh_data.data, g.density_data.data, self._row0, z)
+        if peer is not None and width == peer.WIDTH:
+            if self.rank == self._row0_owner:
+                _C.peer_store(peer.ptrs, peer.off_p * 4, z)
+            self._row0_pending = True
+            return
+        dist.broadcast(z, src=self._row0_owner, group=self.group)
+        if not self._holds_row0:
+            _C.unpack_rows(z, self._row0, g.sh_data.data, g.density_data.data, False)
+
+    def _refresh_row0(self):
+        if not self._row0_pending:
+            return
+        self._row0_pending = False
+        peer = self._peer if (self._peer not in (None, False)) else None
+        if peer is None or self._holds_row0:
+            return
+        g = self.grid
+        slot = peer.buf[peer.off_p:peer.off_p + peer.WIDTH].view(1, peer.WIDTH)
+        _C.unpack_rows(slot, self._row0, g.sh_data.data, g.density_data.data, False)
 
     def _halo_grads(self):
         """The first voxel plane of every slab is co-owned with the left neighbour (its last cell
@@ -337,6 +397,7 @@ class SlabTrainer:
     def gather_params(self):
         """Re-replicate: every rank receives the owners' density / SH rows (one-off, e.g. before
         rendering or saving)."""
+        self.check_overflow()
         if self.world_size == 1:
             return
         g = self.grid

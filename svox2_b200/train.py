@@ -254,6 +254,10 @@ class Trainer:
         gq = c.batch_size * W                       # global batch: batch_size rays per GPU
         self.pool.shuffle()
         n_batches = len(self.pool) // gq
+        if n_batches == 0:
+            raise ValueError(
+                f"the ray pool ({len(self.pool)} rays) is smaller than one global batch "
+                f"({c.batch_size} rays x {W} GPUs): lower batch_size or use fewer GPUs")
         sq_err = torch.zeros((), device=self.pool.rgb.device)
         seen = 0
         for b in range(n_batches):
@@ -270,6 +274,8 @@ class Trainer:
             sq_err += ((rgb.detach() - gt) ** 2).mean()
             seen += 1
             self.step_id += 1
+            if seen % c.print_every == 0 and self.slab:
+                self.stepper.check_overflow()               # every rank, at the logging sync point
             if seen % c.print_every == 0 and self.rank == 0:
                 mse = (sq_err / c.print_every).item()       # the only host sync of the loop
                 sq_err.zero_()

@@ -16,10 +16,10 @@ pytestmark = pytest.mark.gpu
 OPTS = dict(sigma_thresh=1e-8, stop_thresh=1e-7)
 
 
-def _reference_step(sv, sc, dev, seed, **kw):
+def _reference_step(sv, sc, dev, seed, opts=OPTS, **kw):
     from svox2_b200.dist import ShardedTrainer
     ref = make_grid(sv, sc, dev)
-    set_opt(ref, **OPTS)
+    set_opt(ref, **opts)
     np.random.seed(seed)
     tr = ShardedTrainer(ref, world_size=1, rank=0, **kw)
     rgb = tr.step(sv.Rays(t(sc["origins"], dev), t(sc["dirs"], dev)), t(sc["rgb_gt"], dev))
@@ -65,7 +65,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, case="default"):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     import torch.distributed as dist
@@ -79,11 +79,27 @@ def _worker(rank, world, port, out):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
     try:
         m = {}
-        sc = make_scene(reso=48, basis_dim=9, seed=41, n_rays=4096)
+        opts = OPTS
+        if case == "stop":
+            # rays that terminate by the stop threshold INSIDE a later slab: dense blobs and a high
+            # threshold make most rays stop; the mask then tells whether every slab agreed on the
+            # sample at which the reference stops (per-slab partial sums of logT)
+            sc = make_scene(reso=48, basis_dim=9, seed=43, n_rays=4096, sigma_peak=150.0)
+            opts = dict(sigma_thresh=1e-8, stop_thresh=1e-2)
+        else:
+            sc = make_scene(reso=48, basis_dim=9, seed=41, n_rays=4096)
         kw = dict(beta_loss=0.05)
-        ref, rgb1 = _reference_step(sv, sc, dev, 7, **kw)
+        ref, rgb1 = _reference_step(sv, sc, dev, 7, opts=opts, **kw)
+        if case == "stop":
+            free = make_grid(sv, sc, dev)
+            set_opt(free, sigma_thresh=1e-8, stop_thresh=0.0)
+            with torch.no_grad():
+                rgb_free = free.volume_render(sv.Rays(t(sc["origins"], dev), t(sc["dirs"], dev)))
+            m["rays_stopped"] = int(((rgb_free - rgb1).abs().max(1)[0] > 1e-6).sum().item())
+            assert m["rays_stopped"] > 500, m
+            del free
         grid = make_grid(sv, sc, dev)
-        set_opt(grid, **OPTS)
+        set_opt(grid, **opts)
         np.random.seed(7)
         tr = SlabTrainer(grid, world_size=world, rank=rank, **kw)
         rays = sv.Rays(t(sc["origins"], dev), t(sc["dirs"], dev))
@@ -110,26 +126,43 @@ def _worker(rank, world, port, out):
         rgbb = tr.step(rays, t(sc["rgb_gt"], dev))
         m["rgb_step2"] = (rgbb - rgb1b).abs().max().item()
         ok = ok and m["rgb_step2"] < 2e-3   # parameters after step 1 differ by RMSProp sign noise
+        # two more steps WITHOUT gather_params: row 0 (read by the TV face cells of every slab,
+        # reference quirk B5) must follow its owner's updates on every rank
+        for it in (9, 10):
+            np.random.seed(it)
+            tr.step(rays, t(sc["rgb_gt"], dev))
+        tr._refresh_row0()                   # the pick-up normally happens inside the next step
+        torch.cuda.synchronize()
+        dist.barrier()
+        row0 = torch.cat([grid.sh_data.data[0], grid.density_data.data[0]]).contiguous()
+        every = [torch.empty_like(row0) for _ in range(world)]
+        dist.all_gather(every, row0)
+        m["row0_in_sync"] = bool(all(torch.equal(e, every[tr._row0_owner]) for e in every))
+        m["row0_moved"] = bool(not torch.equal(row0[:-1], t(sc["sh"][0], dev)))
+        ok = ok and m["row0_in_sync"]
+        tr.check_overflow()
         out[rank] = (bool(ok), m)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_multi_gpu_slab_step_equals_single_gpu_step(world):
+@pytest.mark.parametrize("world,case", [(2, "default"), (2, "stop"), (4, "default"), (4, "stop"),
+                                        (8, "default"), (8, "stop")])
+def test_multi_gpu_slab_step_equals_single_gpu_step(world, case):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs (run under gpurun --gpus {world})")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     out = ctx.Manager().dict()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out, case)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
         p.join(300)
         assert p.exitcode == 0
     res = dict(out)
+    print(f"slab parity world={world} case={case}: {res}")      # kept in the pytest -s logs (profiles/)
     assert all(res[r][0] for r in range(world)), res
 
 

@@ -243,3 +243,20 @@ def test_slab_compositing_algebra():
     for k in range(G):
         start = rgb_seq @ gout - sum(part[j] @ gout for j in range(k))
         assert np.isclose(start, accum[cuts[k]], rtol=1e-10)
+
+
+def test_compat_alias_exposes_importable_submodules():
+    """`PYTHONPATH=compat:repo` must satisfy every `svox2` import of the reference's opt/ scripts:
+    `import svox2.utils` (render_imgs.py), `from svox2.utils import convert_to_ndc`
+    (util/llff_dataset.py), `svox2.csrc`.  Run in a fresh interpreter: the reference fixture of this
+    session may already own the name `svox2`."""
+    import subprocess
+    import sys
+    code = ("import svox2, svox2.utils, svox2.csrc\n"
+            "from svox2.utils import convert_to_ndc, eval_sh_bases, Timing\n"
+            "from svox2 import SparseGrid, Camera, Rays, RenderOptions\n"
+            "assert svox2.utils.SH_C0 > 0.28 and callable(convert_to_ndc)\n"
+            "assert hasattr(svox2.csrc, 'sample_grid') and svox2.BASIS_TYPE_MLP == 255\n"
+            "assert svox2.SparseGrid.__module__.startswith('svox2_b200')\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "compat"), ROOT]))
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, cwd="/")

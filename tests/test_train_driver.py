@@ -95,3 +95,30 @@ def test_ray_pool_is_deterministic_across_ranks_and_covers_every_pixel():
     assert rays.origins.shape == (15, 3) and gt.shape == (15, 3)
     assert torch.allclose(rays.dirs.norm(dim=-1), torch.ones(15), atol=1e-5)
     assert not torch.equal(T.RayPool(data, seed=8).rgb, T.RayPool(data, seed=7).rgb)
+
+
+def test_pool_smaller_than_one_global_batch_is_an_error_not_a_spin():
+    """`run()` must not reshuffle forever when the ray pool cannot fill one batch."""
+    from svox2_b200 import train as T
+    c2w = T.hemisphere_cameras(2, 2.687, "cpu")
+    data = T.PosedImages(c2w, torch.zeros(2, 4, 4, 3), fx=5.0, width=4, height=4)
+    cfg = T.TrainConfig(reso="[[8,8,8]]", n_iters=10, batch_size=64)
+    tr = T.Trainer(cfg, data, log=lambda m: None)
+    with pytest.raises(ValueError, match="smaller than one global batch"):
+        tr.run()
+
+
+def test_multi_gpu_steps_reject_dense_tv():
+    """tv_sparsity >= 1 means the dense TV kernel upstream; the multi-GPU steps are built
+    on the sparse cell run and must say so instead of failing on a None unpack."""
+    import svox2_b200 as sv
+    from svox2_b200.dist import ShardedTrainer
+    from svox2_b200.slab import SlabTrainer
+    g = sv.SparseGrid(reso=8, basis_dim=1, device="cpu")
+    with pytest.raises(ValueError, match="tv_sparsity"):
+        ShardedTrainer(g, world_size=2, rank=0, tv_sparsity=1.0)
+    with pytest.raises(ValueError, match="tv_sparsity"):
+        SlabTrainer(g, world_size=2, rank=0, tv_sparsity=1.0)
+    ShardedTrainer(g, world_size=1, rank=0, tv_sparsity=1.0)      # single GPU: dense path, allowed
+    tr = SlabTrainer(g, world_size=3, rank=1)
+    assert tr._row0_owner == 0 and not tr._holds_row0
