@@ -15,6 +15,16 @@ OUT="$HERE/_ref"
 if [ ! -d "$REF/svox2" ]; then
   echo "reference tree not found at $REF (expected on the build container only)"; exit 0
 fi
+# The reference's own callers (opt/opt.py, opt/render_imgs.py, opt/util/*): run UNMODIFIED by the
+# drop-in tests against compat/svox2 and against the reference build (tests/test_gpu_dropin.py).
+if [ ! -f "$OUT/opt/opt.py" ]; then
+  mkdir -p "$OUT/opt"
+  cp "$REF"/opt/*.py "$OUT/opt/"
+  cp -r "$REF"/opt/util "$REF"/opt/configs "$OUT/opt/"
+  find "$OUT/opt" -name __pycache__ -prune -exec rm -rf {} +
+  chmod -R u+w "$OUT/opt"
+  echo "reference callers installed into $OUT/opt"
+fi
 if ls "$OUT"/svox2/csrc*.so >/dev/null 2>&1; then
   echo "oracle/_ref already built"; exit 0
 fi

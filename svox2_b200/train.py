@@ -208,6 +208,29 @@ def load_nerf_synthetic(root: str, split: str, device, scene_scale: float = 2.0 
     return PosedImages(torch.stack(c2w).to(device), images, fx, w, h)
 
 
+def save_nerf_synthetic(data: PosedImages, root: str, split: str, scene_scale: float = 2.0 / 3.0):
+    """Inverse of ``load_nerf_synthetic``: writes ``transforms_<split>.json`` + ``<split>/r_<i>.png``
+    in the NeRF-synthetic (Blender) layout the reference's loader reads
+    (opt/util/nerf_dataset.py:57-98): OpenGL camera convention, unscaled translations."""
+    import os
+    from PIL import Image
+    os.makedirs(os.path.join(root, split), exist_ok=True)
+    flip = torch.diag(torch.tensor([1.0, -1.0, -1.0, 1.0]))
+    frames = []
+    for i in range(data.c2w.size(0)):
+        m = data.c2w[i].detach().cpu().float().clone()
+        if m.size(0) == 3:
+            m = torch.cat([m, torch.tensor([[0.0, 0.0, 0.0, 1.0]])])
+        m[:3, 3] /= scene_scale
+        m = m @ flip
+        im = (data.images[i].detach().clamp(0, 1) * 255.0 + 0.5).to(torch.uint8).cpu().numpy()
+        Image.fromarray(im).save(os.path.join(root, split, f"r_{i}.png"))
+        frames.append({"file_path": f"./{split}/r_{i}", "transform_matrix": m.tolist()})
+    meta = {"camera_angle_x": 2.0 * math.atan(0.5 * data.width / data.fx), "frames": frames}
+    with open(os.path.join(root, f"transforms_{split}.json"), "w") as f:
+        json.dump(meta, f)
+
+
 class Trainer:
     """One process of the training job.  ``dist_mode``: "slab" (grid sharded) or "rays"."""
 

@@ -1,0 +1,196 @@
+"""The drop-in claim, executed (INTEGRATION.md options A.1 and A.2):
+
+  A.2  the reference's OWN Python layer (oracle/_ref/svox2/svox2.py, unmodified) with its operator
+       module `_C` replaced by `svox2_b200.csrc` -- fused step, TV, RMSProp, resample and image
+       render compared with the same layer on the reference's CUDA extension;
+  A.1  the reference's OWN training and evaluation scripts (oracle/_ref/opt/opt.py and
+       opt/render_imgs.py, unmodified) run as subprocesses on a generated NeRF-synthetic-format
+       scene, once with PYTHONPATH=compat (svox2 -> svox2_b200) and once on the reference build;
+       PSNR must rise and agree within 0.5 dB.
+
+`imageio`, `matplotlib` and `lpips` are not in this image: tests/stubs holds minimal stand-ins
+(PIL-backed image IO, a colour map) that BOTH runs use.
+"""
+import importlib.util
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import svox2_b200 as sv
+from gpu_helpers import _fill_grid, t
+from scenes import make_scene, rel_err
+from test_gpu_parity import _cam
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref")
+STUBS = os.path.join(ROOT, "tests", "stubs")
+
+
+@pytest.fixture(scope="module")
+def ref_layer_on_b200(ref_svox2):
+    """A second instance of the reference's svox2/svox2.py whose `_C` is svox2_b200.csrc: the
+    module is executed again inside the reference package with utils._get_c_extension
+    (svox2/utils.py:29-42) patched, exactly the one-line change INTEGRATION.md option A.2 shows."""
+    from svox2_b200 import csrc
+    utils = ref_svox2.utils
+    orig = utils._get_c_extension
+    utils._get_c_extension = lambda: csrc
+    try:
+        spec = importlib.util.spec_from_file_location(
+            "svox2.svox2_on_b200", os.path.join(REF, "svox2", "svox2.py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[spec.name] = mod
+        spec.loader.exec_module(mod)
+    finally:
+        utils._get_c_extension = orig
+    assert mod._C is csrc and ref_svox2.svox2._C is not csrc
+    return mod
+
+
+def _ref_grid(mod, sc, **kw):
+    g = mod.SparseGrid(reso=list(sc["links"].shape), radius=sc["radius"].tolist(),
+                       center=sc["center"].tolist(), basis_dim=sc["basis_dim"], device="cuda", **kw)
+    return _fill_grid(g, sc, "cuda")
+
+
+@pytest.mark.parametrize("bg", [False, True])
+def test_reference_python_layer_runs_on_our_operator_module(ref_svox2, ref_layer_on_b200, bg):
+    """Same Python code (the reference's), two operator modules.  The tensors are the reference's
+    plain contiguous [N,27] arrays (row stride 27 -> the scalar-load variants of our kernels)."""
+    on_ours, on_ref = ref_layer_on_b200, ref_svox2.svox2
+    sc = make_scene(reso=32, basis_dim=9, seed=12, n_rays=2048, bg=(32, 8) if bg else None,
+                    inside=bg)
+    kw = dict(background_nlayers=8, background_reso=32) if bg else {}
+    a, b = _ref_grid(on_ours, sc, **kw), _ref_grid(on_ref, sc, **kw)
+    for g in (a, b):
+        g.opt.sigma_thresh, g.opt.stop_thresh = 1e-8, 1e-7
+    o, d, gt = t(sc["origins"]), t(sc["dirs"]), t(sc["rgb_gt"])
+    out = []
+    for g, mod in ((a, on_ours), (b, on_ref)):
+        np.random.seed(5)
+        rgb = g.volume_render_fused(mod.Rays(o, d), gt, beta_loss=1e-3, sparsity_loss=1e-4)
+        g.inplace_tv_grad(g.density_data.grad, scaling=1e-4)
+        g.inplace_tv_color_grad(g.sh_data.grad, scaling=1e-3)
+        if bg:
+            g.inplace_tv_background_grad(g.background_data.grad, scaling=1e-3, scaling_density=1e-3,
+                                         contiguous=True)
+        out.append(rgb)
+    assert a.sh_data.stride(0) == 27 and a.sh_data.grad.stride(0) == 27     # the reference layout
+    assert (out[0] - out[1]).abs().max().item() < 1e-5
+    assert a.sparse_grad_indexer.dtype == torch.bool
+    assert torch.equal(a.sparse_grad_indexer, b.sparse_grad_indexer)
+    assert torch.equal(a.sparse_sh_grad_indexer, b.sparse_sh_grad_indexer)
+    assert rel_err(a.density_data.grad.cpu().numpy(), b.density_data.grad.cpu().numpy()) < 1e-4
+    assert rel_err(a.sh_data.grad.cpu().numpy(), b.sh_data.grad.cpu().numpy()) < 1e-4
+    if bg:
+        assert torch.equal(a.sparse_background_indexer, b.sparse_background_indexer)
+        assert rel_err(a.background_data.grad.cpu().numpy(), b.background_data.grad.cpu().numpy()) < 1e-4
+    # same gradients into both optimiser kernels (the reference layer turns small masks into index
+    # lists, svox2.py:2215-2221: exercises the int64-index variant)
+    b.density_data.grad.copy_(a.density_data.grad)
+    b.sh_data.grad.copy_(a.sh_data.grad)
+    for g in (a, b):
+        g.optim_density_step(30.0, beta=0.95)
+        g.optim_sh_step(1e-2, beta=0.95)
+    assert torch.equal(a.density_rms, b.density_rms) and torch.equal(a.sh_rms, b.sh_rms)
+    assert rel_err(a.sh_data.detach().cpu().numpy(), b.sh_data.detach().cpu().numpy()) < 1e-6
+    if bg:
+        b.background_data.grad.copy_(a.background_data.grad)
+        for g in (a, b):
+            g.optim_background_step(3.0, 0.1, beta=0.95)
+        assert torch.equal(a.background_rms, b.background_rms)
+    # autograd render through the reference's _VolumeRenderFunction
+    b.sh_data.data.copy_(a.sh_data.data)
+    b.density_data.data.copy_(a.density_data.data)
+    w = torch.randn(o.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    for g, mod in ((a, on_ours), (b, on_ref)):
+        g.sh_data.grad = g.density_data.grad = None
+        (g.volume_render(mod.Rays(o, d), use_kernel=True) * w).sum().backward()
+    assert rel_err(a.sh_data.grad.cpu().numpy(), b.sh_data.grad.cpu().numpy()) < 1e-4
+    assert rel_err(a.density_data.grad.cpu().numpy(), b.density_data.grad.cpu().numpy()) < 1e-4
+    # image + depth + sample + resample (weight-threshold branch: grid_weight_render, dilate,
+    # sample_grid, accel_dist_prop)
+    cm = _cam(sc, W=96, H=64)
+    ckw = dict(fx=cm["fx"], fy=cm["fy"], cx=cm["cx"], cy=cm["cy"], width=96, height=64)
+    with torch.no_grad():
+        ia = a.volume_render_image(on_ours.Camera(t(cm["c2w"]), **ckw))
+        ib = b.volume_render_image(on_ref.Camera(t(cm["c2w"]), **ckw))
+        assert (ia - ib).abs().max().item() < 1e-5
+        assert torch.equal(a.volume_render_depth(on_ours.Rays(o, d), 3.0),
+                           b.volume_render_depth(on_ref.Rays(o, d), 3.0))
+        pts = torch.rand(5000, 3, device="cuda") * 2.2 - 1.1
+        for x, y in zip(a.sample(pts), b.sample(pts)):
+            assert torch.equal(x, y)
+    if not bg:
+        a.resample(48, weight_thresh=0.05, dilate=2, cameras=[on_ours.Camera(t(cm["c2w"]), **ckw)])
+        b.resample(48, weight_thresh=0.05, dilate=2, cameras=[on_ref.Camera(t(cm["c2w"]), **ckw)])
+        assert torch.equal(a.links, b.links)
+        assert torch.equal(a.density_data, b.density_data) and torch.equal(a.sh_data, b.sh_data)
+
+
+# ----------------------------------------------------------------------------------------------
+# the reference's scripts, unmodified
+# ----------------------------------------------------------------------------------------------
+def _write_scene(root):
+    """A NeRF-synthetic-format scene (transforms_*.json + PNGs) rendered from a hidden analytic
+    scene with this package's renderer."""
+    from svox2_b200 import train as T
+    dev = torch.device("cuda:0")
+    data = T.synthetic_dataset(dev, n_images=30, width=80, height=80, reso=48)
+    T.save_nerf_synthetic(T.PosedImages(data.c2w[:24], data.images[:24], data.fx, 80, 80), root, "train")
+    T.save_nerf_synthetic(T.PosedImages(data.c2w[24:], data.images[24:], data.fx, 80, 80), root, "test")
+
+
+def _run(script, args, pythonpath, cwd):
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join(pythonpath), CUDA_VISIBLE_DEVICES="0")
+    p = subprocess.run([sys.executable, os.path.join(REF, "opt", script)] + args, env=env, cwd=cwd,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-4000:]
+    return p.stdout
+
+
+def test_reference_opt_py_and_render_imgs_run_unmodified_on_compat(tmp_path):
+    if not os.path.isfile(os.path.join(REF, "opt", "opt.py")):
+        pytest.skip("oracle/_ref/opt not installed (oracle/build_ref.sh)")
+    scene = str(tmp_path / "scene")
+    _write_scene(scene)
+    train_args = ["--reso", "[[32,32,32],[64,64,64]]", "--n_iters", "240", "--epoch_size", "40",
+                  "--upsamp_every", "120", "--batch_size", "2048", "--print_every", "10",
+                  "--lr_sigma_delay_steps", "60", "--weight_thresh", str(0.0005 * 64),
+                  "--dataset_type", "nerf", "--eval_every", "1"]
+    arms = {"ours": [STUBS, os.path.join(ROOT, "compat"), ROOT], "reference": [STUBS, REF]}
+    psnr, final = {}, {}
+    for name, pp in arms.items():
+        out_dir = str(tmp_path / f"ckpt_{name}")
+        log = _run("opt.py", [scene, "-t", out_dir] + train_args, pp, str(tmp_path))
+        vals = [float(m) for m in re.findall(r"eval stats: \{'psnr': ([0-9.eE+-]+)", log)]
+        assert len(vals) >= 3, log[-3000:]
+        assert "* Upsampling from [32, 32, 32] to [64, 64, 64]" in log
+        psnr[name] = vals
+        assert os.path.isfile(os.path.join(out_dir, "ckpt.npz"))
+        # the reference's evaluation script on the checkpoint the run wrote (PSNR + SSIM)
+        rlog = _run("render_imgs.py", [os.path.join(out_dir, "ckpt.npz"), scene, "--no_lpips", "--no_vid",
+                                      "--dataset_type", "nerf"], pp, str(tmp_path))
+        m = re.search(r"AVERAGES\s+PSNR: ([0-9.]+)\s+SSIM: ([0-9.]+)", rlog)
+        assert m, rlog[-3000:]
+        final[name] = (float(m.group(1)), float(m.group(2)))
+        assert os.path.isfile(os.path.join(out_dir, "test_renders", "0000.png"))
+    print("opt.py eval PSNR per epoch:", json.dumps(psnr), "render_imgs.py:", json.dumps(final))
+    for name in arms:
+        assert psnr[name][-1] > psnr[name][0] + 5.0, psnr       # it trains
+    assert abs(psnr["ours"][-1] - psnr["reference"][-1]) < 0.5, psnr
+    assert abs(final["ours"][0] - final["reference"][0]) < 0.5 and \
+        abs(final["ours"][1] - final["reference"][1]) < 0.02, final
+    # cross-load: each implementation renders the other's checkpoint (on-disk format either side)
+    rlog = _run("render_imgs.py", [str(tmp_path / "ckpt_reference" / "ckpt.npz"), scene, "--no_lpips",
+                                  "--no_vid", "--no_imsave", "--dataset_type", "nerf"],
+                arms["ours"], str(tmp_path))
+    m = re.search(r"AVERAGES\s+PSNR: ([0-9.]+)", rlog)
+    assert m and abs(float(m.group(1)) - final["reference"][0]) < 0.05, rlog[-2000:]

@@ -277,6 +277,20 @@ def test_config_c3_training_steps_follow_the_reference_cuda(ref_svox2):
         gt = torch.cat([ours.volume_render(sv.Rays(o[i:i + 25000], d[i:i + 25000]))
                         for i in range(0, o.size(0), 25000)])
         gt = (gt + 0.05 * torch.randn(gt.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(3))).clamp_(0, 1)
+    # gradients of step 0 (fused march + both sparse TVs, identical parameters) at the 1e-4 bar
+    syn = bench.SYN
+    oo, dd, gg = o[:bench.BATCH].contiguous(), d[:bench.BATCH].contiguous(), gt[:bench.BATCH].contiguous()
+    for g, mod in ((ours, sv), (ref, ref_svox2)):
+        np.random.seed(499)
+        g.volume_render_fused(mod.Rays(oo, dd), gg)
+        g.inplace_tv_grad(g.density_data.grad, scaling=syn["lambda_tv"], sparse_frac=syn["tv_sparsity"])
+        g.inplace_tv_color_grad(g.sh_data.grad, scaling=syn["lambda_tv_sh"], sparse_frac=syn["tv_sparsity"])
+    assert torch.equal(ours.sparse_sh_grad_indexer, ref.sparse_sh_grad_indexer)
+    assert rel_err(ours.density_data.grad.cpu().numpy(), ref.density_data.grad.cpu().numpy()) < TOL
+    assert rel_err(ours.sh_data.grad.cpu().numpy(), ref.sh_data.grad.cpu().numpy()) < TOL
+    for g in (ours, ref):
+        g.density_data.grad.zero_()
+        g.sh_data.grad.zero_()
     trainer = ShardedTrainer(ours, **bench.SYN)
     for it in range(10):
         s = slice(it * bench.BATCH, (it + 1) * bench.BATCH)

@@ -122,3 +122,13 @@ def test_multi_gpu_steps_reject_dense_tv():
     ShardedTrainer(g, world_size=1, rank=0, tv_sparsity=1.0)      # single GPU: dense path, allowed
     tr = SlabTrainer(g, world_size=3, rank=1)
     assert tr._row0_owner == 0 and not tr._holds_row0
+
+
+def test_nerf_synthetic_export_roundtrips_through_the_loader(tmp_path):
+    c2w = T.hemisphere_cameras(3, 2.687, "cpu", seed=4)
+    imgs = torch.rand(3, 6, 8, 3, generator=torch.Generator().manual_seed(1))
+    data = T.PosedImages(c2w, imgs, fx=11.0, width=8, height=6)
+    T.save_nerf_synthetic(data, str(tmp_path), "train")
+    back = T.load_nerf_synthetic(str(tmp_path), "train", "cpu")
+    assert torch.allclose(back.c2w, c2w, atol=1e-6) and abs(back.fx - 11.0) < 1e-4
+    assert (back.images - imgs).abs().max().item() <= 0.5 / 255 + 1e-6
