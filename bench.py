@@ -156,76 +156,124 @@ def time_images(render, cams, reps=3):
     return e0.elapsed_time(e1) / (reps * len(cams))
 
 
-class ClockSampler:
-    """nvidia-smi clocks / throttle reasons, sampled every 20 ms in a side process.  nvidia-smi
-    needs ~0.1 s before its first line, longer than a short timed region, so it is started before
-    the warm-up; `mark()` brackets the timed region on the host clock and only samples whose
-    receive time falls inside are reported (all samples under load as a fallback, flagged)."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+_NVML_POLLER = r"""
+import sys, time
+import pynvml as N
+N.nvmlInit()
+h = N.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+period = float(sys.argv[2])
+mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+R = {"hw_slowdown": N.nvmlClocksThrottleReasonHwSlowdown,
+     "hw_thermal_slowdown": N.nvmlClocksThrottleReasonHwThermalSlowdown,
+     "sw_thermal_slowdown": N.nvmlClocksThrottleReasonSwThermalSlowdown,
+     "sw_power_cap": N.nvmlClocksThrottleReasonSwPowerCap}
+out = sys.stdout
+while True:
+    sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+    try:
+        bits = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+    except Exception:
+        bits = 0
+    names = "|".join(k for k, v in R.items() if bits & v)
+    out.write("%.6f,%d,%d,%s\n" % (time.monotonic(), sm, mx, names))
+    out.flush()
+    time.sleep(period)
+"""
 
-    def __init__(self, index):
+
+class ClockSampler:
+    """SM clock and throttle reasons sampled through NVML every 2 ms by a side PROCESS (no GIL
+    contention with the launching thread; `nvidia-smi -lms` cannot go below ~20 ms, longer than a
+    20-step timed region).  Samples carry the poller's CLOCK_MONOTONIC stamp (system-wide on Linux);
+    `mark()` brackets the timed region and only samples inside it are reported (all samples under
+    load as a flagged fallback)."""
+
+    def __init__(self, index, period_s=0.002):
         self.proc = None
-        self.lines = []          # (host receive time, line)
+        self.lines = []
         self.t0 = self.t1 = None
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "20"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            phys = index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    phys = int(vis.split(",")[index])
+                except (ValueError, IndexError):
+                    phys = index
+            self.proc = subprocess.Popen([sys.executable, "-c", _NVML_POLLER, str(phys), str(period_s)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
+        # second source, used only if the NVML poller yields nothing: nvidia-smi at its 20 ms floor
+        self.smi, self.smi_lines = None, []
+        try:
+            self.smi = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}", "--query-gpu=clocks.sm,clocks.max.sm,"
+                 "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                 "--format=csv,noheader,nounits", "-lms", "20"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read_smi, daemon=True).start()
+        except Exception:
+            self.smi = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append((time.perf_counter(), line.strip()))
+            self.lines.append(line.strip())
+
+    def _read_smi(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.smi.stdout:
+            p = [x.strip() for x in line.split(",")]
+            if len(p) >= 6:
+                why = "|".join(n for n, v in zip(names, p[2:6]) if v.lower().startswith("active"))
+                self.smi_lines.append(f"{time.monotonic():.6f},{p[0]},{p[1]},{why}")
 
     def mark(self):
         """Call right after the synchronising barrier at the start and at the end of the region."""
         if self.t0 is None:
-            self.t0 = time.perf_counter()
+            self.t0 = time.monotonic()
         else:
-            self.t1 = time.perf_counter()
+            self.t1 = time.monotonic()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-
-        def digest(lines):
-            sm, mx, reasons = [], [], set()
-            for _, ln in lines:
-                p = [x.strip() for x in ln.split(",")]
-                if len(p) < 6:
-                    continue
-                try:
-                    sm.append(float(p[0]))
-                    mx.append(float(p[1]))
-                except ValueError:
-                    continue
-                for nm, v in zip(names, p[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            return sm, mx, reasons
-
-        inside = [x for x in self.lines if self.t0 is not None and self.t1 is not None and
-                  self.t0 <= x[0] <= self.t1 + 0.02]
-        sm, mx, reasons = digest(inside)
+        time.sleep(0.01)
+        for pr in (self.proc, self.smi):
+            if pr is None:
+                continue
+            pr.terminate()
+            try:
+                pr.wait(timeout=2)
+            except Exception:
+                pr.kill()
+        how = "NVML (pynvml) polled every 2 ms by a side process"
+        lines = self.lines
+        if not lines:
+            lines, how = self.smi_lines, "nvidia-smi -lms 20 (NVML poller produced nothing)"
+        if not lines:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock sampler available"]}
+        rows = []
+        for ln in lines:
+            p = ln.split(",")
+            if len(p) < 4:
+                continue
+            try:
+                rows.append((float(p[0]), float(p[1]), float(p[2]), [x for x in p[3].split("|") if x]))
+            except ValueError:
+                continue
+        inside = [r for r in rows if self.t0 is not None and self.t1 is not None and
+                  self.t0 <= r[0] <= self.t1]
         window = "timed region"
-        if not sm:      # region shorter than the sampling period: everything sampled under load
-            sm, mx, reasons = digest(self.lines)
-            window = "warm-up + timed region"
+        if len(inside) < 3:     # a region shorter than a few periods: everything sampled under load
+            inside, window = rows, "warm-up + timed region"
+        sm = [r[1] for r in inside]
+        reasons = sorted({x for r in inside for x in r[3]})
         return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm), "window": window}
+                "sm_max_mhz": float(max(r[2] for r in inside)) if inside else None,
+                "reasons": reasons, "samples": len(sm), "window": window,
+                "how": how}
 
 
 def peaks():
@@ -233,6 +281,83 @@ def peaks():
     if os.path.exists(path):
         return json.load(open(path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic(workload):
+    """DRAM bytes (read + write) of the dominant kernels from the committed `ncu --set full` capture
+    of THIS workload, written by tools/ncu_traffic.py into profiles/r2_traffic.json together with
+    the git head it was taken at.  None (and why) when there is no such file / entry."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(path):
+        return None, "no ncu capture committed for this build (profiles/r2_traffic.json)"
+    rec = json.load(open(path)).get(workload)
+    if not rec:
+        return None, f"profiles/r2_traffic.json has no entry for workload {workload}"
+    return rec, f"profiles/r2_traffic.json ({rec.get('source')}, head {rec.get('head')})"
+
+
+def _frac_bad(a, b, tol=1e-4):
+    """Fraction of elements whose error exceeds tol * max|b| (tests/scenes.py::frac_bad on device)."""
+    if b.numel() == 0:
+        return 0.0
+    denom = max(float(b.abs().max()), 1e-30)
+    return float(((a - b).abs() > tol * denom).float().mean())
+
+
+def multi_gpu_parity(sv, grid, trainer, slab, step, global_batches, local_batches, rank, world, dev):
+    """Before anything is timed: the N-GPU step on global batch B must equal the 1-GPU step on the
+    same B.  Every rank clones the starting grid, runs the single-GPU trainer on the
+    whole global batch with the same TV seed, then the multi-GPU step, and compares colours, the
+    sparse masks (bit for bit on the rows this rank is responsible for), the updated parameters
+    (fraction of elements off by more than 1e-4 of the max) and the colours of a second step.
+    Returns the per-job summary (worst rank); the caller fails the run when `ok` is false."""
+    import torch.distributed as dist
+    from svox2_b200.dist import ShardedTrainer
+    ref = sv.SparseGrid(reso=[2, 2, 2], basis_dim=grid.basis_dim, device="cpu")
+    ref.links = grid.links
+    ref.density_data = torch.nn.Parameter(grid.density_data.data.clone())
+    ref.sh_data = torch.nn.Parameter(grid.sh_data.data.clone())
+    ref.capacity = grid.capacity
+    for k in RENDER:
+        setattr(ref.opt, k, getattr(grid.opt, k))
+    single = ShardedTrainer(ref, world_size=1, rank=0, **SYN)
+    out = {}
+    for it in range(2):
+        go, gd, gg = global_batches[it]
+        np.random.seed(4242 + it)
+        rgb1 = single.step(sv.Rays(go, gd), gg)
+        np.random.seed(4242 + it)
+        rgb = step(*local_batches[it])
+        torch.cuda.synchronize()
+        mine = slice(None) if slab else slice(rank * rgb.size(0), (rank + 1) * rgb.size(0))
+        out["rgb_max_abs" if it == 0 else "rgb_max_abs_step2"] = float((rgb - rgb1[mine]).abs().max())
+        if it == 0:
+            rows = trainer.own_mask if slab else torch.ones_like(ref.sparse_grad_indexer)
+            out["mask_equal"] = bool(
+                torch.equal(grid.sparse_grad_indexer[rows], ref.sparse_grad_indexer[rows]) and
+                torch.equal(grid.sparse_sh_grad_indexer[rows], ref.sparse_sh_grad_indexer[rows]))
+            out["rows_checked"] = int(rows.sum())
+            out["rows_touched"] = int(ref.sparse_sh_grad_indexer[rows].sum())
+            out["fb_density"] = _frac_bad(grid.density_data.data[rows], ref.density_data.data[rows])
+            out["fb_sh"] = _frac_bad(grid.sh_data.data[rows], ref.sh_data.data[rows])
+    ok = (out["rgb_max_abs"] < 1e-5 and out["mask_equal"] and out["fb_density"] < 1e-3 and
+          out["fb_sh"] < 1e-3 and out["rgb_max_abs_step2"] < 2e-3)
+    vec = torch.tensor([out["rgb_max_abs"], out["rgb_max_abs_step2"], out["fb_density"], out["fb_sh"],
+                        0.0 if out["mask_equal"] else 1.0, 0.0 if ok else 1.0],
+                       dtype=torch.float64, device=dev)
+    cnt = torch.tensor([out["rows_checked"], out["rows_touched"]], dtype=torch.int64, device=dev)
+    dist.all_reduce(vec, op=dist.ReduceOp.MAX)
+    dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    v = vec.tolist()
+    del ref, single
+    torch.cuda.empty_cache()
+    return {"ok": v[5] == 0.0,
+            "against": "1-GPU step (ShardedTrainer, world 1) on the same global batch, grid and TV seed",
+            "rgb_max_abs": v[0], "mask_equal_on_owned_rows": v[4] == 0.0,
+            "frac_bad_density_1e-4": v[2], "frac_bad_sh_1e-4": v[3], "rgb_max_abs_step2": v[1],
+            "rows_checked": int(cnt[0]), "rows_touched": int(cnt[1]), "ranks": world,
+            "bars": {"rgb_max_abs": 1e-5, "mask": "bit-exact", "frac_bad": 1e-3, "rgb_max_abs_step2": 2e-3},
+            "reduction": "worst rank (max), row counts summed"}
 
 
 def algorithmic_bytes_fused(q, c):
@@ -261,7 +386,7 @@ def run_ours(args):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
     sc = build_scene(args.workload, dev)
-    grid = sv.SparseGrid(reso=sc["reso"], basis_dim=9, device=dev)
+    grid = sv.SparseGrid(reso=[2, 2, 2], basis_dim=9, device=dev)   # geometry follows links.shape
     grid.links = sc["links"]
     grid.density_data = torch.nn.Parameter(sc["density"])
     grid.sh_data = torch.nn.Parameter(sc["sh"])
@@ -270,8 +395,12 @@ def run_ours(args):
     for k, v in RENDER.items():
         setattr(grid.opt, k, v)
 
-    # global ray pool: POOL batches of BATCH*world rays; rank r owns a contiguous slice of each
-    gq = BATCH * world
+    # global ray pool: POOL global batches; rank r owns a contiguous slice of each.  Weak scaling:
+    # BATCH rays per GPU (global batch BATCH*world); strong: the reference's global batch of BATCH
+    # rays (opt.py:79-81) split over the ranks.
+    strong = args.scaling == "strong"
+    per_rank = BATCH // world if strong else BATCH
+    gq = per_rank * world
     origins, dirs = build_rays(POOL * gq, dev)
     with torch.no_grad():
         gt = torch.cat([grid.volume_render(sv.Rays(origins[i:i + 50000], dirs[i:i + 50000]))
@@ -280,10 +409,10 @@ def run_ours(args):
         gt = (gt + 0.02 * torch.randn(gt.shape, generator=ggen, device=dev)).clamp_(0, 1)
     slab = world > 1 and args.dist == "slab"
     # this rank's BATCH rays of every pooled global batch (kernel-only timing, counters)
-    sl = [slice(b * gq + rank * BATCH, b * gq + (rank + 1) * BATCH) for b in range(POOL)]
+    sl = [slice(b * gq + rank * per_rank, b * gq + (rank + 1) * per_rank) for b in range(POOL)]
     own = [(origins[s].contiguous(), dirs[s].contiguous(), gt[s].contiguous()) for s in sl]
+    gsl = [slice(b * gq, (b + 1) * gq) for b in range(POOL)]
     if slab:    # grid sharded by x-slabs: every rank takes the whole global batch
-        gsl = [slice(b * gq, (b + 1) * gq) for b in range(POOL)]
         batches = [(origins[s].contiguous(), dirs[s].contiguous(), gt[s].contiguous()) for s in gsl]
         trainer = SlabTrainer(grid, world_size=world, rank=rank, **SYN)
     else:       # rays sharded, grid replicated
@@ -312,6 +441,13 @@ def run_ours(args):
     torch.cuda.synchronize()
     cnt = [c / POOL for c in counters.cpu().tolist()]
 
+    parity = None
+    if world > 1 and not args.no_parity:
+        # N-GPU step == 1-GPU step on the same global batch, checked on every rank before timing
+        gb = [(origins[s].contiguous(), dirs[s].contiguous(), gt[s].contiguous()) for s in gsl[:2]]
+        parity = multi_gpu_parity(sv, grid, trainer, slab, step, gb, batches, rank, world, dev)
+        np.random.seed(1234)
+
     sampler = ClockSampler(local) if rank == 0 else None
     for i in range(args.warmup):
         step(*batches[i % POOL])
@@ -325,6 +461,8 @@ def run_ours(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    # rows the last step's optimisers updated (the masks survive the step): whole-step roofline
+    touched = (int(grid.sparse_grad_indexer.sum()), int(grid.sparse_sh_grad_indexer.sum()))
 
     # end to end: pinned host inputs -> H2D, step, D2H of the loss, every step.  The loss of step i
     # lands in a double-buffered pinned scalar and is read while step i+1 is already enqueued (the
@@ -389,8 +527,8 @@ def run_ours(args):
     torch.cuda.synchronize()
     if args.profile:
         np.random.seed(4321)
-        for i in range(2):
-            step(*batches[i % POOL])    # two full steps (TV + optimiser kernels) for the launch list
+        for i in range(args.profile_steps):
+            step(*batches[i % POOL])    # full steps (TV + optimiser kernels) for the launch list
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
     ms_fused = k0.elapsed_time(k1) / args.steps
@@ -409,29 +547,42 @@ def run_ours(args):
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
+        if parity is not None and not parity["ok"]:
+            sys.exit(1)
         return
     peak, peak_src = peaks()
-    abytes = algorithmic_bytes_fused(BATCH, cnt)
+    abytes = algorithmic_bytes_fused(per_rank, cnt)
     achieved = abytes / (ms_fused * 1e-3) / 1e9
+    traffic, traffic_src = measured_traffic(args.workload)
+    # whole step: fused call + optimisers (24 B per updated element) + sparse TV
+    # (16 B of link probes per cell of the run; 16 B data + 32 B read-modify-write per channel of
+    # a non-empty cell, expected count = occupancy x cells)
+    n_tv = max(int(SYN["tv_sparsity"] * sc["reso"] ** 3), 1)
+    tv_bytes = 2 * n_tv * 16 + sc["occupancy"] * n_tv * 28 * 48
+    opt_bytes = 24 * (touched[0] + 27 * touched[1])
+    step_bytes = abytes + opt_bytes + tv_bytes
     line = {
         "metric": "train rays/sec (fused fwd+bwd step) at 512^3 SH2",
         "value": gq * args.steps / (ms * 1e-3),
         "unit": "rays/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {
             "workload": sc["name"], "reso": sc["reso"], "stored_voxels": sc["n_rows"],
-            "occupancy": round(sc["occupancy"], 4), "rays_per_gpu": BATCH, "global_batch": gq,
+            "occupancy": round(sc["occupancy"], 4), "rays_per_gpu": per_rank, "global_batch": gq,
             "step": "volume_render_fused + tv_grad_sparse(sigma,sh) + rmsprop(sigma,sh)",
             "l2": "inputs larger than L2 (grid+grads+rms >> 126 MB); 8 distinct ray batches cycled",
             "parallelism": (f"grid sharded into {world} x-slabs, every rank traverses the global "
-                            "batch; per-ray scalar all-gathers + halo planes (NCCL)") if slab else
+                            "batch; per-ray scalars and halo planes exchanged with " +
+                            ("symmetric-memory peer stores over NVLink + device-side barriers"
+                             if getattr(trainer, "_peer", None) not in (None, False) else
+                             "NCCL all-gathers / P2P (no symmetric memory)")) if slab else
                            (f"ray-sharded x{world}, replicated grid" +
                             (", masked packed grad all-reduce (NCCL)" if world > 1 else "")),
-            "samples_per_ray": {"skip": cnt[0] / BATCH, "visited": cnt[1] / BATCH,
-                                "active": cnt[2] / BATCH},
+            "samples_per_ray": {"skip": cnt[0] / per_rank, "visited": cnt[1] / per_rank,
+                                "active": cnt[2] / per_rank},
         },
         "e2e": {"value": gq * args.steps / (ms_e2e * 1e-3), "unit": "rays/s",
                 "h2d_bytes_per_step": 3 * batches[0][0].size(0) * 3 * 4, "d2h_bytes_per_step": 4,
@@ -443,10 +594,20 @@ def run_ours(args):
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes,
                      "ms_per_launch": ms_fused,
-                     # dram__bytes_read+write of K1..K4 of one fused call, ncu --set full capture
-                     # of this command (profiles/r1_ncu_step_kernels_full.txt): 335+252+45+419 MB
-                     "traffic": 1.051e9 if args.workload == "c3" else None},
+                     # dram__bytes_read+write of the kernels of one fused call (ncu --set full)
+                     "traffic": traffic["fused_call_dram_bytes"] if traffic else None,
+                     "traffic_source": traffic_src},
     }
+    if world == 1:
+        line["step_roofline"] = {
+            "bound": "hbm", "what": "whole train step: fused call + sparse TV x2 + RMSProp x2",
+            "achieved": step_bytes / (ms / args.steps * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak,
+            "algorithmic_bytes": {"fused": abytes, "optimisers": opt_bytes, "tv": tv_bytes},
+            "rows_updated": {"density": touched[0], "sh": touched[1]},
+            "traffic": traffic.get("step_dram_bytes") if traffic else None}
+    if parity is not None:
+        line["parity"] = parity
     line["render"] = {"value": world * 0.64 / (ms_img * 1e-3), "unit": "MPix/s",
                       "ms_per_image": ms_img, "what": "volume_render_image, 800x800, fx 1111.11, "
                       f"{N_CAMS} hemisphere cameras per GPU (images sharded over GPUs)"}
@@ -466,6 +627,8 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        sys.exit("bench.py: multi-GPU parity check FAILED (see the `parity` object of the line above)")
 
 
 # ----------------------------------------------------------------------------------------------
@@ -530,7 +693,7 @@ class CpuPortStep:
                 f"port of the reference algorithm, {self.cores} pthreads")
 
 
-def cpu_port_baseline(sc, grid, batch, budget_rays=1024, reps=3):
+def cpu_port_baseline(sc, grid, batch, budget_rays=BATCH, reps=2):
     """cpu_baseline of the N=1 line: CpuPortStep on the first `budget_rays` rays of batch 0."""
     step = CpuPortStep(sc, grid.links.cpu().numpy(), budget_rays)
     o, d, gt = (np.ascontiguousarray(x[:budget_rays].cpu().numpy()) for x in batch)
@@ -601,9 +764,11 @@ def run_reference(args):
     """Reference arm: the reference algorithm on the host cores.  The reference's own
     pure-PyTorch path cannot run the 512^3 workload (its autograd materialises a dense [N,27]
     gradient per gather: ~50 TB of traffic per batch), so the timed number is the C port of the
-    same algorithm (oracle, all cores) on a bounded sample of each batch; the reference's own
-    Python path is timed beside it on its own CPU-runnable config (C1) and reported as an
-    extra key."""
+    same algorithm (oracle, all cores) on the SAME config as our arm: whole 5000-ray batches of the
+    same pool, one whole step each (march + TV on the full 1 % cell run + RMSProp).  Only if K such
+    steps would not finish within a few minutes on this host is the per-step sample shrunk (and
+    said so in `cpu_baseline.sample`).  The reference's own Python path is timed beside it on its
+    own CPU-runnable config (C1) and reported as an extra key."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -611,37 +776,60 @@ def run_reference(args):
     sc = build_scene(args.workload, dev)
     import oracle as og
     world = args.gpus
-    gq = BATCH * world
+    per_rank = BATCH // world if args.scaling == "strong" else BATCH
+    gq = per_rank * world
     origins, dirs = build_rays(POOL * gq, "cpu")
-    sample = args.cpu_rays
-    step = CpuPortStep(sc, og.accel_dist_prop(sc["links"].cpu().numpy()), sample)
-    cores, n_tv = step.cores, step.n_tv
+    links = og.accel_dist_prop(sc["links"].cpu().numpy())
+    sample = min(args.cpu_rays, gq)
+    budget_s = 150.0
     rng = np.random.default_rng(1)
 
-    def one(i):
-        s = (i % POOL) * gq
-        o = np.ascontiguousarray(origins[s:s + sample].numpy())
-        d = np.ascontiguousarray(dirs[s:s + sample].numpy())
-        step(o, d, rng.uniform(0, 1, o.shape).astype(np.float32))
+    def make(sample):
+        step = CpuPortStep(sc, links, sample)
 
-    for i in range(min(args.warmup, 1)):
+        def one(i):
+            s = (i % POOL) * gq
+            o = np.ascontiguousarray(origins[s:s + sample].numpy())
+            d = np.ascontiguousarray(dirs[s:s + sample].numpy())
+            step(o, d, rng.uniform(0, 1, o.shape).astype(np.float32))
+        return step, one
+
+    step, one = make(sample)
+    one(0)                                          # page-faults the 1.4 GB arrays
+    t = time.perf_counter()
+    one(1)
+    t_step = time.perf_counter() - t
+    shrunk = False
+    if t_step * (args.steps + max(args.warmup - 2, 0)) > budget_s:
+        step.close()
+        sample = max(256, int(sample * budget_s / (t_step * (args.steps + max(args.warmup - 2, 0)))))
+        step, one = make(sample)
+        one(0)
+        shrunk = True
+    cores, n_tv = step.cores, step.n_tv
+    for i in range(max(args.warmup - 2, 0)):
         one(i)
     t = time.perf_counter()
     for i in range(args.steps):
         one(i)
     dt = time.perf_counter() - t
+    step.close()
     val = sample * args.steps / dt
+    what = (f"{sample} rays per step" + (" (the whole batch)" if sample == gq else
+            f" of each {gq}-ray batch" + (" (shrunk to keep the run within minutes)" if shrunk else "")))
     line = {
         "impl": "reference", "metric": "train rays/sec (fused fwd+bwd step) at 512^3 SH2",
         "value": val, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": sc["name"], "reso": sc["reso"], "stored_voxels": sc["n_rows"],
+                   "occupancy": round(sc["occupancy"], 4), "rays_per_gpu": per_rank, "global_batch": gq,
+                   "step": "volume_render_fused + tv_grad_sparse(sigma,sh) + rmsprop(sigma,sh)",
                    "rays_per_step": sample},
         "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} rays of each pooled batch per step: fused fwd+bwd march + "
-                                   f"sparse TV on {n_tv} cells x2 + masked RMSProp x2 "
-                                   f"(oracle C port of the reference algorithm, {cores} pthreads)"},
+                         "sample": f"{what}: fused fwd+bwd march + sparse TV on {n_tv} cells x2 + "
+                                   f"masked RMSProp x2 (oracle C port of the reference algorithm, "
+                                   f"{cores} pthreads)"},
         "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     if args.ref_pytorch:
@@ -694,11 +882,19 @@ def main():
     ap.add_argument("--dist", default="slab", choices=["slab", "rays"],
                     help="multi-GPU decomposition: grid sharded by x-slabs (default) or rays "
                          "sharded over a replicated grid with a packed gradient all-reduce")
-    ap.add_argument("--cpu-rays", type=int, default=2048, help="bounded CPU sample (rays)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 5000 rays per GPU per step; strong: the reference's global batch of "
+                         "5000 rays (opt.py:79-81) whatever the GPU count")
+    ap.add_argument("--no-parity", dest="no_parity", action="store_true",
+                    help="skip the N-GPU == 1-GPU parity block that precedes the timed loop when N > 1")
+    ap.add_argument("--cpu-rays", type=int, default=BATCH,
+                    help="CPU arm / cpu_baseline: rays per step (default: the full 5000-ray batch)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-ref-cuda", dest="ref_cuda", action="store_false")
     ap.add_argument("--no-ref-pytorch", dest="ref_pytorch", action="store_false")
     ap.add_argument("--ref-pytorch-rays", type=int, default=256)
+    ap.add_argument("--profile-steps", type=int, default=2,
+                    help="whole steps inside the --profile bracket (1 for the ncu --set full capture)")
     ap.add_argument("--profile", action="store_true",
                     help="bracket the kernel-only loop + 2 full steps with cudaProfilerStart/Stop")
     args = ap.parse_args()
