@@ -156,6 +156,24 @@ SVOX2_API int svox2_volume_render_sigma_thresh(const svox2_grid_t* grid, const f
                                      const svox2_render_opts_t* opt, float sigma_thresh,
                                      float* out, svox2_stream_t stream);
 
+/* volume_render_nvol / _backward / _fused (svox2.cpp:80-85; render_lerp_kernel_nvol.cu:406-502):
+ * the Neural-Volumes compositing ablation (absolute transmittance) -- the backend the reference's
+ * own parity script exercises (test/test_render_gradcheck.py:20).  No MSI background, no beta
+ * loss (the reference ignores that argument too).  No workspace is needed. */
+SVOX2_API int svox2_volume_render_nvol(const svox2_grid_t* grid, const float* origins,
+                             const float* dirs, int64_t n_rays, const svox2_render_opts_t* opt,
+                             float* out, svox2_stream_t stream);
+SVOX2_API int svox2_volume_render_nvol_backward(const svox2_grid_t* grid, const float* origins,
+                                      const float* dirs, int64_t n_rays,
+                                      const svox2_render_opts_t* opt, const float* grad_out,
+                                      const float* color_cache, const svox2_grads_t* grads,
+                                      svox2_stream_t stream);
+SVOX2_API int svox2_volume_render_nvol_fused(const svox2_grid_t* grid, const float* origins,
+                                   const float* dirs, int64_t n_rays, int64_t norm_rays,
+                                   const svox2_render_opts_t* opt, const float* rgb_gt,
+                                   float sparsity_loss, float* rgb_out,
+                                   const svox2_grads_t* grads, svox2_stream_t stream);
+
 /* sample_grid / sample_grid_backward  (svox2.cpp:11-17, svox2_kernel.cu:178-267)
  * out_density [P,1]; out_sh [P,3*basis_dim] or NULL (want_colors=false).
  * Unlike the reference no extra streams are created and nothing is synchronised. */

@@ -233,6 +233,39 @@ def volume_render_fused(grid, opt, origins, dirs, rgb_gt, beta_loss=0.0, sparsit
                 mask_bg=None if mbg is None else mbg.astype(bool), counts=_counts_dict(cnt))
 
 
+def volume_render_nvol(grid, opt, origins, dirs):
+    origins, dirs = _f32(origins), _f32(dirs)
+    rgb = np.zeros((origins.shape[0], 3), np.float32)
+    g = grid.c()
+    lib().og_volume_render_nvol(C.byref(g), C.byref(opt), _ptr(origins), _ptr(dirs),
+                                C.c_int64(origins.shape[0]), _ptr(rgb))
+    return rgb
+
+
+def volume_render_nvol_backward(grid, opt, origins, dirs, grad_out, color_cache):
+    origins, dirs = _f32(origins), _f32(dirs)
+    grad_out, color_cache = _f32(grad_out), _f32(color_cache)
+    gd, gsh, _, mask, _ = _alloc_grads(grid, want_bg=False)
+    g = grid.c()
+    lib().og_volume_render_nvol_backward(C.byref(g), C.byref(opt), _ptr(origins), _ptr(dirs),
+                                         C.c_int64(origins.shape[0]), _ptr(grad_out),
+                                         _ptr(color_cache), _ptr(gd), _ptr(gsh), _ptr(mask))
+    return dict(grad_density=gd, grad_sh=gsh, mask=mask.astype(bool))
+
+
+def volume_render_nvol_fused(grid, opt, origins, dirs, rgb_gt, sparsity_loss=0.0, norm_rays=None):
+    origins, dirs, rgb_gt = _f32(origins), _f32(dirs), _f32(rgb_gt)
+    Q = origins.shape[0]
+    gd, gsh, _, mask, _ = _alloc_grads(grid, want_bg=False)
+    rgb = np.zeros((Q, 3), np.float32)
+    g = grid.c()
+    lib().og_volume_render_nvol_fused(C.byref(g), C.byref(opt), _ptr(origins), _ptr(dirs),
+                                      C.c_int64(Q), C.c_int64(Q if norm_rays is None else norm_rays),
+                                      _ptr(rgb_gt), C.c_float(sparsity_loss), _ptr(rgb), _ptr(gd),
+                                      _ptr(gsh), _ptr(mask))
+    return dict(rgb=rgb, grad_density=gd, grad_sh=gsh, mask=mask.astype(bool))
+
+
 def render_expected_term(grid, opt, origins, dirs):
     origins, dirs = _f32(origins), _f32(dirs)
     out = np.zeros(origins.shape[0], np.float32)

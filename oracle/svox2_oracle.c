@@ -776,6 +776,197 @@ void og_volume_render_fused(const og_grid_t* g, const og_opt_t* o, const float* 
 }
 
 /* ---------------------------------------------------------------------------------------
+ * nvol backend (Neural-Volumes compositing): trace_ray_nvol, render_lerp_kernel_nvol.cu:30-111;
+ * trace_ray_nvol_backward :113-296; launchers :406-502.  No MSI background, no beta loss.
+ * ------------------------------------------------------------------------------------- */
+static void trace_ray_nvol_fwd(const og_grid_t* g, const og_opt_t* opt, ray_t* ray, const float* sph,
+                               float* out) {
+    const int B = g->basis_dim, D = 3 * B;
+    const float bgb = (g->bg_nlayers == 0) ? opt->background_brightness : 0.f;
+    if (ray->tmin > ray->tmax) {
+        for (int c = 0; c < 3; ++c) out[c] = bgb;
+        return;
+    }
+    float t = ray->tmin, total_alpha = 0.f;
+    float outv[3] = {0.f, 0.f, 0.f};
+    while (t <= ray->tmax) {
+        ray_locate(ray, g, t);
+        const float skip = compute_skip_dist(ray, g);
+        if (skip >= opt->step_size) {
+            t += ceilf(skip / opt->step_size) * opt->step_size;
+            continue;
+        }
+        int32_t lk[8];
+        corner_links(ray, g, lk);
+        const float sigma = trilerp_links(lk, g->density, 1, 0, ray->pos);
+        if (sigma > opt->sigma_thresh) {
+            float col[3] = {0.f, 0.f, 0.f};
+            for (int j = 0; j < D; ++j)
+                col[j / B] += trilerp_links(lk, g->sh, D, j, ray->pos) * sph[j % B];
+            const float nta = minf(total_alpha + 1.f - EXPF(-ray->world_step * sigma), 1.f);
+            const float weight = nta - total_alpha;
+            total_alpha = nta;
+            for (int c = 0; c < 3; ++c) outv[c] += weight * maxf(col[c] + 0.5f, 0.f);
+            if (total_alpha >= 1.f) break;
+        }
+        t += opt->step_size;
+    }
+    for (int c = 0; c < 3; ++c) out[c] = outv[c] + (1.f - total_alpha) * bgb;
+}
+
+static void trace_ray_nvol_bwd(const og_grid_t* g, const og_opt_t* opt, ray_t* ray, const float* sph,
+                               const float* gout, float sparsity_loss, grads_t* gr) {
+    const int B = g->basis_dim, D = 3 * B;
+    if (ray->tmin > ray->tmax) return;
+    float t = ray->tmin, total_alpha = 0.f, last_total_color = 0.f;
+    float w[8];
+    while (t <= ray->tmax) { /* pass 1: active samples (:137-241) */
+        ray_locate(ray, g, t);
+        const float skip = compute_skip_dist(ray, g);
+        if (skip >= opt->step_size) {
+            t += ceilf(skip / opt->step_size) * opt->step_size;
+            continue;
+        }
+        int32_t lk[8];
+        corner_links(ray, g, lk);
+        const float sigma = trilerp_links(lk, g->density, 1, 0, ray->pos);
+        if (sigma > opt->sigma_thresh) {
+            float col[3] = {0.f, 0.f, 0.f};
+            for (int j = 0; j < D; ++j)
+                col[j / B] += trilerp_links(lk, g->sh, D, j, ray->pos) * sph[j % B];
+            const float curr_transmit = EXPF(-ray->world_step * sigma);
+            const float nta = minf(total_alpha + 1.f - curr_transmit, 1.f);
+            const float weight = nta - total_alpha;
+            const int not_last = nta < 1.f;
+            total_alpha = nta;
+            float tc[3], in01[3];
+            for (int c = 0; c < 3; ++c) {
+                const float lct = col[c] + 0.5f;
+                const float clamped = maxf(lct, 0.f);
+                in01[c] = (clamped == lct) ? 1.f : 0.f;
+                tc[c] = clamped * gout[c];
+            }
+            float total_color = tc[0];
+            total_color += tc[2];
+            total_color += tc[1];
+            for (int j = 0; j < D; ++j) {
+                const int c = j / B;
+                const float grad_common = weight * in01[c] * gout[c];
+                trilerp_weights(ray->pos, sph[j % B] * grad_common, w);
+                for (int q = 0; q < 8; ++q)
+                    if (lk[q] >= 0) acc_sh(gr, (int64_t)lk[q] * D + j, w[q]);
+            }
+            if (not_last) {
+                float curr_grad_sigma = ray->world_step * curr_transmit * total_color;
+                if (sparsity_loss > 0.f)
+                    curr_grad_sigma += sparsity_loss * (4 * sigma / (1 + 2 * (sigma * sigma)));
+                trilerp_weights(ray->pos, curr_grad_sigma, w);
+                for (int q = 0; q < 8; ++q)
+                    if (lk[q] >= 0) {
+                        acc_d(gr, lk[q], w[q]);
+                        if (gr->mask) gr->mask[lk[q]] = 1;
+                    }
+            } else {
+                ray->tmax = t;
+                last_total_color = total_color;
+                break;
+            }
+        }
+        t += opt->step_size;
+    }
+    if (total_alpha < 1.f) /* never saturated (:243-247) */
+        last_total_color = opt->background_brightness * (gout[0] + gout[1] + gout[2]);
+    if (last_total_color == 0.f) return;
+    t = ray->tmin;
+    total_alpha = 0.f;
+    while (t <= ray->tmax) { /* pass 2: every visited sample before saturation (:248-293) */
+        ray_locate(ray, g, t);
+        const float skip = compute_skip_dist(ray, g);
+        if (skip >= opt->step_size) {
+            t += ceilf(skip / opt->step_size) * opt->step_size;
+            continue;
+        }
+        int32_t lk[8];
+        corner_links(ray, g, lk);
+        const float sigma = trilerp_links(lk, g->density, 1, 0, ray->pos);
+        const float curr_transmit = EXPF(-ray->world_step * sigma);
+        total_alpha = minf(total_alpha + 1.f - curr_transmit, 1.f);
+        if (total_alpha >= 1.f) break;
+        trilerp_weights(ray->pos, -ray->world_step * curr_transmit * last_total_color, w);
+        for (int q = 0; q < 8; ++q)
+            if (lk[q] >= 0) {
+                acc_d(gr, lk[q], w[q]);
+                if (gr->mask) gr->mask[lk[q]] = 1;
+            }
+        t += opt->step_size;
+    }
+}
+
+typedef struct {
+    const og_grid_t* g; const og_opt_t* o; const float* origins; const float* dirs;
+    float* rgb_out; const float* grad_in; const float* color_cache; int fused; int64_t norm_rays;
+    float sparsity; grads_t* gr;
+} nvol_ctx_t;
+static void nvol_fwd_range(int64_t b, int64_t e, void* vctx) {
+    nvol_ctx_t* c = (nvol_ctx_t*)vctx;
+    for (int64_t r = b; r < e; ++r) {
+        ray_t ray;
+        float sph[9];
+        set_ray(&ray, c->origins + 3 * r, c->dirs + 3 * r);
+        calc_sh(c->g->basis_dim, c->dirs + 3 * r, sph);
+        ray_find_bounds(&ray, c->g, c->o);
+        trace_ray_nvol_fwd(c->g, c->o, &ray, sph, c->rgb_out + 3 * r);
+    }
+}
+static void nvol_bwd_range(int64_t b, int64_t e, void* vctx) {
+    nvol_ctx_t* c = (nvol_ctx_t*)vctx;
+    for (int64_t r = b; r < e; ++r) {
+        ray_t ray;
+        float sph[9], gout[3];
+        set_ray(&ray, c->origins + 3 * r, c->dirs + 3 * r);
+        calc_sh(c->g->basis_dim, c->dirs + 3 * r, sph);
+        ray_find_bounds(&ray, c->g, c->o);
+        if (c->fused) { /* :364-370 */
+            const float norm_factor = 2.f / (float)(3 * (int)c->norm_rays);
+            for (int i = 0; i < 3; ++i)
+                gout[i] = (c->color_cache[3 * r + i] - c->grad_in[3 * r + i]) * norm_factor;
+        } else {
+            for (int i = 0; i < 3; ++i) gout[i] = c->grad_in[3 * r + i];
+        }
+        trace_ray_nvol_bwd(c->g, c->o, &ray, sph, gout, c->fused ? c->sparsity : 0.f, c->gr);
+    }
+}
+
+void og_volume_render_nvol(const og_grid_t* g, const og_opt_t* o, const float* origins,
+                           const float* dirs, int64_t Q, float* rgb_out) {
+    nvol_ctx_t c = {g, o, origins, dirs, rgb_out, NULL, NULL, 0, Q, 0.f, NULL};
+    parallel_for(Q, nvol_fwd_range, &c);
+}
+
+void og_volume_render_nvol_backward(const og_grid_t* g, const og_opt_t* o, const float* origins,
+                                    const float* dirs, int64_t Q, const float* grad_out,
+                                    const float* color_cache, float* grad_density, float* grad_sh,
+                                    uint8_t* mask) {
+    grads_t gr;
+    grads_begin_f(g, &gr, grad_density, grad_sh, NULL, mask, NULL);
+    nvol_ctx_t c = {g, o, origins, dirs, NULL, grad_out, color_cache, 0, Q, 0.f, &gr};
+    parallel_for(Q, nvol_bwd_range, &c);
+    grads_end(g, &gr, grad_density, grad_sh, NULL);
+}
+
+void og_volume_render_nvol_fused(const og_grid_t* g, const og_opt_t* o, const float* origins,
+                                 const float* dirs, int64_t Q, int64_t norm_rays,
+                                 const float* rgb_gt, float sparsity_loss, float* rgb_out,
+                                 float* grad_density, float* grad_sh, uint8_t* mask) {
+    og_volume_render_nvol(g, o, origins, dirs, Q, rgb_out);
+    grads_t gr;
+    grads_begin_f(g, &gr, grad_density, grad_sh, NULL, mask, NULL);
+    nvol_ctx_t c = {g, o, origins, dirs, NULL, rgb_gt, rgb_out, 1, norm_rays, sparsity_loss, &gr};
+    parallel_for(Q, nvol_bwd_range, &c);
+    grads_end(g, &gr, grad_density, grad_sh, NULL);
+}
+
+/* ---------------------------------------------------------------------------------------
  * depth: trace_ray_expected_term cuvol.cu:122-177, trace_ray_sigma_thresh cuvol.cu:180-225
  * ------------------------------------------------------------------------------------- */
 void og_render_expected_term(const og_grid_t* g, const og_opt_t* opt, const float* origins,

@@ -87,6 +87,9 @@ SIGNATURES = {
                                                   _SZ, _P, _P]),
     "svox2_volume_render_expected_term": (C.c_int, [_G, _P, _P, _I64, _O, _P, _P]),
     "svox2_volume_render_sigma_thresh": (C.c_int, [_G, _P, _P, _I64, _O, _F, _P, _P]),
+    "svox2_volume_render_nvol": (C.c_int, [_G, _P, _P, _I64, _O, _P, _P]),
+    "svox2_volume_render_nvol_backward": (C.c_int, [_G, _P, _P, _I64, _O, _P, _P, _GR, _P]),
+    "svox2_volume_render_nvol_fused": (C.c_int, [_G, _P, _P, _I64, _I64, _O, _P, _F, _P, _GR, _P]),
     "svox2_sample_grid": (C.c_int, [_G, _P, _I64, _P, _P, _P]),
     "svox2_sample_grid_backward": (C.c_int, [_G, _P, _I64, _P, _P, _P, _I64, _P, _I64, _P]),
     "svox2_dilate": (C.c_int, [_P, _I32, _I32, _I32, _P, _P]),

@@ -380,16 +380,58 @@ def volume_render_sigma_thresh(grid, rays, opt, sigma_thresh):
 def _out_of_scope(name):
     def fn(*args, **kwargs):
         raise NotImplementedError(
-            f"{name}: the nvol / svox1 ablation backends and the lumisphere regulariser are outside "
-            "the B200 hot path (SURVEY.md 2.1); use backend='cuvol'.")
+            f"{name}: the svox1 ablation backend is outside the B200 hot path (SURVEY.md 2.1); "
+            "use backend='cuvol' or 'nvol'.")
     fn.__name__ = name
     return fn
 
 
-# Name-visible in the reference module (svox2.cpp:80-92); ablation backends, not built here.
-volume_render_nvol = _out_of_scope("volume_render_nvol")
-volume_render_nvol_backward = _out_of_scope("volume_render_nvol_backward")
-volume_render_nvol_fused = _out_of_scope("volume_render_nvol_fused")
+def volume_render_nvol(grid, rays, opt):
+    """svox2.cpp:80 -> svox2_volume_render_nvol (render_lerp_kernel_nvol.cu:406-426).  Returns [Q,3]."""
+    g = _grid_struct(grid)
+    origins, dirs = _rays(rays)
+    out = torch.empty_like(origins)
+    o = _opt_struct(opt)
+    with torch.cuda.device(origins.device):
+        check(_lib.lib().svox2_volume_render_nvol(
+            C.byref(g), origins.data_ptr(), dirs.data_ptr(), origins.size(0), C.byref(o),
+            out.data_ptr(), _stream()))
+    return out
+
+
+def volume_render_nvol_backward(grid, rays, opt, grad_out, color_cache, grads):
+    """svox2.cpp:81-82 -> svox2_volume_render_nvol_backward (nvol.cu:428-459)."""
+    g = _grid_struct(grid)
+    origins, dirs = _rays(rays)
+    _check_input(grad_out, "grad_out", torch.float32, 2)
+    _check_input(color_cache, "color_cache", torch.float32, 2)
+    gr, _ = _grads_struct(grads, grid)
+    o = _opt_struct(opt)
+    with torch.cuda.device(origins.device):
+        check(_lib.lib().svox2_volume_render_nvol_backward(
+            C.byref(g), origins.data_ptr(), dirs.data_ptr(), origins.size(0), C.byref(o),
+            grad_out.data_ptr(), color_cache.data_ptr(), C.byref(gr), _stream()))
+
+
+def volume_render_nvol_fused(grid, rays, opt, rgb_gt, beta_loss, sparsity_loss, rgb_out, grads,
+                             _norm_rays=None, _counters=None):
+    """svox2.cpp:83-85 -> svox2_volume_render_nvol_fused (nvol.cu:461-502); ``beta_loss`` is
+    ignored exactly as upstream ("not supported")."""
+    g = _grid_struct(grid)
+    origins, dirs = _rays(rays)
+    _check_input(rgb_gt, "rgb_gt", torch.float32, 2)
+    _check_input(rgb_out, "rgb_out", torch.float32, 2)
+    gr, _ = _grads_struct(grads, grid)
+    o = _opt_struct(opt)
+    Q = origins.size(0)
+    with torch.cuda.device(origins.device):
+        check(_lib.lib().svox2_volume_render_nvol_fused(
+            C.byref(g), origins.data_ptr(), dirs.data_ptr(), Q, Q if _norm_rays is None else _norm_rays,
+            C.byref(o), rgb_gt.data_ptr(), float(sparsity_loss), rgb_out.data_ptr(), C.byref(gr),
+            _stream()))
+
+
+# Name-visible in the reference module (svox2.cpp:86-92); the svox1 ablation is not built here.
 volume_render_svox1 = _out_of_scope("volume_render_svox1")
 volume_render_svox1_backward = _out_of_scope("volume_render_svox1_backward")
 volume_render_svox1_fused = _out_of_scope("volume_render_svox1_fused")

@@ -448,10 +448,12 @@ class SparseGrid(nn.Module):
 
     # ---- rendering ------------------------------------------------------------------------
     def _backend(self):
-        if self.opt.backend != "cuvol":
+        if self.opt.backend not in ("cuvol", "nvol"):
             raise NotImplementedError(
-                f"backend '{self.opt.backend}': only 'cuvol' is built (nvol/svox1 are ablations)")
-        return "cuvol"
+                f"backend '{self.opt.backend}': 'cuvol' and 'nvol' are built (svox1 is an ablation)")
+        if self.opt.backend == "nvol" and self.use_background:
+            raise NotImplementedError("the nvol backend does not support an MSI background (upstream: same)")
+        return self.opt.backend
 
     def volume_render(self, rays: Rays, use_kernel: bool = True, randomize: bool = False,
                       return_raylen: bool = False):
@@ -517,9 +519,10 @@ class SparseGrid(nn.Module):
     def volume_render_image(self, camera: Camera, use_kernel: bool = True, randomize: bool = False,
                             batch_size: int = 5000, return_raylen: bool = False):
         """Whole-image render -> [H,W,3] (svox2.py:1144-1179)."""
-        if not torch.is_grad_enabled() and not return_raylen:
+        image_fn = f"volume_render_{self._backend()}_image"  # only cuvol has one (svox2.py:1158-1161)
+        if hasattr(_C, image_fn) and not torch.is_grad_enabled() and not return_raylen:
             self._require_cuda("SparseGrid.volume_render_image")
-            return getattr(_C, f"volume_render_{self._backend()}_image")(
+            return getattr(_C, image_fn)(
                 self._to_cpp(), camera._to_cpp(), self.opt._to_cpp())
         rays = camera.gen_rays()
         parts = [self.volume_render(rays[b:b + batch_size], use_kernel=use_kernel,

@@ -32,7 +32,10 @@ def rays_into_grid(n, radius, center, gen, spread=0.5, dist=2.7):
     return origins.float(), dirs.float()
 
 
-def render_case(name, reso, basis_dim, radius, center, sphere, n_rays, step, bgb, seed, near_clip=0.0):
+def render_case(name, reso, basis_dim, radius, center, sphere, n_rays, step, bgb, seed, near_clip=0.0,
+                backend="cuvol", dens_scale=3.0):
+    """backend="nvol": the reference's _volume_render_gradcheck_nvol_lerp (svox2.py:886-1034), the
+    path its own test/test_render_gradcheck.py compares the nvol kernels with."""
     gen = torch.Generator().manual_seed(seed)
     grid = svox2.SparseGrid(reso=reso, radius=radius, center=center, basis_dim=basis_dim,
                             use_z_order=False, use_sphere_bound=sphere, device="cpu")
@@ -40,7 +43,7 @@ def render_case(name, reso, basis_dim, radius, center, sphere, n_rays, step, bgb
     with torch.no_grad():
         grid.sh_data[:] = torch.randn(N, 3 * basis_dim, generator=gen) * 0.3
         grid.sh_data[:, ::basis_dim] += 0.3
-        dens = torch.rand(N, 1, generator=gen) * 3.0
+        dens = torch.rand(N, 1, generator=gen) * dens_scale
         dens[torch.rand(N, 1, generator=gen) < 0.3] = 0.0
         grid.density_data[:] = dens
     grid.opt.step_size = step
@@ -48,6 +51,7 @@ def render_case(name, reso, basis_dim, radius, center, sphere, n_rays, step, bgb
     grid.opt.sigma_thresh = 0.0
     grid.opt.stop_thresh = 0.0
     grid.opt.near_clip = near_clip
+    grid.opt.backend = backend
     r = [radius] * 3 if isinstance(radius, float) else radius
     origins, dirs = rays_into_grid(n_rays, r, center, gen)
     rgb_gt = torch.rand(n_rays, 3, generator=gen)
@@ -138,9 +142,20 @@ def structure_case():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "nvol":  # only the nvol fixtures (added in round 2)
+        render_case("nvol_dense14_sh4", 14, 4, 1.0, [0.0, 0.0, 0.0], False, 80, 0.5, 0.8, 4,
+                    backend="nvol", dens_scale=40.0)
+        render_case("nvol_sphere_16x12x14_sh9", [16, 12, 14], 9, [1.0, 0.8, 0.9], [0.0, 0.05, 0.0],
+                    True, 64, 0.43, 1.0, 5, backend="nvol", dens_scale=6.0)
+        sys.exit(0)
     render_case("render_dense16_sh9", 16, 9, 1.0, [0.0, 0.0, 0.0], False, 96, 0.5, 1.0, 1)
     render_case("render_sphere_20x16x12_sh4", [20, 16, 12], 4, [1.0, 0.8, 0.6], [0.1, -0.05, 0.0],
                 True, 64, 0.5, 0.5, 2)
     render_case("render_dense12_sh1_step037", 12, 1, 1.3, [0.0, 0.0, 0.0], False, 48, 0.37, 0.0, 3)
+    # nvol backend: dense enough that about half of the rays saturate (alpha_total reaches 1)
+    render_case("nvol_dense14_sh4", 14, 4, 1.0, [0.0, 0.0, 0.0], False, 80, 0.5, 0.8, 4,
+                backend="nvol", dens_scale=40.0)
+    render_case("nvol_sphere_16x12x14_sh9", [16, 12, 14], 9, [1.0, 0.8, 0.9], [0.0, 0.05, 0.0], True,
+                64, 0.43, 1.0, 5, backend="nvol", dens_scale=6.0)
     sample_case()
     structure_case()

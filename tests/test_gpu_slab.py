@@ -131,9 +131,12 @@ def _worker(rank, world, port, out, case="default"):
         for it in (9, 10):
             np.random.seed(it)
             tr.step(rays, t(sc["rgb_gt"], dev))
-        tr._refresh_row0()                   # the pick-up normally happens inside the next step
+        # the pick-up normally happens inside the next step, behind the barrier of its first
+        # exchange; here the owner's store has to be made visible by hand first
         torch.cuda.synchronize()
         dist.barrier()
+        tr._refresh_row0()
+        torch.cuda.synchronize()
         row0 = torch.cat([grid.sh_data.data[0], grid.density_data.data[0]]).contiguous()
         every = [torch.empty_like(row0) for _ in range(world)]
         dist.all_gather(every, row0)
