@@ -235,6 +235,18 @@ SVOX2_API int svox2_msi_tv_grad_sparse(const int32_t* background_links, int32_t 
                              int64_t n_cells, int64_t scale_cells, uint8_t* mask_out, float scale,
                              float scale_last, float* grad_msi, svox2_stream_t stream);
 
+/* lumisphere_tv_grad_sparse (svox2.cpp:50-51, loss_kernel.cu:335-434, 643-678): TV of the colour
+ * seen from one view direction; basis_fn / basis_fn_u = SH basis values [basis_dim] of that
+ * direction and of a perturbed one (weight dir_factor).  scale is divided by n_cells inside.
+ * Cells whose decoded x lies outside the grid (the reference reads past `links` there) are skipped. */
+SVOX2_API int svox2_lumisphere_tv_grad_sparse(const int32_t* links, int32_t X, int32_t Y, int32_t Z,
+                                    const float* sh_data, int64_t sh_stride, int32_t basis_dim,
+                                    const int32_t* rand_cells, int64_t n_cells,
+                                    const float* basis_fn, const float* basis_fn_u, float scale,
+                                    float ndc_coeffx, float ndc_coeffy, float dir_factor,
+                                    uint8_t* mask_out, float* grad_sh, int64_t grad_stride,
+                                    svox2_stream_t stream);
+
 /* rmsprop_step / sgd_step  (svox2.cpp:52-58, optim_kernel.cu:154-267)
  * data/rms/grad [rows, row_stride] with n_channels logical channels; the last channel uses
  * lr_last (lr_last < 0 => lr).  indexer_kind: 0 dense, 1 uint8 mask[rows], 2 int64 index[n_index].

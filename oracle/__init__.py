@@ -377,6 +377,21 @@ def msi_tv_grad_sparse(bg_links, msi, rand_cells, scale, scale_last, grad=None, 
     return out, m.astype(bool)
 
 
+def lumisphere_tv_grad_sparse(links, sh, rand_cells, basis_fn, basis_fn_u, scale, dir_factor,
+                              grad=None, mask=None):
+    links = np.ascontiguousarray(links, np.int32)
+    sh = _f32(sh)
+    cells = np.ascontiguousarray(rand_cells, np.int32)
+    fn, fnu = _f32(basis_fn).reshape(-1), _f32(basis_fn_u).reshape(-1)
+    out = np.zeros_like(sh) if grad is None else _f32(grad).copy()
+    m = np.zeros(sh.shape[0], np.uint8) if mask is None else np.ascontiguousarray(mask, np.uint8).copy()
+    X, Y, Z = links.shape
+    lib().og_lumisphere_tv_grad_sparse(_ptr(links), X, Y, Z, _ptr(sh), sh.shape[1] // 3, _ptr(cells),
+                                       C.c_int64(cells.shape[0]), _ptr(fn), _ptr(fnu), C.c_float(scale),
+                                       C.c_float(dir_factor), _ptr(m), _ptr(out))
+    return out, m.astype(bool)
+
+
 def _indexer(indexer):
     if indexer is None:
         return 0, None, None, 0

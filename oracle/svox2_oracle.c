@@ -1393,6 +1393,62 @@ void og_msi_tv_grad_sparse(const int32_t* bg_links, int32_t reso, const float* m
 #undef MSI
 }
 
+/* lumisphere_tv_grad_sparse, loss_kernel.cu:335-434, 643-678.  Cells whose index decodes (with
+ * Y-1, Z-1, as upstream) to x >= X-1 are skipped: the reference reads past `links` there. */
+void og_lumisphere_tv_grad_sparse(const int32_t* links, int32_t X, int32_t Y, int32_t Z,
+                                  const float* sh, int32_t basis_dim, const int32_t* rand_cells,
+                                  int64_t n_cells, const float* basis_fn, const float* basis_fn_u,
+                                  float scale, float dir_factor, uint8_t* mask, float* grad) {
+    const int B = basis_dim, D = 3 * B;
+    const int64_t offx = (int64_t)Y * Z;
+    const float sc[3] = {(float)X / 256.f, (float)Y / 256.f, (float)Z / 256.f};
+    const float scl = scale / (float)n_cells;
+    for (int64_t i = 0; i < n_cells; ++i) {
+        const int xyz = rand_cells[i];
+        const int z = xyz % (Z - 1), xy = xyz / (Z - 1);
+        const int y = xy % (Y - 1), x = xy / (Y - 1);
+        if (xyz < 0 || x >= X - 1) continue;
+        const int32_t* lp = links + (x * offx + (int64_t)y * Z + z);
+        if (lp[0] == 0) continue;
+        const int32_t L[4] = {lp[0], lp[1], lp[Z], lp[offx]};
+        float s[3][5]; /* per colour: sums of v000a, v001a, v010a, v100a, v000u */
+        for (int c = 0; c < 3; ++c) {
+            for (int k = 0; k < 5; ++k) s[c][k] = 0.f;
+            for (int k = 0; k < B; ++k) {
+                const int idx = c * B + k;
+                const float v000 = L[0] >= 0 ? sh[(int64_t)L[0] * D + idx] : 0.f;
+                const float v001 = L[1] >= 0 ? sh[(int64_t)L[1] * D + idx] : v000;
+                const float v010 = L[2] >= 0 ? sh[(int64_t)L[2] * D + idx] : v000;
+                const float v100 = L[3] >= 0 ? sh[(int64_t)L[3] * D + idx] : v000;
+                s[c][0] += v000 * basis_fn[k];
+                s[c][1] += v001 * basis_fn[k];
+                s[c][2] += v010 * basis_fn[k];
+                s[c][3] += v100 * basis_fn[k];
+                s[c][4] += v000 * basis_fn_u[k];
+            }
+        }
+        for (int c = 0; c < 3; ++c) {
+            float dx = (s[c][3] - s[c][0]) * sc[0];
+            float dy = (s[c][2] - s[c][0]) * sc[1];
+            float dz = (s[c][1] - s[c][0]) * sc[2];
+            float du = (s[c][4] - s[c][0]) * dir_factor;
+            const float idelta = scl * (1.f / sqrtf(1e-9f + dx * dx + dy * dy + dz * dz + du * du));
+            dx *= sc[0]; dy *= sc[1]; dz *= sc[2]; du *= dir_factor;
+            for (int k = 0; k < B; ++k) {
+                const int idx = c * B + k;
+                const float sv = basis_fn[k];
+                const float val[4] = {-dx * sv - dy * sv - dz * sv + du * (basis_fn_u[k] - sv),
+                                      dz * sv, dy * sv, dx * sv};
+                for (int q = 0; q < 4; ++q)
+                    if (L[q] >= 0 && val[q] != 0.f) {
+                        grad[(int64_t)L[q] * D + idx] += val[q] * idelta;
+                        if (mask) mask[L[q]] = 1;
+                    }
+            }
+        }
+    }
+}
+
 /* ---------------------------------------------------------------------------------------
  * optimisers: optim_kernel.cu:15-25 (rmsprop_once), :97-103 (sgd_once), dispatch :154-267
  * ------------------------------------------------------------------------------------- */

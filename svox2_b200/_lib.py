@@ -103,6 +103,8 @@ SIGNATURES = {
     "svox2_tv_grad_sparse_run": (C.c_int, [_P, _I32, _I32, _I32, _P, _I64, _I64, _I64, _I64, _P, _I32,
                                            _I32, _F, _I32, _I32, _P, _I64, _P]),
     "svox2_msi_tv_grad_sparse": (C.c_int, [_P, _I32, _P, _I32, _I32, _P, _I64, _I64, _P, _F, _F, _P, _P]),
+    "svox2_lumisphere_tv_grad_sparse": (C.c_int, [_P, _I32, _I32, _I32, _P, _I64, _I32, _P, _I64, _P, _P,
+                                                  _F, _F, _F, _F, _P, _P, _I64, _P]),
     "svox2_rmsprop_step": (C.c_int, [_P, _P, _P, _I64, _I32, _I64, _I32, _P, _P, _I64, _F, _F, _F, _F,
                                      _F, _P]),
     "svox2_sgd_step": (C.c_int, [_P, _P, _I64, _I32, _I64, _I32, _P, _P, _I64, _F, _F, _P]),

@@ -435,7 +435,36 @@ def volume_render_nvol_fused(grid, rays, opt, rgb_gt, beta_loss, sparsity_loss, 
 volume_render_svox1 = _out_of_scope("volume_render_svox1")
 volume_render_svox1_backward = _out_of_scope("volume_render_svox1_backward")
 volume_render_svox1_fused = _out_of_scope("volume_render_svox1_fused")
-lumisphere_tv_grad_sparse = _out_of_scope("lumisphere_tv_grad_sparse")
+
+
+def lumisphere_tv_grad_sparse(grid, rand_cells, sphfunc_val, sphfunc_val_u, scale, ndc_coeffx,
+                              ndc_coeffy, dir_factor, grads):
+    """svox2.cpp:50-51 -> svox2_lumisphere_tv_grad_sparse (loss_kernel.cu:643-678).  Like upstream
+    only the first ``basis_dim`` floats of ``sphfunc_val_u`` are read (it may be [cells, basis_dim])."""
+    _grid_struct(grid)  # SparseGridSpec.check()
+    _check_input(rand_cells, "rand_cells", torch.int32)
+    _check_input(sphfunc_val, "basis_fn", torch.float32, 1)
+    _check_input(sphfunc_val_u, "basis_fn_u", torch.float32)
+    B = int(grid.basis_dim)
+    if sphfunc_val.numel() < B or sphfunc_val_u.numel() < B:
+        _fail("basis_fn / basis_fn_u must hold basis_dim values")
+    if not _defined(grads.grad_sh_out):
+        _fail("grad_sh_out is required")
+    _check_rows(grads.grad_sh_out, "grad_sh_out")
+    if grads.grad_sh_out.shape != grid.sh_data.shape:
+        _fail("grad_sh_out must have the shape of sh_data")
+    mask = grads.mask_out
+    mask_ptr = None
+    if _defined(mask) and mask.dim() > 0 and mask.numel() > 0:
+        _check_input(mask, "mask_out", torch.bool)
+        mask_ptr = mask.data_ptr()
+    X, Y, Z = grid.links.shape
+    with torch.cuda.device(grid.sh_data.device):
+        check(_lib.lib().svox2_lumisphere_tv_grad_sparse(
+            grid.links.data_ptr(), X, Y, Z, grid.sh_data.data_ptr(), _row_stride(grid.sh_data), B,
+            rand_cells.data_ptr(), rand_cells.size(0), sphfunc_val.data_ptr(), sphfunc_val_u.data_ptr(),
+            float(scale), float(ndc_coeffx), float(ndc_coeffy), float(dir_factor), mask_ptr,
+            grads.grad_sh_out.data_ptr(), _row_stride(grads.grad_sh_out), _stream()))
 
 
 def dilate(grid):

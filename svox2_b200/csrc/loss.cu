@@ -357,6 +357,77 @@ msi_tv_grad_sparse_kernel(const int32_t* __restrict__ links, int reso,
 #undef MSI_AT
 }
 
+// lumisphere_tv_grad_sparse_kernel, loss_kernel.cu:335-434: TV of the COLOUR seen from one random
+// view direction (+ its difference to a slightly rotated direction, weighted by dir_factor).
+// Warp per cell, lane = SH channel; per colour the basis-weighted channel sums are formed with a
+// group-wise shuffle loop (the same order for every corner, so equal corners give an exact 0 and
+// the mask decisions `val != 0` match the reference's segmented sums).  The reference decodes the
+// cell index with (Y-1, Z-1) although the caller draws it from [0, X*Y*Z) (svox2.py:1846,
+// 2224-2241) and reads links out of bounds for x >= X-1; such cells are skipped here.
+__global__ void __launch_bounds__(TV_THREADS)
+lumisphere_tv_grad_sparse_kernel(const int32_t* __restrict__ links, int X, int Y, int Z,
+                                 const float* __restrict__ sh, int64_t stride, int B,
+                                 const int32_t* __restrict__ rand_cells, int64_t n_cells,
+                                 const float* __restrict__ basis_fn,
+                                 const float* __restrict__ basis_fn_u, float scale, float dir_factor,
+                                 uint8_t* __restrict__ mask_out, float* __restrict__ grad,
+                                 int64_t gstride) {
+    const int64_t cell = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (cell >= n_cells) return;
+    const int lane = threadIdx.x & 31;
+    const int D = 3 * B;
+    const int xyz = __ldg(rand_cells + cell);
+    const int z = xyz % (Z - 1);
+    const int xy = xyz / (Z - 1);
+    const int y = xy % (Y - 1);
+    const int x = xy / (Y - 1);
+    if (xyz < 0 || x >= X - 1) return;
+    const int64_t offx = (int64_t)Y * Z;
+    const int32_t* lp = links + (x * offx + (int64_t)y * Z + z);
+    const int32_t l000 = __ldg(lp);
+    if (l000 == 0) return;  // sic (loss_kernel.cu:374)
+    const int32_t l001 = __ldg(lp + 1), l010 = __ldg(lp + Z), l100 = __ldg(lp + offx);
+    float sc[3];
+    ray_scale(X, Y, Z, sc);
+    const bool on = lane < D;
+    const int idx = on ? lane : 0;
+    const int cg = idx % B, grp0 = (idx / B) * B;
+    const float v000 = (on && l000 >= 0) ? __ldg(sh + (int64_t)l000 * stride + idx) : 0.f;
+    const float v001 = on ? (l001 >= 0 ? __ldg(sh + (int64_t)l001 * stride + idx) : v000) : 0.f;
+    const float v010 = on ? (l010 >= 0 ? __ldg(sh + (int64_t)l010 * stride + idx) : v000) : 0.f;
+    const float v100 = on ? (l100 >= 0 ? __ldg(sh + (int64_t)l100 * stride + idx) : v000) : 0.f;
+    const float sv = __ldg(basis_fn + cg), svu = __ldg(basis_fn_u + cg);
+    const float a000 = v000 * sv, a001 = v001 * sv, a010 = v010 * sv, a100 = v100 * sv, u000 = v000 * svu;
+    float s000 = 0.f, s001 = 0.f, s010 = 0.f, s100 = 0.f, su = 0.f;
+    for (int k = 0; k < B; ++k) {  // colour-group sums, identical order for all five
+        const int src = grp0 + k;
+        s000 += __shfl_sync(FULL, a000, src);
+        s001 += __shfl_sync(FULL, a001, src);
+        s010 += __shfl_sync(FULL, a010, src);
+        s100 += __shfl_sync(FULL, a100, src);
+        su += __shfl_sync(FULL, u000, src);
+    }
+    if (!on) return;
+    float dx = __fmul_rn(__fsub_rn(s100, s000), sc[0]);
+    float dy = __fmul_rn(__fsub_rn(s010, s000), sc[1]);
+    float dz = __fmul_rn(__fsub_rn(s001, s000), sc[2]);
+    float du = __fmul_rn(__fsub_rn(su, s000), dir_factor);
+    const float idelta = scale * rsqrtf(1e-9f + dx * dx + dy * dy + dz * dz + du * du);
+    dx = __fmul_rn(dx, sc[0]);
+    dy = __fmul_rn(dy, sc[1]);
+    dz = __fmul_rn(dz, sc[2]);
+    du = __fmul_rn(du, dir_factor);
+    const float sm = -dx * sv - dy * sv - dz * sv + du * (svu - sv);
+    const int32_t L[4] = {l000, l001, l010, l100};
+    const float val[4] = {sm, __fmul_rn(dz, sv), __fmul_rn(dy, sv), __fmul_rn(dx, sv)};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (L[q] >= 0 && val[q] != 0.f) {
+            atomicAdd(grad + (int64_t)L[q] * gstride + idx, val[q] * idelta);
+            if (mask_out) mask_out[L[q]] = 1;
+        }
+}
+
 int check_tv_args(const int32_t* links, int X, int Y, int Z, const float* data, int64_t stride,
                   int start_dim, int end_dim, const char* who) {
     if (!links || !data) {
@@ -488,5 +559,25 @@ extern "C" SVOX2_API int svox2_msi_tv_grad_sparse(const int32_t* background_link
     msi_tv_grad_sparse_kernel<<<div_up(Q, TV_THREADS), TV_THREADS, 0, (cudaStream_t)stream>>>(
         background_links, reso, msi, nlayers, nchannels, rand_cells,
         scale / (float)(int)scale_cells, scale_last / (float)(int)scale_cells, Q, mask_out, grad_msi);
+    return check_launch(__func__);
+}
+
+extern "C" SVOX2_API int svox2_lumisphere_tv_grad_sparse(
+    const int32_t* links, int32_t X, int32_t Y, int32_t Z, const float* sh_data, int64_t sh_stride,
+    int32_t basis_dim, const int32_t* rand_cells, int64_t n_cells, const float* basis_fn,
+    const float* basis_fn_u, float scale, float ndc_coeffx, float ndc_coeffy, float dir_factor,
+    uint8_t* mask_out, float* grad_sh, int64_t grad_stride, svox2_stream_t stream) {
+    (void)ndc_coeffx; (void)ndc_coeffy;  // the NDC branch of calculate_ray_scale is commented out upstream
+    SVOX2_REQUIRE(links && sh_data && grad_sh && basis_fn && basis_fn_u, "null argument");
+    SVOX2_REQUIRE(X > 1 && Y > 1 && Z > 1, "grid must be at least 2 voxels along every axis");
+    SVOX2_REQUIRE(basis_dim >= 1 && 3 * basis_dim <= WARP, "basis_dim must be in 1..10");
+    SVOX2_REQUIRE(sh_stride >= 3 * basis_dim, "bad sh row stride");
+    SVOX2_REQUIRE(n_cells >= 0 && (n_cells == 0 || rand_cells), "rand_cells must not be null");
+    if (n_cells == 0) return SVOX2_OK;
+    lumisphere_tv_grad_sparse_kernel<<<div_up(n_cells * WARP, TV_THREADS), TV_THREADS, 0,
+                                       (cudaStream_t)stream>>>(
+        links, X, Y, Z, sh_data, sh_stride, basis_dim, rand_cells, n_cells, basis_fn, basis_fn_u,
+        scale / (float)n_cells, dir_factor, mask_out, grad_sh,
+        grad_stride > 0 ? grad_stride : sh_stride);
     return check_launch(__func__);
 }

@@ -801,8 +801,41 @@ class SparseGrid(nn.Module):
                        logalpha_delta, True, ndc_coeffs[0], ndc_coeffs[1], grad)
             self.sparse_sh_grad_indexer = None
 
-    def inplace_tv_lumisphere_grad(self, *args, **kwargs):
-        raise NotImplementedError("the lumisphere regulariser is out of scope (off by default upstream)")
+    def inplace_tv_lumisphere_grad(self, grad: torch.Tensor, start_dim: int = 0,
+                                   end_dim: Optional[int] = None, scaling: float = 1.0,
+                                   sparse_frac: float = 0.01, logalpha: bool = False,
+                                   logalpha_delta: float = 2.0,
+                                   ndc_coeffs: Tuple[float, float] = (-1.0, -1.0),
+                                   dir_factor: float = 1.0, dir_perturb_radians: float = 0.05):
+        """Add the "lumisphere" TV gradient -- TV of the colour seen from one random direction, plus
+        its change under a small random rotation of that direction -- into ``grad``
+        (svox2.py:1822-1895; consumes the numpy / torch RNGs in the reference's order)."""
+        assert self.sh_data.is_cuda and grad.is_cuda, "CUDA is required for total variation"
+        self._ensure_layout()
+        rand_cells = self._get_rand_cells(sparse_frac)
+        if rand_cells is None:  # sparse_frac >= 1: upstream would fail on None.size(0)
+            rand_cells = self._get_rand_cells(sparse_frac, force=True)
+        holder = _C.GridOutputGrads()
+        holder.mask_out = self._get_sparse_sh_grad_indexer()
+        holder.grad_sh_out = grad
+        batch_size = rand_cells.size(0)
+        dirs = torch.randn(3, device=rand_cells.device)
+        dirs /= torch.norm(dirs)
+        sh_mult = utils.eval_sh_bases(self.basis_dim, dirs[None])[0]
+        if dir_factor > 0.0:
+            from scipy.spatial.transform import Rotation
+            axis = torch.randn((batch_size, 3))
+            axis /= torch.norm(axis, dim=-1, keepdim=True)
+            axis *= dir_perturb_radians
+            R = torch.from_numpy(Rotation.from_rotvec(axis.numpy()).as_matrix()).float().to(
+                device=rand_cells.device)
+            dirs_perturb = (R * dirs.unsqueeze(-2)).sum(-1)
+        else:
+            dirs_perturb = dirs
+        sh_mult_u = utils.eval_sh_bases(self.basis_dim, dirs_perturb[None])[0]
+        _C.lumisphere_tv_grad_sparse(self._to_cpp(), rand_cells, sh_mult.contiguous(),
+                                     sh_mult_u.contiguous(), scaling, ndc_coeffs[0], ndc_coeffs[1],
+                                     dir_factor, holder)
 
     def inplace_l2_color_grad(self, grad: torch.Tensor, start_dim: int = 0,
                               end_dim: Optional[int] = None, scaling: float = 1.0):

@@ -1,0 +1,197 @@
+"""nvol backend (Neural-Volumes compositing, render_lerp_kernel_nvol.cu).
+
+CPU: the C oracle's nvol restatement against golden vectors produced by the reference's own
+PyTorch nvol renderer + autograd (svox2.py:886-1034; tests/golden/make_golden.py nvol) -- the
+comparison the reference's test/test_render_gradcheck.py makes.
+GPU: the CUDA kernels against the oracle, against the golden vectors, against the reference's CUDA
+extension (mask bit-exact), and the gradcheck script's own procedure through the public API."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle as og
+from scenes import frac_bad, make_scene, oracle_grid, rel_err
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+NVOL = sorted(glob.glob(os.path.join(GOLD, "nvol_*.npz")))
+
+
+def _golden(path):
+    z = np.load(path)
+    g = og.Grid(z["links"], z["density"], z["sh"], z["offset"], z["scaling"])
+    opt = dict(background_brightness=float(z["background_brightness"]), step_size=float(z["step_size"]),
+               sigma_thresh=0.0, stop_thresh=0.0, near_clip=float(z["near_clip"]))
+    return z, g, opt
+
+
+@pytest.mark.parametrize("path", NVOL)
+def test_oracle_nvol_matches_reference_pytorch_renderer(path):
+    z, g, opt = _golden(path)
+    o = og.make_opt(**opt)
+    rgb = og.volume_render_nvol(g, o, z["origins"], z["dirs"])
+    assert np.abs(rgb - z["rgb"]).max() < 2e-6
+    res = og.volume_render_nvol_fused(g, o, z["origins"], z["dirs"], z["rgb_gt"])
+    assert np.abs(res["rgb"] - z["rgb"]).max() < 2e-6
+    assert rel_err(res["grad_density"], z["grad_density"].reshape(-1)) < 1e-4
+    assert rel_err(res["grad_sh"], z["grad_sh"]) < 1e-4
+    Q = z["origins"].shape[0]
+    gout = ((z["rgb"] - z["rgb_gt"]) * (2.0 / (3 * Q))).astype(np.float32)
+    res2 = og.volume_render_nvol_backward(g, o, z["origins"], z["dirs"], gout, z["rgb"])
+    assert rel_err(res2["grad_density"], z["grad_density"].reshape(-1)) < 1e-4
+    assert rel_err(res2["grad_sh"], z["grad_sh"]) < 1e-4
+    # the fixtures exercise both regimes: rays that saturate (alpha_total == 1) and rays that do not
+    lum = np.abs(og.volume_render_nvol(g, og.make_opt(**dict(opt, background_brightness=0.0)),
+                                       z["origins"], z["dirs"]) - rgb).max(1)
+    assert (lum < 1e-7).any() and (lum > 1e-3).any()
+
+
+# --------------------------------------------------------------------------------------------
+# GPU
+# --------------------------------------------------------------------------------------------
+def _our_grid_from_golden(z, opt):
+    import svox2_b200 as sv
+    from gpu_helpers import _fill_grid, set_opt
+    sc = dict(links=z["links"], density=z["density"], sh=z["sh"])
+    grid = sv.SparseGrid(reso=list(z["links"].shape), radius=z["radius"].tolist(),
+                         center=z["center"].tolist(), basis_dim=z["sh"].shape[1] // 3, device="cuda")
+    _fill_grid(grid, sc, "cuda")
+    set_opt(grid, backend="nvol", **opt)
+    return sv, grid
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", NVOL)
+def test_cuda_nvol_matches_golden_vectors(path):
+    from gpu_helpers import t
+    z, _, opt = _golden(path)
+    sv, grid = _our_grid_from_golden(z, opt)
+    rays = sv.Rays(t(z["origins"]), t(z["dirs"]))
+    rgb = grid.volume_render(rays)
+    assert np.abs(rgb.detach().cpu().numpy() - z["rgb"]).max() < 1e-5
+    torch.nn.functional.mse_loss(rgb, t(z["rgb_gt"])).backward()
+    assert rel_err(grid.density_data.grad.cpu().numpy(), z["grad_density"]) < 1e-4
+    assert rel_err(grid.sh_data.grad.cpu().numpy(), z["grad_sh"]) < 1e-4
+    grid.density_data.grad = grid.sh_data.grad = None
+    rgb2 = grid.volume_render_fused(rays, t(z["rgb_gt"]))
+    assert np.abs(rgb2.cpu().numpy() - z["rgb"]).max() < 1e-5
+    assert rel_err(grid.density_data.grad.cpu().numpy(), z["grad_density"]) < 1e-4
+    assert rel_err(grid.sh_data.grad.cpu().numpy(), z["grad_sh"]) < 1e-4
+
+
+NV_SCENES = {
+    "sparse32_sh9": dict(reso=32, basis_dim=9, seed=3, n_rays=1024),
+    "dense24_sh4": dict(reso=24, basis_dim=4, seed=5, n_rays=700, sparse=False, sigma_peak=60.0),
+    "sparse40_sh1_thin": dict(reso=40, basis_dim=1, seed=9, n_rays=900, sigma_peak=3.0),
+}
+NV_OPTS = dict(step_size=0.5, sigma_thresh=1e-8, stop_thresh=1e-7, background_brightness=0.75)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene", sorted(NV_SCENES))
+def test_cuda_nvol_matches_oracle(scene):
+    import svox2_b200 as sv
+    from gpu_helpers import make_grid, set_opt, t
+    sc = make_scene(**NV_SCENES[scene])
+    o = og.make_opt(**NV_OPTS)
+    ref = og.volume_render_nvol_fused(oracle_grid(sc), o, sc["origins"], sc["dirs"], sc["rgb_gt"],
+                                      sparsity_loss=1e-3)
+    grid = make_grid(sv, sc)
+    set_opt(grid, backend="nvol", **NV_OPTS)
+    rgb = grid.volume_render_fused(sv.Rays(t(sc["origins"]), t(sc["dirs"])), t(sc["rgb_gt"]),
+                                   sparsity_loss=1e-3)
+    assert np.abs(rgb.cpu().numpy() - ref["rgb"]).max() < 1e-4
+    assert frac_bad(grid.density_data.grad.cpu().numpy().reshape(-1), ref["grad_density"]) < 2e-3
+    assert frac_bad(grid.sh_data.grad.cpu().numpy(), ref["grad_sh"]) < 2e-3
+    mism = (grid.sparse_grad_indexer.cpu().numpy() != ref["mask"]).sum()
+    assert mism <= 2e-3 * max(ref["mask"].sum(), 1)      # CUDA libm vs C libm, see DESIGN.md 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene", sorted(NV_SCENES))
+def test_cuda_nvol_vs_reference_cuda(ref_svox2, scene):
+    """Against the reference's own nvol kernels: colours 1e-5, mask bit-exact, gradients 1e-4."""
+    import svox2_b200 as sv
+    from gpu_helpers import make_grid, set_opt, t
+    sc = make_scene(**NV_SCENES[scene])
+    ours, ref = make_grid(sv, sc), make_grid(ref_svox2, sc)
+    set_opt(ours, backend="nvol", **NV_OPTS)
+    set_opt(ref, backend="nvol", **NV_OPTS)
+    gt = t(sc["rgb_gt"])
+    rgb_o = ours.volume_render_fused(sv.Rays(t(sc["origins"]), t(sc["dirs"])), gt, sparsity_loss=1e-3)
+    rgb_r = ref.volume_render_fused(ref_svox2.Rays(t(sc["origins"]), t(sc["dirs"])), gt, sparsity_loss=1e-3)
+    torch.cuda.synchronize()
+    assert (rgb_o - rgb_r).abs().max().item() < 1e-5
+    assert torch.equal(ours.sparse_grad_indexer, ref.sparse_grad_indexer)
+    assert rel_err(ours.density_data.grad.cpu().numpy(), ref.density_data.grad.cpu().numpy()) < 1e-4
+    assert rel_err(ours.sh_data.grad.cpu().numpy(), ref.sh_data.grad.cpu().numpy()) < 1e-4
+    # non-fused autograd path
+    for g in (ours, ref):
+        g.density_data.grad = g.sh_data.grad = None
+    w = t(np.random.default_rng(1).standard_normal(sc["origins"].shape).astype(np.float32))
+    out_o = ours.volume_render(sv.Rays(t(sc["origins"]), t(sc["dirs"])))
+    out_r = ref.volume_render(ref_svox2.Rays(t(sc["origins"]), t(sc["dirs"])))
+    assert (out_o - out_r).abs().max().item() < 1e-5
+    (out_o * w).sum().backward()
+    (out_r * w).sum().backward()
+    assert rel_err(ours.density_data.grad.cpu().numpy(), ref.density_data.grad.cpu().numpy()) < 1e-4
+    assert rel_err(ours.sh_data.grad.cpu().numpy(), ref.sh_data.grad.cpu().numpy()) < 1e-4
+    # image rendering falls back to rays for this backend (svox2.py:1158-1179)
+    c2w = torch.eye(4, device="cuda")
+    c2w[2, 3] = -2.5
+    with torch.no_grad():
+        im_o = ours.volume_render_image(sv.Camera(c2w, fx=60.0, width=48, height=40))
+        im_r = ref.volume_render_image(ref_svox2.Camera(c2w, fx=60.0, width=48, height=40))
+    assert (im_o - im_r).abs().max().item() < 1e-5
+
+
+@pytest.mark.gpu
+def test_reference_gradcheck_procedure_nvol(ref_svox2):
+    """test/test_render_gradcheck.py, verbatim in structure: 128^3 z-order grid, density 100,
+    sigma_thresh = stop_thresh = 0, backend nvol, 40 000 random rays, MSE against zeros; the kernel
+    path is compared with the reference's PyTorch nvol renderer + autograd (here on a 2 000-ray
+    subset of the same rays: the PyTorch path materialises dense gradients per step)."""
+    import torch.nn.functional as F
+    import svox2_b200 as sv
+    torch.random.manual_seed(2)
+    dev = "cuda:0"
+    grid = sv.SparseGrid(reso=128, center=[0.0, 0.0, 0.0], radius=[1.0, 1.0, 1.0], basis_dim=9,
+                         use_z_order=True, device=dev, background_nlayers=0)
+    grid.opt.backend = "nvol"
+    grid.opt.sigma_thresh = 0.0
+    grid.opt.stop_thresh = 0.0
+    grid.opt.background_brightness = 1.0
+    grid.sh_data.data[..., 0] = 0.5
+    grid.sh_data.data[..., 1:].normal_(std=0.1)
+    grid.density_data.data[:] = 100.0
+    n_rays = 200 * 200
+    origins = torch.randn((n_rays, 3), device=dev) * 3
+    dirs = torch.randn((n_rays, 3), device=dev)
+    dirs /= torch.norm(dirs, dim=-1, keepdim=True)
+    sub = slice(0, 2000)
+    rgb_gt = torch.zeros((n_rays, 3), device=dev)
+
+    samps = grid.volume_render(sv.Rays(origins, dirs), use_kernel=True)
+    assert samps.shape == (n_rays, 3) and torch.isfinite(samps).all()
+    samps = grid.volume_render(sv.Rays(origins[sub].contiguous(), dirs[sub].contiguous()))
+    F.mse_loss(samps, rgb_gt[sub]).backward()
+    gs, gd = grid.sh_data.grad.clone(), grid.density_data.grad.clone()
+
+    ref = ref_svox2.SparseGrid(reso=128, center=[0.0, 0.0, 0.0], radius=[1.0, 1.0, 1.0], basis_dim=9,
+                               use_z_order=True, device=dev, background_nlayers=0)
+    assert torch.equal(ref.links, grid.links)
+    ref.opt.backend = "nvol"
+    ref.opt.sigma_thresh = ref.opt.stop_thresh = 0.0
+    ref.opt.background_brightness = 1.0
+    ref.sh_data.data[:] = grid.sh_data.data
+    ref.density_data.data[:] = 100.0
+    sampt = ref.volume_render(ref_svox2.Rays(origins[sub].contiguous(), dirs[sub].contiguous()),
+                              use_kernel=False)
+    F.mse_loss(sampt, rgb_gt[sub]).backward()
+    assert (samps - sampt).abs().max().item() < 1e-4                        # 'err'
+    E = (gs - ref.sh_data.grad).abs()
+    Ed = (gd - ref.density_data.grad).abs()
+    assert E.max().item() <= 1e-4 * ref.sh_data.grad.abs().max().item() + 1e-9       # 'err_sh_grad'
+    assert Ed.max().item() <= 1e-4 * ref.density_data.grad.abs().max().item() + 1e-9  # 'err_density_grad'
