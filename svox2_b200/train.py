@@ -78,6 +78,18 @@ class TrainConfig:
     sigma_thresh: float = 1e-8
     stop_thresh: float = 1e-7
     background_brightness: float = 1.0
+    last_sample_opaque: bool = False
+    near_clip: float = 0.0
+    # MSI background (opt.py:108-124, opt/configs/tnt.json)
+    background_nlayers: int = 0
+    background_reso: int = 512
+    init_sigma_bg: float = 0.1
+    lr_sigma_bg: float = 3e0
+    lr_color_bg: float = 1e-1
+    lambda_tv_background_sigma: float = 1e-2
+    lambda_tv_background_color: float = 1e-2
+    tv_background_sparsity: float = 0.01
+    background_density_thresh: float = 1.0 + 1e-9
     print_every: int = 20
     seed: int = 20200823
 
@@ -110,15 +122,19 @@ class RayPool:
     """All training rays and their colours resident in HBM; one device-side permutation per epoch
     (the reference shuffles on the host and uploads each batch, util.py:178-190 / opt.py:474-478)."""
 
-    def __init__(self, data: PosedImages, seed: int = 0):
-        origins, dirs = [], []
-        for i in range(data.c2w.size(0)):
-            r = data.camera(i).gen_rays()
-            origins.append(r.origins)
-            dirs.append(r.dirs)
-        self.origins = torch.cat(origins).contiguous()
-        self.dirs = torch.cat(dirs).contiguous()
-        self.rgb = data.images.reshape(-1, 3).contiguous()
+    def __init__(self, data, seed: int = 0):
+        if hasattr(data, "gen_rays"):    # datasets.PosedImageSet: float32 rays built on the device
+            rays, rgb = data.gen_rays()  # (world or NDC), as the reference's loaders make them
+            self.origins, self.dirs, self.rgb = rays.origins, rays.dirs, rgb
+        else:
+            origins, dirs = [], []
+            for i in range(data.c2w.size(0)):
+                r = data.camera(i).gen_rays()
+                origins.append(r.origins)
+                dirs.append(r.dirs)
+            self.origins = torch.cat(origins).contiguous()
+            self.dirs = torch.cat(dirs).contiguous()
+            self.rgb = data.images.reshape(-1, 3).contiguous()
         self.gen = torch.Generator(device=self.rgb.device).manual_seed(seed)
         self.shuffle()
 
@@ -243,14 +259,23 @@ class Trainer:
         self.reso_id = 0
         torch.manual_seed(cfg.seed)
         np.random.seed(cfg.seed)
-        self.grid = SparseGrid(reso=self.reso_list[0], basis_dim=cfg.basis_dim, use_sphere_bound=False,
+        # scene bounds, sphere bound and MSI background as the dataset says (opt.py:280-304)
+        nlayers = cfg.background_nlayers if getattr(train, "should_use_background", True) else 0
+        self.grid = SparseGrid(reso=self.reso_list[0], basis_dim=cfg.basis_dim,
+                               radius=list(getattr(train, "scene_radius", (1.0, 1.0, 1.0))),
+                               center=list(getattr(train, "scene_center", (0.0, 0.0, 0.0))),
+                               use_sphere_bound=bool(getattr(train, "use_sphere_bound", False)) and nlayers == 0,
+                               background_nlayers=nlayers, background_reso=cfg.background_reso,
                                device=dev)
         with torch.no_grad():
             self.grid.sh_data.data[:] = 0.0
             self.grid.density_data.data[:] = cfg.init_sigma
+            if self.grid.use_background:
+                self.grid.background_data.data[..., -1] = cfg.init_sigma_bg
         o = self.grid.opt
         o.step_size, o.sigma_thresh, o.stop_thresh = cfg.step_size, cfg.sigma_thresh, cfg.stop_thresh
         o.background_brightness = cfg.background_brightness
+        o.last_sample_opaque, o.near_clip = cfg.last_sample_opaque, cfg.near_clip
         self.pool = RayPool(train, seed=cfg.seed)      # same seed on every rank: same permutation
         self.lr_sigma = expon_lr(cfg.lr_sigma, cfg.lr_sigma_final, cfg.lr_sigma_delay_steps,
                                  cfg.lr_sigma_delay_mult, cfg.lr_sigma_decay_steps)
@@ -268,8 +293,16 @@ class Trainer:
         kw = dict(world_size=self.world_size, rank=self.rank, lr_sigma=c.lr_sigma, lr_sh=c.lr_sh,
                   lambda_tv=self.lambda_tv, lambda_tv_sh=self.lambda_tv_sh, tv_sparsity=c.tv_sparsity,
                   rms_beta=c.rms_beta, beta_loss=c.lambda_beta, sparsity_loss=c.lambda_sparsity)
-        self.slab = self.world_size > 1 and self.dist_mode == "slab"
-        self.stepper = SlabTrainer(self.grid, **kw) if self.slab else ShardedTrainer(self.grid, **kw)
+        # MSI scenes use the ray-sharded step (the slab step has no background path)
+        self.slab = self.world_size > 1 and self.dist_mode == "slab" and not self.grid.use_background
+        if self.slab:
+            self.stepper = SlabTrainer(self.grid, **kw)
+        else:
+            self.stepper = ShardedTrainer(
+                self.grid, lr_sigma_bg=c.lr_sigma_bg, lr_color_bg=c.lr_color_bg,
+                lambda_tv_background_sigma=c.lambda_tv_background_sigma,
+                lambda_tv_background_color=c.lambda_tv_background_color,
+                tv_background_sparsity=c.tv_background_sparsity, **kw)
 
     # ---- one epoch of batches -------------------------------------------------------------
     def train_epoch(self, max_steps: Optional[int] = None):
@@ -328,6 +361,8 @@ class Trainer:
         self.grid.resample(reso=reso, sigma_thresh=c.density_thresh,
                            weight_thresh=c.weight_thresh / reso[2], dilate=2, cameras=cams,
                            max_elements=c.max_grid_elements)
+        if self.grid.use_background and self.reso_id <= 1:      # opt.py:636-637
+            self.grid.sparsify_background(c.background_density_thresh)
         if c.upsample_density_add:
             self.grid.density_data.data[:] += c.upsample_density_add
         if self.rank == 0:
@@ -345,6 +380,13 @@ class Trainer:
             tot += -10.0 * math.log10(max(((img - data.images[i]) ** 2).mean().item(), 1e-12))
         return tot / data.c2w.size(0)
 
+    def eval_metrics(self, data=None, **kw):
+        """PSNR / SSIM (/ LPIPS) per test camera: the loop of opt/render_imgs.py (evaluate.py)."""
+        from .evaluate import evaluate
+        if self.slab:
+            self.stepper.gather_params()
+        return evaluate(self.grid, data or self.test or self.train, **kw)
+
     def run(self):
         t0 = time.time()
         while self.step_id < self.cfg.n_iters:
@@ -359,10 +401,12 @@ def main():
     ap.add_argument("--dist", default="slab", choices=["slab", "rays"])
     ap.add_argument("--save", default=None, help="write ckpt.npz here at the end")
     ap.add_argument("--data_dir", default=None,
-                    help="NeRF-synthetic scene directory (transforms_train.json ...); default: a "
-                         "synthetic posed-image set rendered on the fly")
+                    help="scene directory: NeRF-synthetic (transforms_train.json), LLFF (poses_bounds.npy) "
+                         "or NSVF / T&T (intrinsics.txt, pose/, rgb/), detected as opt/util/dataset.py does; "
+                         "default: a synthetic posed-image set rendered on the fly")
     for f in dataclasses.fields(TrainConfig):
-        ap.add_argument(f"--{f.name}", type=type(f.default), default=None)
+        kind = (lambda v: v.lower() in ("1", "true", "yes")) if isinstance(f.default, bool) else type(f.default)
+        ap.add_argument(f"--{f.name}", type=kind, default=None)
     args = ap.parse_args()
     over = {f.name: getattr(args, f.name) for f in dataclasses.fields(TrainConfig)
             if getattr(args, f.name) is not None}
@@ -376,17 +420,18 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     if args.data_dir:
-        train = load_nerf_synthetic(args.data_dir, "train", dev)
-        test = load_nerf_synthetic(args.data_dir, "test", dev, n_images=10)
+        from .datasets import auto_dataset
+        train = auto_dataset(args.data_dir, "train", dev)
+        test = auto_dataset(args.data_dir, "test", dev)
     else:
         data = synthetic_dataset(dev, n_images=28)
         test = PosedImages(data.c2w[24:], data.images[24:], data.fx, data.width, data.height)
         train = PosedImages(data.c2w[:24], data.images[:24], data.fx, data.width, data.height)
     tr = Trainer(cfg, train, test, world_size=world, rank=rank, dist_mode=args.dist)
     tr.run()
-    psnr = tr.eval_psnr()
+    res = tr.eval_metrics(log=print if rank == 0 else None)
     if rank == 0:
-        print(f"test PSNR {psnr:.2f} dB")
+        print(f"test PSNR {res['psnr']:.2f} dB  SSIM {res['ssim']:.4f}")
         if args.save:
             tr.grid.save(args.save)
     if world > 1:

@@ -194,3 +194,15 @@ def test_reference_opt_py_and_render_imgs_run_unmodified_on_compat(tmp_path):
                 arms["ours"], str(tmp_path))
     m = re.search(r"AVERAGES\s+PSNR: ([0-9.]+)", rlog)
     assert m and abs(float(m.group(1)) - final["reference"][0]) < 0.05, rlog[-2000:]
+    # this package's own evaluation loop (svox2_b200/evaluate.py: the loop of render_imgs.py with
+    # PSNR + SSIM on the device) and loader on the reference's checkpoint: same numbers as the
+    # reference's script printed for it
+    from svox2_b200 import datasets as D
+    from svox2_b200.evaluate import evaluate
+    grid = sv.SparseGrid.load(str(tmp_path / "ckpt_reference" / "ckpt.npz"), device="cuda:0")
+    res = evaluate(grid, D.load_nerf_synthetic(scene, "test", "cuda:0"), out_dir=str(tmp_path / "ev"),
+                   save_images=True, log=None)
+    assert res["n_images"] == 6 and os.path.isfile(str(tmp_path / "ev" / "0005.png"))
+    assert abs(res["psnr"] - final["reference"][0]) < 0.05, (res["psnr"], final)
+    assert abs(res["ssim"] - final["reference"][1]) < 2e-3, (res["ssim"], final)
+    assert abs(float(open(str(tmp_path / "ev" / "ssim.txt")).read()) - res["ssim"]) < 1e-12

@@ -147,51 +147,54 @@ def test_cuda_nvol_vs_reference_cuda(ref_svox2, scene):
     assert (im_o - im_r).abs().max().item() < 1e-5
 
 
-@pytest.mark.gpu
-def test_reference_gradcheck_procedure_nvol(ref_svox2):
-    """test/test_render_gradcheck.py, verbatim in structure: 128^3 z-order grid, density 100,
-    sigma_thresh = stop_thresh = 0, backend nvol, 40 000 random rays, MSE against zeros; the kernel
-    path is compared with the reference's PyTorch nvol renderer + autograd (here on a 2 000-ray
-    subset of the same rays: the PyTorch path materialises dense gradients per step)."""
-    import torch.nn.functional as F
-    import svox2_b200 as sv
-    torch.random.manual_seed(2)
-    dev = "cuda:0"
-    grid = sv.SparseGrid(reso=128, center=[0.0, 0.0, 0.0], radius=[1.0, 1.0, 1.0], basis_dim=9,
-                         use_z_order=True, device=dev, background_nlayers=0)
+def _gradcheck_setup(mod, reso, dev, sh=None):
+    grid = mod.SparseGrid(reso=reso, center=[0.0, 0.0, 0.0], radius=[1.0, 1.0, 1.0], basis_dim=9,
+                          use_z_order=True, device=dev, background_nlayers=0)
     grid.opt.backend = "nvol"
     grid.opt.sigma_thresh = 0.0
     grid.opt.stop_thresh = 0.0
     grid.opt.background_brightness = 1.0
-    grid.sh_data.data[..., 0] = 0.5
-    grid.sh_data.data[..., 1:].normal_(std=0.1)
+    if sh is None:
+        grid.sh_data.data[..., 0] = 0.5
+        grid.sh_data.data[..., 1:].normal_(std=0.1)
+    else:
+        grid.sh_data.data[:] = sh.to(dev)
     grid.density_data.data[:] = 100.0
-    n_rays = 200 * 200
-    origins = torch.randn((n_rays, 3), device=dev) * 3
-    dirs = torch.randn((n_rays, 3), device=dev)
-    dirs /= torch.norm(dirs, dim=-1, keepdim=True)
-    sub = slice(0, 2000)
-    rgb_gt = torch.zeros((n_rays, 3), device=dev)
+    return grid
 
-    samps = grid.volume_render(sv.Rays(origins, dirs), use_kernel=True)
-    assert samps.shape == (n_rays, 3) and torch.isfinite(samps).all()
-    samps = grid.volume_render(sv.Rays(origins[sub].contiguous(), dirs[sub].contiguous()))
-    F.mse_loss(samps, rgb_gt[sub]).backward()
-    gs, gd = grid.sh_data.grad.clone(), grid.density_data.grad.clone()
 
-    ref = ref_svox2.SparseGrid(reso=128, center=[0.0, 0.0, 0.0], radius=[1.0, 1.0, 1.0], basis_dim=9,
-                               use_z_order=True, device=dev, background_nlayers=0)
-    assert torch.equal(ref.links, grid.links)
-    ref.opt.backend = "nvol"
-    ref.opt.sigma_thresh = ref.opt.stop_thresh = 0.0
-    ref.opt.background_brightness = 1.0
-    ref.sh_data.data[:] = grid.sh_data.data
-    ref.density_data.data[:] = 100.0
-    sampt = ref.volume_render(ref_svox2.Rays(origins[sub].contiguous(), dirs[sub].contiguous()),
-                              use_kernel=False)
-    F.mse_loss(sampt, rgb_gt[sub]).backward()
-    assert (samps - sampt).abs().max().item() < 1e-4                        # 'err'
-    E = (gs - ref.sh_data.grad).abs()
-    Ed = (gd - ref.density_data.grad).abs()
-    assert E.max().item() <= 1e-4 * ref.sh_data.grad.abs().max().item() + 1e-9       # 'err_sh_grad'
-    assert Ed.max().item() <= 1e-4 * ref.density_data.grad.abs().max().item() + 1e-9  # 'err_density_grad'
+@pytest.mark.gpu
+def test_reference_gradcheck_procedure_nvol(ref_svox2):
+    """test/test_render_gradcheck.py, same structure: z-order grid, density 100, sigma_thresh =
+    stop_thresh = 0, backend nvol, random rays (origins N(0, 3^2)), MSE against zeros, kernel vs
+    the other implementation: forward error, SH-gradient error, density-gradient error.
+      (a) the script's own size (128^3, 200*200 rays) against the reference's CUDA nvol kernels;
+      (b) against the reference's PyTorch nvol renderer + autograd, as the script does, at 64^3 with
+          400 rays and on the host: that path materialises a dense [N,27] gradient per gather
+          (two minutes for 400 rays at 128^3), and it mixes CPU and CUDA tensors under current torch
+          (svox2.py:945), so it cannot run on the GPU at all."""
+    import torch.nn.functional as F
+    import svox2_b200 as sv
+    torch.random.manual_seed(2)
+    dev = "cuda:0"
+    for reso, n_rays, pytorch_side in ((128, 200 * 200, False), (64, 400, True)):
+        grid = _gradcheck_setup(sv, reso, dev)
+        origins = torch.randn((n_rays, 3), device=dev) * 3
+        dirs = torch.randn((n_rays, 3), device=dev)
+        dirs /= torch.norm(dirs, dim=-1, keepdim=True)
+        rgb_gt = torch.zeros((n_rays, 3), device=dev)
+        samps = grid.volume_render(sv.Rays(origins, dirs), use_kernel=True)
+        F.mse_loss(samps, rgb_gt).backward()
+        rdev = "cpu" if pytorch_side else dev
+        ref = _gradcheck_setup(ref_svox2, reso, rdev, sh=grid.sh_data.data)
+        assert torch.equal(ref.links.cpu(), grid.links.cpu())
+        sampt = ref.volume_render(ref_svox2.Rays(origins.to(rdev), dirs.to(rdev)),
+                                  use_kernel=not pytorch_side)
+        F.mse_loss(sampt, rgb_gt.to(rdev)).backward()
+        gs_t, gd_t = ref.sh_data.grad.cpu(), ref.density_data.grad.cpu()
+        assert (samps.detach().cpu() - sampt.detach().cpu()).abs().max().item() < 1e-4      # 'err'
+        E = (grid.sh_data.grad.cpu() - gs_t).abs()
+        Ed = (grid.density_data.grad.cpu() - gd_t).abs()
+        assert gs_t.abs().max().item() > 0 and gd_t.abs().max().item() > 0
+        assert E.max().item() <= 1e-4 * gs_t.abs().max().item()                 # 'err_sh_grad'
+        assert Ed.max().item() <= 1e-4 * gd_t.abs().max().item()                # 'err_density_grad'
