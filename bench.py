@@ -140,12 +140,14 @@ def bench_cameras(device, seed=5):
     return [m.float().to(device).contiguous() for m in c2w]
 
 
-def time_images(render, cams, reps=3):
+def time_images(render, cams, reps=3, sampler=None):
     """ms per image (CUDA events), after one warm-up pass over the cameras."""
     with torch.no_grad():
         for c in cams:
             render(c)
         torch.cuda.synchronize()
+        if sampler:
+            sampler.mark()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
@@ -760,6 +762,324 @@ def reference_cuda_baseline(sc, grid, batches, args, gq):
             "same grid/rays/step on this GPU, 1 GPU"}
 
 
+# ----------------------------------------------------------------------------------------------
+# the other two GPU configurations of BASELINE.json: C4 (NDC full-image render), C5 (MSI train step)
+# ----------------------------------------------------------------------------------------------
+def _load_ref():
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "svox2")):
+        return None
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import svox2 as ref
+    return ref
+
+
+def build_c4(device, seed=11):
+    """LLFF NDC grid 1408x1156x128 (llff.json): content slabs at three NDC depths, ~4 % stored."""
+    reso = [1408, 1156, 128]
+    gen = torch.Generator(device=device).manual_seed(seed)
+    keep = torch.zeros(reso, dtype=torch.bool, device=device)
+    for z0 in (20, 52, 90):
+        blob = torch.rand(reso[0] // 16 + 1, reso[1] // 16 + 1, generator=gen, device=device) < 0.45
+        keep[:, :, z0:z0 + 4] |= blob.repeat_interleave(16, 0).repeat_interleave(16, 1)[:reso[0], :reso[1], None]
+    n_rows = int(keep.sum())
+    links = torch.cumsum(keep.view(-1).to(torch.int32), 0, dtype=torch.int32) - 1
+    links[~keep.view(-1)] = -1
+    links = links.view(*reso).contiguous()
+    density = torch.rand(n_rows, 1, generator=gen, device=device) * 40.0
+    sh = torch.randn(n_rows, 27, generator=gen, device=device) * 0.1
+    sh[:, ::9] += 0.5
+    return dict(links=links, density=density, sh=sh, n_rows=n_rows, reso=reso,
+                radius=[1.496031746031746, 1.6613756613756614, 1.0],
+                name="C4: LLFF NDC grid 1408x1156x128 SH deg 2, full-image render at 1008x756")
+
+
+def c4_grid(mod, sc, device):
+    g = mod.SparseGrid(reso=[8, 8, 8], radius=sc["radius"], basis_dim=9, use_sphere_bound=False,
+                       device=device)
+    g.links = sc["links"].clone()
+    g.density_data = torch.nn.Parameter(sc["density"].clone())
+    g.sh_data = torch.nn.Parameter(sc["sh"].clone())
+    g.capacity = sc["n_rows"]
+    g.accelerate()
+    g.opt.step_size, g.opt.sigma_thresh, g.opt.stop_thresh = 0.5, 1e-8, 1e-7
+    g.opt.background_brightness, g.opt.last_sample_opaque = 0.5, False
+    return g
+
+
+C4_CAM = dict(fx=820.0, width=1008, height=756)
+
+
+def c4_cameras(device, n=8):
+    cams = []
+    for i in range(n):      # a small forward-facing rig around the origin (LLFF poses after recentring)
+        c2w = torch.eye(4)
+        a = 2 * math.pi * i / n
+        c2w[:3, 3] = torch.tensor([0.08 * math.cos(a), 0.06 * math.sin(a), 0.0])
+        cams.append(c2w.to(device))
+    return cams
+
+
+def run_c4(args):
+    import svox2_b200 as sv
+    assert torch.cuda.is_available()
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    sc = build_c4(dev)
+    grid = c4_grid(sv, sc, dev)
+    W, H, fx = C4_CAM["width"], C4_CAM["height"], C4_CAM["fx"]
+    ndc = (2 * fx / W, 2 * fx / H)
+    cams = c4_cameras(dev)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_img = time_images(lambda c: grid.volume_render_image(sv.Camera(c, ndc_coeffs=ndc, **C4_CAM)), cams,
+                         reps=max(3, args.steps // len(cams)), sampler=sampler)
+    # end to end through the public call: camera pose from pinned host memory, image back to the host
+    host_c2w = [c.cpu().pin_memory() for c in cams]
+    out_host = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    n_e2e = max(len(cams), args.steps // 4)
+    for i in range(n_e2e):
+        c = host_c2w[i % len(cams)].to(dev, non_blocking=True)
+        out_host.copy_(grid.volume_render_image(sv.Camera(c, ndc_coeffs=ndc, **C4_CAM)), non_blocking=True)
+    t1.record()
+    torch.cuda.synchronize()
+    ms_e2e = t0.elapsed_time(t1) / n_e2e
+    if sampler:
+        sampler.mark()
+    clocks = sampler.stop() if sampler else None
+    counters = torch.zeros(4, dtype=torch.int64, device=dev)
+    from svox2_b200 import csrc as C
+    rays = sv.Camera(cams[0], ndc_coeffs=ndc, **C4_CAM).gen_rays()
+    C.volume_render_cuvol(grid._to_cpp(), rays._to_cpp(), grid.opt._to_cpp(), _counters=counters)
+    cnt = counters.cpu().tolist()
+    if world > 1:
+        import torch.distributed as dist
+        tt = torch.tensor([ms_img, ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_img, ms_e2e = tt.tolist()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    mpix = W * H / 1e6
+    peak, peak_src = peaks()
+    abytes = 36 * W * H + 4 * cnt[0] + 64 * cnt[1] + 864 * cnt[2]          # SURVEY 8d forward bytes
+    line = {"metric": "render MPix/s (volume_render_image, LLFF NDC grid)", "value": world * mpix / (ms_img * 1e-3),
+            "unit": "MPix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_img, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": sc["name"], "reso": sc["reso"], "stored_voxels": sc["n_rows"],
+                       "image": [W, H], "fx": fx, "ndc_coeffs": ndc, "step": "one 1008x756 image",
+                       "l2": "links alone are 833 MB >> L2; 8 cameras cycled",
+                       "parallelism": f"images sharded over {world} GPU(s), replicated grid",
+                       "samples_per_ray": {"skip": cnt[0] / (W * H), "visited": cnt[1] / (W * H),
+                                           "active": cnt[2] / (W * H)}},
+            "e2e": {"value": world * mpix / (ms_e2e * 1e-3), "unit": "MPix/s", "h2d_bytes_per_step": 64,
+                    "d2h_bytes_per_step": W * H * 12, "ms_per_step": ms_e2e},
+            "gpu_launches": args.steps, "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "lattice_march_kernel<FWD, FROM_CAM>",
+                         "achieved": abytes / (ms_img * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": abytes / (ms_img * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": abytes, "ms_per_launch": ms_img, "traffic": None,
+                         "note": "issue-bound, not bandwidth-bound (profiles/r1_ncu_image_render.txt)"}}
+    if args.ref_cuda and world == 1:
+        ref = _load_ref()
+        if ref is None:
+            line["ref_cuda"] = {"unavailable": "oracle/_ref not built"}
+        else:
+            rg = c4_grid(ref, sc, dev)
+            ms_ref = time_images(lambda c: rg.volume_render_image(ref.Camera(c, ndc_coeffs=ndc, **C4_CAM)), cams)
+            line["ref_cuda"] = {"value": mpix / (ms_ref * 1e-3), "unit": "MPix/s", "ms_per_image": ms_ref,
+                                "what": "sxyu/svox2 CUDA extension, same grid / cameras / GPU"}
+    print(json.dumps(line), flush=True)
+
+
+def build_c5(device, reso=640, bg_reso=1024, bg_layers=64, seed=17):
+    """tnt.json-sized scene: sparsified 640^3 foreground (~6 % stored), MSI 2048x1024x64 with sparse
+    shells of density (the state after the first upsamples of a T&T run)."""
+    gen0 = torch.Generator().manual_seed(99)
+    nb = 40
+    centers = (torch.rand(nb, 3, generator=gen0) - 0.5) * 1.3
+    radii = torch.rand(nb, 3, generator=gen0) * 0.17 + 0.08
+    inside = _inside_blobs(reso, centers, radii, 0.85, device)
+    keep = _dilate(inside, 2)
+    n_rows = int(keep.sum())
+    links = torch.cumsum(keep.view(-1).to(torch.int32), 0, dtype=torch.int32) - 1
+    links[~keep.view(-1)] = -1
+    links = links.view(reso, reso, reso).contiguous()
+    gen = torch.Generator(device=device).manual_seed(seed)
+    density = (inside[keep].float() * 25.0).view(n_rows, 1).contiguous()
+    del inside, keep
+    sh = torch.randn(n_rows, 27, generator=gen, device=device) * 0.1
+    sh[:, ::9] += 0.5
+    nbg = 2 * bg_reso * bg_reso
+    bg = torch.zeros(nbg, bg_layers, 4, device=device)
+    bg[..., :3] = torch.randn(nbg, bg_layers, 3, generator=gen, device=device) * 0.4
+    lay = torch.rand(nbg, bg_layers, generator=gen, device=device)
+    tex = torch.rand(nbg, 1, generator=gen, device=device) < 0.2
+    bg[..., 3] = torch.where((lay < 0.15) & tex, lay * 40.0, torch.zeros_like(lay))
+    return dict(links=links, density=density, sh=sh, bg=bg, n_rows=n_rows, reso=reso, bg_reso=bg_reso,
+                bg_layers=bg_layers,
+                name=f"C5: T&T {reso}^3 foreground + {bg_layers}-layer MSI {2 * bg_reso}x{bg_reso} (tnt.json)")
+
+
+def c5_grid(mod, sc, device):
+    g = mod.SparseGrid(reso=[8, 8, 8], basis_dim=9, use_sphere_bound=False, device=device,
+                       background_nlayers=sc["bg_layers"], background_reso=sc["bg_reso"])
+    g.links = sc["links"].clone()
+    g.density_data = torch.nn.Parameter(sc["density"].clone())
+    g.sh_data = torch.nn.Parameter(sc["sh"].clone())
+    g.capacity = sc["n_rows"]
+    g.background_data = torch.nn.Parameter(sc["bg"].clone())
+    g.accelerate()
+    g.opt.step_size, g.opt.sigma_thresh, g.opt.stop_thresh = 0.5, 1e-8, 1e-7
+    g.opt.background_brightness = 1.0
+    return g
+
+
+def c5_rays(n, seed, device):
+    """Cameras INSIDE the grid at radius ~0.85 (the NSVF loader scales T&T cameras by 0.95,
+    nsvf_dataset.py:46,167-170) looking at the centre region; most rays leave the foreground box and
+    composite the MSI shells."""
+    gen = torch.Generator().manual_seed(seed)
+    v = torch.nn.functional.normalize(torch.randn(n, 3, generator=gen), dim=-1)
+    origins = v * 0.85
+    target = (torch.rand(n, 3, generator=gen) - 0.5) * 1.2
+    dirs = torch.nn.functional.normalize(target - origins, dim=-1)
+    return origins.to(device).contiguous(), dirs.to(device).contiguous()
+
+
+TNT = dict(lr_sigma=30.0, lr_sh=1e-2, lambda_tv=5e-5, lambda_tv_sh=5e-3, tv_sparsity=0.01, rms_beta=0.95,
+           beta_loss=1e-5, sparsity_loss=1e-11, lr_sigma_bg=3.0, lr_color_bg=0.1,
+           lambda_tv_background_sigma=1e-3, lambda_tv_background_color=1e-3, tv_background_sparsity=0.01)
+
+
+def run_c5(args):
+    """tnt.json train step: fused render with MSI + beta/sparsity losses, sparse TV (sigma, SH, MSI),
+    RMSProp (sigma, SH, MSI).  N > 1: rays sharded over a replicated grid (ShardedTrainer)."""
+    import svox2_b200 as sv
+    from svox2_b200.dist import ShardedTrainer
+    assert torch.cuda.is_available()
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    sc = build_c5(dev)
+    grid = c5_grid(sv, sc, dev)
+    gq = BATCH * world
+    o, d = c5_rays(POOL * gq, 5, dev)
+    with torch.no_grad():
+        gt = torch.cat([grid.volume_render(sv.Rays(o[i:i + 50000], d[i:i + 50000]))
+                        for i in range(0, POOL * gq, 50000)])
+        gt = (gt + 0.02 * torch.randn(gt.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(99))).clamp_(0, 1)
+    sl = [slice(b * gq + rank * BATCH, b * gq + (rank + 1) * BATCH) for b in range(POOL)]
+    batches = [(o[s].contiguous(), d[s].contiguous(), gt[s].contiguous()) for s in sl]
+    trainer = ShardedTrainer(grid, world_size=world, rank=rank, **TNT)
+    np.random.seed(1234)
+    torch.manual_seed(1234)
+    step = lambda bo, bd, bg: trainer.step(sv.Rays(bo, bd), bg, global_batch=gq)
+    sampler = ClockSampler(local) if rank == 0 else None
+    for i in range(args.warmup):
+        step(*batches[i % POOL])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    if sampler:
+        sampler.mark()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(*batches[i % POOL])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    n_bg = int(grid.sparse_background_indexer.sum())
+    host = [tuple(x.cpu().pin_memory() for x in b) for b in batches]
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        bo, bd, bg = (x.to(dev, non_blocking=True) for x in host[i % POOL])
+        rgb = step(bo, bd, bg)
+        loss_host.copy_(torch.mean((rgb - bg) ** 2), non_blocking=True)
+    t1.record()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.mark()
+    ms_e2e = t0.elapsed_time(t1) / args.steps
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        tt = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = tt.tolist()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {"metric": "train rays/sec (fused fwd+bwd step with MSI background), tnt.json", "value": gq / (ms * 1e-3),
+            "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": sc["name"], "reso": sc["reso"], "stored_voxels": sc["n_rows"],
+                       "msi_texels": int(sc["bg"].size(0)), "rays_per_gpu": BATCH, "global_batch": gq,
+                       "step": "volume_render_fused(beta, sparsity) + tv_grad_sparse(sigma, sh) + msi_tv_grad_sparse "
+                               "+ rmsprop(sigma, sh, background)",
+                       "msi_shell_rows_touched_last_step": n_bg,
+                       "l2": "inputs larger than L2; 8 distinct ray batches cycled",
+                       "parallelism": f"ray-sharded x{world}, replicated grid" +
+                                      (", masked packed grad all-reduce (NCCL)" if world > 1 else "")},
+            "e2e": {"value": gq / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 3 * BATCH * 12,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "last_loss": float(loss_host)},
+            "gpu_launches": 12 * args.steps, "clocks": clocks,
+            "roofline": None}
+    if args.ref_cuda and world == 1:
+        ref = _load_ref()
+        if ref is None:
+            line["ref_cuda"] = {"unavailable": "oracle/_ref not built"}
+        else:
+            del trainer
+            rg = c5_grid(ref, sc, dev)
+            np.random.seed(1234)
+
+            def rstep(bo, bd, bg):
+                rgb = rg.volume_render_fused(ref.Rays(bo, bd), bg, beta_loss=TNT["beta_loss"],
+                                             sparsity_loss=TNT["sparsity_loss"])
+                rg.inplace_tv_grad(rg.density_data.grad, scaling=TNT["lambda_tv"], sparse_frac=0.01)
+                rg.inplace_tv_color_grad(rg.sh_data.grad, scaling=TNT["lambda_tv_sh"], sparse_frac=0.01)
+                rg.inplace_tv_background_grad(rg.background_data.grad, scaling=TNT["lambda_tv_background_color"],
+                                              scaling_density=TNT["lambda_tv_background_sigma"],
+                                              sparse_frac=0.01, contiguous=True)
+                rg.optim_density_step(30.0, beta=0.95)
+                rg.optim_sh_step(1e-2, beta=0.95)
+                rg.optim_background_step(3.0, 0.1, beta=0.95)
+                return rgb
+
+            for i in range(min(args.warmup, 5)):
+                rstep(*batches[i % POOL])
+            torch.cuda.synchronize()
+            n_ref = max(5, args.steps // 4)
+            e0.record()
+            for i in range(n_ref):
+                rstep(*batches[i % POOL])
+            e1.record()
+            torch.cuda.synchronize()
+            ms_ref = e0.elapsed_time(e1) / n_ref
+            line["ref_cuda"] = {"value": BATCH / (ms_ref * 1e-3), "unit": "rays/s", "ms_per_step": ms_ref,
+                                "what": "sxyu/svox2 CUDA extension, same grid / rays / step / GPU"}
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(args):
     """Reference arm: the reference algorithm on the host cores.  The reference's own
     pure-PyTorch path cannot run the 512^3 workload (its autograd materialises a dense [N,27]
@@ -878,7 +1198,9 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=list(WORKLOADS) + ["c4", "c5"],
+                    help="c3 (default, the config the metric is quoted on), c2 / small (same step on smaller "
+                         "grids), c4 (LLFF NDC full-image render), c5 (tnt.json MSI train step)")
     ap.add_argument("--dist", default="slab", choices=["slab", "rays"],
                     help="multi-GPU decomposition: grid sharded by x-slabs (default) or rays "
                          "sharded over a replicated grid with a packed gradient all-reduce")
@@ -900,6 +1222,10 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c4":
+        run_c4(args)
+    elif args.workload == "c5":
+        run_c5(args)
     else:
         run_ours(args)
 
