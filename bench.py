@@ -322,7 +322,7 @@ def multi_gpu_parity(sv, grid, trainer, slab, step, global_batches, local_batche
     ref.capacity = grid.capacity
     for k in RENDER:
         setattr(ref.opt, k, getattr(grid.opt, k))
-    single = ShardedTrainer(ref, world_size=1, rank=0, **SYN)
+    single = ShardedTrainer(ref, world_size=1, rank=0, fused=False, **SYN)     # operator-by-operator
     out = {}
     for it in range(2):
         go, gd, gg = global_batches[it]
@@ -360,6 +360,57 @@ def multi_gpu_parity(sv, grid, trainer, slab, step, global_batches, local_batche
             "rows_checked": int(cnt[0]), "rows_touched": int(cnt[1]), "ranks": world,
             "bars": {"rgb_max_abs": 1e-5, "mask": "bit-exact", "frac_bad": 1e-3, "rgb_max_abs_step2": 2e-3},
             "reduction": "worst rank (max), row counts summed"}
+
+
+def single_gpu_parity(sv, grid, batches):
+    """N = 1: the fused step (one C call, compact gradient buffer) must equal the operator-by-operator
+    sequence of opt.py (volume_render_fused, inplace_tv_grad, inplace_tv_color_grad, optim_density_step,
+    optim_sh_step through SparseGrid) on the same grid, batch and TV cells: colours, both sparse masks
+    bit for bit, RMS state and parameters.  Runs on two clones before anything is timed."""
+    from svox2_b200.dist import ShardedTrainer
+
+    def clone():
+        g = sv.SparseGrid(reso=[2, 2, 2], basis_dim=grid.basis_dim, device="cpu")
+        g.links = grid.links
+        g.density_data = torch.nn.Parameter(grid.density_data.data.clone())
+        g.sh_data = torch.nn.Parameter(grid.sh_data.data.clone())
+        g.capacity = grid.capacity
+        for k in RENDER:
+            setattr(g.opt, k, getattr(grid.opt, k))
+        return g
+
+    a, b = clone(), clone()
+    fused, plain = ShardedTrainer(a, fused=True, **SYN), ShardedTrainer(b, fused=False, **SYN)
+    out = {}
+    for it in range(2):
+        o, d, g = batches[it]
+        np.random.seed(777 + it)
+        ra = fused.step(sv.Rays(o, d), g)
+        np.random.seed(777 + it)
+        rb = plain.step(sv.Rays(o, d), g)
+        torch.cuda.synchronize()
+        out["rgb_max_abs" if it == 0 else "rgb_max_abs_step2"] = float((ra - rb).abs().max())
+        if it == 0:
+            st = fused.export_masks()
+            out["mask_equal"] = bool(torch.equal(a.sparse_grad_indexer, b.sparse_grad_indexer) and
+                                     torch.equal(a.sparse_sh_grad_indexer, b.sparse_sh_grad_indexer))
+            out["rows_touched"] = int(st[0])
+            out["overflow"] = bool(st[1] or st[2])
+            out["rms_rel_err"] = max(float((a.sh_rms - b.sh_rms).abs().max() / b.sh_rms.abs().max()),
+                                     float((a.density_rms - b.density_rms).abs().max() / b.density_rms.abs().max()))
+            out["fb_density"] = _frac_bad(a.density_data.data, b.density_data.data)
+            out["fb_sh"] = _frac_bad(a.sh_data.data, b.sh_data.data)
+    ok = (out["rgb_max_abs"] < 1e-5 and out["mask_equal"] and not out["overflow"] and out["rms_rel_err"] < 1e-4
+          and out["fb_density"] < 1e-3 and out["fb_sh"] < 1e-3 and out["rgb_max_abs_step2"] < 2e-3)
+    del a, b, fused, plain
+    torch.cuda.empty_cache()
+    return {"ok": bool(ok), "against": "operator-by-operator step through SparseGrid (dense .grad, bool masks) "
+            "on the same batch, grid and TV seed", "rgb_max_abs": out["rgb_max_abs"],
+            "masks_bit_exact": out["mask_equal"], "rms_rel_err": out["rms_rel_err"],
+            "frac_bad_density_1e-4": out["fb_density"], "frac_bad_sh_1e-4": out["fb_sh"],
+            "rgb_max_abs_step2": out["rgb_max_abs_step2"], "rows_touched": out["rows_touched"],
+            "bars": {"rgb_max_abs": 1e-5, "masks": "bit-exact", "rms_rel_err": 1e-4, "frac_bad": 1e-3,
+                     "rgb_max_abs_step2": 2e-3}}
 
 
 def algorithmic_bytes_fused(q, c):
@@ -450,6 +501,10 @@ def run_ours(args):
         parity = multi_gpu_parity(sv, grid, trainer, slab, step, gb, batches, rank, world, dev)
         np.random.seed(1234)
 
+    if world == 1 and not args.no_parity and trainer._can_fuse():
+        parity = single_gpu_parity(sv, grid, batches)
+        np.random.seed(1234)
+
     sampler = ClockSampler(local) if rank == 0 else None
     for i in range(args.warmup):
         step(*batches[i % POOL])
@@ -464,6 +519,9 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     # rows the last step's optimisers updated (the masks survive the step): whole-step roofline
+    if getattr(trainer, "_step_ws", None) is not None:    # fused single-GPU step: masks on demand
+        trainer.export_masks()
+        trainer.check_overflow()
     touched = (int(grid.sparse_grad_indexer.sum()), int(grid.sparse_sh_grad_indexer.sum()))
 
     # end to end: pinned host inputs -> H2D, step, D2H of the loss, every step.  The loss of step i
@@ -511,7 +569,7 @@ def run_ours(args):
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     spec, ropt = grid._to_cpp(), grid.opt._to_cpp()
     holder = C.GridOutputGrads()
-    holder.grad_density_out, holder.grad_sh_out = grid.density_data.grad, grid.sh_data.grad
+    holder.grad_density_out, holder.grad_sh_out, _ = grid._get_data_grads()     # dense .grad arrays
     holder.mask_out = torch.zeros(sc["n_rows"], dtype=torch.bool, device=dev)
     rgb_out = torch.zeros_like(own[0][2])
     rspecs = [sv.Rays(o, d)._to_cpp() for o, d, _ in own]
@@ -574,7 +632,8 @@ def run_ours(args):
         "config": {
             "workload": sc["name"], "reso": sc["reso"], "stored_voxels": sc["n_rows"],
             "occupancy": round(sc["occupancy"], 4), "rays_per_gpu": per_rank, "global_batch": gq,
-            "step": "volume_render_fused + tv_grad_sparse(sigma,sh) + rmsprop(sigma,sh)",
+            "step": "volume_render_fused + tv_grad_sparse(sigma,sh) + rmsprop(sigma,sh)" +
+                    (" as one svox2_train_step call (compact gradient buffer)" if getattr(trainer, "_step_ws", None) is not None else ""),
             "l2": "inputs larger than L2 (grid+grads+rms >> 126 MB); 8 distinct ray batches cycled",
             "parallelism": (f"grid sharded into {world} x-slabs, every rank traverses the global "
                             "batch; per-ray scalars and halo planes exchanged with " +

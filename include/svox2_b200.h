@@ -235,6 +235,47 @@ SVOX2_API int svox2_msi_tv_grad_sparse(const int32_t* background_links, int32_t 
                              int64_t n_cells, int64_t scale_cells, uint8_t* mask_out, float scale,
                              float scale_last, float* grad_msi, svox2_stream_t stream);
 
+/* ---- Extension: the whole train step of opt/opt.py:474-603 as one call ------------------------
+ * volume_render_cuvol_fused + tv_grad_sparse (density, contiguous run) + tv_grad_sparse (SH) +
+ * rmsprop_step (density, SH), with the step's gradients kept in a compact [touched rows, W] buffer
+ * inside the workspace instead of dense .grad arrays.  Same kernels / arithmetic as
+ * the separate entry points; density_data, sh_data (through `grid`, written despite the const) and
+ * the two RMS arrays are updated in place.  No MSI background; sh rows must be 16-byte aligned.
+ * The workspace is created once (svox2_train_step_workspace_bytes + svox2_train_step_init) and
+ * must be passed unchanged to every step on this grid / batch size.  slots_per_ray sizes the
+ * sample-record queue (records per ray on average); if it overflows the step's ray gradients are
+ * dropped and the sticky counter reported by svox2_train_step_masks is incremented. */
+typedef struct {
+    int64_t tv_density_start;   /* first cell of the wrapped contiguous run (svox2.py:2230-2237)  */
+    int64_t tv_density_count;   /* 0 disables the density TV                                      */
+    float tv_density_scale;     /* lambda_tv                                                      */
+    int64_t tv_sh_start;
+    int64_t tv_sh_count;
+    float tv_sh_scale;          /* lambda_tv_sh                                                   */
+    int64_t tv_scale_cells;     /* cells the TV is normalised by; 0 = the run's count             */
+    float beta_loss;            /* lambda_beta (divided by norm_rays inside, cuvol.cu:1127)       */
+    float sparsity_loss;
+    int64_t norm_rays;          /* batch size of the MSE normalisation (global batch if sharded)  */
+    float lr_density, lr_sh, rms_beta, epsilon;
+} svox2_step_params_t;
+SVOX2_API size_t svox2_train_step_workspace_bytes(int64_t n_rows, int32_t basis_dim, int64_t n_rays,
+                                                  int64_t slots_per_ray);
+SVOX2_API int svox2_train_step_init(void* workspace, size_t workspace_bytes, int64_t n_rows,
+                                    int32_t basis_dim, int64_t n_rays, int64_t slots_per_ray,
+                                    svox2_stream_t stream);
+SVOX2_API int svox2_train_step(const svox2_grid_t* grid, float* density_rms, float* sh_rms,
+                               const float* origins, const float* dirs, int64_t n_rays,
+                               const svox2_render_opts_t* opt, const float* rgb_gt, float* rgb_out,
+                               const svox2_step_params_t* params, void* workspace,
+                               size_t workspace_bytes, int64_t slots_per_ray, int64_t* counters,
+                               svox2_stream_t stream);
+/* The two sparse masks of the LAST step as uint8[N] (OR-ed into the arrays; either may be NULL) and
+ * device int32[3] = {touched rows, queue overflow flag of the last step, overflowed steps before it}. */
+SVOX2_API int svox2_train_step_masks(void* workspace, size_t workspace_bytes, int64_t n_rows,
+                                     int32_t basis_dim, int64_t n_rays, int64_t slots_per_ray,
+                                     uint8_t* mask_density, uint8_t* mask_sh, int32_t* status3,
+                                     svox2_stream_t stream);
+
 /* lumisphere_tv_grad_sparse (svox2.cpp:50-51, loss_kernel.cu:335-434, 643-678): TV of the colour
  * seen from one view direction; basis_fn / basis_fn_u = SH basis values [basis_dim] of that
  * direction and of a perturbed one (weight dir_factor).  scale is divided by n_cells inside.

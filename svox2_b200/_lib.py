@@ -69,6 +69,16 @@ class GradsT(C.Structure):
     ]
 
 
+class StepParamsT(C.Structure):
+    _fields_ = [
+        ("tv_density_start", C.c_int64), ("tv_density_count", C.c_int64), ("tv_density_scale", C.c_float),
+        ("tv_sh_start", C.c_int64), ("tv_sh_count", C.c_int64), ("tv_sh_scale", C.c_float),
+        ("tv_scale_cells", C.c_int64), ("beta_loss", C.c_float), ("sparsity_loss", C.c_float),
+        ("norm_rays", C.c_int64), ("lr_density", C.c_float), ("lr_sh", C.c_float),
+        ("rms_beta", C.c_float), ("epsilon", C.c_float),
+    ]
+
+
 _P = C.c_void_p
 _I32, _I64, _F, _SZ = C.c_int32, C.c_int64, C.c_float, C.c_size_t
 _G, _O, _CAM, _GR = C.POINTER(GridT), C.POINTER(RenderOptsT), C.POINTER(CameraT), C.POINTER(GradsT)
@@ -90,6 +100,11 @@ SIGNATURES = {
     "svox2_volume_render_nvol": (C.c_int, [_G, _P, _P, _I64, _O, _P, _P]),
     "svox2_volume_render_nvol_backward": (C.c_int, [_G, _P, _P, _I64, _O, _P, _P, _GR, _P]),
     "svox2_volume_render_nvol_fused": (C.c_int, [_G, _P, _P, _I64, _I64, _O, _P, _F, _P, _GR, _P]),
+    "svox2_train_step_workspace_bytes": (_SZ, [_I64, _I32, _I64, _I64]),
+    "svox2_train_step_init": (C.c_int, [_P, _SZ, _I64, _I32, _I64, _I64, _P]),
+    "svox2_train_step": (C.c_int, [_G, _P, _P, _P, _P, _I64, _O, _P, _P, C.POINTER(StepParamsT), _P, _SZ,
+                                   _I64, _P, _P]),
+    "svox2_train_step_masks": (C.c_int, [_P, _SZ, _I64, _I32, _I64, _I64, _P, _P, _P, _P]),
     "svox2_sample_grid": (C.c_int, [_G, _P, _I64, _P, _P, _P]),
     "svox2_sample_grid_backward": (C.c_int, [_G, _P, _I64, _P, _P, _P, _I64, _P, _I64, _P]),
     "svox2_dilate": (C.c_int, [_P, _I32, _I32, _I32, _P, _P]),

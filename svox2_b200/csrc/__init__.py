@@ -737,6 +737,65 @@ def rmsprop_step_packed(sh_data, sh_rms, density_data, density_rms, rows, packed
             float(lr_density), float(epsilon), float(minval_sh), float(minval_density), _stream()))
 
 
+# ---- fused train step on a compact gradient buffer (csrc/step.cu) ---------------------------
+class TrainStepWorkspace:
+    """Persistent scratch of ``train_step`` for one (grid rows, basis, batch size): the sample-record
+    queue plus the touched-row bit set, slot numbering and compact gradient rows.  Zero-initialised
+    once; every step leaves it in the state the next one expects."""
+
+    def __init__(self, n_rows: int, basis_dim: int, n_rays: int, slots_per_ray: int, device):
+        self.key = (int(n_rows), int(basis_dim), int(n_rays), int(slots_per_ray))
+        self.nbytes = _lib.lib().svox2_train_step_workspace_bytes(*self.key)
+        self.buf = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
+        with torch.cuda.device(device):
+            check(_lib.lib().svox2_train_step_init(self.buf.data_ptr(), self.nbytes, *self.key, _stream()))
+
+    def status(self, want_masks: bool = False):
+        """(touched rows, overflowed last step, overflowed steps before) and optionally the two sparse
+        masks of the LAST step as bool[N] (host sync)."""
+        dev = self.buf.device
+        st = torch.zeros(3, dtype=torch.int32, device=dev)
+        md = msh = None
+        if want_masks:
+            md = torch.zeros(self.key[0], dtype=torch.bool, device=dev)
+            msh = torch.zeros(self.key[0], dtype=torch.bool, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.lib().svox2_train_step_masks(self.buf.data_ptr(), self.nbytes, *self.key, _ptr(md),
+                                                    _ptr(msh), st.data_ptr(), _stream()))
+        n, ov, sticky = st.tolist()
+        return (n, ov, max(sticky, 0)), md, msh
+
+
+def train_step(grid, density_rms, sh_rms, rays, opt, rgb_gt, rgb_out, workspace: TrainStepWorkspace, *,
+               tv_density=(0, 0, 0.0), tv_sh=(0, 0, 0.0), tv_scale_cells=0, beta_loss=0.0,
+               sparsity_loss=0.0, norm_rays=None, lr_density=0.0, lr_sh=0.0, rms_beta=0.95,
+               epsilon=1e-8, _counters=None):
+    """Extension: svox2_train_step -- fused render + sparse TV (density, SH; contiguous cell runs
+    ``(start, count, lambda)``) + RMSProp (density, SH) in one call; density_data / sh_data (through
+    ``grid``) and the RMS arrays are updated in place, ``rgb_out`` receives the colours."""
+    g = _grid_struct(grid)
+    origins, dirs = _rays(rays)
+    _check_input(rgb_gt, "rgb_gt", torch.float32, 2)
+    _check_input(rgb_out, "rgb_out", torch.float32, 2)
+    _check_rows(density_rms, "density_rms")
+    _check_rows(sh_rms, "sh_rms")
+    if _row_stride(sh_rms) != _row_stride(grid.sh_data) or _row_stride(density_rms) != _row_stride(grid.density_data):
+        _fail("data and rms must share one layout")
+    Q = origins.size(0)
+    if workspace.key != (grid.sh_data.size(0), int(grid.basis_dim), Q, workspace.key[3]):
+        _fail("train_step workspace was created for another grid / batch size")
+    o = _opt_struct(opt)
+    p = _lib.StepParamsT(int(tv_density[0]), int(tv_density[1]), float(tv_density[2]), int(tv_sh[0]),
+                         int(tv_sh[1]), float(tv_sh[2]), int(tv_scale_cells), float(beta_loss),
+                         float(sparsity_loss), int(Q if norm_rays is None else norm_rays), float(lr_density),
+                         float(lr_sh), float(rms_beta), float(epsilon))
+    with torch.cuda.device(origins.device):
+        check(_lib.lib().svox2_train_step(
+            C.byref(g), density_rms.data_ptr(), sh_rms.data_ptr(), origins.data_ptr(), dirs.data_ptr(), Q,
+            C.byref(o), rgb_gt.data_ptr(), rgb_out.data_ptr(), C.byref(p), workspace.buf.data_ptr(),
+            workspace.nbytes, workspace.key[3], _ptr(_counters), _stream()))
+
+
 # ---- slab mode (grid sharded over GPUs by x-range of cells; svox2_b200/slab.py) --------------
 def slab_workspace(n_rays: int, slots_per_ray: int, device):
     """Sample-record scratch shared by slab_trace / slab_shade / slab_backward."""

@@ -3,11 +3,21 @@
 // tests that decide mask bits use the same separately-rounded operations as the reference's
 // sm_100 SASS (FMUL by size/256, FADD sums, FFMA chain inside the rsqrt).
 #include "common.cuh"
+#include "slots.cuh"
+#include "step.cuh"
 
 namespace svox2b {
 namespace {
 
 constexpr int TV_THREADS = 256;
+
+// Destination of the fused train step (step.cu): gradients go to the compact slot rows, mask bits
+// to the slot flags (slots.cuh).  ch_off = column of channel 0 inside a slot row, which = flag byte.
+struct SlotDest {
+    SlotMap m;
+    int ch_off;
+    int which;
+};
 
 // calculate_ray_scale, loss_kernel.cu:22-52 (the NDC branch is commented out upstream)
 __device__ __forceinline__ void ray_scale(int X, int Y, int Z, float* s) {
@@ -145,10 +155,12 @@ __device__ __forceinline__ TvCell tv_probe(const int32_t* __restrict__ links, in
     return c;
 }
 
+template <bool SLOTS>
 __device__ __forceinline__ void tv_channel(const TvCell& c, int idx, const float* __restrict__ data,
                                            int64_t stride, const float* sc, float scale,
                                            int ignore_edge, uint8_t* __restrict__ mask_out,
-                                           float* __restrict__ grad, int64_t gstride) {
+                                           float* __restrict__ grad, int64_t gstride,
+                                           const SlotDest& sd) {
     const float v000 = c.l000 >= 0 ? __ldg(data + (int64_t)c.l000 * stride + idx) : 0.f;
     const float nullv = ignore_edge ? v000 : 0.f;
     const float v001 = c.l001 >= 0 ? __ldg(data + (int64_t)c.l001 * stride + idx) : nullv;
@@ -162,8 +174,14 @@ __device__ __forceinline__ void tv_channel(const TvCell& c, int idx, const float
     const float sm = -__fadd_rn(__fadd_rn(dx, dy), dz);
 #define MAYBE_ADD_SET(lnk, val)                                                      \
     if ((lnk) >= 0 && (val) != 0.f) {                                                \
-        atomicAdd(grad + (int64_t)(lnk) * gstride + idx, __fmul_rn((val), idelta));   \
-        if (mask_out) mask_out[(lnk)] = 1;                                           \
+        if (SLOTS) {                                                                 \
+            const int64_t slot = slot_of(sd.m, (lnk));                               \
+            atomicAdd(sd.m.grad + slot * sd.m.width + sd.ch_off + idx, __fmul_rn((val), idelta)); \
+            sd.m.flags[2 * slot + sd.which] = 1;                                     \
+        } else {                                                                     \
+            atomicAdd(grad + (int64_t)(lnk) * gstride + idx, __fmul_rn((val), idelta)); \
+            if (mask_out) mask_out[(lnk)] = 1;                                       \
+        }                                                                            \
     }
     MAYBE_ADD_SET(c.l000, sm);
     MAYBE_ADD_SET(c.l001, dz);
@@ -172,13 +190,14 @@ __device__ __forceinline__ void tv_channel(const TvCell& c, int idx, const float
 #undef MAYBE_ADD_SET
 }
 
-template <bool COOP>
+template <bool COOP, bool SLOTS>
 __global__ void __launch_bounds__(TV_THREADS)
 tv_grad_sparse_kernel(const int32_t* __restrict__ links, int X, int Y, int Z,
                       const float* __restrict__ data, int64_t stride,
                       const int32_t* __restrict__ rand_cells, int64_t cell_start, int start_dim,
                       int end_dim, float scale, int64_t n_cells, int ignore_edge, int ignore_last_z,
-                      uint8_t* __restrict__ mask_out, float* __restrict__ grad, int64_t gstride) {
+                      uint8_t* __restrict__ mask_out, float* __restrict__ grad, int64_t gstride,
+                      SlotDest sd) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     if (tid - lane >= n_cells) return;  // whole warp past the end
@@ -188,7 +207,7 @@ tv_grad_sparse_kernel(const int32_t* __restrict__ links, int X, int Y, int Z,
     if (!COOP) {
         if (mine.on)
             for (int idx = start_dim; idx < end_dim; ++idx)
-                tv_channel(mine, idx, data, stride, sc, scale, ignore_edge, mask_out, grad, gstride);
+                tv_channel<SLOTS>(mine, idx, data, stride, sc, scale, ignore_edge, mask_out, grad, gstride, sd);
         return;
     }
     unsigned m = __ballot_sync(FULL, mine.on);
@@ -202,7 +221,7 @@ tv_grad_sparse_kernel(const int32_t* __restrict__ links, int X, int Y, int Z,
         c.l100 = __shfl_sync(FULL, mine.l100, j);
         c.on = true;
         for (int idx = start_dim + lane; idx < end_dim; idx += WARP)
-            tv_channel(c, idx, data, stride, sc, scale, ignore_edge, mask_out, grad, gstride);
+            tv_channel<SLOTS>(c, idx, data, stride, sc, scale, ignore_edge, mask_out, grad, gstride, sd);
     }
 }
 
@@ -218,13 +237,14 @@ tv_grad_sparse_kernel(const int32_t* __restrict__ links, int X, int Y, int Z,
 #ifndef TV_VEC_PASSES
 #define TV_VEC_PASSES 2
 #endif
+template <bool SLOTS>
 __global__ void __launch_bounds__(TV_THREADS)
 tv_grad_sparse_vec_kernel(const int32_t* __restrict__ links, int X, int Y, int Z,
                           const float* __restrict__ data, int64_t stride,
                           const int32_t* __restrict__ rand_cells, int64_t cell_start, int start_dim,
                           int end_dim, float scale, int64_t n_cells, int ignore_edge,
                           int ignore_last_z, uint8_t* __restrict__ mask_out,
-                          float* __restrict__ grad, int64_t gstride, int qpr) {
+                          float* __restrict__ grad, int64_t gstride, int qpr, SlotDest sd) {
     constexpr int U = TV_VEC_PASSES;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -301,11 +321,18 @@ tv_grad_sparse_vec_kernel(const int32_t* __restrict__ links, int X, int Y, int Z
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 if (l[u][k] >= 0 && any[k]) {
-                    float* gp = grad + (int64_t)l[u][k] * gstride + ch0;
+                    float* gp;
+                    if (SLOTS) {
+                        const int64_t slot = slot_of(sd.m, l[u][k]);
+                        gp = sd.m.grad + slot * sd.m.width + sd.ch_off + ch0;
+                        sd.m.flags[2 * slot + sd.which] = 1;
+                    } else {
+                        gp = grad + (int64_t)l[u][k] * gstride + ch0;
+                        if (mask_out) mask_out[l[u][k]] = 1;
+                    }
                     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gp),
                                  "f"(out[k][0]), "f"(out[k][1]), "f"(out[k][2]), "f"(out[k][3])
                                  : "memory");
-                    if (mask_out) mask_out[l[u][k]] = 1;
                 }
         }
     }
@@ -428,6 +455,25 @@ lumisphere_tv_grad_sparse_kernel(const int32_t* __restrict__ links, int X, int Y
         }
 }
 
+// Fused train step: every stored voxel that a TV cell of this step can add to is entered into the
+// touched-row set BEFORE the slots are numbered (a superset of the rows the TV kernels will flag:
+// those depend on the data, loss_kernel.cu:232-237).  Cells [0, n_a) belong to run A (density TV:
+// ignore_edge = 0, ignore_last_z as given), cells [n_a, n_a + n_b) to run B (SH TV: ignore_edge = 1).
+__global__ void __launch_bounds__(TV_THREADS)
+tv_mark_kernel(const int32_t* __restrict__ links, int X, int Y, int Z, int64_t start_a, int64_t n_a,
+               int ignore_last_z_a, int64_t start_b, int64_t n_b, SlotMap sm) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n_a + n_b) return;
+    const bool a = tid < n_a;
+    const TvCell c = tv_probe(links, X, Y, Z, nullptr, a ? start_a : start_b, a ? tid : tid - n_a,
+                              a ? n_a : n_b, a ? 0 : 1, a ? ignore_last_z_a : 0);
+    if (!c.on) return;
+    if (c.l000 >= 0) slot_mark(sm, c.l000);
+    if (c.l001 >= 0) slot_mark(sm, c.l001);
+    if (c.l010 >= 0) slot_mark(sm, c.l010);
+    if (c.l100 >= 0) slot_mark(sm, c.l100);
+}
+
 int check_tv_args(const int32_t* links, int X, int Y, int Z, const float* data, int64_t stride,
                   int start_dim, int end_dim, const char* who) {
     if (!links || !data) {
@@ -447,6 +493,44 @@ int check_tv_args(const int32_t* links, int X, int Y, int Z, const float* data, 
 }
 
 }  // namespace
+
+void launch_tv_mark(const int32_t* links, int X, int Y, int Z, int64_t start_a, int64_t n_a,
+                    int ignore_last_z_a, int64_t start_b, int64_t n_b, const SlotMap& sm,
+                    cudaStream_t st) {
+    if (n_a + n_b <= 0) return;
+    tv_mark_kernel<<<div_up(n_a + n_b, TV_THREADS), TV_THREADS, 0, st>>>(links, X, Y, Z, start_a, n_a,
+                                                                       ignore_last_z_a, start_b, n_b, sm);
+}
+
+// tv_grad_sparse over the contiguous wrapped run [cell_start, cell_start + n_cells) into slot rows;
+// the same kernels and arithmetic as svox2_tv_grad_sparse_run.
+void launch_tv_slots(const int32_t* links, int X, int Y, int Z, const float* data, int64_t data_stride,
+                     int64_t cell_start, int64_t n_cells, int64_t scale_cells, int start_dim, int end_dim,
+                     float scale, int ignore_edge, int ignore_last_z, const SlotMap& sm, int ch_off,
+                     int which, cudaStream_t st) {
+    if (n_cells <= 0) return;
+    if (scale_cells <= 0) scale_cells = n_cells;
+    const float s = scale / (float)(int)scale_cells;
+    const int nd = end_dim - start_dim;
+    const int qpr = (nd + 3) / 4;
+    const SlotDest sd{sm, ch_off, which};
+    const unsigned blocks = div_up(n_cells, TV_THREADS);
+    if (nd <= 2)
+        tv_grad_sparse_kernel<false, true><<<blocks, TV_THREADS, 0, st>>>(
+            links, X, Y, Z, data, data_stride, nullptr, cell_start, start_dim, end_dim, s, n_cells,
+            ignore_edge, ignore_last_z, nullptr, nullptr, 0, sd);
+    else if (qpr <= WARP && start_dim % 4 == 0 && data_stride % 4 == 0 && ch_off % 4 == 0 &&
+             start_dim + qpr * 4 <= data_stride && ch_off + start_dim + qpr * 4 <= sm.width &&
+             (reinterpret_cast<uintptr_t>(data) & 15u) == 0)
+        tv_grad_sparse_vec_kernel<true><<<blocks, TV_THREADS, 0, st>>>(
+            links, X, Y, Z, data, data_stride, nullptr, cell_start, start_dim, end_dim, s, n_cells,
+            ignore_edge, ignore_last_z, nullptr, nullptr, 0, qpr, sd);
+    else
+        tv_grad_sparse_kernel<true, true><<<blocks, TV_THREADS, 0, st>>>(
+            links, X, Y, Z, data, data_stride, nullptr, cell_start, start_dim, end_dim, s, n_cells,
+            ignore_edge, ignore_last_z, nullptr, nullptr, 0, sd);
+}
+
 }  // namespace svox2b
 
 using namespace svox2b;
@@ -502,17 +586,17 @@ static int tv_grad_sparse_impl(const int32_t* links, int32_t X, int32_t Y, int32
     const int64_t gs = grad_stride > 0 ? grad_stride : data_stride;
     cudaStream_t st = (cudaStream_t)stream;
 #define TV_LAUNCH(COOP)                                                                         \
-    tv_grad_sparse_kernel<COOP><<<div_up(n_cells, TV_THREADS), TV_THREADS, 0, st>>>(            \
+    tv_grad_sparse_kernel<COOP, false><<<div_up(n_cells, TV_THREADS), TV_THREADS, 0, st>>>(     \
         links, X, Y, Z, data, data_stride, rand_cells, cell_start, start_dim, end_dim, s,       \
-        n_cells, ignore_edge, ignore_last_z, mask_out, grad_data, gs)
+        n_cells, ignore_edge, ignore_last_z, mask_out, grad_data, gs, SlotDest{})
     const int qpr = (nd + 3) / 4;
     const uintptr_t al = reinterpret_cast<uintptr_t>(data) | reinterpret_cast<uintptr_t>(grad_data);
     if (nd <= 2) TV_LAUNCH(false);
     else if (TV_USE_VEC && qpr <= WARP && start_dim % 4 == 0 && data_stride % 4 == 0 && gs % 4 == 0 &&
              start_dim + qpr * 4 <= data_stride && start_dim + qpr * 4 <= gs && (al & 15u) == 0)
-        tv_grad_sparse_vec_kernel<<<div_up(n_cells, TV_THREADS), TV_THREADS, 0, st>>>(
+        tv_grad_sparse_vec_kernel<false><<<div_up(n_cells, TV_THREADS), TV_THREADS, 0, st>>>(
             links, X, Y, Z, data, data_stride, rand_cells, cell_start, start_dim, end_dim, s,
-            n_cells, ignore_edge, ignore_last_z, mask_out, grad_data, gs, qpr);
+            n_cells, ignore_edge, ignore_last_z, mask_out, grad_data, gs, qpr, SlotDest{});
     else TV_LAUNCH(true);
 #undef TV_LAUNCH
     return check_launch(who);

@@ -36,6 +36,13 @@ size_t queue_workspace_bytes(int64_t n_rays, int64_t records);
 bool launch_queue_fused(const GridView& g, const Opts& opt, const MarchArgs& a, const GradView& gr,
                         void* workspace, size_t workspace_bytes, const int** overflow_flag,
                         cudaStream_t st);
+// fused train step with the compact gradient buffer (step.cu, slots.cuh)
+struct SlotMap;
+bool launch_step_trace_shade(const GridView& g, const Opts& opt, const MarchArgs& a, void* workspace,
+                             size_t workspace_bytes, const SlotMap& sm, const int** overflow_flag,
+                             cudaStream_t st);
+bool launch_step_seed_scatter(const GridView& g, const Opts& opt, const MarchArgs& a, void* workspace,
+                              size_t workspace_bytes, const SlotMap& sm, cudaStream_t st);
 // slab mode (grid sharded by x-range over GPUs): trace | exchange | shade | exchange | backward
 bool launch_slab_trace(const GridView& g, const Opts& opt, const MarchArgs& a, void* workspace,
                        size_t workspace_bytes, int x_lo, int x_hi, float* logT_local,

@@ -29,6 +29,7 @@
 // set and mask; colours/gradients are reassociated sums (float atomics), within 1e-6 relative.
 #include "common.cuh"
 #include "march.cuh"
+#include "slots.cuh"
 #include "traverse.cuh"
 
 namespace svox2b {
@@ -256,9 +257,9 @@ __device__ __forceinline__ void corner_weights(float px, float py, float pz, flo
 // ---------------------------------------------------------------------------------------
 // K2: gather + colours, 8 lanes per sample
 // ---------------------------------------------------------------------------------------
-template <bool VEC, bool SLAB>
+template <bool VEC, bool SLAB, bool MARK>
 __global__ void __launch_bounds__(SAMPLE_THREADS)
-shade_kernel(GridView g, QueueView qv, float* __restrict__ rgb_out, SlabView sl) {
+shade_kernel(GridView g, QueueView qv, float* __restrict__ rgb_out, SlabView sl, SlotMap sm) {
     if (*qv.overflow) return;
     const int n = min(*qv.counter, qv.capacity);
     const int qi = threadIdx.x & 7;
@@ -308,6 +309,12 @@ shade_kernel(GridView g, QueueView qv, float* __restrict__ rgb_out, SlabView sl)
         for (int q = 0; q < 8; ++q) {
             const unsigned row = L[q] >= 0 ? (unsigned)L[q] : 0u;
             v[q] = load_quad<VEC>(shq + (size_t)row * (unsigned)g.sh_stride, qi, D);
+        }
+        if (MARK) {  // fused train step: lane q enters corner q into the step's touched-row set
+            int32_t Lown = L[0];
+#pragma unroll
+            for (int q = 1; q < 8; ++q) Lown = (qi == q) ? L[q] : Lown;
+            if (Lown >= 0) slot_mark(sm, Lown);
         }
         const float4 Y = __ldcg(qv.ray_Y + (int64_t)ray * 8 + qi);
         float wq[8];
@@ -421,9 +428,9 @@ seed_kernel(Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
 // ray lie next to each other in the queue) and keeps the gradient of the current cell in
 // registers; consecutive samples that fall into the same cell (~35 % at step 0.5) are merged
 // before the REDs leave the SM.  The basis table of the ray is re-read only when the ray changes.
-template <bool VEC, bool SLAB>
+template <bool VEC, bool SLAB, bool SLOTS>
 __global__ void __launch_bounds__(SAMPLE_THREADS)
-scatter_kernel(GridView g, QueueView qv, GradView gr, int64_t gsh_stride, int64_t gd_stride) {
+scatter_kernel(GridView g, QueueView qv, GradView gr, int64_t gsh_stride, int64_t gd_stride, SlotMap sm) {
     if (*qv.overflow) return;
     const int n = min(*qv.counter, qv.capacity);
     const int qi = threadIdx.x & 7;
@@ -444,21 +451,40 @@ scatter_kernel(GridView g, QueueView qv, GradView gr, int64_t gsh_stride, int64_
     int cur_ray = -1;
     float4 Y = make_float4(0.f, 0.f, 0.f, 0.f);
 
+    int sown = -1;  // SLOTS: slot of this lane's corner of the pending cell
     auto flush = [&]() {
         const int32_t L[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
-        if (quad_on) {
+        if (SLOTS) {
+            // compact gradient rows: SH and density gradients of a row land in ONE slot row
+            const unsigned gm = 0xffu << (threadIdx.x & 24);
+            const int lane0 = threadIdx.x & 24;
+            float* const base = sm.grad + 4 * qi;
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-                if (L[q] >= 0)
-                    red_quad<VEC>(gr.grad_sh + (int64_t)L[q] * gsh_stride + 4 * qi, qi, D, acc[q][0],
-                                  acc[q][1], acc[q][2], acc[q][3]);
-        }
-        int32_t Lown = L[0];
+            for (int q = 0; q < 8; ++q) {
+                const int sq = __shfl_sync(gm, sown, lane0 + q);
+                if (quad_on && sq >= 0)
+                    red_quad<true>(base + (size_t)(unsigned)sq * (unsigned)sm.width, qi, D, acc[q][0],
+                                   acc[q][1], acc[q][2], acc[q][3]);
+            }
+            if (sown >= 0) {
+                atomicAdd(sm.grad + (size_t)(unsigned)sown * (unsigned)sm.width + sm.sigma_at, dacc);
+                *reinterpret_cast<uint16_t*>(sm.flags + 2 * (size_t)(unsigned)sown) = 0x0101;  // both masks
+            }
+        } else {
+            if (quad_on) {
 #pragma unroll
-        for (int q = 1; q < 8; ++q) Lown = (qi == q) ? L[q] : Lown;
-        if (Lown >= 0) {
-            atomicAdd(gr.grad_density + (int64_t)Lown * gd_stride, dacc);
-            if (gr.mask) gr.mask[Lown] = 1;
+                for (int q = 0; q < 8; ++q)
+                    if (L[q] >= 0)
+                        red_quad<VEC>(gr.grad_sh + (int64_t)L[q] * gsh_stride + 4 * qi, qi, D, acc[q][0],
+                                      acc[q][1], acc[q][2], acc[q][3]);
+            }
+            int32_t Lown = L[0];
+#pragma unroll
+            for (int q = 1; q < 8; ++q) Lown = (qi == q) ? L[q] : Lown;
+            if (Lown >= 0) {
+                atomicAdd(gr.grad_density + (int64_t)Lown * gd_stride, dacc);
+                if (gr.mask) gr.mask[Lown] = 1;
+            }
         }
     };
 
@@ -491,7 +517,10 @@ scatter_kernel(GridView g, QueueView qv, GradView gr, int64_t gsh_stride, int64_
                 const int32_t Ls[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
 #pragma unroll
                 for (int q = 1; q < 8; ++q) ln = (qi == q) ? Ls[q] : ln;
-                if (ln >= 0) {
+                if (SLOTS) {  // rank query for this lane's corner; the slot row is prefetched instead
+                    sown = ln >= 0 ? slot_of(sm, ln) : -1;
+                    if (sown >= 0) prefetch_l2(sm.grad + (size_t)(unsigned)sown * (unsigned)sm.width);
+                } else if (ln >= 0) {
                     const float* row = gr.grad_sh + (int64_t)ln * gsh_stride;
                     prefetch_l2(row);
                     prefetch_l2(row + (D - 1));
@@ -574,11 +603,41 @@ bool launch_queue_fused(const GridView& g, const Opts& opt, const MarchArgs& a, 
     else trace_kernel<false, false><<<ray_blocks, TRACE_THREADS, 0, st>>>(g, opt, a, qv, none);
     const bool vec = march_vec_ok(g, &gr, a.gsh_stride);
     const unsigned sblocks = 148 * QM_SAMPLE_CTAS;  // persistent grid-stride CTAs of 256 threads
-    if (vec) shade_kernel<true, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, a.rgb_out, none);
-    else shade_kernel<false, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, a.rgb_out, none);
+    if (vec) shade_kernel<true, false, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, a.rgb_out, none, SlotMap{});
+    else shade_kernel<false, false, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, a.rgb_out, none, SlotMap{});
     seed_kernel<false><<<ray_blocks, TRACE_THREADS, 0, st>>>(opt, a, qv, none);
-    if (vec) scatter_kernel<true, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride);
-    else scatter_kernel<false, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride);
+    if (vec) scatter_kernel<true, false, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride, SlotMap{});
+    else scatter_kernel<false, false, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride, SlotMap{});
+    return true;
+}
+
+// ---- fused train step (step.cu): the queue kernels with the compact gradient buffer ----------
+// Phase A: trace + shade; the shade kernel also enters every touched row into sm.bits.  The caller
+// then runs the TV marking pass and the rank scan (slot numbering) before phase B.
+bool launch_step_trace_shade(const GridView& g, const Opts& opt, const MarchArgs& a, void* workspace,
+                             size_t workspace_bytes, const SlotMap& sm, const int** overflow_flag,
+                             cudaStream_t st) {
+    QueueView qv;
+    if (!carve_queue(workspace, workspace_bytes, a.n_rays, qv)) return false;
+    if (!march_vec_ok(g, nullptr, 0)) return false;
+    *overflow_flag = qv.overflow;
+    const SlabView none{};
+    clear_flags_kernel<<<1, 1, 0, st>>>(qv.counter, qv.overflow, qv.sticky);
+    const unsigned ray_blocks = div_up(a.n_rays * WARP, TRACE_THREADS);
+    if (a.counters) trace_kernel<true, false><<<ray_blocks, TRACE_THREADS, 0, st>>>(g, opt, a, qv, none);
+    else trace_kernel<false, false><<<ray_blocks, TRACE_THREADS, 0, st>>>(g, opt, a, qv, none);
+    shade_kernel<true, false, true><<<148 * QM_SAMPLE_CTAS, SAMPLE_THREADS, 0, st>>>(g, qv, a.rgb_out, none, sm);
+    return true;
+}
+
+// Phase B: gradient seed per ray, then the scatter into slot rows.
+bool launch_step_seed_scatter(const GridView& g, const Opts& opt, const MarchArgs& a, void* workspace,
+                              size_t workspace_bytes, const SlotMap& sm, cudaStream_t st) {
+    QueueView qv;
+    if (!carve_queue(workspace, workspace_bytes, a.n_rays, qv)) return false;
+    const SlabView none{};
+    seed_kernel<false><<<div_up(a.n_rays * WARP, TRACE_THREADS), TRACE_THREADS, 0, st>>>(opt, a, qv, none);
+    scatter_kernel<true, false, true><<<148 * QM_SAMPLE_CTAS, SAMPLE_THREADS, 0, st>>>(g, qv, GradView{}, 0, 0, sm);
     return true;
 }
 
@@ -609,9 +668,9 @@ bool launch_slab_shade(const GridView& g, const Opts& opt, int64_t n_rays, void*
     sl.stop_thresh = opt.stop_thresh;
     const unsigned sblocks = 148 * QM_SAMPLE_CTAS;
     if (march_vec_ok(g, nullptr, 0))
-        shade_kernel<true, true><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, part, sl);
+        shade_kernel<true, true, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, part, sl, SlotMap{});
     else
-        shade_kernel<false, true><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, part, sl);
+        shade_kernel<false, true, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, part, sl, SlotMap{});
     return true;
 }
 
@@ -628,9 +687,9 @@ bool launch_slab_backward(const GridView& g, const Opts& opt, const MarchArgs& a
     seed_kernel<true><<<div_up(a.n_rays * WARP, TRACE_THREADS), TRACE_THREADS, 0, st>>>(opt, a, qv, sl);
     const unsigned sblocks = 148 * QM_SAMPLE_CTAS;
     if (march_vec_ok(g, &gr, a.gsh_stride))
-        scatter_kernel<true, true><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride);
+        scatter_kernel<true, true, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride, SlotMap{});
     else
-        scatter_kernel<false, true><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride);
+        scatter_kernel<false, true, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride, SlotMap{});
     return true;
 }
 

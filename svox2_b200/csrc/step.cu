@@ -1,0 +1,407 @@
+// Fused train step: opt/opt.py's inner loop (opt.py:474-603) as ONE C-ABI call on a compact
+// per-step gradient buffer (slots.cuh).
+//
+//   reference (per batch)                                  here (one call, 10 launches, no host sync)
+//   ----------------------------------------------------   -------------------------------------------
+//   volume_render_fused   (svox2.py:1072-1142)              clear | trace | shade (+ touched-row bits)
+//   inplace_tv_grad       (svox2.py:1731-1766)              tv_mark | rank scan (slot numbering)
+//   inplace_tv_color_grad (svox2.py:1768-1820)              seed | scatter -> slot rows
+//   optim_density_step / optim_sh_step (svox2.py:1972-2034) TV sigma -> slots | TV SH -> slots
+//   (mask -> index list with .item(), svox2.py:2215-2221)   RMSProp over the slot list
+//
+// What changes against the operator-by-operator path (grid.py) is only WHERE a gradient lives
+// during the step: a [touched, W] buffer in row order instead of dense [N,1] / [N,27] `.grad`
+// arrays.  Sample set, per-sample arithmetic, TV arithmetic, the two masks (slot flags) and the
+// RMSProp formula are the same code; `svox2_train_step_masks` exports the masks as bool[N] for the
+// parity tests.  The dense `.grad` tensors are not touched by this entry point.
+//
+// Cost model per touched row: the old optimiser pair moved 6 sparse 112-byte rows (grad, data, rms
+// read + written) + 6 sparse floats; here 4 sparse rows (data, rms) + 2 dense ones (slot read, slot
+// zeroing) and the scatter's vector reductions land in a buffer 10x smaller than `.grad`.
+#include "common.cuh"
+#include "march.cuh"
+#include "slots.cuh"
+#include "step.cuh"
+
+namespace svox2b {
+namespace {
+
+constexpr int RANK_THREADS = 256;   // words per block of the rank scan
+constexpr int OPT_THREADS = 128;
+
+struct StepWs {
+    void* queue;            // sample-record queue of the march kernels
+    size_t queue_bytes;
+    uint32_t* bits;         // [n_words]
+    uint32_t* prefix;       // [n_words]
+    uint32_t* block_sums;   // [n_blocks]
+    int32_t* n_slots;       // [0] slots of the current step, [1] of the previous step (flags to clear)
+    int32_t* slot_row;      // [cap]
+    uint8_t* flags;         // [cap, 2]
+    float* grad;            // [cap, width]
+    int64_t n_words, n_blocks, cap;
+    int width;
+};
+
+inline size_t up256(size_t x) { return (x + 255) / 256 * 256; }
+
+size_t step_ws_bytes(int64_t n_rows, int basis_dim, int64_t n_rays, int64_t slots_per_ray) {
+    const int64_t n_words = (n_rows + 31) / 32, n_blocks = (n_words + RANK_THREADS - 1) / RANK_THREADS;
+    const int W = slot_width(basis_dim);
+    return up256(queue_workspace_bytes(n_rays, slots_per_ray * n_rays)) + up256((size_t)n_words * 4) * 2 +
+           up256((size_t)n_blocks * 4) + 256 + up256((size_t)n_rows * 4) + up256((size_t)n_rows * 2) +
+           up256((size_t)n_rows * W * 4);
+}
+
+bool carve_step_ws(void* workspace, size_t bytes, int64_t n_rows, int basis_dim, int64_t n_rays,
+                   int64_t slots_per_ray, StepWs& w) {
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u) ||
+        bytes < step_ws_bytes(n_rows, basis_dim, n_rays, slots_per_ray))
+        return false;
+    w.n_words = (n_rows + 31) / 32;
+    w.n_blocks = (w.n_words + RANK_THREADS - 1) / RANK_THREADS;
+    w.cap = n_rows;
+    w.width = slot_width(basis_dim);
+    char* p = static_cast<char*>(workspace);
+    w.queue = p;
+    w.queue_bytes = up256(queue_workspace_bytes(n_rays, slots_per_ray * n_rays));
+    p += w.queue_bytes;
+    w.bits = reinterpret_cast<uint32_t*>(p);
+    p += up256((size_t)w.n_words * 4);
+    w.prefix = reinterpret_cast<uint32_t*>(p);
+    p += up256((size_t)w.n_words * 4);
+    w.block_sums = reinterpret_cast<uint32_t*>(p);
+    p += up256((size_t)w.n_blocks * 4);
+    w.n_slots = reinterpret_cast<int32_t*>(p);
+    p += 256;
+    w.slot_row = reinterpret_cast<int32_t*>(p);
+    p += up256((size_t)n_rows * 4);
+    w.flags = reinterpret_cast<uint8_t*>(p);
+    p += up256((size_t)n_rows * 2);
+    w.grad = reinterpret_cast<float*>(p);
+    return true;
+}
+
+SlotMap slot_map(const StepWs& w, int basis_dim) {
+    return SlotMap{w.bits, w.prefix, w.grad, w.flags, w.width, 3 * basis_dim};
+}
+
+// ---- start of a step: forget the previous step's touched set --------------------------------
+__global__ void __launch_bounds__(256)
+step_clear_kernel(uint32_t* __restrict__ bits, int64_t n_words, uint16_t* __restrict__ flags,
+                  int32_t* __restrict__ n_slots) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n_prev = n_slots[0];
+    for (int64_t i = t0; i < n_words; i += stride) bits[i] = 0u;
+    for (int64_t i = t0; i < n_prev; i += stride) flags[i] = 0;
+}
+
+// ---- rank scan: slot numbering in row order ---------------------------------------------------
+__global__ void __launch_bounds__(RANK_THREADS)
+rank_count_kernel(const uint32_t* __restrict__ bits, int64_t n_words, uint32_t* __restrict__ block_sums) {
+    const int64_t w = (int64_t)blockIdx.x * RANK_THREADS + threadIdx.x;
+    unsigned c = w < n_words ? __popc(__ldcg(bits + w)) : 0;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(FULL, c, off);
+    __shared__ unsigned s[RANK_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+#pragma unroll
+        for (int i = 0; i < RANK_THREADS / 32; ++i) t += s[i];
+        block_sums[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(RANK_THREADS)
+rank_scan_kernel(const uint32_t* __restrict__ bits, int64_t n_words,
+                 const uint32_t* __restrict__ block_sums, uint32_t* __restrict__ prefix,
+                 int32_t* __restrict__ slot_row, int32_t* __restrict__ n_slots) {
+    __shared__ unsigned s_warp[RANK_THREADS / 32];
+    __shared__ unsigned s_base;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // offset of this block = sum of the counts of all earlier blocks (a few hundred values)
+    unsigned part = 0;
+    for (int i = threadIdx.x; i < (int)blockIdx.x; i += RANK_THREADS) part += __ldcg(block_sums + i);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(FULL, part, off);
+    if (lane == 0) s_warp[wid] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+#pragma unroll
+        for (int i = 0; i < RANK_THREADS / 32; ++i) t += s_warp[i];
+        s_base = t;
+    }
+    __syncthreads();
+    const unsigned base = s_base;
+    __syncthreads();
+    const int64_t w = (int64_t)blockIdx.x * RANK_THREADS + threadIdx.x;
+    const uint32_t word = w < n_words ? __ldcg(bits + w) : 0u;
+    const unsigned c = __popc(word);
+    unsigned incl = c;  // inclusive scan inside the warp, then across the block's warps
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned o = __shfl_up_sync(FULL, incl, off);
+        if (lane >= off) incl += o;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    unsigned before = 0;
+#pragma unroll
+    for (int i = 0; i < RANK_THREADS / 32; ++i) before += (i < wid) ? s_warp[i] : 0u;
+    const unsigned excl = base + before + incl - c;
+    if (w < n_words) {
+        prefix[w] = excl;
+        uint32_t m = word;
+        unsigned k = excl;
+        while (m) {  // the list of touched rows, ascending
+            slot_row[k++] = (int32_t)(w * 32 + (__ffs(m) - 1));
+            m &= m - 1;
+        }
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == RANK_THREADS - 1) {
+        n_slots[1] = n_slots[0];
+        n_slots[0] = (int32_t)(excl + c);
+    }
+}
+
+// ---- RMSProp over the slot list (optim_kernel.cu:15-25; same arithmetic as optim.cu) -----------
+struct SlotOptArgs {
+    float* __restrict__ sh_data;
+    float* __restrict__ sh_rms;
+    int64_t sh_stride;
+    int C;                       // SH channels
+    float* __restrict__ density;
+    float* __restrict__ density_rms;
+    int64_t density_stride;
+    const int32_t* __restrict__ slot_row;
+    const uint8_t* __restrict__ flags;
+    float* __restrict__ grad;    // [n_slots, width]; zeroed behind the read
+    const int32_t* __restrict__ n_slots;
+    int width;
+    float beta, lr_sh, lr_density, eps, minval;
+};
+
+__device__ __forceinline__ void rmsprop_update(float& d, float& rms, float g, float beta, float lr,
+                                               float eps, float minval) {
+    const float g2 = __fmul_rn(g, g);
+    rms = (rms == 0.f) ? g2 : __fmaf_rn(beta, __fsub_rn(rms, g2), g2);
+    d = fmaxf(__fsub_rn(d, __fdiv_rn(__fmul_rn(lr, g), __fadd_rn(sqrtf(rms), eps))), minval);
+}
+
+// Zero that depends on the loaded value: an INDEPENDENT store to an address whose load is still in
+// flight stalls the memory pipeline badly (measured in round 1).
+__device__ __forceinline__ float dependent_zero(float x) {
+    int z;
+    asm volatile("and.b32 %0, %1, 0;" : "=r"(z) : "r"(__float_as_int(x)));
+    return __int_as_float(z);
+}
+
+#ifndef SLOT_OPT_PASSES
+#define SLOT_OPT_PASSES 2
+#endif
+__global__ void __launch_bounds__(OPT_THREADS)
+slot_rmsprop_kernel(SlotOptArgs a) {
+    constexpr int U = SLOT_OPT_PASSES;
+    const int lane = threadIdx.x & 31;
+    const int qpr = a.width >> 2;          // lanes per slot row
+    const int rpp = WARP / qpr;            // slot rows per warp pass
+    const int grp = lane / qpr;
+    const int ch0 = (lane - grp * qpr) * 4;
+    if (grp >= rpp) return;
+    const int64_t n = *a.n_slots;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const bool has_sh = ch0 < a.C;
+    const bool has_den = ch0 <= a.C && a.C < ch0 + 4;
+    for (int64_t i0 = warp * rpp * U; i0 < n; i0 += nwarps * rpp * U) {
+        int64_t slot[U], row[U];
+        float4 g[U], d[U], r[U];
+        float dd[U], dr[U];
+        bool on_sh[U], on_den[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            slot[u] = i0 + u * rpp + grp;
+            const bool in = slot[u] < n;
+            row[u] = in ? __ldg(a.slot_row + slot[u]) : 0;
+            const uint16_t f = in ? __ldcg(reinterpret_cast<const uint16_t*>(a.flags) + slot[u]) : 0;
+            on_den[u] = in && has_den && (f & 0x00ffu);
+            on_sh[u] = in && has_sh && (f & 0xff00u);
+            if (!in) slot[u] = -1;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (slot[u] >= 0) g[u] = __ldcg(reinterpret_cast<const float4*>(a.grad + slot[u] * a.width + ch0));
+            if (on_sh[u]) {
+                d[u] = *reinterpret_cast<const float4*>(a.sh_data + row[u] * a.sh_stride + ch0);
+                r[u] = *reinterpret_cast<const float4*>(a.sh_rms + row[u] * a.sh_stride + ch0);
+            }
+            if (on_den[u]) {
+                dd[u] = a.density[row[u] * a.density_stride];
+                dr[u] = a.density_rms[row[u] * a.density_stride];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (slot[u] < 0) continue;
+            const float* ge = reinterpret_cast<const float*>(&g[u]);
+            if (on_sh[u]) {
+                float* de = reinterpret_cast<float*>(&d[u]);
+                float* re = reinterpret_cast<float*>(&r[u]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (ch0 + e < a.C) rmsprop_update(de[e], re[e], ge[e], a.beta, a.lr_sh, a.eps, a.minval);
+                *reinterpret_cast<float4*>(a.sh_data + row[u] * a.sh_stride + ch0) = d[u];
+                *reinterpret_cast<float4*>(a.sh_rms + row[u] * a.sh_stride + ch0) = r[u];
+            }
+            if (on_den[u]) {
+                const int k = a.C - ch0;  // position of the density gradient inside this lane's quad
+                const float gden = k == 0 ? ge[0] : (k == 1 ? ge[1] : (k == 2 ? ge[2] : ge[3]));
+                rmsprop_update(dd[u], dr[u], gden, a.beta, a.lr_density, a.eps, a.minval);
+                a.density[row[u] * a.density_stride] = dd[u];
+                a.density_rms[row[u] * a.density_stride] = dr[u];
+            }
+            const float z = dependent_zero(ge[0]);
+            *reinterpret_cast<float4*>(a.grad + slot[u] * a.width + ch0) = make_float4(z, z, z, z);
+        }
+    }
+}
+
+// ---- masks of the last step as bool[N] (tests, bench bookkeeping) -------------------------------
+__global__ void __launch_bounds__(256)
+export_masks_kernel(const int32_t* __restrict__ slot_row, const uint8_t* __restrict__ flags,
+                    const int32_t* __restrict__ n_slots, uint8_t* __restrict__ mask_density,
+                    uint8_t* __restrict__ mask_sh) {
+    const int64_t n = n_slots[0];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int32_t row = slot_row[i];
+        if (mask_density && flags[2 * i]) mask_density[row] = 1;
+        if (mask_sh && flags[2 * i + 1]) mask_sh[row] = 1;
+    }
+}
+
+}  // namespace
+}  // namespace svox2b
+
+using namespace svox2b;
+
+extern "C" SVOX2_API size_t svox2_train_step_workspace_bytes(int64_t n_rows, int32_t basis_dim,
+                                                             int64_t n_rays, int64_t slots_per_ray) {
+    if (n_rows < 0 || n_rays < 0 || slots_per_ray < 0) return 0;
+    return step_ws_bytes(n_rows, basis_dim, n_rays, slots_per_ray);
+}
+
+extern "C" SVOX2_API int svox2_train_step_init(void* workspace, size_t workspace_bytes, int64_t n_rows,
+                                               int32_t basis_dim, int64_t n_rays, int64_t slots_per_ray,
+                                               svox2_stream_t stream) {
+    StepWs w;
+    SVOX2_REQUIRE(carve_step_ws(workspace, workspace_bytes, n_rows, basis_dim, n_rays, slots_per_ray, w),
+                  "workspace too small or not 256-byte aligned (svox2_train_step_workspace_bytes)");
+    cudaStream_t st = (cudaStream_t)stream;
+    // queue header (counter / overflow / sticky), bit set, prefix, counters, flags and slot rows: the
+    // step relies on `slot rows all zero` and `flags all zero` between steps
+    cudaMemsetAsync(w.queue, 0, 256, st);
+    const size_t tail = static_cast<char*>(workspace) + step_ws_bytes(n_rows, basis_dim, n_rays, slots_per_ray) -
+                        reinterpret_cast<char*>(w.bits);
+    cudaMemsetAsync(w.bits, 0, tail, st);
+    return check_launch(__func__);
+}
+
+extern "C" SVOX2_API int svox2_train_step(
+    const svox2_grid_t* grid, float* density_rms, float* sh_rms, const float* origins, const float* dirs,
+    int64_t n_rays, const svox2_render_opts_t* opt, const float* rgb_gt, float* rgb_out,
+    const svox2_step_params_t* p, void* workspace, size_t workspace_bytes, int64_t slots_per_ray,
+    int64_t* counters, svox2_stream_t stream) {
+    if (int e = validate_grid(grid, __func__)) return e;
+    SVOX2_REQUIRE(opt && opt->step_size > 0.f, "opt must be non-null with a positive step_size");
+    SVOX2_REQUIRE(p, "params must not be null");
+    SVOX2_REQUIRE(n_rays > 0 && origins && dirs && rgb_gt && rgb_out, "rays / rgb_gt / rgb_out must be non-null");
+    SVOX2_REQUIRE(density_rms && sh_rms, "RMSProp state must not be null");
+    SVOX2_REQUIRE(grid->background_nlayers == 0, "the fused step has no MSI background path");
+    SVOX2_REQUIRE(p->norm_rays > 0, "norm_rays must be positive");
+    const int need = ((3 * grid->basis_dim + 3) / 4) * 4;
+    SVOX2_REQUIRE(grid->sh_stride % 4 == 0 && grid->sh_stride >= need &&
+                      (reinterpret_cast<uintptr_t>(grid->sh_data) & 15u) == 0 &&
+                      (reinterpret_cast<uintptr_t>(sh_rms) & 15u) == 0,
+                  "sh_data / sh_rms need 16-byte aligned rows padded to a multiple of 4 floats");
+    StepWs w;
+    if (!carve_step_ws(workspace, workspace_bytes, grid->n_rows, grid->basis_dim, n_rays, slots_per_ray, w)) {
+        set_error("%s: workspace too small or not 256-byte aligned (svox2_train_step_workspace_bytes)", __func__);
+        return SVOX2_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const GridView g = make_grid_view(grid);
+    const SlotMap sm = slot_map(w, grid->basis_dim);
+    const int X = grid->size[0], Y = grid->size[1], Z = grid->size[2];
+
+    // 1. forget the previous step's touched set
+    step_clear_kernel<<<148 * 4, 256, 0, st>>>(w.bits, w.n_words, reinterpret_cast<uint16_t*>(w.flags), w.n_slots);
+
+    // 2. traversal + colours; the shade kernel enters every touched row into the bit set
+    MarchArgs a{};
+    a.origins = origins;
+    a.dirs = dirs;
+    a.n_rays = n_rays;
+    a.rgb_out = rgb_out;
+    a.grad_in = rgb_gt;
+    a.beta_loss = p->beta_loss / (float)p->norm_rays;        // cuvol.cu:1127
+    a.sparsity_loss = p->sparsity_loss;
+    a.norm_factor = 2.f / (float)(3 * (int)p->norm_rays);    // cuvol.cu:736
+    a.fused_seed = 1;
+    a.counters = reinterpret_cast<unsigned long long*>(counters);
+    const int* overflow = nullptr;
+    SVOX2_REQUIRE(launch_step_trace_shade(g, *opt, a, w.queue, w.queue_bytes, sm, &overflow, st),
+                  "sample-record queue could not be carved");
+
+    // 3. rows the TV cells of this step can reach, then the slot numbering
+    const bool tv_d = p->tv_density_count > 0 && p->tv_density_scale != 0.f;
+    const bool tv_s = p->tv_sh_count > 0 && p->tv_sh_scale != 0.f;
+    launch_tv_mark(grid->links, X, Y, Z, p->tv_density_start, tv_d ? p->tv_density_count : 0,
+                   opt->last_sample_opaque, p->tv_sh_start, tv_s ? p->tv_sh_count : 0, sm, st);
+    rank_count_kernel<<<(unsigned)w.n_blocks, RANK_THREADS, 0, st>>>(w.bits, w.n_words, w.block_sums);
+    rank_scan_kernel<<<(unsigned)w.n_blocks, RANK_THREADS, 0, st>>>(w.bits, w.n_words, w.block_sums, w.prefix,
+                                                                 w.slot_row, w.n_slots);
+
+    // 4. gradient seed per ray, scatter into the slot rows
+    SVOX2_REQUIRE(launch_step_seed_scatter(g, *opt, a, w.queue, w.queue_bytes, sm, st),
+                  "sample-record queue could not be carved");
+
+    // 5. sparse TV on the step's contiguous cell runs (svox2.py:1751-1759, 1803-1812)
+    if (tv_d)
+        launch_tv_slots(grid->links, X, Y, Z, grid->density_data, grid->density_stride, p->tv_density_start,
+                        p->tv_density_count, p->tv_scale_cells, 0, 1, p->tv_density_scale, 0,
+                        opt->last_sample_opaque, sm, sm.sigma_at, 0, st);
+    if (tv_s)
+        launch_tv_slots(grid->links, X, Y, Z, grid->sh_data, grid->sh_stride, p->tv_sh_start, p->tv_sh_count,
+                        p->tv_scale_cells, 0, 3 * grid->basis_dim, p->tv_sh_scale, 1, 0, sm, 0, 1, st);
+
+    // 6. RMSProp over the slot list; slot rows are zeroed behind the read
+    SlotOptArgs o{const_cast<float*>(grid->sh_data), sh_rms, grid->sh_stride, 3 * grid->basis_dim,
+                  const_cast<float*>(grid->density_data), density_rms, grid->density_stride, w.slot_row,
+                  w.flags, w.grad, w.n_slots, w.width, p->rms_beta, p->lr_sh, p->lr_density, p->epsilon,
+                  -1e9f};
+    slot_rmsprop_kernel<<<148 * 8, OPT_THREADS, 0, st>>>(o);
+    return check_launch(__func__);
+}
+
+extern "C" SVOX2_API int svox2_train_step_masks(void* workspace, size_t workspace_bytes, int64_t n_rows,
+                                                int32_t basis_dim, int64_t n_rays, int64_t slots_per_ray,
+                                                uint8_t* mask_density, uint8_t* mask_sh,
+                                                int32_t* n_touched_and_overflow, svox2_stream_t stream) {
+    StepWs w;
+    SVOX2_REQUIRE(carve_step_ws(workspace, workspace_bytes, n_rows, basis_dim, n_rays, slots_per_ray, w),
+                  "workspace too small or not 256-byte aligned (svox2_train_step_workspace_bytes)");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mask_density || mask_sh)
+        export_masks_kernel<<<148 * 4, 256, 0, st>>>(w.slot_row, w.flags, w.n_slots, mask_density, mask_sh);
+    if (n_touched_and_overflow) {  // device int32[3]: slots of the last step, queue overflow flag, sticky count
+        cudaMemcpyAsync(n_touched_and_overflow, w.n_slots, 4, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(n_touched_and_overflow + 1, static_cast<char*>(w.queue) + 128, 4, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(n_touched_and_overflow + 2, static_cast<char*>(w.queue) + 192, 4, cudaMemcpyDeviceToDevice, st);
+    }
+    return check_launch(__func__);
+}

@@ -59,7 +59,8 @@ class ShardedTrainer:
                  tv_sparsity: float = 0.01, rms_beta: float = 0.95, beta_loss: float = 0.0,
                  sparsity_loss: float = 0.0, group=None, lr_sigma_bg: float = 3e0,
                  lr_color_bg: float = 1e-1, lambda_tv_background_sigma: float = 0.0,
-                 lambda_tv_background_color: float = 0.0, tv_background_sparsity: float = 0.01):
+                 lambda_tv_background_color: float = 0.0, tv_background_sparsity: float = 0.01,
+                 fused: Optional[bool] = None):
         self.grid, self.world_size, self.rank, self.group = grid, world_size, rank, group
         self.lr_sigma_bg, self.lr_color_bg = lr_sigma_bg, lr_color_bg
         self.lambda_tv_bg_sigma, self.lambda_tv_bg_color = lambda_tv_background_sigma, lambda_tv_background_color
@@ -78,6 +79,12 @@ class ShardedTrainer:
         self.kernels_per_step = 6 + (lambda_tv > 0) + (lambda_tv_sh > 0) + 2
         self.profile, self._events, self.exchanged_rows = False, [], 0
         self._packed = None
+        # single GPU: the whole step as ONE call on a compact gradient buffer (csrc/step.cu) unless
+        # ``fused=False`` asks for the operator-by-operator sequence of opt.py (dense .grad arrays
+        # and bool masks visible between the calls)
+        self.fused = fused
+        self._step_ws = None
+        self.slots_per_ray = None       # record slots per ray of the fused step's queue (None: worst case)
 
     def _tv_run(self):
         """This rank's slice (start, count) of the step's contiguous wrapped cell run (drawn with
@@ -88,9 +95,68 @@ class ShardedTrainer:
         b, e = shard_range(n, self.world_size, self.rank)
         return (start + b, e - b), n
 
+    def _can_fuse(self) -> bool:
+        g = self.grid
+        return (self.fused is not False and self.world_size == 1 and g.sh_data.is_cuda and
+                not g.use_background and g.opt.backend == "cuvol" and self.tv_sparsity < 1.0)
+
+    def _fused_step(self, rays, rgb_gt, lr_sigma, lr_sh):
+        """One svox2_train_step call: same sample set, TV cells (numpy RNG consumed as by the two
+        inplace_tv_* calls), masks and RMSProp arithmetic as the sequence below; gradients live in a
+        compact buffer for the duration of the call and the dense .grad arrays are not touched."""
+        from . import csrc as _C
+        g = self.grid
+        g._ensure_layout()
+        g._ensure_rms()
+        Q = rgb_gt.size(0)
+        slots = self.slots_per_ray
+        if slots is None:   # worst case: every lattice step along the diagonal is an active sample
+            diag = sum(float(s) ** 2 for s in g.links.shape) ** 0.5
+            slots = int(diag / max(float(g.opt.step_size), 1e-3)) + 2
+            slots = max(64, min(slots, (4 << 30) // (96 * max(Q, 1))))
+        key = (g.sh_data.size(0), int(g.basis_dim), Q, int(slots))
+        if self._step_ws is None or self._step_ws.key != key:
+            self._step_ws = None
+            self._step_ws = _C.TrainStepWorkspace(*key, g.sh_data.device)
+        tv_d = tv_s = (0, 0, 0.0)
+        if self.lambda_tv > 0.0:
+            start, n = g._draw_cell_run(self.tv_sparsity)
+            tv_d = (start, n, self.lambda_tv)
+        if self.lambda_tv_sh > 0.0:
+            start, n = g._draw_cell_run(self.tv_sparsity)
+            tv_s = (start, n, self.lambda_tv_sh)
+        rgb = torch.empty_like(rgb_gt)
+        _C.train_step(g._to_cpp(), g.density_rms, g.sh_rms, rays._to_cpp(), g.opt._to_cpp(), rgb_gt.contiguous(),
+                      rgb, self._step_ws, tv_density=tv_d, tv_sh=tv_s, beta_loss=self.beta_loss,
+                      sparsity_loss=self.sparsity_loss, norm_rays=Q, lr_density=lr_sigma, lr_sh=lr_sh,
+                      rms_beta=self.rms_beta)
+        g.sparse_grad_indexer = g.sparse_sh_grad_indexer = None     # see export_masks()
+        # step_clear, queue clear, trace, shade, tv_mark, rank count + scan, seed, scatter, TV x2, RMSProp
+        self.kernels_per_step = 10 + (self.lambda_tv > 0) + (self.lambda_tv_sh > 0)
+        return rgb
+
+    def export_masks(self):
+        """After a fused step: materialise grid.sparse_grad_indexer / sparse_sh_grad_indexer (bool[N]) of
+        that step and return (touched rows, queue overflowed, overflowed steps before)."""
+        if self._step_ws is None:
+            return None
+        st, md, msh = self._step_ws.status(want_masks=True)
+        self.grid.sparse_grad_indexer, self.grid.sparse_sh_grad_indexer = md, msh
+        return st
+
+    def check_overflow(self):
+        if self._step_ws is not None:
+            st, _, _ = self._step_ws.status()
+            if st[1] or st[2]:
+                raise RuntimeError("ShardedTrainer: the sample-record queue of the fused step overflowed "
+                                   "(ray gradients of those steps were dropped); raise slots_per_ray")
+
     def step(self, rays, rgb_gt: torch.Tensor, global_batch: Optional[int] = None,
              lr_sigma: Optional[float] = None, lr_sh: Optional[float] = None):
         g = self.grid
+        if self._can_fuse() and (global_batch is None or global_batch == rgb_gt.size(0)):
+            return self._fused_step(rays, rgb_gt, self.lr_sigma if lr_sigma is None else lr_sigma,
+                                    self.lr_sh if lr_sh is None else lr_sh)
         rgb = g.volume_render_fused(rays, rgb_gt, beta_loss=self.beta_loss,
                                     sparsity_loss=self.sparsity_loss, _norm_rays=global_batch)
         if self.tv_sparsity >= 1.0:     # single GPU: the reference's dense TV + dense step
