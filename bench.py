@@ -532,12 +532,37 @@ def run_ours(args):
     t1 = torch.cuda.Event(enable_timing=True)
     loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_ev = [torch.cuda.Event() for _ in range(2)]
+    # H2D on a copy stream into double-buffered device staging, one step ahead of the compute stream
+    # (every step's inputs still cross PCIe inside the timed region); the loss comes from the step
+    # itself when it is the fused call (svox2_train_step's mse_out), else from three torch kernels.
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+    stage = [tuple(torch.empty_like(x, device=dev) for x in host[0]) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    free = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(free[i & 1])
+            for dst, src in zip(stage[i & 1], host[i % POOL]):
+                dst.copy_(src, non_blocking=True)
+            ready[i & 1].record(copy_stream)
+
+    for ev in free:
+        ev.record(main_stream)
     t0.record()
     loss_val = 0.0
+    prefetch(0)
     for i in range(args.steps):
-        o, d, g = (x.to(dev, non_blocking=True) for x in host[i % POOL])
+        if i + 1 < args.steps:
+            prefetch(i + 1)
+        main_stream.wait_event(ready[i & 1])
+        o, d, g = stage[i & 1]
         rgb = step(o, d, g)
-        loss_host[i & 1].copy_(torch.mean((rgb - g) ** 2), non_blocking=True)
+        fused_mse = getattr(trainer, "last_mse", None) if getattr(trainer, "_step_ws", None) is not None else None
+        loss_host[i & 1].copy_(fused_mse if fused_mse is not None else torch.mean((rgb - g) ** 2),
+                               non_blocking=True)
+        free[i & 1].record(main_stream)
         loss_ev[i & 1].record()
         if i > 0:
             loss_ev[(i - 1) & 1].synchronize()
@@ -648,7 +673,8 @@ def run_ours(args):
         "e2e": {"value": gq * args.steps / (ms_e2e * 1e-3), "unit": "rays/s",
                 "h2d_bytes_per_step": 3 * batches[0][0].size(0) * 3 * 4, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps, "last_loss": loss_val,
-                "loss_readback": "every step, one step late (double-buffered pinned scalar)"},
+                "loss_readback": "every step, one step late (double-buffered pinned scalar)",
+                "h2d": "pinned host -> double-buffered device staging on a copy stream, one step ahead"},
         "gpu_launches": trainer.kernels_per_step * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "fused call: trace + shade + seed + scatter kernels",

@@ -244,7 +244,10 @@ SVOX2_API int svox2_msi_tv_grad_sparse(const int32_t* background_links, int32_t 
  * The workspace is created once (svox2_train_step_workspace_bytes + svox2_train_step_init) and
  * must be passed unchanged to every step on this grid / batch size.  slots_per_ray sizes the
  * sample-record queue (records per ray on average); if it overflows the step's ray gradients are
- * dropped and the sticky counter reported by svox2_train_step_masks is incremented. */
+ * dropped and the sticky counter reported by svox2_train_step_masks is incremented.
+ * mse_out (device float, may be NULL) receives mean((rgb - rgb_gt)^2) of the batch, the loss opt.py
+ * reads back every step (opt.py:505-508).  The TV work runs on a library-owned side stream between
+ * event pairs recorded on `stream` (capturable; SVOX2_B200_STEP_OVERLAP=0 disables it). */
 typedef struct {
     int64_t tv_density_start;   /* first cell of the wrapped contiguous run (svox2.py:2230-2237)  */
     int64_t tv_density_count;   /* 0 disables the density TV                                      */
@@ -267,8 +270,8 @@ SVOX2_API int svox2_train_step(const svox2_grid_t* grid, float* density_rms, flo
                                const float* origins, const float* dirs, int64_t n_rays,
                                const svox2_render_opts_t* opt, const float* rgb_gt, float* rgb_out,
                                const svox2_step_params_t* params, void* workspace,
-                               size_t workspace_bytes, int64_t slots_per_ray, int64_t* counters,
-                               svox2_stream_t stream);
+                               size_t workspace_bytes, int64_t slots_per_ray, float* mse_out,
+                               int64_t* counters, svox2_stream_t stream);
 /* The two sparse masks of the LAST step as uint8[N] (OR-ed into the arrays; either may be NULL) and
  * device int32[3] = {touched rows, queue overflow flag of the last step, overflowed steps before it}. */
 SVOX2_API int svox2_train_step_masks(void* workspace, size_t workspace_bytes, int64_t n_rows,

@@ -103,7 +103,7 @@ SIGNATURES = {
     "svox2_train_step_workspace_bytes": (_SZ, [_I64, _I32, _I64, _I64]),
     "svox2_train_step_init": (C.c_int, [_P, _SZ, _I64, _I32, _I64, _I64, _P]),
     "svox2_train_step": (C.c_int, [_G, _P, _P, _P, _P, _I64, _O, _P, _P, C.POINTER(StepParamsT), _P, _SZ,
-                                   _I64, _P, _P]),
+                                   _I64, _P, _P, _P]),
     "svox2_train_step_masks": (C.c_int, [_P, _SZ, _I64, _I32, _I64, _I64, _P, _P, _P, _P]),
     "svox2_sample_grid": (C.c_int, [_G, _P, _I64, _P, _P, _P]),
     "svox2_sample_grid_backward": (C.c_int, [_G, _P, _I64, _P, _P, _P, _I64, _P, _I64, _P]),

@@ -769,10 +769,11 @@ class TrainStepWorkspace:
 def train_step(grid, density_rms, sh_rms, rays, opt, rgb_gt, rgb_out, workspace: TrainStepWorkspace, *,
                tv_density=(0, 0, 0.0), tv_sh=(0, 0, 0.0), tv_scale_cells=0, beta_loss=0.0,
                sparsity_loss=0.0, norm_rays=None, lr_density=0.0, lr_sh=0.0, rms_beta=0.95,
-               epsilon=1e-8, _counters=None):
+               epsilon=1e-8, mse_out=None, _counters=None):
     """Extension: svox2_train_step -- fused render + sparse TV (density, SH; contiguous cell runs
     ``(start, count, lambda)``) + RMSProp (density, SH) in one call; density_data / sh_data (through
-    ``grid``) and the RMS arrays are updated in place, ``rgb_out`` receives the colours."""
+    ``grid``) and the RMS arrays are updated in place, ``rgb_out`` receives the colours and
+    ``mse_out`` (optional 0-dim float32 CUDA tensor) the batch's mean squared error."""
     g = _grid_struct(grid)
     origins, dirs = _rays(rays)
     _check_input(rgb_gt, "rgb_gt", torch.float32, 2)
@@ -793,7 +794,7 @@ def train_step(grid, density_rms, sh_rms, rays, opt, rgb_gt, rgb_out, workspace:
         check(_lib.lib().svox2_train_step(
             C.byref(g), density_rms.data_ptr(), sh_rms.data_ptr(), origins.data_ptr(), dirs.data_ptr(), Q,
             C.byref(o), rgb_gt.data_ptr(), rgb_out.data_ptr(), C.byref(p), workspace.buf.data_ptr(),
-            workspace.nbytes, workspace.key[3], _ptr(_counters), _stream()))
+            workspace.nbytes, workspace.key[3], _ptr(mse_out), _ptr(_counters), _stream()))
 
 
 # ---- slab mode (grid sharded over GPUs by x-range of cells; svox2_b200/slab.py) --------------

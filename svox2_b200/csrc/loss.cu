@@ -137,12 +137,21 @@ __device__ __forceinline__ TvCell tv_probe(const int32_t* __restrict__ links, in
     if (cell >= n_cells) return c;
     // rand_cells == NULL: the contiguous wrapped run [cell_start, cell_start + n_cells) that
     // SparseGrid._get_rand_cells(contiguous=True) would materialise (svox2.py:2230-2237)
-    const int xyz = rand_cells ? __ldg(rand_cells + cell)
-                               : (int)((cell_start + cell) % ((int64_t)X * Y * Z));
-    const int z = xyz % Z;
-    const int xy = xyz / Z;
-    const int y = xy % Y;
-    const int x = xy / Y;
+    int xyz;
+    if (rand_cells) {
+        xyz = __ldg(rand_cells + cell);
+    } else {  // wrapped run: one conditional subtraction instead of a 64-bit modulo (X*Y*Z < 2^31)
+        const int64_t total = (int64_t)X * Y * Z;
+        int64_t lin = cell_start + cell;
+        if (lin >= total) lin -= total;
+        if (lin >= total) lin %= total;
+        xyz = (int)lin;
+    }
+    const unsigned uxyz = (unsigned)xyz;    // 32-bit unsigned divisions (cell indices are >= 0)
+    const int z = (int)(uxyz % (unsigned)Z);
+    const unsigned xy = uxyz / (unsigned)Z;
+    const int y = (int)(xy % (unsigned)Y);
+    const int x = (int)(xy / (unsigned)Y);
     const int64_t offx = (int64_t)Y * Z;
     const int32_t* lp = links + (x * offx + (int64_t)y * Z + z);
     c.l000 = __ldg(lp);

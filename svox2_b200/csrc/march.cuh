@@ -26,6 +26,7 @@ struct MarchArgs {
     float4* __restrict__ ccache;            // fused: [Q, ccap] forward->backward colour cache, or NULL
     int ccap;                               // cache slots per ray (overflow samples are re-gathered)
     const int* __restrict__ run_if;         // if set: the kernel is a no-op unless *run_if != 0
+    float* __restrict__ mse_out;            // fused train step: += mean((rgb - rgb_gt)^2) of the batch, or NULL
 };
 
 enum { LB_MODE_FWD = 0, LB_MODE_BWD = 1, LB_MODE_FUSED = 2 };
@@ -39,10 +40,13 @@ bool launch_queue_fused(const GridView& g, const Opts& opt, const MarchArgs& a, 
 // fused train step with the compact gradient buffer (step.cu, slots.cuh)
 struct SlotMap;
 bool launch_step_trace_shade(const GridView& g, const Opts& opt, const MarchArgs& a, void* workspace,
-                             size_t workspace_bytes, const SlotMap& sm, const int** overflow_flag,
-                             cudaStream_t st);
-bool launch_step_seed_scatter(const GridView& g, const Opts& opt, const MarchArgs& a, void* workspace,
-                              size_t workspace_bytes, const SlotMap& sm, cudaStream_t st);
+                             size_t workspace_bytes, const SlotMap& sm, cudaStream_t st);
+bool step_queue_header(void* workspace, size_t workspace_bytes, int64_t n_rays, int** counter,
+                       int** overflow, int** sticky);
+bool launch_step_seed(const GridView& g, const Opts& opt, const MarchArgs& a, void* workspace,
+                      size_t workspace_bytes, cudaStream_t st);
+bool launch_step_scatter(const GridView& g, const MarchArgs& a, void* workspace, size_t workspace_bytes,
+                         const SlotMap& sm, cudaStream_t st);
 // slab mode (grid sharded by x-range over GPUs): trace | exchange | shade | exchange | backward
 bool launch_slab_trace(const GridView& g, const Opts& opt, const MarchArgs& a, void* workspace,
                        size_t workspace_bytes, int x_lo, int x_hi, float* logT_local,

@@ -369,6 +369,15 @@ seed_kernel(Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
             gout[i] = (cc[i] - __ldg(a.grad_in + ray_id * 3 + i)) * a.norm_factor;
         }
     }
+    if (!SLAB && a.mse_out != nullptr && lane == 0) {  // F.mse_loss(rgb, rgb_gt) of opt.py:505
+        float se = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float dlt = cc[i] - __ldg(a.grad_in + ray_id * 3 + i);
+            se = fmaf(dlt, dlt, se);
+        }
+        atomicAdd(a.mse_out, se / (3.f * (float)a.n_rays));
+    }
     int blk = qv.ray_first[ray_id];
     if (blk < 0) return;  // no active sample: nothing to scatter
     float accum = fmaf(cc[0], gout[0], fmaf(cc[1], gout[1], cc[2] * gout[2]));
@@ -615,14 +624,11 @@ bool launch_queue_fused(const GridView& g, const Opts& opt, const MarchArgs& a, 
 // Phase A: trace + shade; the shade kernel also enters every touched row into sm.bits.  The caller
 // then runs the TV marking pass and the rank scan (slot numbering) before phase B.
 bool launch_step_trace_shade(const GridView& g, const Opts& opt, const MarchArgs& a, void* workspace,
-                             size_t workspace_bytes, const SlotMap& sm, const int** overflow_flag,
-                             cudaStream_t st) {
+                             size_t workspace_bytes, const SlotMap& sm, cudaStream_t st) {
     QueueView qv;
     if (!carve_queue(workspace, workspace_bytes, a.n_rays, qv)) return false;
     if (!march_vec_ok(g, nullptr, 0)) return false;
-    *overflow_flag = qv.overflow;
-    const SlabView none{};
-    clear_flags_kernel<<<1, 1, 0, st>>>(qv.counter, qv.overflow, qv.sticky);
+    const SlabView none{};   // (the queue header was reset by the step's clear kernel)
     const unsigned ray_blocks = div_up(a.n_rays * WARP, TRACE_THREADS);
     if (a.counters) trace_kernel<true, false><<<ray_blocks, TRACE_THREADS, 0, st>>>(g, opt, a, qv, none);
     else trace_kernel<false, false><<<ray_blocks, TRACE_THREADS, 0, st>>>(g, opt, a, qv, none);
@@ -630,13 +636,32 @@ bool launch_step_trace_shade(const GridView& g, const Opts& opt, const MarchArgs
     return true;
 }
 
-// Phase B: gradient seed per ray, then the scatter into slot rows.
-bool launch_step_seed_scatter(const GridView& g, const Opts& opt, const MarchArgs& a, void* workspace,
-                              size_t workspace_bytes, const SlotMap& sm, cudaStream_t st) {
+// Queue header words, for the step's own clear kernel (same protocol as clear_flags_kernel).
+bool step_queue_header(void* workspace, size_t workspace_bytes, int64_t n_rays, int** counter,
+                       int** overflow, int** sticky) {
+    QueueView qv;
+    if (!carve_queue(workspace, workspace_bytes, n_rays, qv)) return false;
+    *counter = qv.counter;
+    *overflow = qv.overflow;
+    *sticky = qv.sticky;
+    return true;
+}
+
+// Phase B: gradient seed per ray (needs the colours only) ...
+bool launch_step_seed(const GridView& g, const Opts& opt, const MarchArgs& a, void* workspace,
+                      size_t workspace_bytes, cudaStream_t st) {
     QueueView qv;
     if (!carve_queue(workspace, workspace_bytes, a.n_rays, qv)) return false;
     const SlabView none{};
     seed_kernel<false><<<div_up(a.n_rays * WARP, TRACE_THREADS), TRACE_THREADS, 0, st>>>(opt, a, qv, none);
+    return true;
+}
+
+// ... and, once the slots are numbered, the scatter into slot rows.
+bool launch_step_scatter(const GridView& g, const MarchArgs& a, void* workspace, size_t workspace_bytes,
+                         const SlotMap& sm, cudaStream_t st) {
+    QueueView qv;
+    if (!carve_queue(workspace, workspace_bytes, a.n_rays, qv)) return false;
     scatter_kernel<true, false, true><<<148 * QM_SAMPLE_CTAS, SAMPLE_THREADS, 0, st>>>(g, qv, GradView{}, 0, 0, sm);
     return true;
 }

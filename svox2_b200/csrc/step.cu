@@ -18,6 +18,8 @@
 // Cost model per touched row: the old optimiser pair moved 6 sparse 112-byte rows (grad, data, rms
 // read + written) + 6 sparse floats; here 4 sparse rows (data, rms) + 2 dense ones (slot read, slot
 // zeroing) and the scatter's vector reductions land in a buffer 10x smaller than `.grad`.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "march.cuh"
 #include "slots.cuh"
@@ -27,7 +29,10 @@ namespace svox2b {
 namespace {
 
 constexpr int RANK_THREADS = 256;   // words per block of the rank scan
-constexpr int OPT_THREADS = 128;
+#ifndef SLOT_OPT_THREADS
+#define SLOT_OPT_THREADS 128
+#endif
+constexpr int OPT_THREADS = SLOT_OPT_THREADS;
 
 struct StepWs {
     void* queue;            // sample-record queue of the march kernels
@@ -89,12 +94,33 @@ SlotMap slot_map(const StepWs& w, int basis_dim) {
 // ---- start of a step: forget the previous step's touched set --------------------------------
 __global__ void __launch_bounds__(256)
 step_clear_kernel(uint32_t* __restrict__ bits, int64_t n_words, uint16_t* __restrict__ flags,
-                  int32_t* __restrict__ n_slots) {
+                  int32_t* __restrict__ n_slots, int* __restrict__ q_counter, int* __restrict__ q_overflow,
+                  int* __restrict__ q_sticky, float* __restrict__ mse_out) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n_prev = n_slots[0];
     for (int64_t i = t0; i < n_words; i += stride) bits[i] = 0u;
     for (int64_t i = t0; i < n_prev; i += stride) flags[i] = 0;
+    if (t0 == 0) {  // sample-record queue header: fold the last overflow into the sticky count
+        if (*q_overflow) *q_sticky = (*q_sticky < 0 ? 0 : *q_sticky) + 1;
+        *q_counter = 0;
+        *q_overflow = 0;
+        if (mse_out) *mse_out = 0.f;
+    }
+}
+
+// Slot rows consumed by the previous step's optimiser are zeroed HERE, on the side stream while the
+// latency-bound trace kernel runs, instead of by the optimiser behind its own reads (a dense
+// 112-byte store per slot taken off the critical path).
+#ifndef SLOT_ZERO_IN_OPT
+#define SLOT_ZERO_IN_OPT 1   // A/B (profiles/r2_ab_variants.txt): zeroing on the side stream gained nothing
+#endif
+__global__ void __launch_bounds__(256)
+zero_slots_kernel(float4* __restrict__ grad, int width4, const int32_t* __restrict__ n_slots) {
+    const int64_t n4 = (int64_t)n_slots[0] * width4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride)
+        grad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // ---- rank scan: slot numbering in row order ---------------------------------------------------
@@ -203,6 +229,9 @@ __device__ __forceinline__ float dependent_zero(float x) {
 #ifndef SLOT_OPT_PASSES
 #define SLOT_OPT_PASSES 2
 #endif
+#ifndef SLOT_OPT_BLOCKS
+#define SLOT_OPT_BLOCKS 8
+#endif
 __global__ void __launch_bounds__(OPT_THREADS)
 slot_rmsprop_kernel(SlotOptArgs a) {
     constexpr int U = SLOT_OPT_PASSES;
@@ -264,8 +293,10 @@ slot_rmsprop_kernel(SlotOptArgs a) {
                 a.density[row[u] * a.density_stride] = dd[u];
                 a.density_rms[row[u] * a.density_stride] = dr[u];
             }
+#if SLOT_ZERO_IN_OPT
             const float z = dependent_zero(ge[0]);
             *reinterpret_cast<float4*>(a.grad + slot[u] * a.width + ch0) = make_float4(z, z, z, z);
+#endif
         }
     }
 }
@@ -282,6 +313,37 @@ export_masks_kernel(const int32_t* __restrict__ slot_row, const uint8_t* __restr
         if (mask_density && flags[2 * i]) mask_density[row] = 1;
         if (mask_sh && flags[2 * i + 1]) mask_sh[row] = 1;
     }
+}
+
+// ---- fork / join onto a side stream --------------------------------------------------------------
+// The TV work of a step is independent of the ray work until the optimiser: the marking pass only
+// needs the cleared bit set, the two TV kernels only the slot numbering.  They run on a per-device
+// side stream between event pairs (capturable), next to the latency-bound trace / scatter kernels
+// that leave most issue slots idle.  SVOX2_B200_STEP_OVERLAP=0 keeps everything on one stream.
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork[2] = {nullptr, nullptr}, join[2] = {nullptr, nullptr};
+    bool ok = false;
+};
+
+SideStream* side_stream() {
+    static SideStream per_dev[64];
+    static const bool enabled = [] {
+        const char* e = std::getenv("SVOX2_B200_STEP_OVERLAP");
+        return !(e && e[0] == '0');
+    }();
+    if (!enabled) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    SideStream& s = per_dev[dev];
+    if (!s.stream) {
+        s.ok = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; i < 2 && s.ok; ++i)
+            s.ok = cudaEventCreateWithFlags(&s.fork[i], cudaEventDisableTiming) == cudaSuccess &&
+                   cudaEventCreateWithFlags(&s.join[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!s.ok) cudaGetLastError();
+    }
+    return s.ok ? &s : nullptr;
 }
 
 }  // namespace
@@ -315,7 +377,7 @@ extern "C" SVOX2_API int svox2_train_step(
     const svox2_grid_t* grid, float* density_rms, float* sh_rms, const float* origins, const float* dirs,
     int64_t n_rays, const svox2_render_opts_t* opt, const float* rgb_gt, float* rgb_out,
     const svox2_step_params_t* p, void* workspace, size_t workspace_bytes, int64_t slots_per_ray,
-    int64_t* counters, svox2_stream_t stream) {
+    float* mse_out, int64_t* counters, svox2_stream_t stream) {
     if (int e = validate_grid(grid, __func__)) return e;
     SVOX2_REQUIRE(opt && opt->step_size > 0.f, "opt must be non-null with a positive step_size");
     SVOX2_REQUIRE(p, "params must not be null");
@@ -338,10 +400,32 @@ extern "C" SVOX2_API int svox2_train_step(
     const SlotMap sm = slot_map(w, grid->basis_dim);
     const int X = grid->size[0], Y = grid->size[1], Z = grid->size[2];
 
-    // 1. forget the previous step's touched set
-    step_clear_kernel<<<148 * 4, 256, 0, st>>>(w.bits, w.n_words, reinterpret_cast<uint16_t*>(w.flags), w.n_slots);
+    SideStream* side = side_stream();
+    const bool tv_d = p->tv_density_count > 0 && p->tv_density_scale != 0.f;
+    const bool tv_s = p->tv_sh_count > 0 && p->tv_sh_scale != 0.f;
+    cudaStream_t sd = side ? side->stream : st;     // side stream (== st: everything in order)
+    const bool forked = sd != st;
 
-    // 2. traversal + colours; the shade kernel enters every touched row into the bit set
+    // main: clear | trace | shade ........... | seed | ........ scatter | ............ RMSProp
+    // side:       | tv_mark ... (wait shade) rank count + scan | TV sigma | TV SH |
+    // 1. forget the previous step's touched set, reset the record queue and the loss accumulator
+    int *q_counter = nullptr, *q_overflow = nullptr, *q_sticky = nullptr;
+    SVOX2_REQUIRE(step_queue_header(w.queue, w.queue_bytes, n_rays, &q_counter, &q_overflow, &q_sticky),
+                  "sample-record queue could not be carved");
+    step_clear_kernel<<<148 * 4, 256, 0, st>>>(w.bits, w.n_words, reinterpret_cast<uint16_t*>(w.flags), w.n_slots,
+                                               q_counter, q_overflow, q_sticky, mse_out);
+    if (forked) {
+        cudaEventRecord(side->fork[0], st);
+        cudaStreamWaitEvent(sd, side->fork[0], 0);
+    }
+#if !SLOT_ZERO_IN_OPT
+    zero_slots_kernel<<<148 * 8, 256, 0, sd>>>(reinterpret_cast<float4*>(w.grad), w.width / 4, w.n_slots);
+#endif
+    // 2. (side) rows the TV cells of this step can reach
+    launch_tv_mark(grid->links, X, Y, Z, p->tv_density_start, tv_d ? p->tv_density_count : 0,
+                   opt->last_sample_opaque, p->tv_sh_start, tv_s ? p->tv_sh_count : 0, sm, sd);
+
+    // 3. (main) traversal + colours; the shade kernel enters every touched row into the bit set
     MarchArgs a{};
     a.origins = origins;
     a.dirs = dirs;
@@ -353,38 +437,44 @@ extern "C" SVOX2_API int svox2_train_step(
     a.norm_factor = 2.f / (float)(3 * (int)p->norm_rays);    // cuvol.cu:736
     a.fused_seed = 1;
     a.counters = reinterpret_cast<unsigned long long*>(counters);
-    const int* overflow = nullptr;
-    SVOX2_REQUIRE(launch_step_trace_shade(g, *opt, a, w.queue, w.queue_bytes, sm, &overflow, st),
+    a.mse_out = mse_out;
+    SVOX2_REQUIRE(launch_step_trace_shade(g, *opt, a, w.queue, w.queue_bytes, sm, st),
                   "sample-record queue could not be carved");
 
-    // 3. rows the TV cells of this step can reach, then the slot numbering
-    const bool tv_d = p->tv_density_count > 0 && p->tv_density_scale != 0.f;
-    const bool tv_s = p->tv_sh_count > 0 && p->tv_sh_scale != 0.f;
-    launch_tv_mark(grid->links, X, Y, Z, p->tv_density_start, tv_d ? p->tv_density_count : 0,
-                   opt->last_sample_opaque, p->tv_sh_start, tv_s ? p->tv_sh_count : 0, sm, st);
-    rank_count_kernel<<<(unsigned)w.n_blocks, RANK_THREADS, 0, st>>>(w.bits, w.n_words, w.block_sums);
-    rank_scan_kernel<<<(unsigned)w.n_blocks, RANK_THREADS, 0, st>>>(w.bits, w.n_words, w.block_sums, w.prefix,
+    // 4. (side, after the shade kernel) slot numbering; then the sparse TV of the step's contiguous
+    //    cell runs (svox2.py:1751-1759, 1803-1812) into the slot rows
+    if (forked) {
+        cudaEventRecord(side->fork[1], st);
+        cudaStreamWaitEvent(sd, side->fork[1], 0);
+    }
+    rank_count_kernel<<<(unsigned)w.n_blocks, RANK_THREADS, 0, sd>>>(w.bits, w.n_words, w.block_sums);
+    rank_scan_kernel<<<(unsigned)w.n_blocks, RANK_THREADS, 0, sd>>>(w.bits, w.n_words, w.block_sums, w.prefix,
                                                                  w.slot_row, w.n_slots);
-
-    // 4. gradient seed per ray, scatter into the slot rows
-    SVOX2_REQUIRE(launch_step_seed_scatter(g, *opt, a, w.queue, w.queue_bytes, sm, st),
-                  "sample-record queue could not be carved");
-
-    // 5. sparse TV on the step's contiguous cell runs (svox2.py:1751-1759, 1803-1812)
+    if (forked) cudaEventRecord(side->join[0], sd);
     if (tv_d)
         launch_tv_slots(grid->links, X, Y, Z, grid->density_data, grid->density_stride, p->tv_density_start,
                         p->tv_density_count, p->tv_scale_cells, 0, 1, p->tv_density_scale, 0,
-                        opt->last_sample_opaque, sm, sm.sigma_at, 0, st);
+                        opt->last_sample_opaque, sm, sm.sigma_at, 0, sd);
     if (tv_s)
         launch_tv_slots(grid->links, X, Y, Z, grid->sh_data, grid->sh_stride, p->tv_sh_start, p->tv_sh_count,
-                        p->tv_scale_cells, 0, 3 * grid->basis_dim, p->tv_sh_scale, 1, 0, sm, 0, 1, st);
+                        p->tv_scale_cells, 0, 3 * grid->basis_dim, p->tv_sh_scale, 1, 0, sm, 0, 1, sd);
+    if (forked) cudaEventRecord(side->join[1], sd);
+
+    // 5. (main) gradient seed per ray (needs the colours only), then -- once the slots are numbered --
+    //    the scatter into the slot rows
+    SVOX2_REQUIRE(launch_step_seed(g, *opt, a, w.queue, w.queue_bytes, st),
+                  "sample-record queue could not be carved");
+    if (forked) cudaStreamWaitEvent(st, side->join[0], 0);
+    SVOX2_REQUIRE(launch_step_scatter(g, a, w.queue, w.queue_bytes, sm, st),
+                  "sample-record queue could not be carved");
+    if (forked) cudaStreamWaitEvent(st, side->join[1], 0);
 
     // 6. RMSProp over the slot list; slot rows are zeroed behind the read
     SlotOptArgs o{const_cast<float*>(grid->sh_data), sh_rms, grid->sh_stride, 3 * grid->basis_dim,
                   const_cast<float*>(grid->density_data), density_rms, grid->density_stride, w.slot_row,
                   w.flags, w.grad, w.n_slots, w.width, p->rms_beta, p->lr_sh, p->lr_density, p->epsilon,
                   -1e9f};
-    slot_rmsprop_kernel<<<148 * 8, OPT_THREADS, 0, st>>>(o);
+    slot_rmsprop_kernel<<<148 * SLOT_OPT_BLOCKS, OPT_THREADS, 0, st>>>(o);
     return check_launch(__func__);
 }
 

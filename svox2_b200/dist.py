@@ -85,6 +85,7 @@ class ShardedTrainer:
         self.fused = fused
         self._step_ws = None
         self.slots_per_ray = None       # record slots per ray of the fused step's queue (None: worst case)
+        self.last_mse = None            # fused step: 0-dim device tensor, F.mse_loss(rgb, rgb_gt) of the last step
 
     def _tv_run(self):
         """This rank's slice (start, count) of the step's contiguous wrapped cell run (drawn with
@@ -126,13 +127,15 @@ class ShardedTrainer:
             start, n = g._draw_cell_run(self.tv_sparsity)
             tv_s = (start, n, self.lambda_tv_sh)
         rgb = torch.empty_like(rgb_gt)
+        if self.last_mse is None:
+            self.last_mse = torch.zeros((), dtype=torch.float32, device=rgb_gt.device)
         _C.train_step(g._to_cpp(), g.density_rms, g.sh_rms, rays._to_cpp(), g.opt._to_cpp(), rgb_gt.contiguous(),
                       rgb, self._step_ws, tv_density=tv_d, tv_sh=tv_s, beta_loss=self.beta_loss,
                       sparsity_loss=self.sparsity_loss, norm_rays=Q, lr_density=lr_sigma, lr_sh=lr_sh,
-                      rms_beta=self.rms_beta)
+                      rms_beta=self.rms_beta, mse_out=self.last_mse)
         g.sparse_grad_indexer = g.sparse_sh_grad_indexer = None     # see export_masks()
-        # step_clear, queue clear, trace, shade, tv_mark, rank count + scan, seed, scatter, TV x2, RMSProp
-        self.kernels_per_step = 10 + (self.lambda_tv > 0) + (self.lambda_tv_sh > 0)
+        # clear, trace, shade, tv_mark, rank count + scan, seed, scatter, TV x2, RMSProp
+        self.kernels_per_step = 9 + (self.lambda_tv > 0) + (self.lambda_tv_sh > 0)
         return rgb
 
     def export_masks(self):

@@ -327,7 +327,9 @@ class Trainer:
                 lo = b * gq + self.rank * c.batch_size
                 rays, gt = self.pool.batch(lo, lo + c.batch_size)
                 rgb = self.stepper.step(rays, gt, global_batch=gq, lr_sigma=lr_s, lr_sh=lr_c)
-            sq_err += ((rgb.detach() - gt) ** 2).mean()
+            fused_mse = getattr(self.stepper, "last_mse", None) \
+                if getattr(self.stepper, "_step_ws", None) is not None else None
+            sq_err += fused_mse if fused_mse is not None else ((rgb.detach() - gt) ** 2).mean()
             seen += 1
             self.step_id += 1
             if seen % c.print_every == 0 and self.slab:

@@ -8,8 +8,8 @@ mkdir -p build/variants
 for spec in "$@"; do
   name="${spec%%:*}"; flags="${spec#*:}"
   odir="build/variants/$name"; mkdir -p "$odir"
-  for f in abi render march queue_march render_abi misc loss optim exchange; do
-    case "$f" in march|queue_march|optim|loss|exchange) extra="$flags";; *) extra="";; esac
+  for f in abi render march queue_march render_abi misc loss optim exchange nvol step; do
+    case "$f" in march|queue_march|optim|loss|exchange|step) extra="$flags";; *) extra="";; esac
     if [ -z "$extra" ] && [ -f "build/$f.o" ]; then cp "build/$f.o" "$odir/$f.o"; continue; fi
     /usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a \
       -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr -Xptxas -v $extra \
