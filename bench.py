@@ -58,9 +58,11 @@ def _dilate(mask, iters):
     return m[0, 0] > 0
 
 
-def build_scene(workload, device, seed=20200823):
+def build_scene(workload, device, seed=20200823, zorder=False):
     """sigma = 30 inside a union of seeded ellipsoids, SH ~ N(0, 0.1^2) with DC 0.5, voxels kept =
-    dilate^2(occupied); blob scale bisected so that the stored fraction hits the target."""
+    dilate^2(occupied); blob scale bisected so that the stored fraction hits the target.
+    zorder: rows numbered along the Morton curve -- what SparseGrid.resample(use_z_order=True)
+    produces (svox2.py:1399-1406) -- instead of the row-major cumsum opt.py's resample call yields."""
     cfg = WORKLOADS[workload]
     reso, target = cfg["reso"], cfg["occupancy"]
     gen = torch.Generator().manual_seed(seed)
@@ -76,11 +78,22 @@ def build_scene(workload, device, seed=20200823):
     scale = 0.5 * (lo + hi)
     inside = _inside_blobs(reso, centers, radii, scale, device)
     keep = _dilate(inside, 2)
-    links = torch.cumsum(keep.view(-1).to(torch.int32), 0, dtype=torch.int32) - 1
-    links[~keep.view(-1)] = -1
-    links = links.view(reso, reso, reso).contiguous()
     n_rows = int(keep.sum().item())
-    density = (inside[keep].float() * 30.0).view(n_rows, 1).contiguous()
+    if zorder:
+        from svox2_b200.utils import gen_morton
+        morton = gen_morton(reso, device=device, dtype=torch.long).view(-1)   # cell -> curve position
+        order = torch.argsort(morton)                                          # curve position -> cell
+        kept_cells = order[keep.view(-1)[order]]                               # kept cells along the curve
+        links = torch.full((reso ** 3,), -1, dtype=torch.int32, device=device)
+        links[kept_cells] = torch.arange(n_rows, dtype=torch.int32, device=device)
+        density = torch.zeros(n_rows, 1, device=device)
+        density[links[inside.view(-1)].long(), 0] = 30.0
+        del morton, order, kept_cells
+    else:
+        links = torch.cumsum(keep.view(-1).to(torch.int32), 0, dtype=torch.int32) - 1
+        links[~keep.view(-1)] = -1
+        density = (inside[keep].float() * 30.0).view(n_rows, 1).contiguous()
+    links = links.view(reso, reso, reso).contiguous()
     ggen = torch.Generator(device=device).manual_seed(seed + 1)
     sh = torch.randn(n_rows, 27, generator=ggen, device=device) * 0.1
     sh[:, ::9] += 0.5
@@ -438,7 +451,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
-    sc = build_scene(args.workload, dev)
+    sc = build_scene(args.workload, dev, zorder=args.zorder)
     grid = sv.SparseGrid(reso=[2, 2, 2], basis_dim=9, device=dev)   # geometry follows links.shape
     grid.links = sc["links"]
     grid.density_data = torch.nn.Parameter(sc["density"])
@@ -655,7 +668,8 @@ def run_ours(args):
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {
-            "workload": sc["name"], "reso": sc["reso"], "stored_voxels": sc["n_rows"],
+            "workload": sc["name"] + (" [rows in Morton order]" if args.zorder else ""), "reso": sc["reso"],
+            "stored_voxels": sc["n_rows"],
             "occupancy": round(sc["occupancy"], 4), "rays_per_gpu": per_rank, "global_batch": gq,
             "step": "volume_render_fused + tv_grad_sparse(sigma,sh) + rmsprop(sigma,sh)" +
                     (" as one svox2_train_step call (compact gradient buffer)" if getattr(trainer, "_step_ws", None) is not None else ""),
@@ -1292,6 +1306,9 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: 5000 rays per GPU per step; strong: the reference's global batch of "
                          "5000 rays (opt.py:79-81) whatever the GPU count")
+    ap.add_argument("--zorder", action="store_true",
+                    help="number the voxel rows along the Morton curve (resample(use_z_order=True)) instead of "
+                         "row-major; a layout experiment, not the headline configuration")
     ap.add_argument("--no-parity", dest="no_parity", action="store_true",
                     help="skip the N-GPU == 1-GPU parity block that precedes the timed loop when N > 1")
     ap.add_argument("--cpu-rays", type=int, default=BATCH,

@@ -36,7 +36,7 @@ bool march_vec_ok(const GridView& g, const GradView* gr, int64_t gsh_stride);
 size_t queue_workspace_bytes(int64_t n_rays, int64_t records);
 bool launch_queue_fused(const GridView& g, const Opts& opt, const MarchArgs& a, const GradView& gr,
                         void* workspace, size_t workspace_bytes, const int** overflow_flag,
-                        cudaStream_t st);
+                        float** ray_logT, float** ray_accum, cudaStream_t st);
 // fused train step with the compact gradient buffer (step.cu, slots.cuh)
 struct SlotMap;
 bool launch_step_trace_shade(const GridView& g, const Opts& opt, const MarchArgs& a, void* workspace,
@@ -64,9 +64,10 @@ void launch_lattice_march(int mode, bool from_cam, const GridView& g, const Opts
 namespace svox2b {
 // launchers defined in render.cu (MSI background, depth)
 void launch_bg_fwd(bool from_cam, const GridView& g, const Opts& opt, const MarchArgs& a,
-                   const float* logT, cudaStream_t st);
+                   const float* logT, cudaStream_t st, const int* gate = nullptr, int gate_want = 0);
 void launch_bg_bwd(const GridView& g, const Opts& opt, const MarchArgs& a, const float* color_cache,
-                   const float* logT, const float* accum, const GradView& gr, cudaStream_t st);
+                   const float* logT, const float* accum, const GradView& gr, cudaStream_t st,
+                   const int* gate = nullptr, int gate_want = 0);
 void launch_depth(bool sigma_thresh_mode, const GridView& g, const Opts& opt, const float* origins,
                   const float* dirs, int64_t n_rays, float thresh, float* out, cudaStream_t st);
 }  // namespace svox2b

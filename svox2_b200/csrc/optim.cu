@@ -178,6 +178,30 @@ masked_rows_vec_kernel(OptArgs a, int qpr) {
         for (int c = 0; c < OPT_SUPER / WARP; ++c) {
         unsigned m = __shfl_sync(FULL, h, 2 * c) | (__shfl_sync(FULL, h, 2 * c + 1) << 16);
         const int64_t row0 = sc * OPT_SUPER + c * WARP;
+        if (qpr == 1) {
+            // 4-channel rows (MSI texels): lane = row, adjacent lanes touch adjacent 16-byte rows; the
+            // touched rows of a ray are runs of consecutive layers, so most chunks are empty or dense
+            if ((m >> lane) & 1u) {
+                const int64_t o = (row0 + lane) * a.stride;
+                float4 g4 = *reinterpret_cast<const float4*>(a.grad + o);
+                float4 d4 = *reinterpret_cast<const float4*>(a.data + o);
+                float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (RMS) r4 = *reinterpret_cast<const float4*>(a.rms + o);
+                float* gv = reinterpret_cast<float*>(&g4);
+                float* dv = reinterpret_cast<float*>(&d4);
+                float* rv = reinterpret_cast<float*>(&r4);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (ok[e]) {
+                        if (RMS) rmsprop_once(dv + e, rv + e, gv + e, a.beta, lr4[e], a.eps, a.minval);
+                        else sgd_once(dv + e, gv + e, lr4[e]);
+                    }
+                if (RMS) *reinterpret_cast<float4*>(a.rms + o) = r4;
+                *reinterpret_cast<float4*>(a.data + o) = d4;
+                *reinterpret_cast<float4*>(a.grad + o) = g4;
+            }
+            continue;
+        }
         while (m) {
             // pop the next U*rpp touched rows in address order; group g of pass u keeps row g + u*rpp
             int sel[U];

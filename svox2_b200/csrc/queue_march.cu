@@ -69,6 +69,7 @@ struct QueueView {
     int* __restrict__ ray_first;  // [Q] first block of each ray or -1
     float* __restrict__ ray_logT; // [Q] forward log-transmittance (-1e3 when stopped)
     float4* __restrict__ ray_Y;   // [Q][8] SH basis value of channels 4q..4q+3 (0 for padding)
+    float* __restrict__ ray_accum;// [Q] what is left of the reference's accum behind the foreground (MSI)
 };
 
 // Slab mode (grid sharded over GPUs by x-range of cells, slab.py): the ray is traversed in full so
@@ -203,10 +204,14 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
     if (SLAB) {
         if (lane == 0) sl.logT_local[ray_id] = lt;
     } else {
-        const float bgc = hit ? fexp(logT_fwd) * opt.background_brightness : opt.background_brightness;
+        // with an MSI background the constant-colour term is added by the background kernel from
+        // the transmittance left behind the shells (cuvol.cu:1099-1112)
+        float bgc = hit ? fexp(logT_fwd) * opt.background_brightness : opt.background_brightness;
+        if (g.bg_nlayers > 0) bgc = 0.f;
         if (lane < 3) a.rgb_out[ray_id * 3 + lane] = bgc;
     }
     if (lane == 0) {
+        if (!SLAB && !hit) first_blk = -2;  // the seed kernel tells "missed the grid" from "no active sample"
         qv.ray_first[ray_id] = first_blk;
         qv.ray_logT[ray_id] = logT_fwd;
         if (COUNT) {
@@ -379,15 +384,20 @@ seed_kernel(Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
         atomicAdd(a.mse_out, se / (3.f * (float)a.n_rays));
     }
     int blk = qv.ray_first[ray_id];
-    if (blk < 0) return;  // no active sample: nothing to scatter
     float accum = fmaf(cc[0], gout[0], fmaf(cc[1], gout[1], cc[2] * gout[2]));
+    float beta_term = 0.f;
+    if (!SLAB && a.beta_loss > 0.f && blk != -2) {  // rays that hit the grid (cuvol.cu:259-264)
+        const float transmit_in = fexp(qv.ray_logT[ray_id]);
+        beta_term = (float)((double)a.beta_loss *
+                            (1 - (double)transmit_in / (1 - (double)transmit_in + 1e-3)));
+        accum += beta_term;
+    }
+    if (blk < 0) {  // no active sample: nothing to scatter; MSI hand-over (cuvol.cu:375-377, 1047-1048)
+        if (!SLAB && a.accum_out != nullptr && lane == 0) a.accum_out[ray_id] = accum - beta_term;
+        return;
+    }
     const float lt_in = SLAB ? __ldg(sl.lt_in + ray_id) : 0.f;
     if (SLAB) accum = __ldg(sl.accum_start + ray_id);  // seed and beta term of the whole ray
-    if (!SLAB && a.beta_loss > 0.f) {
-        const float transmit_in = fexp(qv.ray_logT[ray_id]);
-        accum += (float)((double)a.beta_loss *
-                         (1 - (double)transmit_in / (1 - (double)transmit_in + 1e-3)));
-    }
     while (blk >= 0) {
         const int count = __ldcg(&qv.rec[blk].blk_count);
         const int next = __ldcg(&qv.rec[blk].blk_next);
@@ -428,6 +438,7 @@ seed_kernel(Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
         }
         blk = next;
     }
+    if (!SLAB && a.accum_out != nullptr && lane == 0) a.accum_out[ray_id] = accum - beta_term;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -570,7 +581,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 }  // namespace
 
 size_t queue_workspace_bytes(int64_t n_rays, int64_t records) {
-    return 256 + align_up((size_t)n_rays * 4, 256) * 2 + align_up((size_t)n_rays * 8 * 16, 256) +
+    return 256 + align_up((size_t)n_rays * 4, 256) * 3 + align_up((size_t)n_rays * 8 * 16, 256) +
            (size_t)records * sizeof(Record);
 }
 
@@ -589,6 +600,8 @@ static bool carve_queue(void* workspace, size_t workspace_bytes, int64_t n_rays,
     p += align_up((size_t)n_rays * 4, 256);
     qv.ray_logT = reinterpret_cast<float*>(p);
     p += align_up((size_t)n_rays * 4, 256);
+    qv.ray_accum = reinterpret_cast<float*>(p);
+    p += align_up((size_t)n_rays * 4, 256);
     qv.ray_Y = reinterpret_cast<float4*>(p);
     p += align_up((size_t)n_rays * 8 * 16, 256);
     qv.rec = reinterpret_cast<Record*>(p);
@@ -600,10 +613,12 @@ static bool carve_queue(void* workspace, size_t workspace_bytes, int64_t n_rays,
 // Returns false if the workspace is too small (caller uses the lattice path).
 bool launch_queue_fused(const GridView& g, const Opts& opt, const MarchArgs& a, const GradView& gr,
                         void* workspace, size_t workspace_bytes, const int** overflow_flag,
-                        cudaStream_t st) {
+                        float** ray_logT, float** ray_accum, cudaStream_t st) {
     QueueView qv;
     if (!carve_queue(workspace, workspace_bytes, a.n_rays, qv)) return false;
     *overflow_flag = qv.overflow;
+    *ray_logT = qv.ray_logT;      // per-ray scratch the MSI fallback sequence may reuse
+    *ray_accum = qv.ray_accum;
     const SlabView none{};
 
     clear_flags_kernel<<<1, 1, 0, st>>>(qv.counter, qv.overflow, qv.sticky);
@@ -614,9 +629,20 @@ bool launch_queue_fused(const GridView& g, const Opts& opt, const MarchArgs& a, 
     const unsigned sblocks = 148 * QM_SAMPLE_CTAS;  // persistent grid-stride CTAs of 256 threads
     if (vec) shade_kernel<true, false, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, a.rgb_out, none, SlotMap{});
     else shade_kernel<false, false, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, a.rgb_out, none, SlotMap{});
-    seed_kernel<false><<<ray_blocks, TRACE_THREADS, 0, st>>>(opt, a, qv, none);
+    // MSI scenes (cuvol.cu:1099-1149): the shells composite behind the foreground, so the background
+    // forward pass sits between shade and seed (the seed needs the total colour) and its backward
+    // pass takes over the accum the foreground recursion leaves.  Both skip an overflowed batch.
+    const bool has_bg = g.bg_nlayers > 0;
+    MarchArgs s = a;
+    if (has_bg) {
+        launch_bg_fwd(false, g, opt, a, qv.ray_logT, st, qv.overflow, 0);
+        s.accum_out = qv.ray_accum;
+    }
+    seed_kernel<false><<<ray_blocks, TRACE_THREADS, 0, st>>>(opt, s, qv, none);
     if (vec) scatter_kernel<true, false, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride, SlotMap{});
     else scatter_kernel<false, false, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride, SlotMap{});
+    if (has_bg && gr.grad_bg)
+        launch_bg_bwd(g, opt, a, a.rgb_out, qv.ray_logT, qv.ray_accum, gr, st, qv.overflow, 0);
     return true;
 }
 

@@ -1,4 +1,4 @@
-// MSI background (one thread per ray) and depth kernels (warp per ray); the foreground march
+// MSI background (warp per ray, lane = shell) and depth kernels (thread per ray); the foreground march
 // lives in march.cu / queue_march.cu.  Traversal bit-exact with the reference:
 //   MSI       render_lerp_kernel_cuvol.cu:386-607, 775-860
 //   depth     render_lerp_kernel_cuvol.cu:122-225, 862-902
@@ -35,7 +35,10 @@ __device__ __forceinline__ void load_ray(const RaySource& src, int64_t ray_id, f
 }
 
 // ---------------------------------------------------------------------------------------
-// MSI background, one thread per ray
+// MSI background: one warp per ray, lane = shell.  The reference walks the ~130 shells of a ray in
+// one thread (render_background_kernel, cuvol.cu:386-476); a 5000-ray batch is then 40 CTAs of
+// dependent asinf/atan2f -> links -> texel chains.  Here the 32 shells of a round locate, gather
+// and interpolate in parallel; only the running log-transmittance is replayed in shell order.
 // ---------------------------------------------------------------------------------------
 struct BgRay {
     float o[3], d[3];
@@ -151,13 +154,75 @@ __device__ __forceinline__ void bg_scatter(const GridView& g, const GradView& gr
     }
 }
 
+// One ROUND of the MSI march: lane k looks at shell i0 + k (cuvol.cu:404-431).  The reference's
+// `invr_last` -- 1/r of the previous shell the ray actually crossed -- is the only state carried
+// from shell to shell besides the transmittance, and it does not depend on the samples' values, so
+// it is resolved with one ballot: nearest lower crossing lane of the round, else the carry.
+struct BgRound {
+    BgSample s;
+    float4 rgba;
+    float dinv;     // invr_last - invr_mid
+    bool crosses;   // the ray intersects this shell outside the inner radius
+};
+
+__device__ __forceinline__ void bg_round(const BgRay& r, const GridView& g, const SphereIsect& csi,
+                                         float inner_radius, int n_steps, int i0, int lane,
+                                         float& invr_carry, BgRound& b) {
+    const int i = i0 + lane;
+    float t = 0.f;
+    const float rad = n_steps / (n_steps - i - 0.5);
+    b.crosses = i < n_steps && !(rad < inner_radius) && csi.intersect(rad, &t);
+    b.rgba = make_float4(0.f, 0.f, 0.f, 0.f);
+    b.s.invr_mid = 0.f;
+    if (b.crosses) {
+        bg_locate(r, g, t, b.s);
+        b.rgba = bg_trilerp4(g, b.s);
+    }
+    const unsigned cm = __ballot_sync(FULL, b.crosses);
+    const unsigned lower = cm & ((1u << lane) - 1u);
+    const int prev = lower ? 31 - __clz(lower) : 0;
+    const float prev_invr = __shfl_sync(FULL, b.s.invr_mid, prev);
+    b.dinv = __fsub_rn(lower ? prev_invr : invr_carry, b.s.invr_mid);
+    if (cm) invr_carry = __shfl_sync(FULL, b.s.invr_mid, 31 - __clz(cm));
+}
+
+// Running log-transmittance over a round's active samples, in shell order (bit-exact running
+// difference; the exp / stop test of all samples runs in parallel afterwards, cuvol.cu:440-452).
+// Returns the active mask truncated behind the sample that fired the stop threshold.
+__device__ __forceinline__ unsigned bg_chain(bool active, float pcnt, float stop_thresh, int lane,
+                                             float& logT, bool& stop, float& my_before) {
+    unsigned act_m = __ballot_sync(FULL, active);
+    my_before = 0.f;
+    unsigned it = act_m;
+    while (it) {
+        const int i = __ffs(it) - 1;
+        it &= it - 1;
+        const float p = __shfl_sync(FULL, pcnt, i);
+        my_before = (lane == i) ? logT : my_before;
+        logT = __fsub_rn(logT, p);
+    }
+    const float aft = __fsub_rn(my_before, pcnt);
+    const unsigned tm = __ballot_sync(FULL, ((act_m >> lane) & 1u) && fexp(aft) < stop_thresh);
+    if (tm) {
+        const int sidx = __ffs(tm) - 1;
+        act_m &= (2u << sidx) - 1u;
+        stop = true;
+        logT = __shfl_sync(FULL, aft, sidx);
+    }
+    return act_m;
+}
+
+// `gate`: optional device flag; the kernel runs only while (*gate != 0) == gate_want (queue path
+// vs. its overflow fallback, queue_march.cu).
 template <bool FROM_CAM>
 __global__ void __launch_bounds__(BG_THREADS)
 bg_fwd_kernel(GridView g, Opts opt, RaySource src, int64_t n_rays,
               const float* __restrict__ logT_in, float* __restrict__ out,
-              unsigned long long* __restrict__ counters) {
-    const int64_t ray_id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+              unsigned long long* __restrict__ counters, const int* __restrict__ gate, int gate_want) {
+    const int64_t ray_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (ray_id >= n_rays) return;
+    if (gate != nullptr && (*gate != 0) != (gate_want != 0)) return;
+    const int lane = threadIdx.x & 31;
     float logT = logT_in[ray_id];
     if (logT < -25.f) return;
     float ow[3], dw[3];
@@ -170,43 +235,84 @@ bg_fwd_kernel(GridView g, Opts opt, RaySource src, int64_t n_rays,
     const float cy = r.o[2] * r.d[0] - r.o[0] * r.d[2];
     const float cz = r.o[0] * r.d[1] - r.o[1] * r.d[0];
     const float inner_radius = fmaxf(norm3df(cx, cy, cz) + 1e-3f, 1.f);
-    float t, invr_last = 1.f / inner_radius;
+    float invr_carry = 1.f / inner_radius;
     const int n_steps = int(g.bg_nlayers / opt.step_size) + 2;
     float outv[3] = {0.f, 0.f, 0.f};
     unsigned n_act = 0;
-    for (int i = 0; i < n_steps; ++i) {
-        const float rad = n_steps / (n_steps - i - 0.5);
-        if (rad < inner_radius || !csi.intersect(rad, &t)) continue;
-        BgSample s;
-        bg_locate(r, g, t, s);
-        const float4 rgba = bg_trilerp4(g, s);
-        const float sigma = rgba.w;
-        if (sigma > 0.f) {
-            ++n_act;
-            const float pcnt = (invr_last - s.invr_mid) * r.world_step * sigma;
-            const float weight = fexp(logT) * (1.f - fexp(-pcnt));
-            logT -= pcnt;
-            outv[0] += weight * fmaxf(rgba.x * kC0 + 0.5f, 0.f);
-            outv[1] += weight * fmaxf(rgba.y * kC0 + 0.5f, 0.f);
-            outv[2] += weight * fmaxf(rgba.z * kC0 + 0.5f, 0.f);
-            if (fexp(logT) < opt.stop_thresh) break;
+    bool stop = false;
+    for (int i0 = 0; i0 < n_steps && !stop; i0 += WARP) {
+        BgRound b;
+        bg_round(r, g, csi, inner_radius, n_steps, i0, lane, invr_carry, b);
+        const float sigma = b.rgba.w;
+        const bool active = b.crosses && sigma > 0.f;
+        const float pcnt = active ? __fmul_rn(__fmul_rn(b.dinv, r.world_step), sigma) : 0.f;
+        float before;
+        const unsigned act_m = bg_chain(active, pcnt, opt.stop_thresh, lane, logT, stop, before);
+        n_act += __popc(act_m);
+        if ((act_m >> lane) & 1u) {
+            const float weight = fexp(before) * (1.f - fexp(-pcnt));
+            outv[0] += weight * fmaxf(b.rgba.x * kC0 + 0.5f, 0.f);
+            outv[1] += weight * fmaxf(b.rgba.y * kC0 + 0.5f, 0.f);
+            outv[2] += weight * fmaxf(b.rgba.z * kC0 + 0.5f, 0.f);
         }
-        invr_last = s.invr_mid;
     }
-    const float bgc = fexp(logT) * opt.background_brightness;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) out[ray_id * 3 + c] += outv[c] + bgc;
-    if (counters && n_act) atomicAdd(counters + 3, (unsigned long long)n_act);
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) outv[c] += __shfl_xor_sync(FULL, outv[c], off);
+    const float bgc = fexp(logT) * opt.background_brightness;
+    if (lane < 3) {
+        const float v = lane == 0 ? outv[0] : (lane == 1 ? outv[1] : outv[2]);
+        out[ray_id * 3 + lane] += v + bgc;
+    }
+    if (counters && n_act && lane == 0) atomicAdd(counters + 3, (unsigned long long)n_act);
 }
 
+// trilerp_backward_bg_one (render_util.cuh:190-232) for the RGBA texel pair of each corner: one
+// 16-byte vector reduction per texel instead of four scalar atomics (channels whose colour is
+// clamped contribute an exact 0).
+template <bool VEC>
+__device__ __forceinline__ void bg_scatter4(const GridView& g, const GradView& gr, const BgSample& s,
+                                            const float* grad4, const bool* on4) {
+    if (!VEC) {
+        bg_scatter(g, gr, s, grad4, on4);
+        return;
+    }
+    const float ay = 1.f - s.pos[1], az = 1.f - s.pos[2];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (s.lk[q] < 0) continue;
+        const int64_t row = (int64_t)s.lk[q] * g.bg_nlayers + s.l[2];
+        float* gp = gr.grad_bg + row * 4;
+        const float wx = (q & 2) ? s.pos[0] : 1.0f - s.pos[0];
+        const float wy = (q & 1) ? s.pos[1] : ay;
+        float val[4];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) val[ch] = on4[ch] ? wy * (wx * grad4[ch]) : 0.f;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gp), "f"(val[0] * az),
+                     "f"(val[1] * az), "f"(val[2] * az), "f"(val[3] * az)
+                     : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gp + 4), "f"(val[0] * s.pos[2]),
+                     "f"(val[1] * s.pos[2]), "f"(val[2] * s.pos[2]), "f"(val[3] * s.pos[2])
+                     : "memory");
+        if (gr.mask_bg) {
+            gr.mask_bg[row] = 1;
+            gr.mask_bg[row + 1] = 1;
+        }
+    }
+}
+
+template <bool VEC>
 __global__ void __launch_bounds__(BG_THREADS)
 bg_bwd_kernel(GridView g, Opts opt, const float* __restrict__ origins,
               const float* __restrict__ dirs, int64_t n_rays, const float* __restrict__ grad_in,
               const float* __restrict__ color_cache, const float* __restrict__ logT_in,
               const float* __restrict__ accum_in, int fused, float norm_factor,
-              float sparsity_loss, GradView gr) {
-    const int64_t ray_id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+              float sparsity_loss, GradView gr, const int* __restrict__ gate, int gate_want) {
+    const int64_t ray_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (ray_id >= n_rays) return;
+    if (gate != nullptr && (*gate != 0) != (gate_want != 0)) return;
+    const int lane = threadIdx.x & 31;
     float logT = logT_in[ray_id];
     if (logT < -25.f) return;
     float ow[3], dw[3], gout[3];
@@ -215,11 +321,11 @@ bg_bwd_kernel(GridView g, Opts opt, const float* __restrict__ origins,
         ow[i] = __ldg(origins + ray_id * 3 + i);
         dw[i] = __ldg(dirs + ray_id * 3 + i);
         const float gi = __ldg(grad_in + ray_id * 3 + i);
-        gout[i] = fused ? (__ldg(color_cache + ray_id * 3 + i) - gi) * norm_factor : gi;
+        gout[i] = fused ? (__ldcg(color_cache + ray_id * 3 + i) - gi) * norm_factor : gi;
     }
     BgRay r;
     bg_ray_setup(r, ow, dw, g);
-    float accum = accum_in[ray_id];
+    float accum = __ldcg(accum_in + ray_id);
 
     SphereIsect csi(r.o, r.d);
     const int n_steps = int(g.bg_nlayers / opt.step_size) + 2;
@@ -227,39 +333,45 @@ bg_bwd_kernel(GridView g, Opts opt, const float* __restrict__ origins,
     const float cy = r.o[2] * r.d[0] - r.o[0] * r.d[2];
     const float cz = r.o[0] * r.d[1] - r.o[1] * r.d[0];
     const float inner_radius = fmaxf(norm3df(cx, cy, cz) + 1e-3f, 1.f);
-    float t, invr_last = 1.f / inner_radius;
-    for (int i = 0; i < n_steps; ++i) {
-        const float rad = n_steps / (n_steps - i - 0.5);
-        if (rad < inner_radius || !csi.intersect(rad, &t)) continue;
-        BgSample s;
-        bg_locate(r, g, t, s);
-        const float4 rgba = bg_trilerp4(g, s);
-        const float sigma = rgba.w;
-        if (sigma > 0.f) {
-            const float pcnt = r.world_step * (invr_last - s.invr_mid) * sigma;
-            const float weight = fexp(logT) * (1.f - fexp(-pcnt));
-            logT -= pcnt;
-            const float col[3] = {rgba.x * kC0 + 0.5f, rgba.y * kC0 + 0.5f, rgba.z * kC0 + 0.5f};
-            float total_color = 0.f;
-            float grad4[4];
-            bool on4[4];
+    float invr_carry = 1.f / inner_radius;
+    bool stop = false;
+    for (int i0 = 0; i0 < n_steps && !stop; i0 += WARP) {
+        BgRound b;
+        bg_round(r, g, csi, inner_radius, n_steps, i0, lane, invr_carry, b);
+        const float sigma = b.rgba.w;
+        const bool active = b.crosses && sigma > 0.f;
+        const float pcnt = active ? __fmul_rn(__fmul_rn(r.world_step, b.dinv), sigma) : 0.f;
+        float before;
+        const unsigned act_m = bg_chain(active, pcnt, opt.stop_thresh, lane, logT, stop, before);
+        const bool on = (act_m >> lane) & 1u;
+        const float weight = on ? fexp(before) * (1.f - fexp(-pcnt)) : 0.f;
+        const float col[3] = {b.rgba.x * kC0 + 0.5f, b.rgba.y * kC0 + 0.5f, b.rgba.z * kC0 + 0.5f};
+        float total_color = 0.f;
+        float grad4[4];
+        bool on4[4];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                total_color += fmaxf(col[c], 0.f) * gout[c];
-                on4[c] = col[c] > 0.f;
-                grad4[c] = kC0 * weight * gout[c];
-            }
-            accum -= weight * total_color;
-            float curr_grad_sigma = r.world_step * (invr_last - s.invr_mid) *
-                                    (total_color * fexp(logT) - accum);
+        for (int c = 0; c < 3; ++c) {
+            total_color += fmaxf(col[c], 0.f) * gout[c];
+            on4[c] = col[c] > 0.f;
+            grad4[c] = kC0 * weight * gout[c];
+        }
+        // the reference's running `accum -= weight * total_color` as a warp scan in shell order
+        float pre = weight * total_color;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const float o = __shfl_up_sync(FULL, pre, off);
+            if (lane >= off) pre += o;
+        }
+        const float my_accum = accum - pre;
+        accum -= __shfl_sync(FULL, pre, 31);
+        if (on) {
+            float curr_grad_sigma = r.world_step * b.dinv * (total_color * fexp(__fsub_rn(before, pcnt)) - my_accum);
             if (sparsity_loss > 0.f)
                 curr_grad_sigma += sparsity_loss * (4 * sigma / (1 + 2 * (sigma * sigma)));
             grad4[3] = curr_grad_sigma;
             on4[3] = true;
-            bg_scatter(g, gr, s, grad4, on4);
-            if (fexp(logT) < opt.stop_thresh) break;
+            bg_scatter4<VEC>(g, gr, b.s, grad4, on4);
         }
-        invr_last = s.invr_mid;
     }
 }
 
@@ -331,20 +443,30 @@ static RaySource make_source(const MarchArgs& a) {
 }
 
 void launch_bg_fwd(bool from_cam, const GridView& g, const Opts& opt, const MarchArgs& a,
-                   const float* logT, cudaStream_t st) {
+                   const float* logT, cudaStream_t st, const int* gate, int gate_want) {
     const RaySource src = make_source(a);
-    const unsigned blocks = div_up(a.n_rays, BG_THREADS);
+    const unsigned blocks = div_up(a.n_rays * WARP, BG_THREADS);   // one warp per ray
     if (from_cam)
-        bg_fwd_kernel<true><<<blocks, BG_THREADS, 0, st>>>(g, opt, src, a.n_rays, logT, a.rgb_out, a.counters);
+        bg_fwd_kernel<true><<<blocks, BG_THREADS, 0, st>>>(g, opt, src, a.n_rays, logT, a.rgb_out, a.counters,
+                                                           gate, gate_want);
     else
-        bg_fwd_kernel<false><<<blocks, BG_THREADS, 0, st>>>(g, opt, src, a.n_rays, logT, a.rgb_out, a.counters);
+        bg_fwd_kernel<false><<<blocks, BG_THREADS, 0, st>>>(g, opt, src, a.n_rays, logT, a.rgb_out, a.counters,
+                                                            gate, gate_want);
 }
 
 void launch_bg_bwd(const GridView& g, const Opts& opt, const MarchArgs& a, const float* color_cache,
-                   const float* logT, const float* accum, const GradView& gr, cudaStream_t st) {
-    bg_bwd_kernel<<<div_up(a.n_rays, BG_THREADS), BG_THREADS, 0, st>>>(
-        g, opt, a.origins, a.dirs, a.n_rays, a.grad_in, color_cache, logT, accum, a.fused_seed,
-        a.norm_factor, a.sparsity_loss, gr);
+                   const float* logT, const float* accum, const GradView& gr, cudaStream_t st,
+                   const int* gate, int gate_want) {
+    const unsigned blocks = div_up(a.n_rays * WARP, BG_THREADS);
+    const bool vec = (reinterpret_cast<uintptr_t>(gr.grad_bg) & 15u) == 0;
+    if (vec)
+        bg_bwd_kernel<true><<<blocks, BG_THREADS, 0, st>>>(g, opt, a.origins, a.dirs, a.n_rays, a.grad_in,
+                                                           color_cache, logT, accum, a.fused_seed, a.norm_factor,
+                                                           a.sparsity_loss, gr, gate, gate_want);
+    else
+        bg_bwd_kernel<false><<<blocks, BG_THREADS, 0, st>>>(g, opt, a.origins, a.dirs, a.n_rays, a.grad_in,
+                                                            color_cache, logT, accum, a.fused_seed, a.norm_factor,
+                                                            a.sparsity_loss, gr, gate, gate_want);
 }
 
 void launch_depth(bool sigma_thresh_mode, const GridView& g, const Opts& opt, const float* origins,

@@ -229,16 +229,22 @@ extern "C" SVOX2_API int svox2_volume_render_cuvol_fused(
     a.fused_seed = 1;
     a.counters = reinterpret_cast<unsigned long long*>(counters);
 
-    if (!use_bg && use_queue()) {
-        // sample-queue path (queue_march.cu): trace -> shade -> seed -> scatter; the lattice
-        // kernel is enqueued behind it as a conditional fallback for a queue overflow.
-        const int* overflow = nullptr;
-        if (launch_queue_fused(g, *opt, a, gr, workspace, workspace_bytes, &overflow, st)) {
-            MarchArgs fb = a;
-            fb.counters = nullptr;
-            fb.run_if = overflow;
-            launch_lattice_march(LB_MODE_FUSED, false, g, *opt, fb, gr, st);
-            return check_launch(__func__);
+    const int* overflow = nullptr;   // set: the queue path ran; what follows is its conditional fallback
+    float *q_logT = nullptr, *q_accum = nullptr;
+    if (use_queue()) {
+        // sample-queue path (queue_march.cu): trace -> shade -> [MSI fwd] -> seed -> scatter ->
+        // [MSI bwd]; the lattice kernels are enqueued behind it as a conditional fallback for a
+        // queue overflow.
+        if (launch_queue_fused(g, *opt, a, gr, workspace, workspace_bytes, &overflow, &q_logT, &q_accum, st)) {
+            if (!use_bg) {
+                MarchArgs fb = a;
+                fb.counters = nullptr;
+                fb.run_if = overflow;
+                launch_lattice_march(LB_MODE_FUSED, false, g, *opt, fb, gr, st);
+                return check_launch(__func__);
+            }
+            a.counters = nullptr;
+            a.run_if = overflow;
         }
     }
     if (!use_bg) {
@@ -258,12 +264,13 @@ extern "C" SVOX2_API int svox2_volume_render_cuvol_fused(
     }
     // MSI present: the background composites between the two foreground passes, so the sequence
     // of the reference (cuvol.cu:1099-1149) is kept: fwd, bg fwd, bwd, bg bwd.
-    Workspace w{nullptr, nullptr};
-    if (int e = carve_workspace(workspace, workspace_bytes, n_rays, w, __func__)) return e;
+    Workspace w{q_logT, q_accum};   // the fallback must not carve over the queue header it is gated by
+    if (!overflow)
+        if (int e = carve_workspace(workspace, workspace_bytes, n_rays, w, __func__)) return e;
     MarchArgs f = a;
     f.logT_out = w.logT;
     run_fwd(false, g, *opt, f, st);
-    if (use_bg) launch_bg_fwd(false, g, *opt, f, w.logT, st);
+    if (use_bg) launch_bg_fwd(false, g, *opt, f, w.logT, st, overflow, 1);
     MarchArgs b = a;
     b.counters = nullptr;
     b.color_cache = rgb_out;
@@ -271,7 +278,7 @@ extern "C" SVOX2_API int svox2_volume_render_cuvol_fused(
     b.accum_out = use_bg ? w.accum : nullptr;
     b.logT_out = nullptr;
     if (int e = run_bwd(g, *opt, b, gr, st, __func__)) return e;
-    if (use_bg && gr.grad_bg) launch_bg_bwd(g, *opt, b, rgb_out, w.logT, w.accum, gr, st);
+    if (use_bg && gr.grad_bg) launch_bg_bwd(g, *opt, b, rgb_out, w.logT, w.accum, gr, st, overflow, 1);
     return check_launch(__func__);
 }
 

@@ -44,6 +44,7 @@ def _worker(rank, world, port, out, bg=False):
         np.random.seed(7)
         tr1 = ShardedTrainer(ref, world_size=1, rank=0, **kw)
         rgb1 = tr1.step(sv.Rays(t(sc["origins"], dev), t(sc["dirs"], dev)), t(sc["rgb_gt"], dev), global_batch=B)
+        tr1.export_masks()    # fused single-GPU step: masks live as slot flags until asked for
         # sharded: this rank marches its contiguous slice
         grid = make_grid(sv, sc, dev)
         set_opt(grid, **opts)

@@ -23,6 +23,7 @@ def _reference_step(sv, sc, dev, seed, opts=OPTS, **kw):
     np.random.seed(seed)
     tr = ShardedTrainer(ref, world_size=1, rank=0, **kw)
     rgb = tr.step(sv.Rays(t(sc["origins"], dev), t(sc["dirs"], dev)), t(sc["rgb_gt"], dev))
+    tr.export_masks()     # the fused single-GPU step keeps its masks as slot flags until asked
     return ref, rgb
 
 
