@@ -434,6 +434,12 @@ def algorithmic_bytes_fused(q, c):
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
+def ship_mode(trainer):
+    """True when the slab trainer runs with ray-sharded traversal + record shipping (slab.py)."""
+    peer = getattr(trainer, "_peer", None)
+    return peer not in (None, False) and getattr(peer, "ship", None) is not None
+
+
 def run_ours(args):
     import torch.distributed as dist
     import svox2_b200 as sv
@@ -674,11 +680,15 @@ def run_ours(args):
             "step": "volume_render_fused + tv_grad_sparse(sigma,sh) + rmsprop(sigma,sh)" +
                     (" as one svox2_train_step call (compact gradient buffer)" if getattr(trainer, "_step_ws", None) is not None else ""),
             "l2": "inputs larger than L2 (grid+grads+rms >> 126 MB); 8 distinct ray batches cycled",
-            "parallelism": (f"grid sharded into {world} x-slabs, every rank traverses the global "
-                            "batch; per-ray scalars and halo planes exchanged with " +
-                            ("symmetric-memory peer stores over NVLink + device-side barriers"
-                             if getattr(trainer, "_peer", None) not in (None, False) else
-                             "NCCL all-gathers / P2P (no symmetric memory)")) if slab else
+            "parallelism": (f"grid sharded into {world} x-slabs; " +
+                            ("rays sharded for the traversal, sample records shipped to the owning slab with "
+                             "NVLink stores into its queue (symmetric memory), per-ray partial colours and "
+                             "halo planes exchanged with peer stores + device-side barriers"
+                             if ship_mode(trainer) else
+                             "every rank traverses the global batch; per-ray scalars and halo planes exchanged "
+                             "with " + ("symmetric-memory peer stores over NVLink + device-side barriers"
+                                        if getattr(trainer, "_peer", None) not in (None, False) else
+                                        "NCCL all-gathers / P2P (no symmetric memory)"))) if slab else
                            (f"ray-sharded x{world}, replicated grid" +
                             (", masked packed grad all-reduce (NCCL)" if world > 1 else "")),
             "samples_per_ray": {"skip": cnt[0] / per_rank, "visited": cnt[1] / per_rank,
@@ -714,8 +724,8 @@ def run_ours(args):
                       f"{N_CAMS} hemisphere cameras per GPU (images sharded over GPUs)"}
     if slab:
         halo = sum(h.numel() for h in (trainer.halo_left, trainer.halo_right) if h is not None)
-        line["exchange"] = {"mode": "slab", "slab_bounds": trainer.bounds,
-                            "bytes_all_gathered_per_step": gq * 20 * world,
+        line["exchange"] = {"mode": "slab-ship" if ship_mode(trainer) else "slab", "slab_bounds": trainer.bounds,
+                            "bytes_all_gathered_per_step": gq * (16 if ship_mode(trainer) else 20) * world,
                             "halo_rows_rank0": halo, "phase_ms": phase_ms}
     elif world > 1:
         line["exchange"] = {"mode": "rays", "rows_per_step": trainer.exchanged_rows,

@@ -378,6 +378,47 @@ SVOX2_API int svox2_slab_combine(const float* part_all, const float* logT_all, c
                      float background_brightness, float beta_loss, float* rgb, float* gout,
                      float* accum_start, svox2_stream_t stream);
 
+/* Ship mode (default multi-GPU step, svox2_b200/slab.py): the RAYS are sharded for the traversal,
+ * the GRID (x-slabs) for everything else.  The rank that traces a ray composites it exactly as the
+ * single-GPU kernel does (same lattice, same sequential transmittance: masks stay bit-exact) and
+ * ships every active sample's 96-byte record to the rank that owns the sample's cell, straight
+ * into that rank's queue over NVLink: `peer_workspaces[d]` is rank d's workspace mapped into this
+ * process (symmetric memory), all of identical size / layout; region `rank` of every queue belongs
+ * to the records shipped by `rank` (region_cap records).  After a cross-GPU barrier each rank
+ * shades the records it received (part[Qg,4] partial colours), the partials are all-gathered,
+ * svox2_ship_combine makes total colour / dL/drgb / the reference's accum at slab entry, and
+ * svox2_ship_backward scatters the gradients of the received records and resets the queue.
+ * origins / dirs / rgb_gt hold the GLOBAL batch on every rank; rank r traces
+ * [ray_begin, ray_begin + ray_count). */
+SVOX2_API size_t svox2_ship_workspace_bytes(int64_t n_rays_global, int32_t n_slabs, int64_t region_cap);
+SVOX2_API int svox2_ship_trace(const svox2_grid_t* grid, const float* origins, const float* dirs,
+                     int64_t n_rays_global, int64_t ray_begin, int64_t ray_count,
+                     const svox2_render_opts_t* opt, const int32_t* slab_bounds, int32_t n_slabs,
+                     int32_t rank, const uint64_t* peer_workspaces, size_t workspace_bytes,
+                     int64_t region_cap, int64_t* counters, svox2_stream_t stream);
+SVOX2_API int svox2_ship_shade(const svox2_grid_t* grid, int64_t n_rays_global, int32_t n_slabs,
+                     int64_t region_cap, float* part, void* workspace, size_t workspace_bytes,
+                     svox2_stream_t stream);
+SVOX2_API const float* svox2_ship_ray_logT(void* workspace, size_t workspace_bytes, int64_t n_rays_global,
+                     int32_t n_slabs, int64_t region_cap);
+SVOX2_API int svox2_ship_combine(const float* part_all, const float* ray_logT, const float* dirs,
+                     const float* rgb_gt, int64_t n_rays, int32_t n_slabs, int32_t rank,
+                     float background_brightness, float beta_loss, float* rgb, float* gout,
+                     float* accum_start, svox2_stream_t stream);
+SVOX2_API int svox2_ship_backward(const svox2_grid_t* grid, int64_t n_rays_global,
+                     const svox2_render_opts_t* opt, int32_t n_slabs, int64_t region_cap,
+                     const float* gout, const float* accum_start, float sparsity_loss,
+                     const svox2_grads_t* grads, void* workspace, size_t workspace_bytes,
+                     svox2_stream_t stream);
+
+/* Ship mode keeps density_data replicated (the tracer needs sigma along the whole ray): for every
+ * row with mask[row] && own[row], data[row*stride] is stored at the same offset of every peer's
+ * array (peer_base_ptrs[p] = rank p's density array mapped into this process; self and null
+ * entries are skipped). */
+SVOX2_API int svox2_publish_rows(const uint8_t* mask, const uint8_t* own, const float* data, int64_t n_rows,
+                     int64_t stride, const uint64_t* peer_base_ptrs, int32_t n_peers, int32_t self_rank,
+                     svox2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

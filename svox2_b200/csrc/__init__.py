@@ -852,6 +852,111 @@ def slab_backward(grid, n_rays, opt, lt_in, gout, accum_start, sparsity_loss, gr
             workspace.numel(), _stream()))
 
 
+# ---- ship mode (default multi-GPU step): rays sharded for the traversal, records shipped to the
+# ---- slab that owns the sample's cell (svox2_b200/slab.py, include/svox2_b200.h) -----------------
+class ShipWorkspace:
+    """Geometry of the per-rank symmetric record workspace: ``peer_ptrs[d]`` is rank d's buffer
+    mapped into this process, ``local`` the uint8 tensor over this rank's own buffer."""
+
+    def __init__(self, n_rays_global: int, n_slabs: int, rank: int, region_cap: int):
+        self.n_rays, self.n_slabs, self.rank, self.region_cap = int(n_rays_global), int(n_slabs), int(rank), int(region_cap)
+        self.nbytes = int(_lib.lib().svox2_ship_workspace_bytes(self.n_rays, self.n_slabs, self.region_cap))
+        self.local, self.peer_ptrs = None, None
+
+    def bind(self, local: torch.Tensor, peer_ptrs):
+        if local.dtype != torch.uint8 or local.numel() < self.nbytes or len(peer_ptrs) != self.n_slabs:
+            _fail("ShipWorkspace.bind: local must be a uint8 tensor of >= nbytes bytes, one pointer per slab")
+        self.local = local
+        self.peer_ptrs = [int(p) for p in peer_ptrs]
+        self._arr = (C.c_uint64 * self.n_slabs)(*self.peer_ptrs)
+        local[:512].zero_()            # header, counts, counters (the rest is written before it is read)
+
+    def ray_logT(self) -> torch.Tensor:
+        """[Qg] forward log-transmittance of every ray of the global batch (written by its tracer)."""
+        ptr = _lib.lib().svox2_ship_ray_logT(self.local.data_ptr(), self.nbytes, self.n_rays, self.n_slabs,
+                                             self.region_cap)
+        if not ptr:
+            _fail("ShipWorkspace: bad geometry")
+        off = int(ptr) - self.local.data_ptr()
+        return self.local[off:off + 4 * self.n_rays].view(torch.float32)
+
+    def overflowed(self) -> bool:
+        hdr = self.local[:256].view(torch.int32)
+        return bool((hdr[32] != 0).item() or (hdr[48] != 0).item())
+
+
+def ship_trace(grid, rays, opt, ray_begin, ray_count, slab_bounds, ws: ShipWorkspace, _counters=None):
+    """Traverse rays [ray_begin, ray_begin + ray_count) of the global batch and ship their sample
+    records to the owning slabs (NVLink stores into the peers' workspaces)."""
+    g = _grid_struct(grid)
+    origins, dirs = _rays(rays)
+    o = _opt_struct(opt)
+    if origins.size(0) != ws.n_rays or len(slab_bounds) != ws.n_slabs + 1:
+        _fail("ship_trace: rays must hold the global batch the workspace was sized for")
+    b = (C.c_int32 * len(slab_bounds))(*[int(x) for x in slab_bounds])
+    with torch.cuda.device(origins.device):
+        check(_lib.lib().svox2_ship_trace(
+            C.byref(g), origins.data_ptr(), dirs.data_ptr(), ws.n_rays, int(ray_begin), int(ray_count),
+            C.byref(o), C.addressof(b), ws.n_slabs, ws.rank, C.addressof(ws._arr), ws.nbytes, ws.region_cap,
+            _ptr(_counters), _stream()))
+
+
+def ship_shade(grid, part, ws: ShipWorkspace):
+    """part [Qg,4] (zeroed by the caller): .xyz += colour of the records this rank received."""
+    g = _grid_struct(grid)
+    _check_input(part, "part", torch.float32, 2)
+    if part.size(1) != 4 or part.size(0) != ws.n_rays:
+        _fail("part must be [Qg, 4]")
+    with torch.cuda.device(part.device):
+        check(_lib.lib().svox2_ship_shade(C.byref(g), ws.n_rays, ws.n_slabs, ws.region_cap, part.data_ptr(),
+                                          ws.local.data_ptr(), ws.nbytes, _stream()))
+
+
+def ship_combine(part_all, ray_logT, dirs, rgb_gt, rank, background_brightness, beta_loss, rgb, gout,
+                 accum_start):
+    """slab_combine with the ray's total log-transmittance taken from its tracer."""
+    _check_input(part_all, "part_all", torch.float32, 3)
+    _check_input(ray_logT, "ray_logT", torch.float32, 1)
+    for t_, n_ in ((dirs, "dirs"), (rgb_gt, "rgb_gt"), (rgb, "rgb"), (gout, "gout")):
+        _check_input(t_, n_, torch.float32, 2)
+    _check_input(accum_start, "accum_start", torch.float32, 1)
+    if part_all.size(2) != 4:
+        _fail("part_all must be [slabs, Q, 4]")
+    with torch.cuda.device(dirs.device):
+        check(_lib.lib().svox2_ship_combine(
+            part_all.data_ptr(), ray_logT.data_ptr(), dirs.data_ptr(), rgb_gt.data_ptr(), dirs.size(0),
+            part_all.size(0), int(rank), float(background_brightness), float(beta_loss),
+            rgb.data_ptr(), gout.data_ptr(), accum_start.data_ptr(), _stream()))
+
+
+def ship_backward(grid, opt, gout, accum_start, sparsity_loss, grads, ws: ShipWorkspace):
+    g = _grid_struct(grid)
+    o = _opt_struct(opt)
+    gr, _ = _grads_struct(grads, grid)
+    _check_input(gout, "gout", torch.float32, 2)
+    _check_input(accum_start, "accum_start", torch.float32, 1)
+    with torch.cuda.device(gout.device):
+        check(_lib.lib().svox2_ship_backward(
+            C.byref(g), ws.n_rays, C.byref(o), ws.n_slabs, ws.region_cap, gout.data_ptr(),
+            accum_start.data_ptr(), float(sparsity_loss), C.byref(gr), ws.local.data_ptr(), ws.nbytes,
+            _stream()))
+
+
+def publish_rows(mask, own, data, peer_ptrs, self_rank):
+    """data[row] -> the same row of every peer's array, for rows with mask & own (ship mode keeps
+    density_data replicated; ``peer_ptrs[p]`` = rank p's array mapped into this process)."""
+    _check_cuda(mask, "mask", torch.bool, 1)
+    _check_cuda(own, "own", torch.bool, 1)
+    _check_rows(data, "data")
+    if mask.numel() != data.size(0) or own.numel() != data.size(0):
+        _fail("mask / own must have one entry per row")
+    arr = (C.c_uint64 * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+    with torch.cuda.device(data.device):
+        check(_lib.lib().svox2_publish_rows(mask.data_ptr(), own.data_ptr(), data.data_ptr(), data.size(0),
+                                            _row_stride(data), C.addressof(arr), len(peer_ptrs), int(self_rank),
+                                            _stream()))
+
+
 def peer_store(peer_ptrs, dst_offset_bytes, src):
     """src -> (base + dst_offset_bytes) of every peer buffer (list of device pointers mapped into
     this process, e.g. torch symmetric memory ``buffer_ptrs``); one launch, NVLink P2P stores."""

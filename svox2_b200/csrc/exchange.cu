@@ -142,7 +142,8 @@ __global__ void slab_combine_kernel(const float* __restrict__ part_all /*[G,Q,4]
                                     const float* __restrict__ dirs, const float* __restrict__ rgb_gt,
                                     int64_t Q, int G, int rank, float background_brightness,
                                     float norm_factor, float beta_loss, float* __restrict__ rgb,
-                                    float* __restrict__ gout, float* __restrict__ accum_start) {
+                                    float* __restrict__ gout, float* __restrict__ accum_start,
+                                    int logT_is_total) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= Q) return;
     const bool fwd = __ldg(dirs + q * 3) >= 0.f;
@@ -153,10 +154,14 @@ __global__ void slab_combine_kernel(const float* __restrict__ part_all /*[G,Q,4]
         const int j = fwd ? i : G - 1 - i;
         const float4 p = __ldg(reinterpret_cast<const float4*>(part_all) + (int64_t)j * Q + q);
         c[0] += p.x; c[1] += p.y; c[2] += p.z;
-        stopped = stopped || p.w != 0.f;
-        lt = __fadd_rn(lt, __ldg(logT_all + (int64_t)j * Q + q));
+        if (!logT_is_total) {
+            stopped = stopped || p.w != 0.f;
+            lt = __fadd_rn(lt, __ldg(logT_all + (int64_t)j * Q + q));
+        }
     }
     if (stopped) lt = -1e3f;
+    // ship mode: the rank that traced the ray composited it in one piece (-1e3 if it stopped)
+    if (logT_is_total) lt = __ldcg(logT_all + q);
     const float T = __expf(lt);
     float g[3], accum = 0.f;
 #pragma unroll
@@ -197,6 +202,21 @@ peer_store_kernel(PeerPtrs peers, int64_t dst_off4, const float4* __restrict__ s
         const float4 v = __ldg(src + i);
         for (int p = 0; p < peers.n; ++p) reinterpret_cast<float4*>(peers.base[p])[dst_off4 + i] = v;
     }
+}
+
+// Ship mode: the rank that traces a ray evaluates sigma along the WHOLE ray, so the density array
+// (4 B per voxel, unlike the SH rows) is kept replicated: after its RMSProp every rank stores the
+// rows it just updated (mask & exclusively-owned) into every peer's copy.  lane = row, so runs of
+// updated rows leave the SM as coalesced NVLink writes.
+__global__ void __launch_bounds__(256)
+publish_rows_kernel(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ own,
+                    const float* __restrict__ data, int64_t n_rows, int64_t stride, PeerPtrs peers, int self) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    if (!__ldg(mask + row) || !__ldg(own + row)) return;
+    const float v = data[row * stride];
+    for (int p = 0; p < peers.n; ++p)
+        if (p != self && peers.base[p] != nullptr) peers.base[p][row * stride] = v;
 }
 
 struct PackedOptArgs {
@@ -391,7 +411,23 @@ extern "C" SVOX2_API int svox2_slab_combine(const float* part_all, const float* 
     SVOX2_REQUIRE(aligned16(part_all), "part_all must be 16-byte aligned");
     slab_combine_kernel<<<div_up(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(
         part_all, logT_all, dirs, rgb_gt, n_rays, n_slabs, rank, background_brightness,
-        2.f / (float)(3 * (int)n_rays), beta_loss / (float)n_rays, rgb, gout, accum_start);
+        2.f / (float)(3 * (int)n_rays), beta_loss / (float)n_rays, rgb, gout, accum_start, 0);
+    return check_launch(__func__);
+}
+
+extern "C" SVOX2_API int svox2_ship_combine(const float* part_all, const float* ray_logT,
+                                            const float* dirs, const float* rgb_gt, int64_t n_rays,
+                                            int32_t n_slabs, int32_t rank,
+                                            float background_brightness, float beta_loss,
+                                            float* rgb, float* gout, float* accum_start,
+                                            svox2_stream_t stream) {
+    SVOX2_REQUIRE(n_rays >= 0 && n_slabs >= 1 && rank >= 0 && rank < n_slabs, "bad slab arguments");
+    if (n_rays == 0) return SVOX2_OK;
+    SVOX2_REQUIRE(part_all && ray_logT && dirs && rgb_gt && rgb && gout && accum_start, "null argument");
+    SVOX2_REQUIRE(aligned16(part_all), "part_all must be 16-byte aligned");
+    slab_combine_kernel<<<div_up(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(
+        part_all, ray_logT, dirs, rgb_gt, n_rays, n_slabs, rank, background_brightness,
+        2.f / (float)(3 * (int)n_rays), beta_loss / (float)n_rays, rgb, gout, accum_start, 1);
     return check_launch(__func__);
 }
 
@@ -414,5 +450,21 @@ extern "C" SVOX2_API int svox2_peer_store(const uint64_t* peer_base_ptrs, int32_
     const int64_t want = (n4 + 255) / 256;
     peer_store_kernel<<<(unsigned)(want < 148 * 4 ? want : 148 * 4), 256, 0, (cudaStream_t)stream>>>(
         peers, dst_offset_bytes / 16, static_cast<const float4*>(src), n4);
+    return check_launch(__func__);
+}
+
+extern "C" SVOX2_API int svox2_publish_rows(const uint8_t* mask, const uint8_t* own, const float* data,
+                                            int64_t n_rows, int64_t stride, const uint64_t* peer_base_ptrs,
+                                            int32_t n_peers, int32_t self_rank, svox2_stream_t stream) {
+    SVOX2_REQUIRE(n_rows >= 0 && stride >= 1 && n_peers >= 1 && n_peers <= SVOX2_MAX_PEERS && self_rank >= 0 &&
+                      self_rank < n_peers,
+                  "bad arguments");
+    if (n_rows == 0 || n_peers == 1) return SVOX2_OK;
+    SVOX2_REQUIRE(mask && own && data && peer_base_ptrs, "null argument");
+    PeerPtrs peers;
+    peers.n = n_peers;
+    for (int p = 0; p < n_peers; ++p) peers.base[p] = reinterpret_cast<float*>(peer_base_ptrs[p]);  // 0: skip
+    publish_rows_kernel<<<div_up(n_rows, 256), 256, 0, (cudaStream_t)stream>>>(mask, own, data, n_rows, stride,
+                                                                             peers, self_rank);
     return check_launch(__func__);
 }

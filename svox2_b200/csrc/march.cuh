@@ -56,6 +56,18 @@ bool launch_slab_shade(const GridView& g, const Opts& opt, int64_t n_rays, void*
 bool launch_slab_backward(const GridView& g, const Opts& opt, const MarchArgs& a, const GradView& gr,
                           void* workspace, size_t workspace_bytes, const float* lt_in,
                           const float* gout, const float* accum_start, cudaStream_t st);
+// ship mode (rays sharded for the traversal, records shipped to the owning slab over NVLink)
+size_t ship_workspace_bytes(int64_t n_rays_global, int n_slabs, int64_t region_cap);
+bool launch_ship_trace(const GridView& g, const Opts& opt, const MarchArgs& a, int64_t ray_offset,
+                       int64_t n_rays_global, const int* bounds, int n_slabs, int rank,
+                       const uint64_t* peer_ws, size_t workspace_bytes, int64_t region_cap, cudaStream_t st);
+bool launch_ship_shade(const GridView& g, int64_t n_rays_global, void* workspace, size_t workspace_bytes,
+                       int n_slabs, int64_t region_cap, float* part, cudaStream_t st);
+const float* ship_ray_logT(void* workspace, size_t workspace_bytes, int64_t n_rays_global, int n_slabs,
+                           int64_t region_cap);
+bool launch_ship_backward(const GridView& g, const Opts& opt, const MarchArgs& a, const GradView& gr,
+                          void* workspace, size_t workspace_bytes, int n_slabs, int64_t region_cap,
+                          const float* gout, const float* accum_start, cudaStream_t st);
 void launch_lattice_march(int mode, bool from_cam, const GridView& g, const Opts& opt,
                           const MarchArgs& a, const GradView& gr, cudaStream_t st);
 

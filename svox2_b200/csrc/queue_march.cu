@@ -70,6 +70,60 @@ struct QueueView {
     float* __restrict__ ray_logT; // [Q] forward log-transmittance (-1e3 when stopped)
     float4* __restrict__ ray_Y;   // [Q][8] SH basis value of channels 4q..4q+3 (0 for padding)
     float* __restrict__ ray_accum;// [Q] what is left of the reference's accum behind the foreground (MSI)
+    // ship mode (record shipping between slabs): the record array is n_regions sub-arrays of
+    // region_cap records, region k filled by rank k; counts[k] = records in region k this step
+    const int* __restrict__ counts;
+    int n_regions, region_cap;
+};
+
+// flat sample index -> record, across the regions of a ship-mode queue.  The prefix table lives in
+// shared memory; a thread's indices only grow, so it keeps a running region cursor.
+struct Regions {
+    int n, cap, total;
+    const int* pre;   // [n + 1] records in the regions before r (shared memory)
+};
+template <int MODE>
+__device__ __forceinline__ void regions_init(const QueueView& qv, Regions& rg, int* s_pre) {
+    rg.n = 0;
+    rg.cap = 0;
+    rg.pre = s_pre;
+    if (MODE == 2) {
+        rg.n = qv.n_regions;
+        rg.cap = qv.region_cap;
+        if (threadIdx.x == 0) {
+            int acc = 0;
+            for (int r = 0; r < rg.n; ++r) {
+                s_pre[r] = acc;
+                acc += min(__ldcg(qv.counts + r), rg.cap);
+            }
+            s_pre[rg.n] = acc;
+        }
+        __syncthreads();
+        rg.total = s_pre[rg.n];
+    } else {
+        rg.total = min(*qv.counter, qv.capacity);
+    }
+}
+template <int MODE>
+__device__ __forceinline__ int region_index(const Regions& rg, int s, int& cursor) {
+    if (MODE != 2) return s;
+    while (cursor + 1 < rg.n && s >= rg.pre[cursor + 1]) ++cursor;
+    return cursor * rg.cap + (s - rg.pre[cursor]);
+}
+
+// Ship mode (slab.py): rays are sharded over the ranks for the TRAVERSAL, the grid for everything
+// else.  The rank that traces a ray composites it exactly as the single-GPU kernel does and ships
+// every active sample's record to the rank that owns the sample's cell, straight into region
+// `rank` of that rank's queue over NVLink (peer-mapped symmetric memory).
+struct ShipView {
+    Record* rec[SVOX2_MAX_PEERS];       // peer d's record array, already offset to MY region
+    int* ray_first[SVOX2_MAX_PEERS];    // peer d's [Qg] chain heads
+    float* ray_logT[SVOX2_MAX_PEERS];   // peer d's [Qg] forward log-transmittance
+    int* overflow[SVOX2_MAX_PEERS];     // peer d's overflow flag
+    int bounds[SVOX2_MAX_PEERS + 1];    // slab x boundaries
+    int* cnt;                           // local [n]: records shipped to each peer so far
+    int n, region_base, region_cap;
+    int64_t ray_offset;                 // global id of this rank's first ray
 };
 
 // Slab mode (grid sharded over GPUs by x-range of cells, slab.py): the ray is traversed in full so
@@ -90,11 +144,13 @@ struct SlabView {
 // ---------------------------------------------------------------------------------------
 // K1: traversal -> records
 // ---------------------------------------------------------------------------------------
-template <bool COUNT, bool SLAB>
+template <bool COUNT, int MODE>
 __global__ void __launch_bounds__(TRACE_THREADS, QM_TRACE_BLOCKS)
-trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
-    const int64_t ray_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv, SlabView sl, ShipView sv) {
+    constexpr bool SLAB = MODE == 1, SHIP = MODE == 2;
+    int64_t ray_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (ray_id >= a.n_rays) return;
+    if (SHIP) ray_id += sv.ray_offset;   // a.n_rays = this rank's share; arrays hold the global batch
     const int lane = threadIdx.x & 31;
     float ow[3], dw[3];
 #pragma unroll
@@ -102,7 +158,7 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
         ow[i] = __ldg(a.origins + ray_id * 3 + i);
         dw[i] = __ldg(a.dirs + ray_id * 3 + i);
     }
-    if (lane < 8) {  // per-ray basis table for the sample-parallel kernels
+    if (!SHIP && lane < 8) {  // per-ray basis table for the sample-parallel kernels
         float y[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -118,6 +174,9 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
     float lt = 0.f;
     bool stopped = false;
     int first_blk = -1, prev_blk = -1;
+    // ship mode: destination of the block whose header is still pending, that block, its size
+    int cur_dest = -1, pend_blk = -1, pend_n = 0;
+    unsigned visited = 0u;
 
     // slab mode: t-interval in which the x coordinate can fall into the slab (one cell of margin;
     // the outermost slabs are open-ended because locate() clamps)
@@ -166,7 +225,59 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
                 cnt[2] += __popc(act_m);
             }
             const int n = __popc(act_m);
-            if (n > 0) {
+            if (SHIP) {
+                // owner of this lane's cell = slab whose x-range holds it
+                int my_dest = 0;
+#pragma unroll
+                for (int k = 1; k < SVOX2_MAX_PEERS; ++k) my_dest = (k < sv.n && c.l[0] >= sv.bounds[k]) ? k : my_dest;
+                unsigned rem = act_m;
+                while (rem) {  // samples of a round are in t-order, owners monotone: 1-2 iterations
+                    const int lead = __ffs(rem) - 1;
+                    const int d = __shfl_sync(FULL, my_dest, lead);
+                    const unsigned dm = __ballot_sync(FULL, my_dest == d) & rem;
+                    rem &= ~dm;
+                    const int nd = __popc(dm);
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(sv.cnt + d, nd);
+                    base = __shfl_sync(FULL, base, 0);
+                    if (base + nd > sv.region_cap) {
+                        if (lane == 0) {
+                            atomicExch(qv.overflow, 1);
+                            *reinterpret_cast<volatile int*>(sv.overflow[d]) = 1;
+                        }
+                        done = true;
+                        break;
+                    }
+                    Record* const rd = sv.rec[d];
+                    if ((dm >> lane) & 1u) {
+                        const int rank = __popc(dm & ((1u << lane) - 1u));
+                        Record* r = rd + base + rank;
+                        int4* r4 = reinterpret_cast<int4*>(r);
+                        r4[0] = make_int4(lk[0], lk[1], lk[2], lk[3]);
+                        r4[1] = make_int4(lk[4], lk[5], lk[6], lk[7]);
+                        const float weight = __fmul_rn(fexp(my_before), __fsub_rn(1.f, fexp(-pcnt)));
+                        reinterpret_cast<float4*>(r)[2] = make_float4(pos[0], pos[1], pos[2], weight);
+                        r4[3] = make_int4(__float_as_int(__fsub_rn(my_before, pcnt)), __float_as_int(sigma),
+                                          __float_as_int(ws), (int)ray_id);
+                    }
+                    if (lane == 0) {
+                        // every header / chain head is written exactly once: the header of a block
+                        // when its successor (or the end of the ray's stay in that slab) is known
+                        const int abs_blk = sv.region_base + base;
+                        if (d == cur_dest) {
+                            reinterpret_cast<int4*>(sv.rec[d] + pend_blk)[5] = make_int4(pend_n, abs_blk, 0, 0);
+                        } else {
+                            if (cur_dest >= 0)
+                                reinterpret_cast<int4*>(sv.rec[cur_dest] + pend_blk)[5] = make_int4(pend_n, -1, 0, 0);
+                            sv.ray_first[d][ray_id] = abs_blk;
+                        }
+                    }
+                    visited |= 1u << d;
+                    cur_dest = d;
+                    pend_blk = base;
+                    pend_n = nd;
+                }
+            } else if (n > 0) {
                 int base = 0;
                 if (lane == 0) base = atomicAdd(qv.counter, n);
                 base = __shfl_sync(FULL, base, 0);
@@ -201,6 +312,20 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
     // forward colour starts from the background term; K2 adds the samples atomically
     const bool hit = ray.tmin <= ray.tmax;
     const float logT_fwd = hit ? (stopped ? -1e3f : lt) : 0.f;
+    if (SHIP) {
+        if (lane == 0 && cur_dest >= 0)
+            reinterpret_cast<int4*>(sv.rec[cur_dest] + pend_blk)[5] = make_int4(pend_n, -1, 0, 0);
+        if (lane < sv.n) {  // lane d tells rank d: the ray's transmittance, and "nothing for you"
+            sv.ray_logT[lane][ray_id] = logT_fwd;
+            if (!((visited >> lane) & 1u)) sv.ray_first[lane][ray_id] = -1;
+        }
+        if (COUNT && lane == 0) {
+            atomicAdd(a.counters + 0, (unsigned long long)cnt[0]);
+            atomicAdd(a.counters + 1, (unsigned long long)cnt[1]);
+            atomicAdd(a.counters + 2, (unsigned long long)cnt[2]);
+        }
+        return;
+    }
     if (SLAB) {
         if (lane == 0) sl.logT_local[ray_id] = lt;
     } else {
@@ -262,11 +387,16 @@ __device__ __forceinline__ void corner_weights(float px, float py, float pz, flo
 // ---------------------------------------------------------------------------------------
 // K2: gather + colours, 8 lanes per sample
 // ---------------------------------------------------------------------------------------
-template <bool VEC, bool SLAB, bool MARK>
+template <bool VEC, int MODE, bool MARK>
 __global__ void __launch_bounds__(SAMPLE_THREADS)
 shade_kernel(GridView g, QueueView qv, float* __restrict__ rgb_out, SlabView sl, SlotMap sm) {
+    constexpr bool SLAB = MODE == 1, SHIP = MODE == 2;
     if (*qv.overflow) return;
-    const int n = min(*qv.counter, qv.capacity);
+    __shared__ int s_pre[SVOX2_MAX_PEERS + 1];
+    Regions rg;
+    regions_init<MODE>(qv, rg, s_pre);
+    int cur0 = 0, cur1 = 0;
+    const int n = rg.total;
     const int qi = threadIdx.x & 7;
     const int D = g.sh_dim, B = g.basis_dim;
     int ce[4];  // colour of each of this lane's channels (lane constant)
@@ -276,10 +406,11 @@ shade_kernel(GridView g, QueueView qv, float* __restrict__ rgb_out, SlabView sl,
     const unsigned gmask = 0xffu << (threadIdx.x & 24);  // the 8 lanes that share a sample
     const int groups = (gridDim.x * blockDim.x) >> 3;
     for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; s < n; s += groups) {
-        const Record* r = qv.rec + s;
+        const int si = region_index<MODE>(rg, s, cur0);
+        const Record* r = qv.rec + si;
 #if QM_GATHER_AHEAD & 1
         if (s + groups < n) {  // lane q of the group pulls corner q of the next record
-            const int32_t ln = __ldcg(&qv.rec[s + groups].lk[qi]);
+            const int32_t ln = __ldcg(&qv.rec[region_index<MODE>(rg, s + groups, cur1)].lk[qi]);
             if (ln >= 0) {
                 const float* row = g.sh + (size_t)ln * (unsigned)g.sh_stride;
                 prefetch_l2(row);
@@ -298,13 +429,13 @@ shade_kernel(GridView g, QueueView qv, float* __restrict__ rgb_out, SlabView sl,
             const float lt_in = __ldg(sl.lt_in + ray);
             const float before = __fadd_rn(lt_in, pw.w);
             if (fexp(before) < sl.stop_thresh) {
-                if (qi == 0) qv.rec[s].w = -1.f;
+                if (qi == 0) qv.rec[si].w = -1.f;
                 continue;
             }
             const float pcnt = __fmul_rn(st.z, st.y);
             pw.w = __fmul_rn(fexp(before), __fsub_rn(1.f, fexp(-pcnt)));
             if (qi == 0) {
-                qv.rec[s].w = pw.w;
+                qv.rec[si].w = pw.w;
                 if (fexp(__fadd_rn(lt_in, st.x)) < sl.stop_thresh) sl.stopped[(int64_t)ray * 4] = 1.f;
             }
         }
@@ -347,18 +478,22 @@ shade_kernel(GridView g, QueueView qv, float* __restrict__ rgb_out, SlabView sl,
         }
         if (qi < 3) {
             const float cv = qi == 0 ? col[0] : (qi == 1 ? col[1] : col[2]);
-            atomicAdd(rgb_out + (int64_t)ray * (SLAB ? 4 : 3) + qi, pw.w * fmaxf(cv, 0.f));
+            atomicAdd(rgb_out + (int64_t)ray * ((SLAB || SHIP) ? 4 : 3) + qi, pw.w * fmaxf(cv, 0.f));
         }
-        if (qi == 0) reinterpret_cast<float4*>(qv.rec + s)[4] = make_float4(col[0], col[1], col[2], 0.f);
+        if (qi == 0) reinterpret_cast<float4*>(qv.rec + si)[4] = make_float4(col[0], col[1], col[2], 0.f);
     }
 }
 
 // ---------------------------------------------------------------------------------------
 // K3: gradient seed + accum recursion per ray (cuvol.cu:248-264, 342-351, 735-747)
 // ---------------------------------------------------------------------------------------
-template <bool SLAB>
+template <int MODE>
 __global__ void __launch_bounds__(TRACE_THREADS)
 seed_kernel(Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
+    // SLAB: per-ray inputs (dL/drgb, accum at slab entry) come from the exchange, weights and
+    // transmittance are relative to the slab entry.  SHIP: the same inputs, but the records carry
+    // the tracer's exact weights / transmittance.
+    constexpr bool SLAB = MODE != 0, REL = MODE == 1;
     if (*qv.overflow) return;
     const int64_t ray_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (ray_id >= a.n_rays) return;
@@ -396,7 +531,7 @@ seed_kernel(Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
         if (!SLAB && a.accum_out != nullptr && lane == 0) a.accum_out[ray_id] = accum - beta_term;
         return;
     }
-    const float lt_in = SLAB ? __ldg(sl.lt_in + ray_id) : 0.f;
+    const float lt_in = REL ? __ldg(sl.lt_in + ray_id) : 0.f;
     if (SLAB) accum = __ldg(sl.accum_start + ray_id);  // seed and beta term of the whole ray
     while (blk >= 0) {
         const int count = __ldcg(&qv.rec[blk].blk_count);
@@ -406,8 +541,8 @@ seed_kernel(Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
         const float4 pw = __ldcg(reinterpret_cast<const float4*>(r) + 2);
         const float4 st = __ldcg(reinterpret_cast<const float4*>(r) + 3);
         const float4 co = __ldcg(reinterpret_cast<const float4*>(r) + 4);
-        if (SLAB) on = on && pw.w >= 0.f;  // dead: behind the stop threshold
-        const float w = pw.w, after = SLAB ? __fadd_rn(lt_in, st.x) : st.x, sigma = st.y, ws = st.z;
+        if (REL) on = on && pw.w >= 0.f;  // dead: behind the stop threshold
+        const float w = pw.w, after = REL ? __fadd_rn(lt_in, st.x) : st.x, sigma = st.y, ws = st.z;
         const float col[3] = {co.x, co.y, co.z};
         float gc[3], total = 0.f;
         {
@@ -448,11 +583,16 @@ seed_kernel(Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
 // ray lie next to each other in the queue) and keeps the gradient of the current cell in
 // registers; consecutive samples that fall into the same cell (~35 % at step 0.5) are merged
 // before the REDs leave the SM.  The basis table of the ray is re-read only when the ray changes.
-template <bool VEC, bool SLAB, bool SLOTS>
+template <bool VEC, int MODE, bool SLOTS>
 __global__ void __launch_bounds__(SAMPLE_THREADS)
 scatter_kernel(GridView g, QueueView qv, GradView gr, int64_t gsh_stride, int64_t gd_stride, SlotMap sm) {
+    constexpr bool SLAB = MODE == 1;
     if (*qv.overflow) return;
-    const int n = min(*qv.counter, qv.capacity);
+    __shared__ int s_pre[SVOX2_MAX_PEERS + 1];
+    Regions rg;
+    regions_init<MODE>(qv, rg, s_pre);
+    int cur0 = 0;
+    const int n = rg.total;
     const int qi = threadIdx.x & 7;
     const int D = g.sh_dim, B = g.basis_dim;
     int ce[4];
@@ -509,7 +649,7 @@ scatter_kernel(GridView g, QueueView qv, GradView gr, int64_t gsh_stride, int64_
     };
 
     for (int s = s0; s < s1; ++s) {
-        const Record* r = qv.rec + s;
+        const Record* r = qv.rec + region_index<MODE>(rg, s, cur0);
         const int4 la = __ldcg(reinterpret_cast<const int4*>(r));
         const int4 lb = __ldcg(reinterpret_cast<const int4*>(r) + 1);
         const float4 pw = __ldcg(reinterpret_cast<const float4*>(r) + 2);
@@ -607,6 +747,9 @@ static bool carve_queue(void* workspace, size_t workspace_bytes, int64_t n_rays,
     qv.rec = reinterpret_cast<Record*>(p);
     const size_t cap = (workspace_bytes - fixed) / sizeof(Record);
     qv.capacity = (int)(cap > (size_t)0x7ff00000 ? (size_t)0x7ff00000 : cap);
+    qv.counts = nullptr;
+    qv.n_regions = 0;
+    qv.region_cap = 0;
     return true;
 }
 
@@ -623,12 +766,12 @@ bool launch_queue_fused(const GridView& g, const Opts& opt, const MarchArgs& a, 
 
     clear_flags_kernel<<<1, 1, 0, st>>>(qv.counter, qv.overflow, qv.sticky);
     const unsigned ray_blocks = div_up(a.n_rays * WARP, TRACE_THREADS);
-    if (a.counters) trace_kernel<true, false><<<ray_blocks, TRACE_THREADS, 0, st>>>(g, opt, a, qv, none);
-    else trace_kernel<false, false><<<ray_blocks, TRACE_THREADS, 0, st>>>(g, opt, a, qv, none);
+    if (a.counters) trace_kernel<true, 0><<<ray_blocks, TRACE_THREADS, 0, st>>>(g, opt, a, qv, none, ShipView{});
+    else trace_kernel<false, 0><<<ray_blocks, TRACE_THREADS, 0, st>>>(g, opt, a, qv, none, ShipView{});
     const bool vec = march_vec_ok(g, &gr, a.gsh_stride);
     const unsigned sblocks = 148 * QM_SAMPLE_CTAS;  // persistent grid-stride CTAs of 256 threads
-    if (vec) shade_kernel<true, false, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, a.rgb_out, none, SlotMap{});
-    else shade_kernel<false, false, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, a.rgb_out, none, SlotMap{});
+    if (vec) shade_kernel<true, 0, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, a.rgb_out, none, SlotMap{});
+    else shade_kernel<false, 0, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, a.rgb_out, none, SlotMap{});
     // MSI scenes (cuvol.cu:1099-1149): the shells composite behind the foreground, so the background
     // forward pass sits between shade and seed (the seed needs the total colour) and its backward
     // pass takes over the accum the foreground recursion leaves.  Both skip an overflowed batch.
@@ -638,9 +781,9 @@ bool launch_queue_fused(const GridView& g, const Opts& opt, const MarchArgs& a, 
         launch_bg_fwd(false, g, opt, a, qv.ray_logT, st, qv.overflow, 0);
         s.accum_out = qv.ray_accum;
     }
-    seed_kernel<false><<<ray_blocks, TRACE_THREADS, 0, st>>>(opt, s, qv, none);
-    if (vec) scatter_kernel<true, false, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride, SlotMap{});
-    else scatter_kernel<false, false, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride, SlotMap{});
+    seed_kernel<0><<<ray_blocks, TRACE_THREADS, 0, st>>>(opt, s, qv, none);
+    if (vec) scatter_kernel<true, 0, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride, SlotMap{});
+    else scatter_kernel<false, 0, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride, SlotMap{});
     if (has_bg && gr.grad_bg)
         launch_bg_bwd(g, opt, a, a.rgb_out, qv.ray_logT, qv.ray_accum, gr, st, qv.overflow, 0);
     return true;
@@ -656,9 +799,9 @@ bool launch_step_trace_shade(const GridView& g, const Opts& opt, const MarchArgs
     if (!march_vec_ok(g, nullptr, 0)) return false;
     const SlabView none{};   // (the queue header was reset by the step's clear kernel)
     const unsigned ray_blocks = div_up(a.n_rays * WARP, TRACE_THREADS);
-    if (a.counters) trace_kernel<true, false><<<ray_blocks, TRACE_THREADS, 0, st>>>(g, opt, a, qv, none);
-    else trace_kernel<false, false><<<ray_blocks, TRACE_THREADS, 0, st>>>(g, opt, a, qv, none);
-    shade_kernel<true, false, true><<<148 * QM_SAMPLE_CTAS, SAMPLE_THREADS, 0, st>>>(g, qv, a.rgb_out, none, sm);
+    if (a.counters) trace_kernel<true, 0><<<ray_blocks, TRACE_THREADS, 0, st>>>(g, opt, a, qv, none, ShipView{});
+    else trace_kernel<false, 0><<<ray_blocks, TRACE_THREADS, 0, st>>>(g, opt, a, qv, none, ShipView{});
+    shade_kernel<true, 0, true><<<148 * QM_SAMPLE_CTAS, SAMPLE_THREADS, 0, st>>>(g, qv, a.rgb_out, none, sm);
     return true;
 }
 
@@ -679,7 +822,7 @@ bool launch_step_seed(const GridView& g, const Opts& opt, const MarchArgs& a, vo
     QueueView qv;
     if (!carve_queue(workspace, workspace_bytes, a.n_rays, qv)) return false;
     const SlabView none{};
-    seed_kernel<false><<<div_up(a.n_rays * WARP, TRACE_THREADS), TRACE_THREADS, 0, st>>>(opt, a, qv, none);
+    seed_kernel<0><<<div_up(a.n_rays * WARP, TRACE_THREADS), TRACE_THREADS, 0, st>>>(opt, a, qv, none);
     return true;
 }
 
@@ -688,7 +831,7 @@ bool launch_step_scatter(const GridView& g, const MarchArgs& a, void* workspace,
                          const SlotMap& sm, cudaStream_t st) {
     QueueView qv;
     if (!carve_queue(workspace, workspace_bytes, a.n_rays, qv)) return false;
-    scatter_kernel<true, false, true><<<148 * QM_SAMPLE_CTAS, SAMPLE_THREADS, 0, st>>>(g, qv, GradView{}, 0, 0, sm);
+    scatter_kernel<true, 0, true><<<148 * QM_SAMPLE_CTAS, SAMPLE_THREADS, 0, st>>>(g, qv, GradView{}, 0, 0, sm);
     return true;
 }
 
@@ -703,8 +846,8 @@ bool launch_slab_trace(const GridView& g, const Opts& opt, const MarchArgs& a, v
     sl.x_hi = x_hi;
     sl.logT_local = logT_local;
     clear_flags_kernel<<<1, 1, 0, st>>>(qv.counter, qv.overflow, qv.sticky);
-    trace_kernel<false, true><<<div_up(a.n_rays * WARP, TRACE_THREADS), TRACE_THREADS, 0, st>>>(
-        g, opt, a, qv, sl);
+    trace_kernel<false, 1><<<div_up(a.n_rays * WARP, TRACE_THREADS), TRACE_THREADS, 0, st>>>(
+        g, opt, a, qv, sl, ShipView{});
     return true;
 }
 
@@ -719,9 +862,9 @@ bool launch_slab_shade(const GridView& g, const Opts& opt, int64_t n_rays, void*
     sl.stop_thresh = opt.stop_thresh;
     const unsigned sblocks = 148 * QM_SAMPLE_CTAS;
     if (march_vec_ok(g, nullptr, 0))
-        shade_kernel<true, true, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, part, sl, SlotMap{});
+        shade_kernel<true, 1, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, part, sl, SlotMap{});
     else
-        shade_kernel<false, true, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, part, sl, SlotMap{});
+        shade_kernel<false, 1, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, part, sl, SlotMap{});
     return true;
 }
 
@@ -735,12 +878,176 @@ bool launch_slab_backward(const GridView& g, const Opts& opt, const MarchArgs& a
     sl.gout = gout;
     sl.accum_start = accum_start;
     sl.stop_thresh = opt.stop_thresh;
-    seed_kernel<true><<<div_up(a.n_rays * WARP, TRACE_THREADS), TRACE_THREADS, 0, st>>>(opt, a, qv, sl);
+    seed_kernel<1><<<div_up(a.n_rays * WARP, TRACE_THREADS), TRACE_THREADS, 0, st>>>(opt, a, qv, sl);
     const unsigned sblocks = 148 * QM_SAMPLE_CTAS;
     if (march_vec_ok(g, &gr, a.gsh_stride))
-        scatter_kernel<true, true, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride, SlotMap{});
+        scatter_kernel<true, 1, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride, SlotMap{});
     else
-        scatter_kernel<false, true, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride, SlotMap{});
+        scatter_kernel<false, 1, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, gr, a.gsh_stride, a.gd_stride, SlotMap{});
+    return true;
+}
+
+
+// ---- ship mode: rays sharded for the traversal, records shipped to the slab that owns the cell ---
+namespace {
+
+// Per-rank symmetric workspace (identical layout on every rank; byte offsets):
+//   0    queue header: [0] counter (unused), [128] overflow, [192] sticky overflow count
+//   256  counts[16]: records rank k shipped to me this step (written by rank k)
+//   384  cnt[16]: records I shipped to rank d so far (local)
+//   512  ray_first[Qg] | ray_logT[Qg] | ray_Y[Qg][8] | rec[G][region_cap]
+struct ShipWs {
+    QueueView qv;
+    int* counts;
+    int* cnt;
+};
+
+bool carve_ship(void* workspace, size_t bytes, int64_t n_rays_global, int n_slabs, int64_t region_cap,
+                ShipWs& w) {
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u) || n_slabs < 1 ||
+        n_slabs > SVOX2_MAX_PEERS || region_cap < 32 ||
+        bytes < ship_workspace_bytes(n_rays_global, n_slabs, region_cap))
+        return false;
+    char* p = static_cast<char*>(workspace);
+    QueueView& qv = w.qv;
+    qv.counter = reinterpret_cast<int*>(p);
+    qv.overflow = reinterpret_cast<int*>(p + 128);
+    qv.sticky = reinterpret_cast<int*>(p + 192);
+    w.counts = reinterpret_cast<int*>(p + 256);
+    w.cnt = reinterpret_cast<int*>(p + 384);
+    p += 512;
+    qv.ray_first = reinterpret_cast<int*>(p);
+    p += align_up((size_t)n_rays_global * 4, 256);
+    qv.ray_logT = reinterpret_cast<float*>(p);
+    p += align_up((size_t)n_rays_global * 4, 256);
+    qv.ray_accum = nullptr;
+    qv.ray_Y = reinterpret_cast<float4*>(p);
+    p += align_up((size_t)n_rays_global * 8 * 16, 256);
+    qv.rec = reinterpret_cast<Record*>(p);
+    qv.capacity = (int)(region_cap * n_slabs);
+    qv.counts = w.counts;
+    qv.n_regions = n_slabs;
+    qv.region_cap = (int)region_cap;
+    return true;
+}
+
+// SH basis table of every ray of the global batch (the sample-parallel kernels of this rank may see
+// samples of any ray)
+__global__ void __launch_bounds__(256)
+ray_basis_kernel(GridView g, const float* __restrict__ dirs, int64_t n_rays, float4* __restrict__ ray_Y) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t ray = t >> 3;
+    const int q = (int)(t & 7);
+    if (ray >= n_rays) return;
+    float dw[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) dw[i] = __ldg(dirs + ray * 3 + i);
+    float y[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int j = q * 4 + e;
+        y[e] = j < g.sh_dim ? sh_basis_k(g.basis_dim, j % g.basis_dim, dw) : 0.f;
+    }
+    ray_Y[ray * 8 + q] = make_float4(y[0], y[1], y[2], y[3]);
+}
+
+struct PeerInts {
+    int* p[SVOX2_MAX_PEERS];
+};
+// rank `me` tells every peer how many records it shipped there
+__global__ void ship_publish_kernel(PeerInts counts, const int* __restrict__ cnt, int n, int me, int cap) {
+    const int d = threadIdx.x;
+    if (d < n) counts.p[d][me] = min(cnt[d], cap);
+}
+
+// end of a step: forget this step's records (overflow folded into the sticky count first)
+__global__ void ship_reset_kernel(int* overflow, int* sticky, int* counts, int* cnt) {
+    const int t = threadIdx.x;
+    if (t == 0) {
+        if (*overflow) *sticky = (*sticky < 0 ? 0 : *sticky) + 1;
+        *overflow = 0;
+    }
+    if (t < SVOX2_MAX_PEERS) {
+        counts[t] = 0;
+        cnt[t] = 0;
+    }
+}
+
+}  // namespace
+
+size_t ship_workspace_bytes(int64_t n_rays_global, int n_slabs, int64_t region_cap) {
+    return 512 + align_up((size_t)n_rays_global * 4, 256) * 2 + align_up((size_t)n_rays_global * 8 * 16, 256) +
+           (size_t)n_slabs * (size_t)region_cap * sizeof(Record);
+}
+
+bool launch_ship_trace(const GridView& g, const Opts& opt, const MarchArgs& a, int64_t ray_offset,
+                       int64_t n_rays_global, const int* bounds, int n_slabs, int rank,
+                       const uint64_t* peer_ws, size_t workspace_bytes, int64_t region_cap, cudaStream_t st) {
+    ShipWs mine;
+    if (!carve_ship(reinterpret_cast<void*>(peer_ws[rank]), workspace_bytes, n_rays_global, n_slabs, region_cap, mine))
+        return false;
+    ShipView sv{};
+    PeerInts pc{};
+    for (int d = 0; d < n_slabs; ++d) {
+        ShipWs w;
+        if (!carve_ship(reinterpret_cast<void*>(peer_ws[d]), workspace_bytes, n_rays_global, n_slabs, region_cap, w))
+            return false;
+        sv.rec[d] = w.qv.rec + (size_t)rank * (size_t)region_cap;
+        sv.ray_first[d] = w.qv.ray_first;
+        sv.ray_logT[d] = w.qv.ray_logT;
+        sv.overflow[d] = w.qv.overflow;
+        pc.p[d] = w.counts;
+    }
+    for (int d = 0; d <= n_slabs; ++d) sv.bounds[d] = bounds[d];
+    sv.cnt = mine.cnt;
+    sv.n = n_slabs;
+    sv.region_base = rank * (int)region_cap;
+    sv.region_cap = (int)region_cap;
+    sv.ray_offset = ray_offset;
+    ray_basis_kernel<<<div_up(n_rays_global * 8, 256), 256, 0, st>>>(g, a.dirs, n_rays_global, mine.qv.ray_Y);
+    const SlabView none{};
+    const unsigned ray_blocks = div_up(a.n_rays * WARP, TRACE_THREADS);
+    if (a.counters) trace_kernel<true, 2><<<ray_blocks, TRACE_THREADS, 0, st>>>(g, opt, a, mine.qv, none, sv);
+    else trace_kernel<false, 2><<<ray_blocks, TRACE_THREADS, 0, st>>>(g, opt, a, mine.qv, none, sv);
+    ship_publish_kernel<<<1, 32, 0, st>>>(pc, mine.cnt, n_slabs, rank, (int)region_cap);
+    return true;
+}
+
+bool launch_ship_shade(const GridView& g, int64_t n_rays_global, void* workspace, size_t workspace_bytes,
+                       int n_slabs, int64_t region_cap, float* part, cudaStream_t st) {
+    ShipWs w;
+    if (!carve_ship(workspace, workspace_bytes, n_rays_global, n_slabs, region_cap, w)) return false;
+    const SlabView none{};
+    const unsigned sblocks = 148 * QM_SAMPLE_CTAS;
+    if (march_vec_ok(g, nullptr, 0))
+        shade_kernel<true, 2, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, w.qv, part, none, SlotMap{});
+    else
+        shade_kernel<false, 2, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, w.qv, part, none, SlotMap{});
+    return true;
+}
+
+const float* ship_ray_logT(void* workspace, size_t workspace_bytes, int64_t n_rays_global, int n_slabs,
+                           int64_t region_cap) {
+    ShipWs w;
+    if (!carve_ship(workspace, workspace_bytes, n_rays_global, n_slabs, region_cap, w)) return nullptr;
+    return w.qv.ray_logT;
+}
+
+bool launch_ship_backward(const GridView& g, const Opts& opt, const MarchArgs& a, const GradView& gr,
+                          void* workspace, size_t workspace_bytes, int n_slabs, int64_t region_cap,
+                          const float* gout, const float* accum_start, cudaStream_t st) {
+    ShipWs w;
+    if (!carve_ship(workspace, workspace_bytes, a.n_rays, n_slabs, region_cap, w)) return false;
+    SlabView sl{};
+    sl.gout = gout;
+    sl.accum_start = accum_start;
+    seed_kernel<2><<<div_up(a.n_rays * WARP, TRACE_THREADS), TRACE_THREADS, 0, st>>>(opt, a, w.qv, sl);
+    const unsigned sblocks = 148 * QM_SAMPLE_CTAS;
+    if (march_vec_ok(g, &gr, a.gsh_stride))
+        scatter_kernel<true, 2, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, w.qv, gr, a.gsh_stride, a.gd_stride, SlotMap{});
+    else
+        scatter_kernel<false, 2, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, w.qv, gr, a.gsh_stride, a.gd_stride, SlotMap{});
+    ship_reset_kernel<<<1, 32, 0, st>>>(w.qv.overflow, w.qv.sticky, w.counts, w.cnt);
     return true;
 }
 

@@ -370,3 +370,76 @@ extern "C" SVOX2_API int svox2_slab_backward(const svox2_grid_t* grid, int64_t n
                   "workspace too small or not 256-byte aligned (svox2_fused_workspace_bytes)");
     return check_launch(__func__);
 }
+
+// ---- ship mode (slab.py): rays sharded for the traversal, the grid for everything else ----------
+extern "C" SVOX2_API size_t svox2_ship_workspace_bytes(int64_t n_rays_global, int32_t n_slabs,
+                                                       int64_t region_cap) {
+    if (n_rays_global < 0 || n_slabs < 1 || region_cap < 0) return 0;
+    return ship_workspace_bytes(n_rays_global, n_slabs, region_cap);
+}
+
+extern "C" SVOX2_API int svox2_ship_trace(const svox2_grid_t* grid, const float* origins, const float* dirs,
+                                          int64_t n_rays_global, int64_t ray_begin, int64_t ray_count,
+                                          const svox2_render_opts_t* opt, const int32_t* slab_bounds,
+                                          int32_t n_slabs, int32_t rank, const uint64_t* peer_workspaces,
+                                          size_t workspace_bytes, int64_t region_cap, int64_t* counters,
+                                          svox2_stream_t stream) {
+    if (int e = validate_grid(grid, __func__)) return e;
+    if (int e = validate_rays(origins, dirs, n_rays_global, __func__)) return e;
+    if (int e = validate_opt(opt, __func__)) return e;
+    SVOX2_REQUIRE(n_slabs >= 1 && n_slabs <= SVOX2_MAX_PEERS && rank >= 0 && rank < n_slabs && slab_bounds &&
+                      peer_workspaces,
+                  "bad slab arguments");
+    SVOX2_REQUIRE(ray_begin >= 0 && ray_count >= 0 && ray_begin + ray_count <= n_rays_global, "bad ray range");
+    SVOX2_REQUIRE(grid->background_nlayers == 0, "slab mode does not support an MSI background");
+    for (int d = 0; d < n_slabs; ++d)
+        SVOX2_REQUIRE(slab_bounds[d] <= slab_bounds[d + 1] && peer_workspaces[d] != 0, "bad slab bounds / peer pointer");
+    if (n_rays_global == 0) return SVOX2_OK;
+    const GridView g = make_grid_view(grid);
+    MarchArgs a = base_args(origins, dirs, ray_count);
+    a.counters = reinterpret_cast<unsigned long long*>(counters);
+    SVOX2_REQUIRE(launch_ship_trace(g, *opt, a, ray_begin, n_rays_global, slab_bounds, n_slabs, rank,
+                                    peer_workspaces, workspace_bytes, region_cap, (cudaStream_t)stream),
+                  "workspace too small or not 256-byte aligned (svox2_ship_workspace_bytes)");
+    return check_launch(__func__);
+}
+
+extern "C" SVOX2_API int svox2_ship_shade(const svox2_grid_t* grid, int64_t n_rays_global, int32_t n_slabs,
+                                          int64_t region_cap, float* part, void* workspace,
+                                          size_t workspace_bytes, svox2_stream_t stream) {
+    if (int e = validate_grid(grid, __func__)) return e;
+    SVOX2_REQUIRE(part || n_rays_global == 0, "null argument");
+    if (n_rays_global == 0) return SVOX2_OK;
+    const GridView g = make_grid_view(grid);
+    SVOX2_REQUIRE(launch_ship_shade(g, n_rays_global, workspace, workspace_bytes, n_slabs, region_cap, part,
+                                    (cudaStream_t)stream),
+                  "workspace too small or not 256-byte aligned (svox2_ship_workspace_bytes)");
+    return check_launch(__func__);
+}
+
+extern "C" SVOX2_API const float* svox2_ship_ray_logT(void* workspace, size_t workspace_bytes,
+                                                      int64_t n_rays_global, int32_t n_slabs,
+                                                      int64_t region_cap) {
+    return ship_ray_logT(workspace, workspace_bytes, n_rays_global, n_slabs, region_cap);
+}
+
+extern "C" SVOX2_API int svox2_ship_backward(const svox2_grid_t* grid, int64_t n_rays_global,
+                                             const svox2_render_opts_t* opt, int32_t n_slabs,
+                                             int64_t region_cap, const float* gout, const float* accum_start,
+                                             float sparsity_loss, const svox2_grads_t* grads, void* workspace,
+                                             size_t workspace_bytes, svox2_stream_t stream) {
+    if (int e = validate_grid(grid, __func__)) return e;
+    if (int e = validate_opt(opt, __func__)) return e;
+    if (int e = validate_grads(grads, __func__)) return e;
+    SVOX2_REQUIRE((gout && accum_start) || n_rays_global == 0, "null argument");
+    if (n_rays_global == 0) return SVOX2_OK;
+    const GridView g = make_grid_view(grid);
+    const GradView gr = make_grad_view(grads);
+    MarchArgs a = base_args(nullptr, nullptr, n_rays_global);
+    set_grad_strides(a, grid, grads);
+    a.sparsity_loss = sparsity_loss;
+    SVOX2_REQUIRE(launch_ship_backward(g, *opt, a, gr, workspace, workspace_bytes, n_slabs, region_cap, gout,
+                                       accum_start, (cudaStream_t)stream),
+                  "workspace too small or not 256-byte aligned (svox2_ship_workspace_bytes)");
+    return check_launch(__func__);
+}

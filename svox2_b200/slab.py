@@ -23,6 +23,15 @@ plane) in its copy of density_data / sh_data goes stale; ``gather_params`` re-re
 
 Parity: same samples, same arithmetic per sample; the per-ray log-transmittance is a sum of
 per-slab partial sums instead of one sequential sum (~1e-7 relative), covered by the 1e-4 bar.
+
+SHIP MODE (default when the ranks can map each other's memory).  The scheme above makes every rank
+traverse the whole global batch -- traversal cost grows with the number of GPUs.  In ship mode the
+RAYS are sharded for the traversal: rank r traces rays [r*Q, (r+1)*Q) of the global batch exactly
+as the single-GPU kernel does (one sequential transmittance per ray, so the sample set, the stop
+decision and the weights are bit-identical to one GPU) and ships every active sample's 96-byte
+record to the rank that owns the sample's cell, with plain NVLink stores into region r of that
+rank's record queue (svox2_ship_trace).  Exchange A disappears; after one device-side barrier each
+rank shades the records it received, exchange B / halo / optimiser are as above.
 """
 from typing import List, Optional
 
@@ -60,7 +69,8 @@ class PeerMemory:
 
     WIDTH = 32
 
-    def __init__(self, group, world_size: int, rank: int, device, n_rays: int, halo_rows: int):
+    def __init__(self, group, world_size: int, rank: int, device, n_rays: int, halo_rows: int,
+                 ship_region_cap: int = 0):
         import torch.distributed._symmetric_memory as symm
         G, Q = world_size, n_rays
         self.world_size, self.rank, self.n_rays = G, rank, Q
@@ -74,6 +84,13 @@ class PeerMemory:
         self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         self.buf.zero_()
+        # ship mode: one record workspace per rank, every rank's mapped into every process
+        self.ship = None
+        if ship_region_cap > 0:
+            self.ship = _C.ShipWorkspace(Q, G, rank, ship_region_cap)
+            self.ship_buf = symm.empty(self.ship.nbytes, dtype=torch.uint8, device=device)
+            self.ship_hdl = symm.rendezvous(self.ship_buf, group if group is not None else dist.group.WORLD)
+            self.ship.bind(self.ship_buf, self.ship_hdl.buffer_ptrs)
         torch.cuda.synchronize()
         self.hdl.barrier(channel=0)
 
@@ -140,10 +157,24 @@ class SlabTrainer:
         x0 = int(at[0, 0].item()) if at.numel() else 0
         self._row0_owner = max(k for k in range(world_size) if self.bounds[k] <= x0)
         self._row0_pending = False      # a published row 0 waits in the peer buffer
+        # rows whose gradient depends on another rank (co-owned planes, row 0 at its holder) and the
+        # rest of the owned rows: the latter are updated while the halo swap is in flight
+        self._boundary = torch.zeros_like(self.own_mask)
+        for h in (self.halo_left, self.halo_right):
+            if h is not None:
+                self._boundary[h] = True
+        if self._holds_row0:
+            self._boundary[0] = True
+        self._interior = self.own_mask & ~self._boundary
+        self.overlap_halo = os.environ.get("SVOX2_B200_HALO_OVERLAP", "1") != "0"
         self._ws = None
         self.slots_per_ray = None  # record slots per ray of the workspace (None: min(diagonal, 512))
         self._peer = None          # PeerMemory for the current batch size, False if unavailable
+        self._density_ptrs = None  # ship mode: every rank's density_data, mapped into this process
         self.use_peer_memory = os.environ.get("SVOX2_B200_PEER", "1") != "0"
+        # "ship": rays sharded for the traversal, records shipped to the owning slab (needs peer
+        # memory and a batch divisible by the world size); "replicated": every rank traverses all rays
+        self.traversal = os.environ.get("SVOX2_B200_SLAB_TRAVERSAL", "ship")
         self._steps = 0
         # clear + trace, prefix, shade, combine, seed + scatter, TV x2, halo pack/unpack, optimiser x2
         self.kernels_per_step = 2 + 1 + 1 + 1 + 2 + (lambda_tv > 0) + (lambda_tv_sh > 0) + 2 + 2
@@ -173,13 +204,60 @@ class SlabTrainer:
                 halo = torch.tensor([max([h.numel() for h in (self.halo_left, self.halo_right)
                                           if h is not None] + [1])], device=self.grid.links.device)
                 dist.all_reduce(halo, op=dist.ReduceOp.MAX, group=self.group)
+                cap = 0
+                if self.traversal == "ship" and n_rays % self.world_size == 0:
+                    g = self.grid
+                    diag = sum(float(s) ** 2 for s in g.links.shape) ** 0.5
+                    slots = max(64, min(int(diag / max(float(g.opt.step_size), 1e-3)) + 2, 512))
+                    if self.slots_per_ray is not None:
+                        slots = max(64, int(self.slots_per_ray))
+                    # region r of a rank's queue holds what rank r traced inside this rank's slab:
+                    # at most all of its samples; the whole queue is capped at 2 GiB per rank
+                    cap = min(slots * (n_rays // self.world_size), (2 << 30) // 96 // self.world_size)
                 self._peer = PeerMemory(self.group, self.world_size, self.rank,
-                                        self.grid.links.device, n_rays, int(halo.item()))
+                                        self.grid.links.device, n_rays, int(halo.item()), cap)
+                if self._peer.ship is not None and self._density_ptrs is None:
+                    self._bind_symmetric_density()
             except Exception as e:      # no symmetric-memory support on this system / build
                 if self.rank == 0:
                     print(f"SlabTrainer: peer memory unavailable ({type(e).__name__}: {e}); using NCCL")
                 self._peer = False
         return self._peer or None
+
+    def _bind_symmetric_density(self):
+        """Ship mode keeps density_data replicated: re-home it in symmetric memory so that the owners
+        can store their updated rows straight into every rank's copy (svox2_publish_rows)."""
+        import torch.distributed._symmetric_memory as symm
+        g = self.grid
+        old = g.density_data.data
+        buf = symm.empty(old.numel(), dtype=torch.float32, device=old.device)
+        self._density_hdl = symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+        buf.copy_(old.reshape(-1))
+        requires_grad = g.density_data.requires_grad
+        g.density_data = torch.nn.Parameter(buf.view(-1, 1), requires_grad=requires_grad)
+        self._density_buf = buf
+        self._density_ptrs = [int(p) for p in self._density_hdl.buffer_ptrs]
+        # the first voxel plane of a slab is co-owned with the left neighbour, which applies the
+        # identical update to its own copy: publishing those rows to it would race with that update
+        self._excl_not_left = self.excl_mask.clone()
+        if self.halo_left is not None:
+            self._excl_not_left[self.halo_left] = False
+        torch.cuda.synchronize()
+        self._peer.hdl.barrier(channel=0)
+
+    def _publish_density(self):
+        """Updated density rows -> every rank's copy (NVLink stores; ordered before anybody's next
+        traversal by the barrier that opens the next step)."""
+        g = self.grid
+        G, r = self.world_size, self.rank
+        ptrs = list(self._density_ptrs)
+        if r > 0:
+            ptrs[r - 1] = 0     # the left neighbour gets everything but the co-owned plane
+        _C.publish_rows(g.sparse_grad_indexer, self.excl_mask, g.density_data.data, ptrs, r)
+        if r > 0:
+            only_left = [0] * G
+            only_left[r - 1] = self._density_ptrs[r - 1]
+            _C.publish_rows(g.sparse_grad_indexer, self._excl_not_left, g.density_data.data, only_left, r)
 
     def _gather(self, t: torch.Tensor, region: str) -> torch.Tensor:
         """[G, *t.shape]: t of every rank (this rank's own row is t itself)."""
@@ -231,6 +309,9 @@ class SlabTrainer:
         g._ensure_layout()
         Q = rgb_gt.size(0)
         dev = rgb_gt.device
+        peer = self._peer_memory(Q) if self.world_size > 1 else None
+        if peer is not None and peer.ship is not None:
+            return self._step_ship(rays, rgb_gt, lr_sigma, lr_sh, peer)
         ws = self._workspace(Q)
         spec, ropt, rspec = g._to_cpp(), g.opt._to_cpp(), rays._to_cpp()
         self._mark("start")
@@ -266,6 +347,55 @@ class SlabTrainer:
         _C.slab_backward(spec, Q, ropt, lt_in, gout, accum_start, self.sparsity_loss, holder, ws)
         g.sparse_sh_grad_indexer = g.sparse_grad_indexer.clone()
         self._mark("backward")
+        return self._finish_step(rgb, lr_sigma, lr_sh)
+
+    def _step_ship(self, rays: Rays, rgb_gt: torch.Tensor, lr_sigma, lr_sh, peer) -> torch.Tensor:
+        """Ship mode: trace my share of the rays, ship the records to their slabs, then shade /
+        back-propagate what I received (module docstring)."""
+        g = self.grid
+        Qg, G = rgb_gt.size(0), self.world_size
+        Q = Qg // G
+        dev = rgb_gt.device
+        ws = peer.ship
+        # basis + trace + publish, shade, peer store, combine, seed + scatter + reset, TV x2,
+        # halo pack/unpack, optimiser x2
+        self.kernels_per_step = 3 + 1 + 1 + 1 + 3 + (self.lambda_tv > 0) + (self.lambda_tv_sh > 0) + 2 + 2
+        spec, ropt = g._to_cpp(), g.opt._to_cpp()
+        # 0. everybody's density rows of the last step have landed in my copy
+        peer.hdl.barrier(channel=0)
+        self._refresh_row0()
+        self._mark("start")
+        # 1. traversal of my rays; records land in the owners' queues (NVLink stores)
+        _C.ship_trace(spec, rays._to_cpp(), ropt, self.rank * Q, Q, self.bounds, ws)
+        self._mark("trace")
+        peer.hdl.barrier(channel=1)
+        self._mark("exchange_a")
+        # 2. colours of the samples inside my slab, whoever traced them
+        part = torch.zeros((Qg, 4), dtype=torch.float32, device=dev)
+        _C.ship_shade(spec, part, ws)
+        self._mark("shade")
+        part_all = self._gather(part, "b")                                       # exchange B
+        rgb = torch.empty((Qg, 3), dtype=torch.float32, device=dev)
+        gout = torch.empty((Qg, 3), dtype=torch.float32, device=dev)
+        accum_start = torch.empty(Qg, dtype=torch.float32, device=dev)
+        _C.ship_combine(part_all, ws.ray_logT(), rays.dirs, rgb_gt, self.rank,
+                        g.opt.background_brightness, self.beta_loss, rgb, gout, accum_start)
+        self._mark("exchange_b")
+        # 3. gradients of my slab's samples; the queue is reset behind the scatter (the step's last
+        #    barrier, in the halo swap, orders that reset before anybody's next trace)
+        grad_density, grad_sh, _ = g._get_data_grads()
+        g.sparse_grad_indexer = torch.zeros(g.density_data.size(0), dtype=torch.bool, device=dev)
+        holder = _C.GridOutputGrads()
+        holder.grad_density_out, holder.grad_sh_out = grad_density, grad_sh
+        holder.mask_out = g.sparse_grad_indexer
+        _C.ship_backward(spec, ropt, gout, accum_start, self.sparsity_loss, holder, ws)
+        g.sparse_sh_grad_indexer = g.sparse_grad_indexer.clone()
+        self._mark("backward")
+        return self._finish_step(rgb, lr_sigma, lr_sh)
+
+    def _finish_step(self, rgb, lr_sigma, lr_sh):
+        """TV on the owned cells, halo swap, RMSProp on the owned rows."""
+        g = self.grid
         if self.lambda_tv > 0.0:
             runs, n = self._tv_runs()
             for run in runs:
@@ -280,14 +410,47 @@ class SlabTrainer:
 
         # 4. boundary planes: both neighbours add each other's gradients (a + b == b + a, so the
         #    two copies of a co-owned plane stay bit-identical), then RMSProp on the owned rows
-        self._halo_grads()
-        g.sparse_grad_indexer &= self.own_mask
-        g.sparse_sh_grad_indexer &= self.own_mask
-        self._mark("halo_grads")
-        g.optim_density_step(self.lr_sigma if lr_sigma is None else lr_sigma, beta=self.rms_beta)
-        g.optim_sh_step(self.lr_sh if lr_sh is None else lr_sh, beta=self.rms_beta)
-        self._publish_row0()
-        self._mark("optimiser")
+        lr_d = self.lr_sigma if lr_sigma is None else lr_sigma
+        lr_s = self.lr_sh if lr_sh is None else lr_sh
+        ship = self._density_ptrs is not None and self._peer not in (None, False) and self._peer.ship is not None
+        peer = self._peer if (self._peer not in (None, False)) else None
+        width = _C.packed_row_floats(g.sh_data.grad.size(1) + 2)
+        if self.world_size > 1 and peer is not None and width == peer.WIDTH and self.overlap_halo:
+            # peer memory: send the boundary planes, update the INTERIOR rows while the packets and
+            # the barrier are in flight, then add what arrived and update the boundary rows
+            self._halo_send(peer, width)
+            md, msh = g.sparse_grad_indexer, g.sparse_sh_grad_indexer
+            self._mark("halo_grads")
+            g.sparse_grad_indexer = md & self._interior
+            g.sparse_sh_grad_indexer = msh & self._interior
+            g.optim_density_step(lr_d, beta=self.rms_beta)
+            g.optim_sh_step(lr_s, beta=self.rms_beta)
+            self._mark("optimiser")
+            self._halo_recv(peer, width, md, msh)
+            g.sparse_grad_indexer = md & self._boundary
+            g.sparse_sh_grad_indexer = msh & self._boundary
+            g.optim_density_step(lr_d, beta=self.rms_beta)
+            g.optim_sh_step(lr_s, beta=self.rms_beta)
+            # the masks of the step, for callers (owned rows; both groups were updated above)
+            g.sparse_grad_indexer, g.sparse_sh_grad_indexer = md, msh
+            if not self._holds_row0:
+                md[0] = False
+                msh[0] = False
+            if ship:
+                self._publish_density()
+            self._publish_row0()
+            self._mark("halo_grads")
+        else:
+            self._halo_grads()
+            g.sparse_grad_indexer &= self.own_mask
+            g.sparse_sh_grad_indexer &= self.own_mask
+            self._mark("halo_grads")
+            g.optim_density_step(lr_d, beta=self.rms_beta)
+            if ship:
+                self._publish_density()
+            g.optim_sh_step(lr_s, beta=self.rms_beta)
+            self._publish_row0()
+            self._mark("optimiser")
 
         if self._steps % 256 == 0:
             self.check_overflow()
@@ -298,7 +461,8 @@ class SlabTrainer:
         """Raise if any step since the last check ran out of sample-record space (its colours and
         gradients were dropped).  The trace kernel keeps a sticky count in the workspace, so the
         check can be made at any host sync point (every 256 steps, logging, gather_params)."""
-        if self._ws is not None and _C.slab_overflowed(self._ws[1]):
+        ship = self._peer.ship if self._peer not in (None, False) else None
+        if (self._ws is not None and _C.slab_overflowed(self._ws[1])) or (ship is not None and ship.overflowed()):
             raise RuntimeError(
                 "SlabTrainer: the sample-record workspace overflowed in at least one step since "
                 "the last check (those steps contributed no colour / gradient); raise "
@@ -335,6 +499,42 @@ class SlabTrainer:
         g = self.grid
         slot = peer.buf[peer.off_p:peer.off_p + peer.WIDTH].view(1, peer.WIDTH)
         _C.unpack_rows(slot, self._row0, g.sh_data.data, g.density_data.data, False)
+
+    def _halo_send(self, peer, width):
+        """Peer-memory halo swap, first half: row-0 packet and the two boundary planes go straight
+        into the neighbours' inboxes (NVLink stores)."""
+        g = self.grid
+        gsh, gd = g.sh_data.grad, g.density_data.grad
+        md, msh = g.sparse_grad_indexer, g.sparse_sh_grad_indexer
+        z = torch.zeros((1, width), dtype=torch.float32, device=gsh.device)
+        if not self._holds_row0:
+            _C.pack_grad_rows(gsh, gd, self._row0, z, mask_a=md, mask_b=msh)
+            gsh[0] = 0.0
+            gd[0] = 0.0
+        _C.peer_store(peer.ptrs, (peer.off_z + self.rank * width) * 4, z)
+        if self.halo_right is not None and self.halo_right.numel():
+            _C.pack_grad_rows(gsh, gd, self.halo_right,
+                              peer.neighbour_inbox(self.rank + 1, True, self.halo_right.numel()),
+                              mask_a=md, mask_b=msh)
+        if self.halo_left is not None and self.halo_left.numel():
+            _C.pack_grad_rows(gsh, gd, self.halo_left,
+                              peer.neighbour_inbox(self.rank - 1, False, self.halo_left.numel()),
+                              mask_a=md, mask_b=msh)
+
+    def _halo_recv(self, peer, width, md, msh):
+        """Second half: barrier, then add what the neighbours sent (gradients and mask bits)."""
+        g = self.grid
+        gsh, gd = g.sh_data.grad, g.density_data.grad
+        peer.hdl.barrier(channel=3)
+        if self.halo_left is not None and self.halo_left.numel():
+            _C.unpack_rows(peer.inbox(True, self.halo_left.numel()), self.halo_left, gsh, gd, True,
+                           mask_a=md, mask_b=msh)
+        if self.halo_right is not None and self.halo_right.numel():
+            _C.unpack_rows(peer.inbox(False, self.halo_right.numel()), self.halo_right, gsh, gd, True,
+                           mask_a=md, mask_b=msh)
+        if self._holds_row0:
+            zs = peer.buf[peer.off_z:peer.off_z + self.world_size * width].view(self.world_size, width)
+            _C.unpack_rows(zs.sum(0, keepdim=True), self._row0, gsh, gd, True, mask_a=md, mask_b=msh)
 
     def _halo_grads(self):
         """The first voxel plane of every slab is co-owned with the left neighbour (its last cell
