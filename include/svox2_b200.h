@@ -419,6 +419,16 @@ SVOX2_API int svox2_publish_rows(const uint8_t* mask, const uint8_t* own, const 
                      int64_t stride, const uint64_t* peer_base_ptrs, int32_t n_peers, int32_t self_rank,
                      svox2_stream_t stream);
 
+/* Masked RMSProp (optim_kernel.cu:15-25) on a single-channel array that ship mode keeps replicated
+ * (density), with the publication fused in: send[row] = 0 keeps the new value local, 1 stores it at
+ * the same offset of every peer's array, 2 of every peer but `skip_peer` (a co-owner of the row that
+ * applies the identical update itself). */
+SVOX2_API int svox2_rmsprop_step_publish(float* data, float* rms, float* grad, int64_t rows,
+                     int64_t row_stride, const uint8_t* mask, const uint8_t* send,
+                     const uint64_t* peer_base_ptrs, int32_t n_peers, int32_t self_rank,
+                     int32_t skip_peer, float beta, float lr, float epsilon, float minval,
+                     svox2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -132,6 +132,7 @@ SIGNATURES = {
     "svox2_ship_ray_logT": (_P, [_P, _SZ, _I64, _I32, _I64]),
     "svox2_ship_combine": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _F, _F, _P, _P, _P, _P]),
     "svox2_ship_backward": (C.c_int, [_G, _I64, _O, _I32, _I64, _P, _P, _F, _GR, _P, _SZ, _P]),
+    "svox2_rmsprop_step_publish": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _P, _P, _I32, _I32, _I32, _F, _F, _F, _F, _P]),
     "svox2_publish_rows": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _I32, _I32, _P]),
     "svox2_pack_grad_rows": (C.c_int, [_P, _I64, _I32, _P, _I64, _P, _I64, _P, _I64, _P, _P, _P]),
     "svox2_unpack_rows": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I32, _P, _I64, _I32, _P, _P, _P]),

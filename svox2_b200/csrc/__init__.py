@@ -942,6 +942,26 @@ def ship_backward(grid, opt, gout, accum_start, sparsity_loss, grads, ws: ShipWo
             _stream()))
 
 
+def rmsprop_step_publish(data, rms, grad, mask, send, peer_ptrs, self_rank, skip_peer, beta, lr, epsilon,
+                         minval=-1e9):
+    """Masked RMSProp on a replicated single-channel array + publication of the updated rows
+    (send: uint8 per row, 0 local only / 1 every peer / 2 every peer but ``skip_peer``)."""
+    for t_, n_ in ((data, "data"), (rms, "rms"), (grad, "grad")):
+        _check_rows(t_, n_)
+    if data.size(1) != 1 or not (_row_stride(data) == _row_stride(rms) == _row_stride(grad)):
+        _fail("data, rms and grad must be [N,1] arrays of one layout")
+    _check_cuda(mask, "mask", torch.bool, 1)
+    _check_cuda(send, "send", torch.uint8, 1)
+    if mask.numel() != data.size(0) or send.numel() != data.size(0):
+        _fail("mask / send must have one entry per row")
+    arr = (C.c_uint64 * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+    with torch.cuda.device(data.device):
+        check(_lib.lib().svox2_rmsprop_step_publish(
+            data.data_ptr(), rms.data_ptr(), grad.data_ptr(), data.size(0), _row_stride(data), mask.data_ptr(),
+            send.data_ptr(), C.addressof(arr), len(peer_ptrs), int(self_rank), int(skip_peer), float(beta),
+            float(lr), float(epsilon), float(minval), _stream()))
+
+
 def publish_rows(mask, own, data, peer_ptrs, self_rank):
     """data[row] -> the same row of every peer's array, for rows with mask & own (ship mode keeps
     density_data replicated; ``peer_ptrs[p]`` = rank p's array mapped into this process)."""

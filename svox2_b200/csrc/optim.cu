@@ -270,6 +270,27 @@ masked_scalar_kernel(OptArgs a) {
         }
 }
 
+// Ship mode (slab.py): masked RMSProp on a single-channel array that is kept REPLICATED over the
+// ranks (density): the owner of a row updates it and stores the new value into every peer's copy
+// (NVLink stores, lane = row).  send[row]: 0 = not mine to publish, 1 = to every peer, 2 = to every
+// peer but `skip_peer` (a co-owner that applies the identical update to its own copy).
+struct PublishPeers {
+    float* base[SVOX2_MAX_PEERS];
+    int n, self, skip_peer;
+};
+__global__ void __launch_bounds__(256)
+masked_scalar_publish_kernel(OptArgs a, const uint8_t* __restrict__ send, PublishPeers peers) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= a.rows || __ldg(a.mask + row) == 0) return;
+    const int64_t off = row * a.stride;
+    rmsprop_once(a.data + off, a.rms + off, a.grad + off, a.beta, a.lr_last, a.eps, a.minval);
+    const int mode = __ldg(send + row);
+    if (mode == 0) return;
+    const float v = a.data[off];
+    for (int p = 0; p < peers.n; ++p)
+        if (p != peers.self && !(mode == 2 && p == peers.skip_peer)) peers.base[p][off] = v;
+}
+
 // dense / index variants and single-channel arrays: one thread per (row, channel) element
 template <bool RMS, int KIND>
 __global__ void __launch_bounds__(OPT_THREADS)
@@ -368,6 +389,30 @@ extern "C" SVOX2_API int svox2_rmsprop_step(float* data, float* rms, float* grad
     OptArgs a{data, rms, grad, rows, n_channels, row_stride, mask, index,
               beta, lr, epsilon, minval, lr_last};
     launch<true>(a, indexer_kind, n_index, (cudaStream_t)stream);
+    return check_launch(__func__);
+}
+
+extern "C" SVOX2_API int svox2_rmsprop_step_publish(float* data, float* rms, float* grad, int64_t rows,
+                                                    int64_t row_stride, const uint8_t* mask,
+                                                    const uint8_t* send, const uint64_t* peer_base_ptrs,
+                                                    int32_t n_peers, int32_t self_rank, int32_t skip_peer,
+                                                    float beta, float lr, float epsilon, float minval,
+                                                    svox2_stream_t stream) {
+    SVOX2_REQUIRE(rows >= 0 && row_stride >= 1, "bad shape");
+    if (rows == 0) return SVOX2_OK;
+    SVOX2_REQUIRE(data && rms && grad && mask && send && peer_base_ptrs, "null argument");
+    SVOX2_REQUIRE(n_peers >= 1 && n_peers <= SVOX2_MAX_PEERS && self_rank >= 0 && self_rank < n_peers,
+                  "bad peer arguments");
+    PublishPeers peers;
+    peers.n = n_peers;
+    peers.self = self_rank;
+    peers.skip_peer = skip_peer;
+    for (int p = 0; p < n_peers; ++p) {
+        SVOX2_REQUIRE(peer_base_ptrs[p] != 0, "bad peer pointer");
+        peers.base[p] = reinterpret_cast<float*>(peer_base_ptrs[p]);
+    }
+    OptArgs a{data, rms, grad, rows, 1, row_stride, mask, nullptr, beta, lr, epsilon, minval, lr};
+    masked_scalar_publish_kernel<<<div_up(rows, 256), 256, 0, (cudaStream_t)stream>>>(a, send, peers);
     return check_launch(__func__);
 }
 

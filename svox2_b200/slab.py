@@ -166,7 +166,9 @@ class SlabTrainer:
         if self._holds_row0:
             self._boundary[0] = True
         self._interior = self.own_mask & ~self._boundary
-        self.overlap_halo = os.environ.get("SVOX2_B200_HALO_OVERLAP", "1") != "0"
+        # A/B on 2 GPUs (profiles/r2_ab_variants.txt): the split costs four mask passes and two extra
+        # optimiser scans over the N-row arrays, more than the barrier wait it hides -> off by default
+        self.overlap_halo = os.environ.get("SVOX2_B200_HALO_OVERLAP", "0") != "0"
         self._ws = None
         self.slots_per_ray = None  # record slots per ray of the workspace (None: min(diagonal, 512))
         self._peer = None          # PeerMemory for the current batch size, False if unavailable
@@ -174,7 +176,11 @@ class SlabTrainer:
         self.use_peer_memory = os.environ.get("SVOX2_B200_PEER", "1") != "0"
         # "ship": rays sharded for the traversal, records shipped to the owning slab (needs peer
         # memory and a batch divisible by the world size); "replicated": every rank traverses all rays
-        self.traversal = os.environ.get("SVOX2_B200_SLAB_TRAVERSAL", "ship")
+        # "auto": ship from 4 ranks up -- at 2 ranks the redundant traversal costs less than the two
+        # extra barriers of ship mode (measured, profiles/r2_ab_variants.txt)
+        self.traversal = os.environ.get("SVOX2_B200_SLAB_TRAVERSAL", "auto")
+        if self.traversal == "auto":
+            self.traversal = "ship" if world_size >= 4 else "replicated"
         self._steps = 0
         # clear + trace, prefix, shade, combine, seed + scatter, TV x2, halo pack/unpack, optimiser x2
         self.kernels_per_step = 2 + 1 + 1 + 1 + 2 + (lambda_tv > 0) + (lambda_tv_sh > 0) + 2 + 2
@@ -239,25 +245,20 @@ class SlabTrainer:
         self._density_ptrs = [int(p) for p in self._density_hdl.buffer_ptrs]
         # the first voxel plane of a slab is co-owned with the left neighbour, which applies the
         # identical update to its own copy: publishing those rows to it would race with that update
-        self._excl_not_left = self.excl_mask.clone()
+        self._send = self.excl_mask.to(torch.uint8)          # 1: publish to every peer
         if self.halo_left is not None:
-            self._excl_not_left[self.halo_left] = False
+            self._send[self.halo_left] = 2                   # 2: every peer but the left neighbour
         torch.cuda.synchronize()
         self._peer.hdl.barrier(channel=0)
 
-    def _publish_density(self):
-        """Updated density rows -> every rank's copy (NVLink stores; ordered before anybody's next
-        traversal by the barrier that opens the next step)."""
+    def _density_step_publish(self, lr):
+        """Masked RMSProp on the (replicated) density array with the publication of the updated rows
+        fused in (NVLink stores; ordered before anybody's next traversal by the barrier that opens
+        the next step)."""
         g = self.grid
-        G, r = self.world_size, self.rank
-        ptrs = list(self._density_ptrs)
-        if r > 0:
-            ptrs[r - 1] = 0     # the left neighbour gets everything but the co-owned plane
-        _C.publish_rows(g.sparse_grad_indexer, self.excl_mask, g.density_data.data, ptrs, r)
-        if r > 0:
-            only_left = [0] * G
-            only_left[r - 1] = self._density_ptrs[r - 1]
-            _C.publish_rows(g.sparse_grad_indexer, self._excl_not_left, g.density_data.data, only_left, r)
+        g._ensure_rms()
+        _C.rmsprop_step_publish(g.density_data.data, g.density_rms, g.density_data.grad, g.sparse_grad_indexer,
+                                self._send, self._density_ptrs, self.rank, self.rank - 1, self.rms_beta, lr, 1e-8)
 
     def _gather(self, t: torch.Tensor, region: str) -> torch.Tensor:
         """[G, *t.shape]: t of every rank (this rank's own row is t itself)."""
@@ -423,31 +424,37 @@ class SlabTrainer:
             self._mark("halo_grads")
             g.sparse_grad_indexer = md & self._interior
             g.sparse_sh_grad_indexer = msh & self._interior
-            g.optim_density_step(lr_d, beta=self.rms_beta)
+            if ship:
+                self._density_step_publish(lr_d)
+            else:
+                g.optim_density_step(lr_d, beta=self.rms_beta)
             g.optim_sh_step(lr_s, beta=self.rms_beta)
             self._mark("optimiser")
             self._halo_recv(peer, width, md, msh)
             g.sparse_grad_indexer = md & self._boundary
             g.sparse_sh_grad_indexer = msh & self._boundary
-            g.optim_density_step(lr_d, beta=self.rms_beta)
+            if ship:
+                self._density_step_publish(lr_d)
+            else:
+                g.optim_density_step(lr_d, beta=self.rms_beta)
             g.optim_sh_step(lr_s, beta=self.rms_beta)
             # the masks of the step, for callers (owned rows; both groups were updated above)
             g.sparse_grad_indexer, g.sparse_sh_grad_indexer = md, msh
             if not self._holds_row0:
                 md[0] = False
                 msh[0] = False
-            if ship:
-                self._publish_density()
             self._publish_row0()
             self._mark("halo_grads")
         else:
             self._halo_grads()
-            g.sparse_grad_indexer &= self.own_mask
-            g.sparse_sh_grad_indexer &= self.own_mask
+            if not self._holds_row0:    # the only rows outside own_mask a step can touch (TV face cells)
+                g.sparse_grad_indexer[0] = False
+                g.sparse_sh_grad_indexer[0] = False
             self._mark("halo_grads")
-            g.optim_density_step(lr_d, beta=self.rms_beta)
             if ship:
-                self._publish_density()
+                self._density_step_publish(lr_d)
+            else:
+                g.optim_density_step(lr_d, beta=self.rms_beta)
             g.optim_sh_step(lr_s, beta=self.rms_beta)
             self._publish_row0()
             self._mark("optimiser")

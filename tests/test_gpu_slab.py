@@ -81,7 +81,13 @@ def _worker(rank, world, port, out, case="default"):
     try:
         m = {}
         opts = OPTS
-        if case == "stop":
+        # traversal mode of the slab step: "auto" ships records from 4 ranks up (slab.py); the
+        # "ship*" / "replicated*" cases force one mode so that both run at every world size
+        if case.startswith("ship"):
+            os.environ["SVOX2_B200_SLAB_TRAVERSAL"] = "ship"
+        elif case.startswith("replicated"):
+            os.environ["SVOX2_B200_SLAB_TRAVERSAL"] = "replicated"
+        if case.endswith("stop"):
             # rays that terminate by the stop threshold INSIDE a later slab: dense blobs and a high
             # threshold make most rays stop; the mask then tells whether every slab agreed on the
             # sample at which the reference stops (per-slab partial sums of logT)
@@ -91,7 +97,7 @@ def _worker(rank, world, port, out, case="default"):
             sc = make_scene(reso=48, basis_dim=9, seed=41, n_rays=4096)
         kw = dict(beta_loss=0.05)
         ref, rgb1 = _reference_step(sv, sc, dev, 7, opts=opts, **kw)
-        if case == "stop":
+        if case.endswith("stop"):
             free = make_grid(sv, sc, dev)
             set_opt(free, sigma_thresh=1e-8, stop_thresh=0.0)
             with torch.no_grad():
@@ -150,7 +156,8 @@ def _worker(rank, world, port, out, case="default"):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,case", [(2, "default"), (2, "stop"), (4, "default"), (4, "stop"),
+@pytest.mark.parametrize("world,case", [(2, "default"), (2, "stop"), (2, "ship"), (2, "ship_stop"),
+                                        (4, "default"), (4, "stop"), (4, "replicated_stop"),
                                         (8, "default"), (8, "stop")])
 def test_multi_gpu_slab_step_equals_single_gpu_step(world, case):
     if torch.cuda.device_count() < world:
