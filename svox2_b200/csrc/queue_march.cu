@@ -46,6 +46,9 @@ namespace {
 #ifndef QM_TRACE_BLOCKS
 #define QM_TRACE_BLOCKS 16
 #endif
+#ifndef QM_SCATTER_BLOCKS
+#define QM_SCATTER_BLOCKS 1   // min resident CTAs per SM asked of ptxas for K4 (register cap = 65536 / (256 * n))
+#endif
 
 constexpr int TRACE_THREADS = 64;
 constexpr int SAMPLE_THREADS = 256;
@@ -584,7 +587,7 @@ seed_kernel(Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
 // registers; consecutive samples that fall into the same cell (~35 % at step 0.5) are merged
 // before the REDs leave the SM.  The basis table of the ray is re-read only when the ray changes.
 template <bool VEC, int MODE, bool SLOTS>
-__global__ void __launch_bounds__(SAMPLE_THREADS)
+__global__ void __launch_bounds__(SAMPLE_THREADS, QM_SCATTER_BLOCKS)
 scatter_kernel(GridView g, QueueView qv, GradView gr, int64_t gsh_stride, int64_t gd_stride, SlotMap sm) {
     constexpr bool SLAB = MODE == 1;
     if (*qv.overflow) return;

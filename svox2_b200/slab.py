@@ -45,6 +45,11 @@ from . import csrc as _C
 from .grid import Rays
 
 
+# "auto" traversal: ship records from this many ranks up (below, the redundant traversal is cheaper
+# than ship mode's two extra barriers)
+SHIP_FROM_WORLD = 4
+
+
 def balanced_slabs(links: torch.Tensor, world_size: int) -> List[int]:
     """x boundaries b_0=0 < ... < b_G=X splitting the stored voxels evenly between ranks."""
     X = links.size(0)
@@ -180,7 +185,7 @@ class SlabTrainer:
         # extra barriers of ship mode (measured, profiles/r2_ab_variants.txt)
         self.traversal = os.environ.get("SVOX2_B200_SLAB_TRAVERSAL", "auto")
         if self.traversal == "auto":
-            self.traversal = "ship" if world_size >= 4 else "replicated"
+            self.traversal = "ship" if world_size >= SHIP_FROM_WORLD else "replicated"
         self._steps = 0
         # clear + trace, prefix, shade, combine, seed + scatter, TV x2, halo pack/unpack, optimiser x2
         self.kernels_per_step = 2 + 1 + 1 + 1 + 2 + (lambda_tv > 0) + (lambda_tv_sh > 0) + 2 + 2
