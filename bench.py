@@ -347,6 +347,8 @@ def multi_gpu_parity(sv, grid, trainer, slab, step, global_batches, local_batche
         mine = slice(None) if slab else slice(rank * rgb.size(0), (rank + 1) * rgb.size(0))
         out["rgb_max_abs" if it == 0 else "rgb_max_abs_step2"] = float((rgb - rgb1[mine]).abs().max())
         if it == 0:
+            if grid.sparse_grad_indexer is None and hasattr(trainer, "export_masks"):
+                trainer.export_masks()      # slot-based step: masks live as slot flags until asked for
             rows = trainer.own_mask if slab else torch.ones_like(ref.sparse_grad_indexer)
             out["mask_equal"] = bool(
                 torch.equal(grid.sparse_grad_indexer[rows], ref.sparse_grad_indexer[rows]) and

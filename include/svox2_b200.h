@@ -429,6 +429,55 @@ SVOX2_API int svox2_rmsprop_step_publish(float* data, float* rms, float* grad, i
                      int32_t skip_peer, float beta, float lr, float epsilon, float minval,
                      svox2_stream_t stream);
 
+/* Multi-GPU train step on the compact gradient buffer (step.cu; host side svox2_b200/slab.py): the
+ * single-call step above cut at the points where the x-slab ranks exchange per-ray scalars and
+ * boundary planes.  `step_ws` is a svox2_train_step workspace sized for the GLOBAL batch; in ship
+ * mode the sample records live in the symmetric ship workspaces instead of its queue part.
+ *   svox2_mg_step_begin     clear, TV marking of this rank's pieces of the step's two TV runs,
+ *                           boundary rows (co-owned planes, row 0) entered into the touched set, traversal
+ *   svox2_mg_step_shade     part[Qg,4] += colours of this slab's records; touched-row bits
+ *   svox2_mg_step_backward  slot numbering, seed, scatter -> slot rows, TV -> slot rows
+ *   svox2_mg_slot_pack / svox2_mg_slot_unpack_add   boundary rows <-> 32-float packets
+ *                           [slot row | density flag | SH flag] (the layout of svox2_pack_grad_rows)
+ *   svox2_mg_step_finish    RMSProp over the slot list; with send / peer_density (ship mode) the new
+ *                           density of a row is also stored into the peers' copies (see
+ *                           svox2_rmsprop_step_publish for the send codes; skip_peer = rank - 1) */
+typedef struct svox2_mg_step_t {
+    int32_t n_slabs, rank, x_lo, x_hi;
+    int32_t ship;                                      /* 0: every rank traverses all rays; 1: ship mode */
+    int64_t tv_density_start[2], tv_density_count[2];  /* this rank's pieces of the density TV run        */
+    int64_t tv_sh_start[2], tv_sh_count[2];
+    float tv_density_scale, tv_sh_scale;               /* lambda; 0 disables                              */
+    int64_t tv_density_scale_cells, tv_sh_scale_cells; /* cells of the WHOLE run (the normaliser)         */
+    float sparsity_loss;
+    float lr_density, lr_sh, rms_beta, epsilon;
+} svox2_mg_step_t;
+SVOX2_API int svox2_mg_step_begin(const svox2_grid_t* grid, const float* origins, const float* dirs,
+                     int64_t n_rays_global, const svox2_render_opts_t* opt, const svox2_mg_step_t* params,
+                     const int64_t* boundary_rows, int64_t n_boundary, void* step_ws, size_t step_ws_bytes,
+                     int64_t slots_per_ray, float* logT_local, const int32_t* slab_bounds,
+                     const uint64_t* peer_ship_workspaces, size_t ship_ws_bytes, int64_t region_cap,
+                     svox2_stream_t stream);
+SVOX2_API int svox2_mg_step_shade(const svox2_grid_t* grid, int64_t n_rays_global,
+                     const svox2_render_opts_t* opt, const svox2_mg_step_t* params, const float* lt_in,
+                     float* part, void* step_ws, size_t step_ws_bytes, int64_t slots_per_ray, void* ship_ws,
+                     size_t ship_ws_bytes, int64_t region_cap, svox2_stream_t stream);
+SVOX2_API int svox2_mg_step_backward(const svox2_grid_t* grid, int64_t n_rays_global,
+                     const svox2_render_opts_t* opt, const svox2_mg_step_t* params, const float* lt_in,
+                     const float* gout, const float* accum_start, void* step_ws, size_t step_ws_bytes,
+                     int64_t slots_per_ray, void* ship_ws, size_t ship_ws_bytes, int64_t region_cap,
+                     svox2_stream_t stream);
+SVOX2_API int svox2_mg_slot_pack(const int64_t* rows, int64_t n_sel, float* packed, int64_t pack_stride,
+                     int32_t clear, void* step_ws, size_t step_ws_bytes, int64_t n_rows, int32_t basis_dim,
+                     int64_t n_rays, int64_t slots_per_ray, svox2_stream_t stream);
+SVOX2_API int svox2_mg_slot_unpack_add(const float* packed, int64_t pack_stride, const int64_t* rows,
+                     int64_t n_sel, void* step_ws, size_t step_ws_bytes, int64_t n_rows, int32_t basis_dim,
+                     int64_t n_rays, int64_t slots_per_ray, svox2_stream_t stream);
+SVOX2_API int svox2_mg_step_finish(const svox2_grid_t* grid, float* density_rms, float* sh_rms,
+                     int64_t n_rays_global, const svox2_mg_step_t* params, const uint8_t* send,
+                     const uint64_t* peer_density, void* step_ws, size_t step_ws_bytes,
+                     int64_t slots_per_ray, svox2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,6 +79,19 @@ class StepParamsT(C.Structure):
     ]
 
 
+class MgStepT(C.Structure):
+    _fields_ = [
+        ("n_slabs", C.c_int32), ("rank", C.c_int32), ("x_lo", C.c_int32), ("x_hi", C.c_int32),
+        ("ship", C.c_int32),
+        ("tv_density_start", C.c_int64 * 2), ("tv_density_count", C.c_int64 * 2),
+        ("tv_sh_start", C.c_int64 * 2), ("tv_sh_count", C.c_int64 * 2),
+        ("tv_density_scale", C.c_float), ("tv_sh_scale", C.c_float),
+        ("tv_density_scale_cells", C.c_int64), ("tv_sh_scale_cells", C.c_int64),
+        ("sparsity_loss", C.c_float),
+        ("lr_density", C.c_float), ("lr_sh", C.c_float), ("rms_beta", C.c_float), ("epsilon", C.c_float),
+    ]
+
+
 _P = C.c_void_p
 _I32, _I64, _F, _SZ = C.c_int32, C.c_int64, C.c_float, C.c_size_t
 _G, _O, _CAM, _GR = C.POINTER(GridT), C.POINTER(RenderOptsT), C.POINTER(CameraT), C.POINTER(GradsT)
@@ -132,6 +145,14 @@ SIGNATURES = {
     "svox2_ship_ray_logT": (_P, [_P, _SZ, _I64, _I32, _I64]),
     "svox2_ship_combine": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _F, _F, _P, _P, _P, _P]),
     "svox2_ship_backward": (C.c_int, [_G, _I64, _O, _I32, _I64, _P, _P, _F, _GR, _P, _SZ, _P]),
+    "svox2_mg_step_begin": (C.c_int, [_G, _P, _P, _I64, _O, C.POINTER(MgStepT), _P, _I64, _P, _SZ, _I64, _P, _P, _P,
+                                      _SZ, _I64, _P]),
+    "svox2_mg_step_shade": (C.c_int, [_G, _I64, _O, C.POINTER(MgStepT), _P, _P, _P, _SZ, _I64, _P, _SZ, _I64, _P]),
+    "svox2_mg_step_backward": (C.c_int, [_G, _I64, _O, C.POINTER(MgStepT), _P, _P, _P, _P, _SZ, _I64, _P, _SZ, _I64,
+                                         _P]),
+    "svox2_mg_slot_pack": (C.c_int, [_P, _I64, _P, _I64, _I32, _P, _SZ, _I64, _I32, _I64, _I64, _P]),
+    "svox2_mg_slot_unpack_add": (C.c_int, [_P, _I64, _P, _I64, _P, _SZ, _I64, _I32, _I64, _I64, _P]),
+    "svox2_mg_step_finish": (C.c_int, [_G, _P, _P, _I64, C.POINTER(MgStepT), _P, _P, _P, _SZ, _I64, _P]),
     "svox2_rmsprop_step_publish": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _P, _P, _I32, _I32, _I32, _F, _F, _F, _F, _P]),
     "svox2_publish_rows": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _I32, _I32, _P]),
     "svox2_pack_grad_rows": (C.c_int, [_P, _I64, _I32, _P, _I64, _P, _I64, _P, _I64, _P, _P, _P]),

@@ -942,6 +942,114 @@ def ship_backward(grid, opt, gout, accum_start, sparsity_loss, grads, ws: ShipWo
             _stream()))
 
 
+# ---- multi-GPU step on the compact gradient buffer (step.cu; driven by svox2_b200/slab.py) --------
+class MgStep:
+    """One x-slab rank's view of the multi-GPU step: the train-step workspace (compact gradient
+    slots, sized for the GLOBAL batch), optionally the ship workspace, and the per-step parameters.
+    The methods are the phases of include/svox2_b200.h `svox2_mg_step_*`."""
+
+    def __init__(self, step_ws: TrainStepWorkspace, n_slabs: int, rank: int, x_lo: int, x_hi: int,
+                 ship: "ShipWorkspace" = None, slab_bounds=None):
+        self.ws, self.ship = step_ws, ship
+        self.p = _lib.MgStepT()
+        self.p.n_slabs, self.p.rank, self.p.x_lo, self.p.x_hi = int(n_slabs), int(rank), int(x_lo), int(x_hi)
+        self.p.ship = 1 if ship is not None else 0
+        self._bounds = None
+        if slab_bounds is not None:
+            self._bounds = (C.c_int32 * len(slab_bounds))(*[int(b) for b in slab_bounds])
+
+    def set_step(self, tv_density_runs, tv_density_total, lambda_tv, tv_sh_runs, tv_sh_total, lambda_tv_sh,
+                 sparsity_loss, lr_density, lr_sh, rms_beta, epsilon=1e-8):
+        p = self.p
+        for k in range(2):
+            d = tv_density_runs[k] if k < len(tv_density_runs) else (0, 0)
+            h = tv_sh_runs[k] if k < len(tv_sh_runs) else (0, 0)
+            p.tv_density_start[k], p.tv_density_count[k] = int(d[0]), int(d[1])
+            p.tv_sh_start[k], p.tv_sh_count[k] = int(h[0]), int(h[1])
+        p.tv_density_scale, p.tv_sh_scale = float(lambda_tv), float(lambda_tv_sh)
+        p.tv_density_scale_cells, p.tv_sh_scale_cells = int(tv_density_total), int(tv_sh_total)
+        p.sparsity_loss = float(sparsity_loss)
+        p.lr_density, p.lr_sh, p.rms_beta, p.epsilon = float(lr_density), float(lr_sh), float(rms_beta), float(epsilon)
+
+    def _ship_args(self):
+        if self.ship is None:
+            return None, 0, 0
+        return self.ship.local.data_ptr(), self.ship.nbytes, self.ship.region_cap
+
+    def begin(self, grid, rays, opt, boundary_rows, logT_local=None):
+        g = _grid_struct(grid)
+        origins, dirs = _rays(rays)
+        o = _opt_struct(opt)
+        _check_cuda(boundary_rows, "boundary_rows", torch.int64, 1)
+        if origins.size(0) != self.ws.key[2]:
+            _fail("the step workspace was sized for another global batch")
+        peers = C.addressof(self.ship._arr) if self.ship is not None else None
+        nb, cap = (self.ship.nbytes, self.ship.region_cap) if self.ship is not None else (0, 0)
+        with torch.cuda.device(origins.device):
+            check(_lib.lib().svox2_mg_step_begin(
+                C.byref(g), origins.data_ptr(), dirs.data_ptr(), origins.size(0), C.byref(o), C.byref(self.p),
+                boundary_rows.data_ptr(), boundary_rows.numel(), self.ws.buf.data_ptr(), self.ws.nbytes,
+                self.ws.key[3], _ptr(logT_local), None if self._bounds is None else C.addressof(self._bounds),
+                peers, nb, cap, _stream()))
+
+    def shade(self, grid, opt, lt_in, part):
+        g = _grid_struct(grid)
+        o = _opt_struct(opt)
+        _check_input(part, "part", torch.float32, 2)
+        sp, nb, cap = self._ship_args()
+        with torch.cuda.device(part.device):
+            check(_lib.lib().svox2_mg_step_shade(
+                C.byref(g), self.ws.key[2], C.byref(o), C.byref(self.p), _ptr(lt_in), part.data_ptr(),
+                self.ws.buf.data_ptr(), self.ws.nbytes, self.ws.key[3], sp, nb, cap, _stream()))
+
+    def backward(self, grid, opt, lt_in, gout, accum_start):
+        g = _grid_struct(grid)
+        o = _opt_struct(opt)
+        _check_input(gout, "gout", torch.float32, 2)
+        _check_input(accum_start, "accum_start", torch.float32, 1)
+        sp, nb, cap = self._ship_args()
+        with torch.cuda.device(gout.device):
+            check(_lib.lib().svox2_mg_step_backward(
+                C.byref(g), self.ws.key[2], C.byref(o), C.byref(self.p), _ptr(lt_in), gout.data_ptr(),
+                accum_start.data_ptr(), self.ws.buf.data_ptr(), self.ws.nbytes, self.ws.key[3], sp, nb, cap,
+                _stream()))
+
+    def slot_pack(self, rows, packed, clear=False):
+        """packed[i] = [slot row of rows[i] | density flag | SH flag | 0, 0] (zeros if untouched)."""
+        _check_cuda(rows, "rows", torch.int64, 1)
+        _check_rows(packed, "packed")
+        if packed.size(0) != rows.numel():
+            _fail("one packet per row")
+        with torch.cuda.device(packed.device):
+            check(_lib.lib().svox2_mg_slot_pack(rows.data_ptr(), rows.numel(), packed.data_ptr(), _row_stride(packed),
+                                                1 if clear else 0, self.ws.buf.data_ptr(), self.ws.nbytes,
+                                                *self.ws.key, _stream()))
+
+    def slot_unpack_add(self, packed, rows):
+        _check_cuda(rows, "rows", torch.int64, 1)
+        _check_rows(packed, "packed")
+        if packed.size(0) != rows.numel():
+            _fail("one packet per row")
+        with torch.cuda.device(packed.device):
+            check(_lib.lib().svox2_mg_slot_unpack_add(packed.data_ptr(), _row_stride(packed), rows.data_ptr(),
+                                                      rows.numel(), self.ws.buf.data_ptr(), self.ws.nbytes,
+                                                      *self.ws.key, _stream()))
+
+    def finish(self, grid, density_rms, sh_rms, send=None, peer_density=None):
+        g = _grid_struct(grid)
+        _check_rows(density_rms, "density_rms")
+        _check_rows(sh_rms, "sh_rms")
+        arr = None
+        if send is not None:
+            _check_cuda(send, "send", torch.uint8, 1)
+            arr = (C.c_uint64 * len(peer_density))(*[int(x) for x in peer_density])
+        with torch.cuda.device(sh_rms.device):
+            check(_lib.lib().svox2_mg_step_finish(
+                C.byref(g), density_rms.data_ptr(), sh_rms.data_ptr(), self.ws.key[2], C.byref(self.p),
+                _ptr(send), None if arr is None else C.addressof(arr), self.ws.buf.data_ptr(), self.ws.nbytes,
+                self.ws.key[3], _stream()))
+
+
 def rmsprop_step_publish(data, rms, grad, mask, send, peer_ptrs, self_rank, skip_peer, beta, lr, epsilon,
                          minval=-1e9):
     """Masked RMSProp on a replicated single-channel array + publication of the updated rows

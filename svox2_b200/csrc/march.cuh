@@ -68,6 +68,20 @@ const float* ship_ray_logT(void* workspace, size_t workspace_bytes, int64_t n_ra
 bool launch_ship_backward(const GridView& g, const Opts& opt, const MarchArgs& a, const GradView& gr,
                           void* workspace, size_t workspace_bytes, int n_slabs, int64_t region_cap,
                           const float* gout, const float* accum_start, cudaStream_t st);
+// multi-GPU step on the compact gradient buffer (step.cu): where the sample records live -- a plain
+// queue workspace (n_slabs == 0: slab mode, every rank traverses all rays) or a ship workspace
+struct QueueRef {
+    void* ws;
+    size_t bytes;
+    int64_t n_rays;        // rays the per-ray arrays of the workspace are sized for (the global batch)
+    int n_slabs;
+    int64_t region_cap;
+};
+bool launch_mg_shade(const GridView& g, const Opts& opt, const QueueRef& q, const float* lt_in, float* part,
+                     const SlotMap& sm, cudaStream_t st);
+bool launch_mg_seed(const Opts& opt, const MarchArgs& a, const QueueRef& q, const float* lt_in,
+                    const float* gout, const float* accum_start, cudaStream_t st);
+bool launch_mg_scatter(const GridView& g, const QueueRef& q, const SlotMap& sm, cudaStream_t st);
 void launch_lattice_march(int mode, bool from_cam, const GridView& g, const Opts& opt,
                           const MarchArgs& a, const GradView& gr, cudaStream_t st);
 

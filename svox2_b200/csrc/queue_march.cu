@@ -47,7 +47,11 @@ namespace {
 #define QM_TRACE_BLOCKS 16
 #endif
 #ifndef QM_SCATTER_BLOCKS
-#define QM_SCATTER_BLOCKS 1   // min resident CTAs per SM asked of ptxas for K4 (register cap = 65536 / (256 * n))
+// min resident CTAs per SM asked of ptxas for the slot-scatter variant of K4 (register cap = 65536 /
+// (256 * n)).  A/B on B200 (profiles/r2_ab_variants.txt): 4 CTAs (64 registers, 92 B of spills) makes
+// the fused step 0.700 -> 0.686 ms; the dense-gradient variant loses with the same cap (fused call
+// 0.376 -> 0.400 ms) and keeps 80 registers.
+#define QM_SCATTER_BLOCKS 4
 #endif
 
 constexpr int TRACE_THREADS = 64;
@@ -587,7 +591,7 @@ seed_kernel(Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
 // registers; consecutive samples that fall into the same cell (~35 % at step 0.5) are merged
 // before the REDs leave the SM.  The basis table of the ray is re-read only when the ray changes.
 template <bool VEC, int MODE, bool SLOTS>
-__global__ void __launch_bounds__(SAMPLE_THREADS, QM_SCATTER_BLOCKS)
+__global__ void __launch_bounds__(SAMPLE_THREADS, SLOTS ? QM_SCATTER_BLOCKS : 3)
 scatter_kernel(GridView g, QueueView qv, GradView gr, int64_t gsh_stride, int64_t gd_stride, SlotMap sm) {
     constexpr bool SLAB = MODE == 1;
     if (*qv.overflow) return;
@@ -1051,6 +1055,63 @@ bool launch_ship_backward(const GridView& g, const Opts& opt, const MarchArgs& a
     else
         scatter_kernel<false, 2, false><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, w.qv, gr, a.gsh_stride, a.gd_stride, SlotMap{});
     ship_reset_kernel<<<1, 32, 0, st>>>(w.qv.overflow, w.qv.sticky, w.counts, w.cnt);
+    return true;
+}
+
+
+// ---- multi-GPU step on the compact gradient buffer (step.cu): the sample-parallel kernels of the
+// ---- slab (MODE 1) / ship (MODE 2) step with slot marking and slot scatter ----------------------
+static bool resolve_queue(const QueueRef& q, QueueView& qv) {
+    if (q.n_slabs > 0) {
+        ShipWs w;
+        if (!carve_ship(q.ws, q.bytes, q.n_rays, q.n_slabs, q.region_cap, w)) return false;
+        qv = w.qv;
+        return true;
+    }
+    return carve_queue(q.ws, q.bytes, q.n_rays, qv);
+}
+
+bool launch_mg_shade(const GridView& g, const Opts& opt, const QueueRef& q, const float* lt_in, float* part,
+                     const SlotMap& sm, cudaStream_t st) {
+    QueueView qv;
+    if (!resolve_queue(q, qv) || !march_vec_ok(g, nullptr, 0)) return false;
+    SlabView sl{};
+    sl.lt_in = lt_in;
+    sl.stopped = part + 3;
+    sl.stop_thresh = opt.stop_thresh;
+    const unsigned sblocks = 148 * QM_SAMPLE_CTAS;
+    if (q.n_slabs > 0) shade_kernel<true, 2, true><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, part, sl, sm);
+    else shade_kernel<true, 1, true><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, part, sl, sm);
+    return true;
+}
+
+bool launch_mg_seed(const Opts& opt, const MarchArgs& a, const QueueRef& q, const float* lt_in,
+                    const float* gout, const float* accum_start, cudaStream_t st) {
+    QueueView qv;
+    if (!resolve_queue(q, qv)) return false;
+    SlabView sl{};
+    sl.lt_in = lt_in;
+    sl.gout = gout;
+    sl.accum_start = accum_start;
+    sl.stop_thresh = opt.stop_thresh;
+    const unsigned blocks = div_up(a.n_rays * WARP, TRACE_THREADS);
+    if (q.n_slabs > 0) seed_kernel<2><<<blocks, TRACE_THREADS, 0, st>>>(opt, a, qv, sl);
+    else seed_kernel<1><<<blocks, TRACE_THREADS, 0, st>>>(opt, a, qv, sl);
+    return true;
+}
+
+bool launch_mg_scatter(const GridView& g, const QueueRef& q, const SlotMap& sm, cudaStream_t st) {
+    QueueView qv;
+    if (!resolve_queue(q, qv)) return false;
+    const unsigned sblocks = 148 * QM_SAMPLE_CTAS;
+    if (q.n_slabs > 0) {
+        scatter_kernel<true, 2, true><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, GradView{}, 0, 0, sm);
+        ShipWs w;
+        carve_ship(q.ws, q.bytes, q.n_rays, q.n_slabs, q.region_cap, w);
+        ship_reset_kernel<<<1, 32, 0, st>>>(w.qv.overflow, w.qv.sticky, w.counts, w.cnt);
+    } else {
+        scatter_kernel<true, 1, true><<<sblocks, SAMPLE_THREADS, 0, st>>>(g, qv, GradView{}, 0, 0, sm);
+    }
     return true;
 }
 

@@ -209,6 +209,11 @@ struct SlotOptArgs {
     const int32_t* __restrict__ n_slots;
     int width;
     float beta, lr_sh, lr_density, eps, minval;
+    // ship mode keeps density_data replicated: send[row] = 0 local only, 1 store the new value into
+    // every peer's copy, 2 into every peer's but `skip_peer` (co-owner applying the same update)
+    const uint8_t* __restrict__ send;
+    float* peer_density[SVOX2_MAX_PEERS];
+    int n_peers, self, skip_peer;
 };
 
 __device__ __forceinline__ void rmsprop_update(float& d, float& rms, float g, float beta, float lr,
@@ -292,12 +297,84 @@ slot_rmsprop_kernel(SlotOptArgs a) {
                 rmsprop_update(dd[u], dr[u], gden, a.beta, a.lr_density, a.eps, a.minval);
                 a.density[row[u] * a.density_stride] = dd[u];
                 a.density_rms[row[u] * a.density_stride] = dr[u];
+                if (a.send != nullptr) {
+                    const int mode = __ldg(a.send + row[u]);
+                    if (mode != 0)
+                        for (int p = 0; p < a.n_peers; ++p)
+                            if (p != a.self && !(mode == 2 && p == a.skip_peer))
+                                a.peer_density[p][row[u] * a.density_stride] = dd[u];
+                }
             }
 #if SLOT_ZERO_IN_OPT
             const float z = dependent_zero(ge[0]);
             *reinterpret_cast<float4*>(a.grad + slot[u] * a.width + ch0) = make_float4(z, z, z, z);
 #endif
         }
+    }
+}
+
+// ---- multi-GPU step: boundary rows in slot space -------------------------------------------------
+// rows whose gradient another rank contributes to (co-owned planes, row 0) get a slot whether or
+// not this rank touches them
+__global__ void __launch_bounds__(256)
+mark_rows_kernel(const int64_t* __restrict__ rows, int64_t n, SlotMap sm) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) slot_mark(sm, (int32_t)__ldg(rows + i));
+}
+
+// packet row = [W slot floats (SH gradients, density gradient at 3*basis_dim) | density flag | SH flag | 0..],
+// the layout of exchange.cu's pack kernel; thread = one float4 of a packet row
+__global__ void __launch_bounds__(256)
+slot_pack_kernel(const int64_t* __restrict__ rows, int64_t n, SlotMap sm, float* __restrict__ packed,
+                 int64_t pack_stride, int clear) {
+    const int qpp = (int)(pack_stride >> 2);
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = t / qpp;
+    const int q = (int)(t - i * qpp);
+    if (i >= n) return;
+    const int32_t row = (int32_t)__ldg(rows + i);
+    const bool has = (__ldcg(sm.bits + (row >> 5)) >> (row & 31)) & 1u;
+    const int slot = has ? slot_of(sm, row) : -1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (slot >= 0) {
+        if (q * 4 < sm.width) {
+            float4* src = reinterpret_cast<float4*>(sm.grad + (size_t)slot * sm.width + q * 4);
+            v = *src;
+            if (clear) *src = make_float4(dependent_zero(v.x), dependent_zero(v.x), dependent_zero(v.x), dependent_zero(v.x));
+        } else if (q * 4 == sm.width) {
+            uint8_t* f = sm.flags + 2 * (size_t)slot;
+            v.x = f[0] ? 1.f : 0.f;
+            v.y = f[1] ? 1.f : 0.f;
+            if (clear) *reinterpret_cast<uint16_t*>(f) = 0;
+        }
+    }
+    *reinterpret_cast<float4*>(packed + i * pack_stride + q * 4) = v;
+}
+
+// slot row += packet row; flags |= packet flags.  Every listed row has a slot (mark_rows_kernel ran
+// before the rank scan); rows are unique, so plain adds (a + b == b + a: both co-owners of a plane
+// end up with bit-identical gradients).
+__global__ void __launch_bounds__(256)
+slot_unpack_add_kernel(const float* __restrict__ packed, int64_t pack_stride, const int64_t* __restrict__ rows,
+                       int64_t n, SlotMap sm) {
+    const int qpp = (int)(pack_stride >> 2);
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = t / qpp;
+    const int q = (int)(t - i * qpp);
+    if (i >= n) return;
+    const int32_t row = (int32_t)__ldg(rows + i);
+    if (!((__ldcg(sm.bits + (row >> 5)) >> (row & 31)) & 1u)) return;   // cannot happen (marked)
+    const int slot = slot_of(sm, row);
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(packed + i * pack_stride + q * 4));
+    if (q * 4 < sm.width) {
+        float4* dst = reinterpret_cast<float4*>(sm.grad + (size_t)slot * sm.width + q * 4);
+        float4 d = *dst;
+        d.x = __fadd_rn(d.x, v.x); d.y = __fadd_rn(d.y, v.y); d.z = __fadd_rn(d.z, v.z); d.w = __fadd_rn(d.w, v.w);
+        *dst = d;
+    } else if (q * 4 == sm.width) {
+        uint8_t* f = sm.flags + 2 * (size_t)slot;
+        if (v.x != 0.f) f[0] = 1;
+        if (v.y != 0.f) f[1] = 1;
     }
 }
 
@@ -470,10 +547,24 @@ extern "C" SVOX2_API int svox2_train_step(
     if (forked) cudaStreamWaitEvent(st, side->join[1], 0);
 
     // 6. RMSProp over the slot list; slot rows are zeroed behind the read
-    SlotOptArgs o{const_cast<float*>(grid->sh_data), sh_rms, grid->sh_stride, 3 * grid->basis_dim,
-                  const_cast<float*>(grid->density_data), density_rms, grid->density_stride, w.slot_row,
-                  w.flags, w.grad, w.n_slots, w.width, p->rms_beta, p->lr_sh, p->lr_density, p->epsilon,
-                  -1e9f};
+    SlotOptArgs o{};
+    o.sh_data = const_cast<float*>(grid->sh_data);
+    o.sh_rms = sh_rms;
+    o.sh_stride = grid->sh_stride;
+    o.C = 3 * grid->basis_dim;
+    o.density = const_cast<float*>(grid->density_data);
+    o.density_rms = density_rms;
+    o.density_stride = grid->density_stride;
+    o.slot_row = w.slot_row;
+    o.flags = w.flags;
+    o.grad = w.grad;
+    o.n_slots = w.n_slots;
+    o.width = w.width;
+    o.beta = p->rms_beta;
+    o.lr_sh = p->lr_sh;
+    o.lr_density = p->lr_density;
+    o.eps = p->epsilon;
+    o.minval = -1e9f;
     slot_rmsprop_kernel<<<148 * SLOT_OPT_BLOCKS, OPT_THREADS, 0, st>>>(o);
     return check_launch(__func__);
 }
@@ -493,5 +584,218 @@ extern "C" SVOX2_API int svox2_train_step_masks(void* workspace, size_t workspac
         cudaMemcpyAsync(n_touched_and_overflow + 1, static_cast<char*>(w.queue) + 128, 4, cudaMemcpyDeviceToDevice, st);
         cudaMemcpyAsync(n_touched_and_overflow + 2, static_cast<char*>(w.queue) + 192, 4, cudaMemcpyDeviceToDevice, st);
     }
+    return check_launch(__func__);
+}
+
+// =====================================================================================================
+// Multi-GPU step on the compact gradient buffer (svox2_b200/slab.py).  The grid is sharded into
+// x-slabs; the phases below are the single-GPU step above cut at the points where the ranks exchange
+// per-ray scalars / boundary planes (the exchanges themselves are peer stores + barriers driven by
+// the host side):
+//   begin    clear | TV marking + boundary-row marking | traversal (slab: all rays, own slab's
+//            records; ship: own rays, records shipped to the owning slabs)
+//   shade    colours of this slab's records (+ touched-row bits)
+//   backward slot numbering | seed | scatter -> slots | TV -> slots
+//   (slot_pack / slot_unpack_add: boundary planes and the row-0 packet in slot space)
+//   finish   RMSProp over the slot list (ship: updated density rows stored into every peer's copy)
+// =====================================================================================================
+namespace {
+
+struct MgCtx {
+    StepWs w;
+    SlotMap sm;
+    QueueRef q;
+};
+
+bool mg_ctx(const svox2_grid_t* grid, int64_t n_rays_global, void* step_ws, size_t step_ws_bytes,
+            int64_t slots_per_ray, void* ship_ws, size_t ship_ws_bytes, int32_t n_slabs, int64_t region_cap,
+            MgCtx& c) {
+    if (!carve_step_ws(step_ws, step_ws_bytes, grid->n_rows, grid->basis_dim, n_rays_global, slots_per_ray, c.w))
+        return false;
+    c.sm = slot_map(c.w, grid->basis_dim);
+    if (ship_ws) c.q = QueueRef{ship_ws, ship_ws_bytes, n_rays_global, n_slabs, region_cap};
+    else c.q = QueueRef{c.w.queue, c.w.queue_bytes, n_rays_global, 0, 0};
+    return true;
+}
+
+}  // namespace
+
+extern "C" SVOX2_API int svox2_mg_step_begin(
+    const svox2_grid_t* grid, const float* origins, const float* dirs, int64_t n_rays_global,
+    const svox2_render_opts_t* opt, const svox2_mg_step_t* p, const int64_t* boundary_rows, int64_t n_boundary,
+    void* step_ws, size_t step_ws_bytes, int64_t slots_per_ray, float* logT_local,
+    const int32_t* slab_bounds, const uint64_t* peer_ship_ws, size_t ship_ws_bytes, int64_t region_cap,
+    svox2_stream_t stream) {
+    if (int e = validate_grid(grid, __func__)) return e;
+    SVOX2_REQUIRE(opt && opt->step_size > 0.f && p, "opt / params must not be null");
+    SVOX2_REQUIRE(n_rays_global > 0 && origins && dirs, "rays must be non-null");
+    SVOX2_REQUIRE(grid->background_nlayers == 0, "the slab step has no MSI background path");
+    SVOX2_REQUIRE(p->n_slabs >= 1 && p->n_slabs <= SVOX2_MAX_PEERS && p->rank >= 0 && p->rank < p->n_slabs,
+                  "bad slab arguments");
+    SVOX2_REQUIRE(p->ship ? (peer_ship_ws && slab_bounds && n_rays_global % p->n_slabs == 0) : logT_local != nullptr,
+                  "ship mode needs the peers' workspaces and a batch divisible by the ranks; slab mode needs logT_local");
+    MgCtx c;
+    void* my_ship = p->ship ? reinterpret_cast<void*>(peer_ship_ws[p->rank]) : nullptr;
+    SVOX2_REQUIRE(mg_ctx(grid, n_rays_global, step_ws, step_ws_bytes, slots_per_ray, my_ship, ship_ws_bytes,
+                         p->n_slabs, region_cap, c),
+                  "workspace too small or not 256-byte aligned (svox2_train_step_workspace_bytes)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const GridView g = make_grid_view(grid);
+    const int X = grid->size[0], Y = grid->size[1], Z = grid->size[2];
+    int *q_counter = nullptr, *q_overflow = nullptr, *q_sticky = nullptr;
+    SVOX2_REQUIRE(step_queue_header(c.w.queue, c.w.queue_bytes, n_rays_global, &q_counter, &q_overflow, &q_sticky),
+                  "sample-record queue could not be carved");
+    step_clear_kernel<<<148 * 4, 256, 0, st>>>(c.w.bits, c.w.n_words, reinterpret_cast<uint16_t*>(c.w.flags),
+                                               c.w.n_slots, q_counter, q_overflow, q_sticky, nullptr);
+    // rows the TV cells of this rank's pieces of the step's runs can reach, and the boundary rows
+    for (int k = 0; k < 2; ++k)
+        launch_tv_mark(grid->links, X, Y, Z, p->tv_density_start[k],
+                       p->tv_density_scale != 0.f ? p->tv_density_count[k] : 0, opt->last_sample_opaque,
+                       p->tv_sh_start[k], p->tv_sh_scale != 0.f ? p->tv_sh_count[k] : 0, c.sm, st);
+    if (n_boundary > 0) {
+        SVOX2_REQUIRE(boundary_rows, "boundary_rows must not be null");
+        mark_rows_kernel<<<div_up(n_boundary, 256), 256, 0, st>>>(boundary_rows, n_boundary, c.sm);
+    }
+    MarchArgs a{};
+    a.origins = origins;
+    a.dirs = dirs;
+    if (p->ship) {
+        const int64_t per = n_rays_global / p->n_slabs;
+        a.n_rays = per;
+        SVOX2_REQUIRE(launch_ship_trace(g, *opt, a, per * p->rank, n_rays_global, slab_bounds, p->n_slabs, p->rank,
+                                        peer_ship_ws, ship_ws_bytes, region_cap, st),
+                      "ship workspace too small or not 256-byte aligned (svox2_ship_workspace_bytes)");
+    } else {
+        a.n_rays = n_rays_global;
+        SVOX2_REQUIRE(launch_slab_trace(g, *opt, a, c.w.queue, c.w.queue_bytes, p->x_lo, p->x_hi, logT_local, st),
+                      "sample-record queue could not be carved");
+    }
+    return check_launch(__func__);
+}
+
+extern "C" SVOX2_API int svox2_mg_step_shade(
+    const svox2_grid_t* grid, int64_t n_rays_global, const svox2_render_opts_t* opt, const svox2_mg_step_t* p,
+    const float* lt_in, float* part, void* step_ws, size_t step_ws_bytes, int64_t slots_per_ray, void* ship_ws,
+    size_t ship_ws_bytes, int64_t region_cap, svox2_stream_t stream) {
+    if (int e = validate_grid(grid, __func__)) return e;
+    SVOX2_REQUIRE(opt && p && part && (p->ship || lt_in), "null argument");
+    MgCtx c;
+    SVOX2_REQUIRE(mg_ctx(grid, n_rays_global, step_ws, step_ws_bytes, slots_per_ray, p->ship ? ship_ws : nullptr,
+                         ship_ws_bytes, p->n_slabs, region_cap, c),
+                  "workspace too small or not 256-byte aligned");
+    SVOX2_REQUIRE(launch_mg_shade(make_grid_view(grid), *opt, c.q, lt_in, part, c.sm, (cudaStream_t)stream),
+                  "sample-record queue could not be carved / SH rows not 16-byte aligned");
+    return check_launch(__func__);
+}
+
+extern "C" SVOX2_API int svox2_mg_step_backward(
+    const svox2_grid_t* grid, int64_t n_rays_global, const svox2_render_opts_t* opt, const svox2_mg_step_t* p,
+    const float* lt_in, const float* gout, const float* accum_start, void* step_ws, size_t step_ws_bytes,
+    int64_t slots_per_ray, void* ship_ws, size_t ship_ws_bytes, int64_t region_cap, svox2_stream_t stream) {
+    if (int e = validate_grid(grid, __func__)) return e;
+    SVOX2_REQUIRE(opt && p && gout && accum_start && (p->ship || lt_in), "null argument");
+    MgCtx c;
+    SVOX2_REQUIRE(mg_ctx(grid, n_rays_global, step_ws, step_ws_bytes, slots_per_ray, p->ship ? ship_ws : nullptr,
+                         ship_ws_bytes, p->n_slabs, region_cap, c),
+                  "workspace too small or not 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const GridView g = make_grid_view(grid);
+    const int X = grid->size[0], Y = grid->size[1], Z = grid->size[2];
+    const StepWs& w = c.w;
+    rank_count_kernel<<<(unsigned)w.n_blocks, RANK_THREADS, 0, st>>>(w.bits, w.n_words, w.block_sums);
+    rank_scan_kernel<<<(unsigned)w.n_blocks, RANK_THREADS, 0, st>>>(w.bits, w.n_words, w.block_sums, w.prefix,
+                                                                 w.slot_row, w.n_slots);
+    MarchArgs a{};
+    a.n_rays = n_rays_global;
+    a.sparsity_loss = p->sparsity_loss;
+    SVOX2_REQUIRE(launch_mg_seed(*opt, a, c.q, lt_in, gout, accum_start, st), "sample-record queue could not be carved");
+    SVOX2_REQUIRE(launch_mg_scatter(g, c.q, c.sm, st), "sample-record queue could not be carved");
+    for (int k = 0; k < 2; ++k) {
+        if (p->tv_density_scale != 0.f && p->tv_density_count[k] > 0)
+            launch_tv_slots(grid->links, X, Y, Z, grid->density_data, grid->density_stride, p->tv_density_start[k],
+                            p->tv_density_count[k], p->tv_density_scale_cells, 0, 1, p->tv_density_scale, 0,
+                            opt->last_sample_opaque, c.sm, c.sm.sigma_at, 0, st);
+        if (p->tv_sh_scale != 0.f && p->tv_sh_count[k] > 0)
+            launch_tv_slots(grid->links, X, Y, Z, grid->sh_data, grid->sh_stride, p->tv_sh_start[k], p->tv_sh_count[k],
+                            p->tv_sh_scale_cells, 0, 3 * grid->basis_dim, p->tv_sh_scale, 1, 0, c.sm, 0, 1, st);
+    }
+    return check_launch(__func__);
+}
+
+extern "C" SVOX2_API int svox2_mg_slot_pack(const int64_t* rows, int64_t n_sel, float* packed, int64_t pack_stride,
+                                            int32_t clear, void* step_ws, size_t step_ws_bytes, int64_t n_rows,
+                                            int32_t basis_dim, int64_t n_rays, int64_t slots_per_ray,
+                                            svox2_stream_t stream) {
+    SVOX2_REQUIRE(n_sel >= 0, "n_sel must be >= 0");
+    if (n_sel == 0) return SVOX2_OK;
+    StepWs w;
+    SVOX2_REQUIRE(carve_step_ws(step_ws, step_ws_bytes, n_rows, basis_dim, n_rays, slots_per_ray, w),
+                  "workspace too small or not 256-byte aligned");
+    SVOX2_REQUIRE(rows && packed && pack_stride % 4 == 0 && pack_stride >= w.width + 4 &&
+                      (reinterpret_cast<uintptr_t>(packed) & 15u) == 0,
+                  "packed rows must be 16-byte aligned and hold the slot row + 4 floats");
+    const int64_t threads = n_sel * (pack_stride / 4);
+    slot_pack_kernel<<<div_up(threads, 256), 256, 0, (cudaStream_t)stream>>>(rows, n_sel, slot_map(w, basis_dim), packed,
+                                                                             pack_stride, clear);
+    return check_launch(__func__);
+}
+
+extern "C" SVOX2_API int svox2_mg_slot_unpack_add(const float* packed, int64_t pack_stride, const int64_t* rows,
+                                                  int64_t n_sel, void* step_ws, size_t step_ws_bytes, int64_t n_rows,
+                                                  int32_t basis_dim, int64_t n_rays, int64_t slots_per_ray,
+                                                  svox2_stream_t stream) {
+    SVOX2_REQUIRE(n_sel >= 0, "n_sel must be >= 0");
+    if (n_sel == 0) return SVOX2_OK;
+    StepWs w;
+    SVOX2_REQUIRE(carve_step_ws(step_ws, step_ws_bytes, n_rows, basis_dim, n_rays, slots_per_ray, w),
+                  "workspace too small or not 256-byte aligned");
+    SVOX2_REQUIRE(rows && packed && pack_stride % 4 == 0 && pack_stride >= w.width + 4 &&
+                      (reinterpret_cast<uintptr_t>(packed) & 15u) == 0,
+                  "packed rows must be 16-byte aligned and hold the slot row + 4 floats");
+    const int64_t threads = n_sel * (pack_stride / 4);
+    slot_unpack_add_kernel<<<div_up(threads, 256), 256, 0, (cudaStream_t)stream>>>(packed, pack_stride, rows, n_sel,
+                                                                                   slot_map(w, basis_dim));
+    return check_launch(__func__);
+}
+
+extern "C" SVOX2_API int svox2_mg_step_finish(
+    const svox2_grid_t* grid, float* density_rms, float* sh_rms, int64_t n_rays_global, const svox2_mg_step_t* p,
+    const uint8_t* send, const uint64_t* peer_density, void* step_ws, size_t step_ws_bytes, int64_t slots_per_ray,
+    svox2_stream_t stream) {
+    if (int e = validate_grid(grid, __func__)) return e;
+    SVOX2_REQUIRE(p && density_rms && sh_rms, "null argument");
+    SVOX2_REQUIRE((send == nullptr) == (peer_density == nullptr), "send and peer_density go together");
+    StepWs w;
+    SVOX2_REQUIRE(carve_step_ws(step_ws, step_ws_bytes, grid->n_rows, grid->basis_dim, n_rays_global, slots_per_ray, w),
+                  "workspace too small or not 256-byte aligned");
+    SlotOptArgs o{};
+    o.sh_data = const_cast<float*>(grid->sh_data);
+    o.sh_rms = sh_rms;
+    o.sh_stride = grid->sh_stride;
+    o.C = 3 * grid->basis_dim;
+    o.density = const_cast<float*>(grid->density_data);
+    o.density_rms = density_rms;
+    o.density_stride = grid->density_stride;
+    o.slot_row = w.slot_row;
+    o.flags = w.flags;
+    o.grad = w.grad;
+    o.n_slots = w.n_slots;
+    o.width = w.width;
+    o.beta = p->rms_beta;
+    o.lr_sh = p->lr_sh;
+    o.lr_density = p->lr_density;
+    o.eps = p->epsilon;
+    o.minval = -1e9f;
+    if (send) {
+        o.send = send;
+        o.n_peers = p->n_slabs;
+        o.self = p->rank;
+        o.skip_peer = p->rank - 1;
+        for (int k = 0; k < p->n_slabs; ++k) {
+            SVOX2_REQUIRE(peer_density[k] != 0, "bad peer pointer");
+            o.peer_density[k] = reinterpret_cast<float*>(peer_density[k]);
+        }
+    }
+    slot_rmsprop_kernel<<<148 * SLOT_OPT_BLOCKS, OPT_THREADS, 0, (cudaStream_t)stream>>>(o);
     return check_launch(__func__);
 }

@@ -178,6 +178,13 @@ class SlabTrainer:
         self.slots_per_ray = None  # record slots per ray of the workspace (None: min(diagonal, 512))
         self._peer = None          # PeerMemory for the current batch size, False if unavailable
         self._density_ptrs = None  # ship mode: every rank's density_data, mapped into this process
+        # the step's gradients live in a compact [touched rows, 28] buffer (step.cu) instead of the
+        # dense .grad arrays; SVOX2_B200_SLAB_SLOTS=0 keeps the dense-gradient step (also the path
+        # without peer memory)
+        self.use_slots = os.environ.get("SVOX2_B200_SLAB_SLOTS", "1") != "0"
+        self._mg = None
+        rows = [h for h in (self.halo_left, self.halo_right) if h is not None] + [self._row0]
+        self._boundary_rows = torch.unique(torch.cat(rows)).contiguous()
         self.use_peer_memory = os.environ.get("SVOX2_B200_PEER", "1") != "0"
         # "ship": rays sharded for the traversal, records shipped to the owning slab (needs peer
         # memory and a batch divisible by the world size); "replicated": every rank traverses all rays
@@ -316,6 +323,9 @@ class SlabTrainer:
         Q = rgb_gt.size(0)
         dev = rgb_gt.device
         peer = self._peer_memory(Q) if self.world_size > 1 else None
+        if self.use_slots and (self.world_size == 1 or
+                               (peer is not None and _C.packed_row_floats(g.sh_data.size(1) + 2) == peer.WIDTH)):
+            return self._step_slots(rays, rgb_gt, lr_sigma, lr_sh, peer)
         if peer is not None and peer.ship is not None:
             return self._step_ship(rays, rgb_gt, lr_sigma, lr_sh, peer)
         ws = self._workspace(Q)
@@ -354,6 +364,118 @@ class SlabTrainer:
         g.sparse_sh_grad_indexer = g.sparse_grad_indexer.clone()
         self._mark("backward")
         return self._finish_step(rgb, lr_sigma, lr_sh)
+
+    def _mg_step(self, n_rays: int, peer):
+        g = self.grid
+        ship = peer.ship if peer is not None else None
+        key = (n_rays, g.sh_data.size(0), id(ship))
+        if self._mg is None or self._mg[0] != key:
+            diag = sum(float(s) ** 2 for s in g.links.shape) ** 0.5
+            slots = max(64, min(int(diag / max(float(g.opt.step_size), 1e-3)) + 2, 512))
+            if self.slots_per_ray is not None:
+                slots = max(64, int(self.slots_per_ray))
+            if ship is not None:
+                slots = 64          # the records live in the ship workspace; keep the unused queue small
+            ws = _C.TrainStepWorkspace(g.sh_data.size(0), g.basis_dim, n_rays, slots, g.links.device)
+            self._mg = (key, _C.MgStep(ws, self.world_size, self.rank, self.x_lo, self.x_hi, ship, self.bounds))
+        return self._mg[1]
+
+    def export_masks(self):
+        """After a slot-based step: materialise grid.sparse_grad_indexer / sparse_sh_grad_indexer
+        (bool[N], this rank's owned rows) of that step; returns (touched rows, overflow, sticky)."""
+        if self._mg is None:
+            return None
+        st, md, msh = self._mg[1].ws.status(want_masks=True)
+        self.grid.sparse_grad_indexer, self.grid.sparse_sh_grad_indexer = md, msh
+        return st
+
+    def _step_slots(self, rays: Rays, rgb_gt: torch.Tensor, lr_sigma, lr_sh, peer) -> torch.Tensor:
+        """The step on the compact gradient buffer (include/svox2_b200.h svox2_mg_step_*): the
+        single-GPU fused step cut where the slabs exchange per-ray scalars and boundary planes."""
+        g = self.grid
+        Qg, G = rgb_gt.size(0), self.world_size
+        dev = rgb_gt.device
+        ship = peer is not None and peer.ship is not None
+        mg = self._mg_step(Qg, peer)
+        lr_d = self.lr_sigma if lr_sigma is None else lr_sigma
+        lr_s = self.lr_sh if lr_sh is None else lr_sh
+        # the step's two TV cell runs, drawn in the reference's order (density, then SH)
+        runs_d, n_d = self._tv_runs() if self.lambda_tv > 0.0 else ([], 0)
+        runs_s, n_s = self._tv_runs() if self.lambda_tv_sh > 0.0 else ([], 0)
+        mg.set_step(runs_d, n_d, self.lambda_tv, runs_s, n_s, self.lambda_tv_sh, self.sparsity_loss, lr_d, lr_s,
+                    self.rms_beta)
+        # clear, TV marking, boundary rows, 2 rank kernels, seed, scatter, TV x2, RMSProp + march / exchange kernels
+        self.kernels_per_step = 12 + (3 if ship else 4) + (6 if G > 1 else 0)
+        spec, ropt = g._to_cpp(), g.opt._to_cpp()
+        if ship:
+            peer.hdl.barrier(channel=0)     # everybody's density rows of the last step have landed
+            self._refresh_row0()
+        self._mark("start")
+        logT_local = None if ship else torch.empty(Qg, dtype=torch.float32, device=dev)
+        mg.begin(spec, rays._to_cpp(), ropt, self._boundary_rows, logT_local)
+        self._mark("trace")
+        lt_in = logT_all = None
+        if ship:
+            peer.hdl.barrier(channel=1)     # the records shipped to me have landed
+        else:
+            logT_all = self._gather(logT_local, "a")                             # exchange A
+            self._refresh_row0()
+            lt_in = torch.empty(Qg, dtype=torch.float32, device=dev)
+            _C.slab_prefix(logT_all, rays.dirs, self.rank, lt_in)
+        self._mark("exchange_a")
+        part = torch.zeros((Qg, 4), dtype=torch.float32, device=dev)
+        mg.shade(spec, ropt, lt_in, part)
+        self._mark("shade")
+        part_all = self._gather(part, "b")                                       # exchange B
+        rgb = torch.empty((Qg, 3), dtype=torch.float32, device=dev)
+        gout = torch.empty((Qg, 3), dtype=torch.float32, device=dev)
+        accum_start = torch.empty(Qg, dtype=torch.float32, device=dev)
+        if ship:
+            _C.ship_combine(part_all, peer.ship.ray_logT(), rays.dirs, rgb_gt, self.rank,
+                            g.opt.background_brightness, self.beta_loss, rgb, gout, accum_start)
+        else:
+            _C.slab_combine(part_all, logT_all, rays.dirs, rgb_gt, self.rank,
+                            g.opt.background_brightness, self.beta_loss, rgb, gout, accum_start)
+        self._mark("exchange_b")
+        mg.backward(spec, ropt, lt_in, gout, accum_start)                         # + TV into the slots
+        self._mark("backward")
+        if G > 1:
+            self._halo_slots(mg, peer)
+        self._mark("halo_grads")
+        g._ensure_rms()
+        mg.finish(spec, g.density_rms, g.sh_rms, self._send if ship else None,
+                  self._density_ptrs if ship else None)
+        self._publish_row0()
+        self._mark("optimiser")
+        g.sparse_grad_indexer = g.sparse_sh_grad_indexer = None      # slot flags; export_masks() on demand
+        if self._steps % 256 == 0:
+            self.check_overflow()
+        self._steps += 1
+        return rgb
+
+    def _halo_slots(self, mg, peer):
+        """The halo swap of _halo_grads in slot space: boundary planes and the row-0 packet go from
+        the slot rows straight into the neighbours' inboxes, and what arrives is added to the slots."""
+        width = peer.WIDTH
+        dev = self.grid.links.device
+        z = torch.zeros((1, width), dtype=torch.float32, device=dev)
+        if not self._holds_row0:
+            mg.slot_pack(self._row0, z, clear=True)
+        _C.peer_store(peer.ptrs, (peer.off_z + self.rank * width) * 4, z)
+        nl = self.halo_left.numel() if self.halo_left is not None else 0
+        nr = self.halo_right.numel() if self.halo_right is not None else 0
+        if nr:
+            mg.slot_pack(self.halo_right, peer.neighbour_inbox(self.rank + 1, True, nr))
+        if nl:
+            mg.slot_pack(self.halo_left, peer.neighbour_inbox(self.rank - 1, False, nl))
+        peer.hdl.barrier(channel=3)
+        if nl:
+            mg.slot_unpack_add(peer.inbox(True, nl), self.halo_left)
+        if nr:
+            mg.slot_unpack_add(peer.inbox(False, nr), self.halo_right)
+        if self._holds_row0:
+            zs = peer.buf[peer.off_z:peer.off_z + self.world_size * width].view(self.world_size, width)
+            mg.slot_unpack_add(zs.sum(0, keepdim=True), self._row0)
 
     def _step_ship(self, rays: Rays, rgb_gt: torch.Tensor, lr_sigma, lr_sh, peer) -> torch.Tensor:
         """Ship mode: trace my share of the rays, ship the records to their slabs, then shade /
@@ -474,7 +596,12 @@ class SlabTrainer:
         gradients were dropped).  The trace kernel keeps a sticky count in the workspace, so the
         check can be made at any host sync point (every 256 steps, logging, gather_params)."""
         ship = self._peer.ship if self._peer not in (None, False) else None
-        if (self._ws is not None and _C.slab_overflowed(self._ws[1])) or (ship is not None and ship.overflowed()):
+        slots_ov = False
+        if self._mg is not None:
+            st, _, _ = self._mg[1].ws.status()
+            slots_ov = bool(st[1] or st[2])
+        if (self._ws is not None and _C.slab_overflowed(self._ws[1])) or (ship is not None and ship.overflowed()) \
+                or slots_ov:
             raise RuntimeError(
                 "SlabTrainer: the sample-record workspace overflowed in at least one step since "
                 "the last check (those steps contributed no colour / gradient); raise "

@@ -40,6 +40,7 @@ def test_slab_single_rank_equals_fused_step(kw):
     np.random.seed(3)
     tr = SlabTrainer(grid, world_size=1, rank=0, **kw)
     rgb = tr.step(sv.Rays(t(sc["origins"], dev), t(sc["dirs"], dev)), t(sc["rgb_gt"], dev))
+    tr.export_masks()
     assert (rgb - rgb1).abs().max().item() < 1e-5
     assert torch.equal(grid.sparse_grad_indexer, ref.sparse_grad_indexer)
     assert torch.equal(grid.sparse_sh_grad_indexer, ref.sparse_sh_grad_indexer)
@@ -83,6 +84,8 @@ def _worker(rank, world, port, out, case="default"):
         opts = OPTS
         # traversal mode of the slab step: "auto" ships records from 4 ranks up (slab.py); the
         # "ship*" / "replicated*" cases force one mode so that both run at every world size
+        if "dense" in case:         # the dense-.grad step instead of the compact gradient buffer
+            os.environ["SVOX2_B200_SLAB_SLOTS"] = "0"
         if case.startswith("ship"):
             os.environ["SVOX2_B200_SLAB_TRAVERSAL"] = "ship"
         elif case.startswith("replicated"):
@@ -111,6 +114,7 @@ def _worker(rank, world, port, out, case="default"):
         tr = SlabTrainer(grid, world_size=world, rank=rank, **kw)
         rays = sv.Rays(t(sc["origins"], dev), t(sc["dirs"], dev))
         rgb = tr.step(rays, t(sc["rgb_gt"], dev))
+        tr.export_masks()       # slot-based step: the masks are slot flags until asked for
         torch.cuda.synchronize()
         m["rgb"] = (rgb - rgb1).abs().max().item()
         ok = m["rgb"] < 1e-5
@@ -118,7 +122,8 @@ def _worker(rank, world, port, out, case="default"):
         m["mask"] = bool(torch.equal(grid.sparse_grad_indexer[own], ref.sparse_grad_indexer[own]) and
                          torch.equal(grid.sparse_sh_grad_indexer[own], ref.sparse_sh_grad_indexer[own]))
         ok = ok and m["mask"]
-        m["grads_zeroed"] = float(grid.sh_data.grad.abs().max().item() + grid.density_data.grad.abs().max().item())
+        m["grads_zeroed"] = 0.0 if grid.sh_data.grad is None else \
+            float(grid.sh_data.grad.abs().max().item() + grid.density_data.grad.abs().max().item())
         ok = ok and m["grads_zeroed"] == 0.0
         tr.gather_params()
         m["density"] = frac_bad(grid.density_data.detach().cpu().numpy(), ref.density_data.detach().cpu().numpy())
@@ -157,6 +162,7 @@ def _worker(rank, world, port, out, case="default"):
 
 
 @pytest.mark.parametrize("world,case", [(2, "default"), (2, "stop"), (2, "ship"), (2, "ship_stop"),
+                                        (2, "replicated_dense"), (2, "ship_dense_stop"),
                                         (4, "default"), (4, "stop"), (4, "replicated_stop"),
                                         (8, "default"), (8, "stop")])
 def test_multi_gpu_slab_step_equals_single_gpu_step(world, case):

@@ -302,6 +302,7 @@ def test_config_c3_training_steps_follow_the_reference_cuda(ref_svox2):
         ref.inplace_tv_grad(ref.density_data.grad, scaling=bench.SYN["lambda_tv"], sparse_frac=bench.SYN["tv_sparsity"])
         ref.inplace_tv_color_grad(ref.sh_data.grad, scaling=bench.SYN["lambda_tv_sh"], sparse_frac=bench.SYN["tv_sparsity"])
         if it == 0:     # march + TV masks of the first step (identical parameters): bit for bit
+            trainer.export_masks()      # the fused step keeps them as slot flags until asked for
             assert torch.equal(ours.sparse_grad_indexer, ref.sparse_grad_indexer)
             assert torch.equal(ours.sparse_sh_grad_indexer, ref.sparse_sh_grad_indexer)
         ref.optim_density_step(bench.SYN["lr_sigma"], beta=bench.SYN["rms_beta"])
