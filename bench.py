@@ -540,8 +540,8 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     # rows the last step's optimisers updated (the masks survive the step): whole-step roofline
-    if getattr(trainer, "_step_ws", None) is not None:    # fused single-GPU step: masks on demand
-        trainer.export_masks()
+    if getattr(trainer, "_step_ws", None) is not None or getattr(trainer, "_mg", None) is not None:
+        trainer.export_masks()          # slot-based steps keep the masks as slot flags until asked for
         trainer.check_overflow()
     touched = (int(grid.sparse_grad_indexer.sum()), int(grid.sparse_sh_grad_indexer.sum()))
 
@@ -680,7 +680,8 @@ def run_ours(args):
             "stored_voxels": sc["n_rows"],
             "occupancy": round(sc["occupancy"], 4), "rays_per_gpu": per_rank, "global_batch": gq,
             "step": "volume_render_fused + tv_grad_sparse(sigma,sh) + rmsprop(sigma,sh)" +
-                    (" as one svox2_train_step call (compact gradient buffer)" if getattr(trainer, "_step_ws", None) is not None else ""),
+                    (" as one svox2_train_step call (compact gradient buffer)" if getattr(trainer, "_step_ws", None) is not None else "") +
+                    (" in svox2_mg_step_* phases on the compact gradient buffer" if getattr(trainer, "_mg", None) is not None else ""),
             "l2": "inputs larger than L2 (grid+grads+rms >> 126 MB); 8 distinct ray batches cycled",
             "parallelism": (f"grid sharded into {world} x-slabs; " +
                             ("rays sharded for the traversal, sample records shipped to the owning slab with "

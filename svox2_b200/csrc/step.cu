@@ -647,15 +647,23 @@ extern "C" SVOX2_API int svox2_mg_step_begin(
                   "sample-record queue could not be carved");
     step_clear_kernel<<<148 * 4, 256, 0, st>>>(c.w.bits, c.w.n_words, reinterpret_cast<uint16_t*>(c.w.flags),
                                                c.w.n_slots, q_counter, q_overflow, q_sticky, nullptr);
-    // rows the TV cells of this rank's pieces of the step's runs can reach, and the boundary rows
+    // rows the TV cells of this rank's pieces of the step's runs can reach, and the boundary rows:
+    // on the side stream, next to the latency-bound traversal
+    SideStream* side = side_stream();
+    cudaStream_t sd = side ? side->stream : st;
+    if (sd != st) {
+        cudaEventRecord(side->fork[0], st);
+        cudaStreamWaitEvent(sd, side->fork[0], 0);
+    }
     for (int k = 0; k < 2; ++k)
         launch_tv_mark(grid->links, X, Y, Z, p->tv_density_start[k],
                        p->tv_density_scale != 0.f ? p->tv_density_count[k] : 0, opt->last_sample_opaque,
-                       p->tv_sh_start[k], p->tv_sh_scale != 0.f ? p->tv_sh_count[k] : 0, c.sm, st);
+                       p->tv_sh_start[k], p->tv_sh_scale != 0.f ? p->tv_sh_count[k] : 0, c.sm, sd);
     if (n_boundary > 0) {
         SVOX2_REQUIRE(boundary_rows, "boundary_rows must not be null");
-        mark_rows_kernel<<<div_up(n_boundary, 256), 256, 0, st>>>(boundary_rows, n_boundary, c.sm);
+        mark_rows_kernel<<<div_up(n_boundary, 256), 256, 0, sd>>>(boundary_rows, n_boundary, c.sm);
     }
+    if (sd != st) cudaEventRecord(side->join[0], sd);
     MarchArgs a{};
     a.origins = origins;
     a.dirs = dirs;
@@ -670,6 +678,7 @@ extern "C" SVOX2_API int svox2_mg_step_begin(
         SVOX2_REQUIRE(launch_slab_trace(g, *opt, a, c.w.queue, c.w.queue_bytes, p->x_lo, p->x_hi, logT_local, st),
                       "sample-record queue could not be carved");
     }
+    if (sd != st) cudaStreamWaitEvent(st, side->join[0], 0);
     return check_launch(__func__);
 }
 
@@ -705,20 +714,29 @@ extern "C" SVOX2_API int svox2_mg_step_backward(
     rank_count_kernel<<<(unsigned)w.n_blocks, RANK_THREADS, 0, st>>>(w.bits, w.n_words, w.block_sums);
     rank_scan_kernel<<<(unsigned)w.n_blocks, RANK_THREADS, 0, st>>>(w.bits, w.n_words, w.block_sums, w.prefix,
                                                                  w.slot_row, w.n_slots);
+    // the TV kernels only need the slot numbering: they run on the side stream next to seed / scatter
+    SideStream* side = side_stream();
+    cudaStream_t sd = side ? side->stream : st;
+    if (sd != st) {
+        cudaEventRecord(side->fork[0], st);
+        cudaStreamWaitEvent(sd, side->fork[0], 0);
+    }
+    for (int k = 0; k < 2; ++k) {
+        if (p->tv_density_scale != 0.f && p->tv_density_count[k] > 0)
+            launch_tv_slots(grid->links, X, Y, Z, grid->density_data, grid->density_stride, p->tv_density_start[k],
+                            p->tv_density_count[k], p->tv_density_scale_cells, 0, 1, p->tv_density_scale, 0,
+                            opt->last_sample_opaque, c.sm, c.sm.sigma_at, 0, sd);
+        if (p->tv_sh_scale != 0.f && p->tv_sh_count[k] > 0)
+            launch_tv_slots(grid->links, X, Y, Z, grid->sh_data, grid->sh_stride, p->tv_sh_start[k], p->tv_sh_count[k],
+                            p->tv_sh_scale_cells, 0, 3 * grid->basis_dim, p->tv_sh_scale, 1, 0, c.sm, 0, 1, sd);
+    }
+    if (sd != st) cudaEventRecord(side->join[0], sd);
     MarchArgs a{};
     a.n_rays = n_rays_global;
     a.sparsity_loss = p->sparsity_loss;
     SVOX2_REQUIRE(launch_mg_seed(*opt, a, c.q, lt_in, gout, accum_start, st), "sample-record queue could not be carved");
     SVOX2_REQUIRE(launch_mg_scatter(g, c.q, c.sm, st), "sample-record queue could not be carved");
-    for (int k = 0; k < 2; ++k) {
-        if (p->tv_density_scale != 0.f && p->tv_density_count[k] > 0)
-            launch_tv_slots(grid->links, X, Y, Z, grid->density_data, grid->density_stride, p->tv_density_start[k],
-                            p->tv_density_count[k], p->tv_density_scale_cells, 0, 1, p->tv_density_scale, 0,
-                            opt->last_sample_opaque, c.sm, c.sm.sigma_at, 0, st);
-        if (p->tv_sh_scale != 0.f && p->tv_sh_count[k] > 0)
-            launch_tv_slots(grid->links, X, Y, Z, grid->sh_data, grid->sh_stride, p->tv_sh_start[k], p->tv_sh_count[k],
-                            p->tv_sh_scale_cells, 0, 3 * grid->basis_dim, p->tv_sh_scale, 1, 0, c.sm, 0, 1, st);
-    }
+    if (sd != st) cudaStreamWaitEvent(st, side->join[0], 0);
     return check_launch(__func__);
 }
 
