@@ -22,6 +22,37 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
+// t0 advanced by `lane` sequentially rounded adds of `step` -- the reference's `t += step` chain.
+// Inside one binade every add moves the mantissa by the same integer number D of ulps (round to
+// nearest of step = S ulp + r: D = S for r < ulp/2, S + 1 for r > ulp/2), so the chain is the exact
+// arithmetic progression t0 + k*(t1 - t0): t1 - t0 is exact (Sterbenz) and so is the fma as long as
+// t_31 stays in t0's binade.  The two cases where that fails -- the progression leaves the binade
+// (ulp changes), or r == ulp/2 exactly (ties round to even, so the first add may differ from the
+// later ones) -- are detected warp-uniformly and take the 31 dependent adds.
+#ifndef TRAVERSE_FAST_LATTICE
+#define TRAVERSE_FAST_LATTICE 1
+#endif
+__device__ __forceinline__ float lattice_position(float t0, float step, int lane) {
+#if TRAVERSE_FAST_LATTICE
+    const float t1 = __fadd_rn(t0, step);
+    const float delta = __fsub_rn(t1, t0);
+    const float t31 = __fmaf_rn(31.f, delta, t0);
+    const int e0 = __float_as_int(t0) & 0x7f800000;                 // sign bit set (t0 < 0) fails the test below
+    const bool in_binade = __float_as_int(t0) == (e0 | (__float_as_int(t0) & 0x007fffff)) &&
+                           (__float_as_int(t31) & 0xff800000) == e0 && e0 >= (64 << 23) && e0 <= (190 << 23);
+    const float half_ulp = __int_as_float(e0 - (24 << 23));
+    const bool tie = fabsf(__fsub_rn(step, delta)) == half_ulp;
+    if (in_binade && !tie && delta > 0.f) return __fmaf_rn((float)lane, delta, t0);
+#endif
+    float t = t0;
+#pragma unroll
+    for (int i = 0; i < 31; ++i) {
+        const float nx = __fadd_rn(t, step);
+        t = (i < lane) ? nx : t;
+    }
+    return t;
+}
+
 struct Candidates {
     float tk;        // this lane's lattice position
     bool valid;      // tk <= tmax
@@ -37,12 +68,7 @@ struct Candidates {
 template <bool TWO_PHASE>
 __device__ __forceinline__ void load_candidates(const Ray& ray, const GridView& g, float t0,
                                                 float step, int lane, Candidates& c) {
-    float t = t0;
-#pragma unroll
-    for (int i = 0; i < 31; ++i) {
-        const float nx = __fadd_rn(t, step);
-        t = (i < lane) ? nx : t;
-    }
+    const float t = lattice_position(t0, step, lane);
     c.tk = t;
     c.valid = t <= ray.tmax;
     locate(ray, g, t, c.l, c.pos);
