@@ -45,9 +45,13 @@ from . import csrc as _C
 from .grid import Rays
 
 
-# "auto" traversal: ship records from this many ranks up (below, the redundant traversal is cheaper
-# than ship mode's two extra barriers)
-SHIP_FROM_WORLD = 4
+# "auto" traversal: ship records from this many ranks up.  Measured on 8 B200s (C3, weak scaling,
+# profiles/r2_ab_variants.txt): ship 0.976 ms/step vs 0.844 with every rank traversing the whole
+# batch -- the records leave the SM as isolated 16-byte NVLink stores (trace 0.115 -> 0.22 ms per
+# rank) and the density publication as isolated 4-byte ones (optimiser 0.14 -> 0.28 ms), which costs
+# more than the redundant traversal it removes (0.26 ms at 8 ranks).  Ship mode therefore stays
+# opt-in (SVOX2_B200_SLAB_TRAVERSAL=ship) until its stores are staged into full 128-byte lines.
+SHIP_FROM_WORLD = 1 << 30
 
 
 def balanced_slabs(links: torch.Tensor, world_size: int) -> List[int]:
@@ -188,8 +192,7 @@ class SlabTrainer:
         self.use_peer_memory = os.environ.get("SVOX2_B200_PEER", "1") != "0"
         # "ship": rays sharded for the traversal, records shipped to the owning slab (needs peer
         # memory and a batch divisible by the world size); "replicated": every rank traverses all rays
-        # "auto": ship from 4 ranks up -- at 2 ranks the redundant traversal costs less than the two
-        # extra barriers of ship mode (measured, profiles/r2_ab_variants.txt)
+        # "auto": see SHIP_FROM_WORLD
         self.traversal = os.environ.get("SVOX2_B200_SLAB_TRAVERSAL", "auto")
         if self.traversal == "auto":
             self.traversal = "ship" if world_size >= SHIP_FROM_WORLD else "replicated"

@@ -163,8 +163,8 @@ def _worker(rank, world, port, out, case="default"):
 
 @pytest.mark.parametrize("world,case", [(2, "default"), (2, "stop"), (2, "ship"), (2, "ship_stop"),
                                         (2, "replicated_dense"), (2, "ship_dense_stop"),
-                                        (4, "default"), (4, "stop"), (4, "replicated_stop"),
-                                        (8, "default"), (8, "stop")])
+                                        (4, "default"), (4, "ship_stop"), (4, "replicated_stop"),
+                                        (8, "default"), (8, "ship_stop")])
 def test_multi_gpu_slab_step_equals_single_gpu_step(world, case):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs (run under gpurun --gpus {world})")
