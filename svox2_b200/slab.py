@@ -92,6 +92,7 @@ class PeerMemory:
         self.buf = symm.empty(total, dtype=torch.float32, device=device)
         self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self._views = {}        # tensor views of the inboxes (hdl.get_buffer is not free: once per shape)
         self.buf.zero_()
         # ship mode: one record workspace per rank, every rank's mapped into every process
         self.ship = None
@@ -114,12 +115,18 @@ class PeerMemory:
 
     def neighbour_inbox(self, peer: int, from_left: bool, rows: int) -> torch.Tensor:
         """The [rows,32] region of ``peer``'s buffer that receives packets from its left / right."""
-        off = self.off_hl if from_left else self.off_hr
-        return self.hdl.get_buffer(peer, (rows, self.WIDTH), torch.float32, off)
+        key = ("n", peer, from_left, rows)
+        if key not in self._views:
+            off = self.off_hl if from_left else self.off_hr
+            self._views[key] = self.hdl.get_buffer(peer, (rows, self.WIDTH), torch.float32, off)
+        return self._views[key]
 
     def inbox(self, from_left: bool, rows: int) -> torch.Tensor:
-        off = self.off_hl if from_left else self.off_hr
-        return self.buf[off:off + rows * self.WIDTH].view(rows, self.WIDTH)
+        key = ("i", from_left, rows)
+        if key not in self._views:
+            off = self.off_hl if from_left else self.off_hr
+            self._views[key] = self.buf[off:off + rows * self.WIDTH].view(rows, self.WIDTH)
+        return self._views[key]
 
 
 class SlabTrainer:
@@ -187,6 +194,7 @@ class SlabTrainer:
         # without peer memory)
         self.use_slots = os.environ.get("SVOX2_B200_SLAB_SLOTS", "1") != "0"
         self._mg = None
+        self._scr = None
         rows = [h for h in (self.halo_left, self.halo_right) if h is not None] + [self._row0]
         self._boundary_rows = torch.unique(torch.cat(rows)).contiguous()
         self.use_peer_memory = os.environ.get("SVOX2_B200_PEER", "1") != "0"
@@ -414,7 +422,8 @@ class SlabTrainer:
             peer.hdl.barrier(channel=0)     # everybody's density rows of the last step have landed
             self._refresh_row0()
         self._mark("start")
-        logT_local = None if ship else torch.empty(Qg, dtype=torch.float32, device=dev)
+        sc = self._scratch(Qg, dev)
+        logT_local = None if ship else sc["logT_local"]
         mg.begin(spec, rays._to_cpp(), ropt, self._boundary_rows, logT_local)
         self._mark("trace")
         lt_in = logT_all = None
@@ -423,16 +432,15 @@ class SlabTrainer:
         else:
             logT_all = self._gather(logT_local, "a")                             # exchange A
             self._refresh_row0()
-            lt_in = torch.empty(Qg, dtype=torch.float32, device=dev)
+            lt_in = sc["lt_in"]
             _C.slab_prefix(logT_all, rays.dirs, self.rank, lt_in)
         self._mark("exchange_a")
-        part = torch.zeros((Qg, 4), dtype=torch.float32, device=dev)
+        part = sc["part"].zero_()
         mg.shade(spec, ropt, lt_in, part)
         self._mark("shade")
         part_all = self._gather(part, "b")                                       # exchange B
-        rgb = torch.empty((Qg, 3), dtype=torch.float32, device=dev)
-        gout = torch.empty((Qg, 3), dtype=torch.float32, device=dev)
-        accum_start = torch.empty(Qg, dtype=torch.float32, device=dev)
+        rgb = torch.empty((Qg, 3), dtype=torch.float32, device=dev)     # handed to the caller: fresh
+        gout, accum_start = sc["gout"], sc["accum_start"]
         if ship:
             _C.ship_combine(part_all, peer.ship.ray_logT(), rays.dirs, rgb_gt, self.rank,
                             g.opt.background_brightness, self.beta_loss, rgb, gout, accum_start)
@@ -456,12 +464,21 @@ class SlabTrainer:
         self._steps += 1
         return rgb
 
+    def _scratch(self, n_rays: int, dev):
+        """Per-ray scratch of the slot-based step, allocated once per batch size."""
+        if self._scr is None or self._scr[0] != n_rays:
+            f = dict(dtype=torch.float32, device=dev)
+            self._scr = (n_rays, {
+                "logT_local": torch.empty(n_rays, **f), "lt_in": torch.empty(n_rays, **f),
+                "part": torch.zeros((n_rays, 4), **f), "gout": torch.empty((n_rays, 3), **f),
+                "accum_start": torch.empty(n_rays, **f), "z": torch.zeros((1, PeerMemory.WIDTH), **f)})
+        return self._scr[1]
+
     def _halo_slots(self, mg, peer):
         """The halo swap of _halo_grads in slot space: boundary planes and the row-0 packet go from
         the slot rows straight into the neighbours' inboxes, and what arrives is added to the slots."""
         width = peer.WIDTH
-        dev = self.grid.links.device
-        z = torch.zeros((1, width), dtype=torch.float32, device=dev)
+        z = self._scr[1]["z"]           # all zeros at the row-0 holder; fully rewritten by the pack elsewhere
         if not self._holds_row0:
             mg.slot_pack(self._row0, z, clear=True)
         _C.peer_store(peer.ptrs, (peer.off_z + self.rank * width) * 4, z)
