@@ -155,6 +155,7 @@ template <bool COUNT, int MODE>
 __global__ void __launch_bounds__(TRACE_THREADS, QM_TRACE_BLOCKS)
 trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv, SlabView sl, ShipView sv) {
     constexpr bool SLAB = MODE == 1, SHIP = MODE == 2;
+    __shared__ int4 ship_stage[SHIP ? TRACE_THREADS / WARP : 1][SHIP ? WARP * 6 : 1];
     int64_t ray_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (ray_id >= a.n_rays) return;
     if (SHIP) ray_id += sv.ray_offset;   // a.n_rays = this rank's share; arrays hold the global batch
@@ -255,18 +256,33 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv, SlabView sl, ShipV
                         done = true;
                         break;
                     }
-                    Record* const rd = sv.rec[d];
+                    // The nd records of this block are contiguous in rank d's queue: stage them in
+                    // shared memory and copy them out with consecutive lanes on consecutive 16-byte
+                    // chunks, so that they cross NVLink as full 128-byte lines (isolated 16-byte
+                    // stores at a 96-byte stride made the kernel twice as slow, r2_ab_variants.txt).
+                    // Chunk 5 of record 0 is the block header: written by lane 0 once its successor
+                    // is known.
+                    int4* const stage = ship_stage[threadIdx.x >> 5];
                     if ((dm >> lane) & 1u) {
                         const int rank = __popc(dm & ((1u << lane) - 1u));
-                        Record* r = rd + base + rank;
-                        int4* r4 = reinterpret_cast<int4*>(r);
+                        int4* r4 = stage + rank * 6;
                         r4[0] = make_int4(lk[0], lk[1], lk[2], lk[3]);
                         r4[1] = make_int4(lk[4], lk[5], lk[6], lk[7]);
                         const float weight = __fmul_rn(fexp(my_before), __fsub_rn(1.f, fexp(-pcnt)));
-                        reinterpret_cast<float4*>(r)[2] = make_float4(pos[0], pos[1], pos[2], weight);
+                        r4[2] = make_int4(__float_as_int(pos[0]), __float_as_int(pos[1]), __float_as_int(pos[2]),
+                                          __float_as_int(weight));
                         r4[3] = make_int4(__float_as_int(__fsub_rn(my_before, pcnt)), __float_as_int(sigma),
                                           __float_as_int(ws), (int)ray_id);
+                        r4[4] = make_int4(0, 0, 0, 0);
+                        r4[5] = make_int4(0, 0, 0, 0);
                     }
+                    __syncwarp();
+                    {
+                        int4* const dst = reinterpret_cast<int4*>(sv.rec[d] + base);
+                        for (int ch = lane; ch < nd * 6; ch += WARP)
+                            if (ch != 5) dst[ch] = stage[ch];
+                    }
+                    __syncwarp();
                     if (lane == 0) {
                         // every header / chain head is written exactly once: the header of a block
                         // when its successor (or the end of the ray's stay in that slab) is known

@@ -209,12 +209,39 @@ struct SlotOptArgs {
     const int32_t* __restrict__ n_slots;
     int width;
     float beta, lr_sh, lr_density, eps, minval;
-    // ship mode keeps density_data replicated: send[row] = 0 local only, 1 store the new value into
-    // every peer's copy, 2 into every peer's but `skip_peer` (co-owner applying the same update)
+};
+
+// Ship mode keeps density_data replicated: after the RMSProp, the new density of every updated row
+// goes into the peers' copies.  send[row] = 0 local only, 1 every peer, 2 every peer but
+// `skip_peer` (a co-owner applying the identical update).  thread = slot: slots are in row order,
+// so runs of updated rows leave the SM as coalesced NVLink writes (publishing from inside the
+// optimiser -- one lane in seven, 4 bytes each -- doubled its run time on 8 GPUs).
+struct SlotPublishArgs {
+    const float* __restrict__ density;
+    int64_t density_stride;
+    const int32_t* __restrict__ slot_row;
+    const uint8_t* __restrict__ flags;
+    const int32_t* __restrict__ n_slots;
     const uint8_t* __restrict__ send;
     float* peer_density[SVOX2_MAX_PEERS];
     int n_peers, self, skip_peer;
 };
+__global__ void __launch_bounds__(256)
+slot_publish_kernel(SlotPublishArgs a) {
+    const int64_t n = *a.n_slots;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (!__ldcg(a.flags + 2 * i)) continue;           // density of this row was not updated
+        const int64_t row = __ldg(a.slot_row + i);
+        const int mode = __ldg(a.send + row);
+        if (mode == 0) continue;
+        const float v = a.density[row * a.density_stride];
+        for (int p = 0; p < a.n_peers; ++p)
+            if (p != a.self && !(mode == 2 && p == a.skip_peer)) a.peer_density[p][row * a.density_stride] = v;
+    }
+}
+
+
 
 __device__ __forceinline__ void rmsprop_update(float& d, float& rms, float g, float beta, float lr,
                                                float eps, float minval) {
@@ -297,13 +324,6 @@ slot_rmsprop_kernel(SlotOptArgs a) {
                 rmsprop_update(dd[u], dr[u], gden, a.beta, a.lr_density, a.eps, a.minval);
                 a.density[row[u] * a.density_stride] = dd[u];
                 a.density_rms[row[u] * a.density_stride] = dr[u];
-                if (a.send != nullptr) {
-                    const int mode = __ldg(a.send + row[u]);
-                    if (mode != 0)
-                        for (int p = 0; p < a.n_peers; ++p)
-                            if (p != a.self && !(mode == 2 && p == a.skip_peer))
-                                a.peer_density[p][row[u] * a.density_stride] = dd[u];
-                }
             }
 #if SLOT_ZERO_IN_OPT
             const float z = dependent_zero(ge[0]);
@@ -804,16 +824,23 @@ extern "C" SVOX2_API int svox2_mg_step_finish(
     o.lr_density = p->lr_density;
     o.eps = p->epsilon;
     o.minval = -1e9f;
+    slot_rmsprop_kernel<<<148 * SLOT_OPT_BLOCKS, OPT_THREADS, 0, (cudaStream_t)stream>>>(o);
     if (send) {
-        o.send = send;
-        o.n_peers = p->n_slabs;
-        o.self = p->rank;
-        o.skip_peer = p->rank - 1;
+        SlotPublishArgs pa{};
+        pa.density = grid->density_data;
+        pa.density_stride = grid->density_stride;
+        pa.slot_row = w.slot_row;
+        pa.flags = w.flags;
+        pa.n_slots = w.n_slots;
+        pa.send = send;
+        pa.n_peers = p->n_slabs;
+        pa.self = p->rank;
+        pa.skip_peer = p->rank - 1;
         for (int k = 0; k < p->n_slabs; ++k) {
             SVOX2_REQUIRE(peer_density[k] != 0, "bad peer pointer");
-            o.peer_density[k] = reinterpret_cast<float*>(peer_density[k]);
+            pa.peer_density[k] = reinterpret_cast<float*>(peer_density[k]);
         }
+        slot_publish_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(pa);
     }
-    slot_rmsprop_kernel<<<148 * SLOT_OPT_BLOCKS, OPT_THREADS, 0, (cudaStream_t)stream>>>(o);
     return check_launch(__func__);
 }
