@@ -411,14 +411,6 @@ SVOX2_API int svox2_ship_backward(const svox2_grid_t* grid, int64_t n_rays_globa
                      const svox2_grads_t* grads, void* workspace, size_t workspace_bytes,
                      svox2_stream_t stream);
 
-/* Ship mode keeps density_data replicated (the tracer needs sigma along the whole ray): for every
- * row with mask[row] && own[row], data[row*stride] is stored at the same offset of every peer's
- * array (peer_base_ptrs[p] = rank p's density array mapped into this process; self and null
- * entries are skipped). */
-SVOX2_API int svox2_publish_rows(const uint8_t* mask, const uint8_t* own, const float* data, int64_t n_rows,
-                     int64_t stride, const uint64_t* peer_base_ptrs, int32_t n_peers, int32_t self_rank,
-                     svox2_stream_t stream);
-
 /* Masked RMSProp (optim_kernel.cu:15-25) on a single-channel array that ship mode keeps replicated
  * (density), with the publication fused in: send[row] = 0 keeps the new value local, 1 stores it at
  * the same offset of every peer's array, 2 of every peer but `skip_peer` (a co-owner of the row that

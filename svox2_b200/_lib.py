@@ -154,7 +154,6 @@ SIGNATURES = {
     "svox2_mg_slot_unpack_add": (C.c_int, [_P, _I64, _P, _I64, _P, _SZ, _I64, _I32, _I64, _I64, _P]),
     "svox2_mg_step_finish": (C.c_int, [_G, _P, _P, _I64, C.POINTER(MgStepT), _P, _P, _P, _SZ, _I64, _P]),
     "svox2_rmsprop_step_publish": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _P, _P, _I32, _I32, _I32, _F, _F, _F, _F, _P]),
-    "svox2_publish_rows": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _I32, _I32, _P]),
     "svox2_pack_grad_rows": (C.c_int, [_P, _I64, _I32, _P, _I64, _P, _I64, _P, _I64, _P, _P, _P]),
     "svox2_unpack_rows": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I32, _P, _I64, _I32, _P, _P, _P]),
     "svox2_peer_store": (C.c_int, [_P, _I32, _I64, _P, _I64, _P]),

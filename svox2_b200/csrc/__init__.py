@@ -1070,21 +1070,6 @@ def rmsprop_step_publish(data, rms, grad, mask, send, peer_ptrs, self_rank, skip
             float(lr), float(epsilon), float(minval), _stream()))
 
 
-def publish_rows(mask, own, data, peer_ptrs, self_rank):
-    """data[row] -> the same row of every peer's array, for rows with mask & own (ship mode keeps
-    density_data replicated; ``peer_ptrs[p]`` = rank p's array mapped into this process)."""
-    _check_cuda(mask, "mask", torch.bool, 1)
-    _check_cuda(own, "own", torch.bool, 1)
-    _check_rows(data, "data")
-    if mask.numel() != data.size(0) or own.numel() != data.size(0):
-        _fail("mask / own must have one entry per row")
-    arr = (C.c_uint64 * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
-    with torch.cuda.device(data.device):
-        check(_lib.lib().svox2_publish_rows(mask.data_ptr(), own.data_ptr(), data.data_ptr(), data.size(0),
-                                            _row_stride(data), C.addressof(arr), len(peer_ptrs), int(self_rank),
-                                            _stream()))
-
-
 def peer_store(peer_ptrs, dst_offset_bytes, src):
     """src -> (base + dst_offset_bytes) of every peer buffer (list of device pointers mapped into
     this process, e.g. torch symmetric memory ``buffer_ptrs``); one launch, NVLink P2P stores."""

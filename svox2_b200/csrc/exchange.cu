@@ -204,21 +204,6 @@ peer_store_kernel(PeerPtrs peers, int64_t dst_off4, const float4* __restrict__ s
     }
 }
 
-// Ship mode: the rank that traces a ray evaluates sigma along the WHOLE ray, so the density array
-// (4 B per voxel, unlike the SH rows) is kept replicated: after its RMSProp every rank stores the
-// rows it just updated (mask & exclusively-owned) into every peer's copy.  lane = row, so runs of
-// updated rows leave the SM as coalesced NVLink writes.
-__global__ void __launch_bounds__(256)
-publish_rows_kernel(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ own,
-                    const float* __restrict__ data, int64_t n_rows, int64_t stride, PeerPtrs peers, int self) {
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= n_rows) return;
-    if (!__ldg(mask + row) || !__ldg(own + row)) return;
-    const float v = data[row * stride];
-    for (int p = 0; p < peers.n; ++p)
-        if (p != self && peers.base[p] != nullptr) peers.base[p][row * stride] = v;
-}
-
 struct PackedOptArgs {
     float* __restrict__ sh_data;
     float* __restrict__ sh_rms;
@@ -450,21 +435,5 @@ extern "C" SVOX2_API int svox2_peer_store(const uint64_t* peer_base_ptrs, int32_
     const int64_t want = (n4 + 255) / 256;
     peer_store_kernel<<<(unsigned)(want < 148 * 4 ? want : 148 * 4), 256, 0, (cudaStream_t)stream>>>(
         peers, dst_offset_bytes / 16, static_cast<const float4*>(src), n4);
-    return check_launch(__func__);
-}
-
-extern "C" SVOX2_API int svox2_publish_rows(const uint8_t* mask, const uint8_t* own, const float* data,
-                                            int64_t n_rows, int64_t stride, const uint64_t* peer_base_ptrs,
-                                            int32_t n_peers, int32_t self_rank, svox2_stream_t stream) {
-    SVOX2_REQUIRE(n_rows >= 0 && stride >= 1 && n_peers >= 1 && n_peers <= SVOX2_MAX_PEERS && self_rank >= 0 &&
-                      self_rank < n_peers,
-                  "bad arguments");
-    if (n_rows == 0 || n_peers == 1) return SVOX2_OK;
-    SVOX2_REQUIRE(mask && own && data && peer_base_ptrs, "null argument");
-    PeerPtrs peers;
-    peers.n = n_peers;
-    for (int p = 0; p < n_peers; ++p) peers.base[p] = reinterpret_cast<float*>(peer_base_ptrs[p]);  // 0: skip
-    publish_rows_kernel<<<div_up(n_rows, 256), 256, 0, (cudaStream_t)stream>>>(mask, own, data, n_rows, stride,
-                                                                             peers, self_rank);
     return check_launch(__func__);
 }

@@ -173,18 +173,6 @@ class SlabTrainer:
         x0 = int(at[0, 0].item()) if at.numel() else 0
         self._row0_owner = max(k for k in range(world_size) if self.bounds[k] <= x0)
         self._row0_pending = False      # a published row 0 waits in the peer buffer
-        # rows whose gradient depends on another rank (co-owned planes, row 0 at its holder) and the
-        # rest of the owned rows: the latter are updated while the halo swap is in flight
-        self._boundary = torch.zeros_like(self.own_mask)
-        for h in (self.halo_left, self.halo_right):
-            if h is not None:
-                self._boundary[h] = True
-        if self._holds_row0:
-            self._boundary[0] = True
-        self._interior = self.own_mask & ~self._boundary
-        # A/B on 2 GPUs (profiles/r2_ab_variants.txt): the split costs four mask passes and two extra
-        # optimiser scans over the N-row arrays, more than the barrier wait it hides -> off by default
-        self.overlap_halo = os.environ.get("SVOX2_B200_HALO_OVERLAP", "0") != "0"
         self._ws = None
         self.slots_per_ray = None  # record slots per ray of the workspace (None: min(diagonal, 512))
         self._peer = None          # PeerMemory for the current batch size, False if unavailable
@@ -255,7 +243,8 @@ class SlabTrainer:
 
     def _bind_symmetric_density(self):
         """Ship mode keeps density_data replicated: re-home it in symmetric memory so that the owners
-        can store their updated rows straight into every rank's copy (svox2_publish_rows)."""
+        can store their updated rows straight into every rank's copy (svox2_rmsprop_step_publish /
+        svox2_mg_step_finish)."""
         import torch.distributed._symmetric_memory as symm
         g = self.grid
         old = g.density_data.data
@@ -561,50 +550,18 @@ class SlabTrainer:
         lr_d = self.lr_sigma if lr_sigma is None else lr_sigma
         lr_s = self.lr_sh if lr_sh is None else lr_sh
         ship = self._density_ptrs is not None and self._peer not in (None, False) and self._peer.ship is not None
-        peer = self._peer if (self._peer not in (None, False)) else None
-        width = _C.packed_row_floats(g.sh_data.grad.size(1) + 2)
-        if self.world_size > 1 and peer is not None and width == peer.WIDTH and self.overlap_halo:
-            # peer memory: send the boundary planes, update the INTERIOR rows while the packets and
-            # the barrier are in flight, then add what arrived and update the boundary rows
-            self._halo_send(peer, width)
-            md, msh = g.sparse_grad_indexer, g.sparse_sh_grad_indexer
-            self._mark("halo_grads")
-            g.sparse_grad_indexer = md & self._interior
-            g.sparse_sh_grad_indexer = msh & self._interior
-            if ship:
-                self._density_step_publish(lr_d)
-            else:
-                g.optim_density_step(lr_d, beta=self.rms_beta)
-            g.optim_sh_step(lr_s, beta=self.rms_beta)
-            self._mark("optimiser")
-            self._halo_recv(peer, width, md, msh)
-            g.sparse_grad_indexer = md & self._boundary
-            g.sparse_sh_grad_indexer = msh & self._boundary
-            if ship:
-                self._density_step_publish(lr_d)
-            else:
-                g.optim_density_step(lr_d, beta=self.rms_beta)
-            g.optim_sh_step(lr_s, beta=self.rms_beta)
-            # the masks of the step, for callers (owned rows; both groups were updated above)
-            g.sparse_grad_indexer, g.sparse_sh_grad_indexer = md, msh
-            if not self._holds_row0:
-                md[0] = False
-                msh[0] = False
-            self._publish_row0()
-            self._mark("halo_grads")
+        self._halo_grads()
+        if not self._holds_row0:    # the only row outside own_mask a step can touch (TV face cells)
+            g.sparse_grad_indexer[0] = False
+            g.sparse_sh_grad_indexer[0] = False
+        self._mark("halo_grads")
+        if ship:
+            self._density_step_publish(lr_d)
         else:
-            self._halo_grads()
-            if not self._holds_row0:    # the only rows outside own_mask a step can touch (TV face cells)
-                g.sparse_grad_indexer[0] = False
-                g.sparse_sh_grad_indexer[0] = False
-            self._mark("halo_grads")
-            if ship:
-                self._density_step_publish(lr_d)
-            else:
-                g.optim_density_step(lr_d, beta=self.rms_beta)
-            g.optim_sh_step(lr_s, beta=self.rms_beta)
-            self._publish_row0()
-            self._mark("optimiser")
+            g.optim_density_step(lr_d, beta=self.rms_beta)
+        g.optim_sh_step(lr_s, beta=self.rms_beta)
+        self._publish_row0()
+        self._mark("optimiser")
 
         if self._steps % 256 == 0:
             self.check_overflow()
@@ -658,42 +615,6 @@ class SlabTrainer:
         g = self.grid
         slot = peer.buf[peer.off_p:peer.off_p + peer.WIDTH].view(1, peer.WIDTH)
         _C.unpack_rows(slot, self._row0, g.sh_data.data, g.density_data.data, False)
-
-    def _halo_send(self, peer, width):
-        """Peer-memory halo swap, first half: row-0 packet and the two boundary planes go straight
-        into the neighbours' inboxes (NVLink stores)."""
-        g = self.grid
-        gsh, gd = g.sh_data.grad, g.density_data.grad
-        md, msh = g.sparse_grad_indexer, g.sparse_sh_grad_indexer
-        z = torch.zeros((1, width), dtype=torch.float32, device=gsh.device)
-        if not self._holds_row0:
-            _C.pack_grad_rows(gsh, gd, self._row0, z, mask_a=md, mask_b=msh)
-            gsh[0] = 0.0
-            gd[0] = 0.0
-        _C.peer_store(peer.ptrs, (peer.off_z + self.rank * width) * 4, z)
-        if self.halo_right is not None and self.halo_right.numel():
-            _C.pack_grad_rows(gsh, gd, self.halo_right,
-                              peer.neighbour_inbox(self.rank + 1, True, self.halo_right.numel()),
-                              mask_a=md, mask_b=msh)
-        if self.halo_left is not None and self.halo_left.numel():
-            _C.pack_grad_rows(gsh, gd, self.halo_left,
-                              peer.neighbour_inbox(self.rank - 1, False, self.halo_left.numel()),
-                              mask_a=md, mask_b=msh)
-
-    def _halo_recv(self, peer, width, md, msh):
-        """Second half: barrier, then add what the neighbours sent (gradients and mask bits)."""
-        g = self.grid
-        gsh, gd = g.sh_data.grad, g.density_data.grad
-        peer.hdl.barrier(channel=3)
-        if self.halo_left is not None and self.halo_left.numel():
-            _C.unpack_rows(peer.inbox(True, self.halo_left.numel()), self.halo_left, gsh, gd, True,
-                           mask_a=md, mask_b=msh)
-        if self.halo_right is not None and self.halo_right.numel():
-            _C.unpack_rows(peer.inbox(False, self.halo_right.numel()), self.halo_right, gsh, gd, True,
-                           mask_a=md, mask_b=msh)
-        if self._holds_row0:
-            zs = peer.buf[peer.off_z:peer.off_z + self.world_size * width].view(self.world_size, width)
-            _C.unpack_rows(zs.sum(0, keepdim=True), self._row0, gsh, gd, True, mask_a=md, mask_b=msh)
 
     def _halo_grads(self):
         """The first voxel plane of every slab is co-owned with the left neighbour (its last cell
