@@ -178,6 +178,30 @@ masked_rows_vec_kernel(OptArgs a, int qpr) {
         for (int c = 0; c < OPT_SUPER / WARP; ++c) {
         unsigned m = __shfl_sync(FULL, h, 2 * c) | (__shfl_sync(FULL, h, 2 * c + 1) << 16);
         const int64_t row0 = sc * OPT_SUPER + c * WARP;
+        if (qpr == 1) {
+            // 4-channel rows (MSI texels): lane = row, adjacent lanes touch adjacent 16-byte rows; the
+            // touched rows of a ray are runs of consecutive layers, so most chunks are empty or dense
+            if ((m >> lane) & 1u) {
+                const int64_t o = (row0 + lane) * a.stride;
+                float4 g4 = *reinterpret_cast<const float4*>(a.grad + o);
+                float4 d4 = *reinterpret_cast<const float4*>(a.data + o);
+                float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (RMS) r4 = *reinterpret_cast<const float4*>(a.rms + o);
+                float* gv = reinterpret_cast<float*>(&g4);
+                float* dv = reinterpret_cast<float*>(&d4);
+                float* rv = reinterpret_cast<float*>(&r4);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (ok[e]) {
+                        if (RMS) rmsprop_once(dv + e, rv + e, gv + e, a.beta, lr4[e], a.eps, a.minval);
+                        else sgd_once(dv + e, gv + e, lr4[e]);
+                    }
+                if (RMS) *reinterpret_cast<float4*>(a.rms + o) = r4;
+                *reinterpret_cast<float4*>(a.data + o) = d4;
+                *reinterpret_cast<float4*>(a.grad + o) = g4;
+            }
+            continue;
+        }
         while (m) {
             // pop the next U*rpp touched rows in address order; group g of pass u keeps row g + u*rpp
             int sel[U];
@@ -219,92 +243,6 @@ masked_rows_vec_kernel(OptArgs a, int qpr) {
                 }
         }
         }
-    }
-}
-
-// bool-mask variant for rows of at most 4 floats (MSI texels, [Nbg*L, 4]): lane = row, adjacent lanes
-// touch adjacent 16-byte rows.  The touched rows of a ray are runs of consecutive layers of one
-// texel, so a non-empty 512-row super-chunk is mostly dense: four 32-row chunks (12 independent
-// 128-bit loads per lane) are in flight at a time instead of one dependent load -> update -> store
-// chain per chunk (the generic kernel above spent 0.39 ms on the 134 M-row MSI array of tnt.json).
-template <bool RMS>
-__global__ void __launch_bounds__(OPT_THREADS, 8)
-masked_quad_rows_kernel(OptArgs a) {
-    const int lane = threadIdx.x & 31;
-    float lr4[4];
-    bool ok[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        ok[e] = e < a.C;
-        lr4[e] = (e == a.C - 1) ? a.lr_last : a.lr;
-    }
-    const int64_t nsuper = (a.rows + OPT_SUPER - 1) / OPT_SUPER;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const bool mask_al = (reinterpret_cast<uintptr_t>(a.mask) & 15u) == 0;
-    // the scan is one dependent global load per super-chunk: a warp keeps QUAD_SCAN of them in flight
-    constexpr int QUAD_SCAN = 4;
-    for (int64_t sc0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * QUAD_SCAN; sc0 < nsuper;
-         sc0 += nwarps * QUAD_SCAN) {
-      uint32_t hh[QUAD_SCAN];
-#pragma unroll
-      for (int u = 0; u < QUAD_SCAN; ++u) {
-        const int64_t base = (sc0 + u) * OPT_SUPER + lane * 16;
-        uint32_t w[4] = {0u, 0u, 0u, 0u};
-        if (mask_al && base + 16 <= a.rows) {
-            const uint4 q = __ldg(reinterpret_cast<const uint4*>(a.mask + base));
-            w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
-        } else {
-            for (int k = 0; k < 16 && base + k < a.rows; ++k)
-                w[k >> 2] |= (uint32_t)(__ldg(a.mask + base + k) != 0) << (8 * (k & 3));
-        }
-        uint32_t h = 0;   // 16 bytes -> 16 bits; two lanes' halves make the ballot of one 32-row chunk
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t nz = __vcmpne4(w[i], 0u) & 0x01010101u;
-            h |= (((nz * 0x01020408u) >> 24) & 0xfu) << (4 * i);
-        }
-        hh[u] = h;
-      }
-#pragma unroll
-      for (int u = 0; u < QUAD_SCAN; ++u) {
-        const uint32_t h = hh[u];
-        const int64_t sc = sc0 + u;
-        if (!__any_sync(FULL, h != 0u)) continue;
-#pragma unroll 1
-        for (int c0 = 0; c0 < OPT_SUPER / WARP; c0 += 4) {
-            int64_t o[4];
-            float4 g4[4], d4[4], r4[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int c = c0 + k;
-                const unsigned m = __shfl_sync(FULL, h, 2 * c) | (__shfl_sync(FULL, h, 2 * c + 1) << 16);
-                o[k] = ((m >> lane) & 1u) ? (sc * OPT_SUPER + c * WARP + lane) * a.stride : -1;
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (o[k] >= 0) {
-                    g4[k] = *reinterpret_cast<const float4*>(a.grad + o[k]);
-                    d4[k] = *reinterpret_cast<const float4*>(a.data + o[k]);
-                    if (RMS) r4[k] = *reinterpret_cast<const float4*>(a.rms + o[k]);
-                }
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (o[k] >= 0) {
-                    float* gv = reinterpret_cast<float*>(&g4[k]);
-                    float* dv = reinterpret_cast<float*>(&d4[k]);
-                    float* rv = reinterpret_cast<float*>(&r4[k]);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (ok[e]) {  // padding floats keep their values
-                            if (RMS) rmsprop_once(dv + e, rv + e, gv + e, a.beta, lr4[e], a.eps, a.minval);
-                            else sgd_once(dv + e, gv + e, lr4[e]);
-                        }
-                    if (RMS) *reinterpret_cast<float4*>(a.rms + o[k]) = r4[k];
-                    *reinterpret_cast<float4*>(a.data + o[k]) = d4[k];
-                    *reinterpret_cast<float4*>(a.grad + o[k]) = g4[k];
-                }
-        }
-      }
     }
 }
 
@@ -381,11 +319,7 @@ void launch(const OptArgs& a, int kind, int64_t n_index, cudaStream_t st) {
             const int64_t want = div_up(supers * WARP, OPT_THREADS);
             const int64_t cap = OPT_VEC_GRID_CAP > 0 ? 148 * OPT_VEC_GRID_CAP : want;
             const unsigned blocks = (unsigned)(want < cap ? want : cap);
-            if (qpr == 1) {  // one warp per 4 super-chunks
-                const unsigned qb = (unsigned)div_up(((supers + 3) / 4) * WARP, OPT_THREADS);
-                masked_quad_rows_kernel<RMS><<<qb, OPT_THREADS, 0, st>>>(a);
-            }
-            else masked_rows_vec_kernel<RMS><<<blocks, OPT_THREADS, 0, st>>>(a, qpr);
+            masked_rows_vec_kernel<RMS><<<blocks, OPT_THREADS, 0, st>>>(a, qpr);
             return;
         }
         const int64_t warps = (a.rows + WARP - 1) / WARP;

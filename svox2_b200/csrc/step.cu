@@ -250,14 +250,6 @@ __device__ __forceinline__ void rmsprop_update(float& d, float& rms, float g, fl
     d = fmaxf(__fsub_rn(d, __fdiv_rn(__fmul_rn(lr, g), __fadd_rn(sqrtf(rms), eps))), minval);
 }
 
-// Zero that depends on the loaded value: an INDEPENDENT store to an address whose load is still in
-// flight stalls the memory pipeline badly (measured in round 1).
-__device__ __forceinline__ float dependent_zero(float x) {
-    int z;
-    asm volatile("and.b32 %0, %1, 0;" : "=r"(z) : "r"(__float_as_int(x)));
-    return __int_as_float(z);
-}
-
 #ifndef SLOT_OPT_PASSES
 #define SLOT_OPT_PASSES 2
 #endif
