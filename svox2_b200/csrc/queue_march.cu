@@ -209,12 +209,16 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv, SlabView sl, ShipV
             if (SLAB && t0 > t_exit) break;  // past the slab: nothing left for this rank
             // one round = 32 lattice candidates t0 + lane*step (traverse.cuh)
             Candidates c;
-            load_candidates<false>(ray, g, t0, step, lane, c);
+            if (SLAB) load_candidates<true>(ray, g, t0, step, lane, c, sl.x_lo, sl.x_hi);
+            else load_candidates<false>(ray, g, t0, step, lane, c);
             float t_next = 0.f;
             unsigned n_skips = 0;
             unsigned members = resolve_lattice(ray, c, step, t_next, done, n_skips);
             if (COUNT) cnt[0] += n_skips;
-            if (!done) prefetch_next_links(ray, g, t_next, step, lane);
+            if (!done) {
+                if (SLAB) prefetch_next_links(ray, g, t_next, step, lane, sl.x_lo, sl.x_hi);
+                else prefetch_next_links(ray, g, t_next, step, lane);
+            }
             if (SLAB) members &= __ballot_sync(FULL, c.l[0] >= sl.x_lo && c.l[0] < sl.x_hi);
             const bool member = (members >> lane) & 1u;
             const float sigma = member_sigma(g, c, member);

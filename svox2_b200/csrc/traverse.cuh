@@ -65,9 +65,12 @@ struct Candidates {
 
 // TWO_PHASE: load the skip-deciding link first and the other seven only for candidates that do
 // not skip (fewer link sectors in empty space, one more dependent round trip for samples).
+// x_lo / x_hi (TWO_PHASE only): the other seven links are loaded only for candidates whose cell lies
+// in [x_lo, x_hi) -- slab mode traverses the part of a ray outside its slab for the lattice alone.
 template <bool TWO_PHASE>
 __device__ __forceinline__ void load_candidates(const Ray& ray, const GridView& g, float t0,
-                                                float step, int lane, Candidates& c) {
+                                                float step, int lane, Candidates& c,
+                                                int x_lo = -0x7fffffff, int x_hi = 0x7fffffff) {
     const float t = lattice_position(t0, step, lane);
     c.tk = t;
     c.valid = t <= ray.tmax;
@@ -79,7 +82,7 @@ __device__ __forceinline__ void load_candidates(const Ray& ray, const GridView& 
         if (c.valid) c.lk[0] = __ldg(lp);
         c.skipd = skip_dist(ray, c.valid ? c.lk[0] : 0, c.l, c.pos);
         c.is_skip = c.valid && (c.skipd >= step);
-        if (c.valid && !c.is_skip) {
+        if (c.valid && !c.is_skip && c.l[0] >= x_lo && c.l[0] < x_hi) {
 #pragma unroll
             for (int q = 1; q < 8; ++q) c.lk[q] = __ldg(lp + corner_off(g, q));
         }
@@ -131,7 +134,8 @@ __device__ __forceinline__ unsigned resolve_lattice(const Ray& ray, const Candid
 
 // Touch the link lines the next round's candidates will probe (positions need not be exact).
 __device__ __forceinline__ void prefetch_next_links(const Ray& ray, const GridView& g, float t_next,
-                                                    float step, int lane) {
+                                                    float step, int lane, int x_lo = -0x7fffffff,
+                                                    int x_hi = 0x7fffffff) {
     const float ta = fmaf((float)lane, step, t_next);
     if (ta <= ray.tmax) {
         int nl[3];
@@ -139,9 +143,11 @@ __device__ __forceinline__ void prefetch_next_links(const Ray& ray, const GridVi
         locate(ray, g, ta, nl, npos);
         const int32_t* np = g.links + ((int64_t)nl[0] * g.offx + (int64_t)nl[1] * g.offy + nl[2]);
         prefetch_l2(np);
-        prefetch_l2(np + g.offy);
-        prefetch_l2(np + g.offx);
-        prefetch_l2(np + g.offx + g.offy);
+        if (nl[0] >= x_lo - 1 && nl[0] <= x_hi) {   // outside the slab only the skip-deciding link is read
+            prefetch_l2(np + g.offy);
+            prefetch_l2(np + g.offx);
+            prefetch_l2(np + g.offx + g.offy);
+        }
     }
 }
 
