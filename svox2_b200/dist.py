@@ -86,6 +86,7 @@ class ShardedTrainer:
         self._step_ws = None
         self.slots_per_ray = None       # record slots per ray of the fused step's queue (None: worst case)
         self.last_mse = None            # fused step: 0-dim device tensor, F.mse_loss(rgb, rgb_gt) of the last step
+        self._mse_pair = None
 
     def _tv_run(self):
         """This rank's slice (start, count) of the step's contiguous wrapped cell run (drawn with
@@ -127,8 +128,12 @@ class ShardedTrainer:
             start, n = g._draw_cell_run(self.tv_sparsity)
             tv_s = (start, n, self.lambda_tv_sh)
         rgb = torch.empty_like(rgb_gt)
-        if self.last_mse is None:
-            self.last_mse = torch.zeros((), dtype=torch.float32, device=rgb_gt.device)
+        # two alternating device scalars: a reader on another stream (bench e2e loop) may still be
+        # copying step i's loss out while step i+1's clear kernel zeroes its own
+        if self._mse_pair is None:
+            self._mse_pair = [torch.zeros((), dtype=torch.float32, device=rgb_gt.device) for _ in range(2)]
+        self._mse_pair.reverse()
+        self.last_mse = self._mse_pair[0]
         _C.train_step(g._to_cpp(), g.density_rms, g.sh_rms, rays._to_cpp(), g.opt._to_cpp(), rgb_gt.contiguous(),
                       rgb, self._step_ws, tv_density=tv_d, tv_sh=tv_s, beta_loss=self.beta_loss,
                       sparsity_loss=self.sparsity_loss, norm_rays=Q, lr_density=lr_sigma, lr_sh=lr_sh,
