@@ -54,6 +54,7 @@ namespace {
 #define QM_SCATTER_BLOCKS 4
 #endif
 
+constexpr int BLK_TABLE = 64;      // blocks per ray kept in the table (later ones: chain only)
 constexpr int TRACE_THREADS = 64;
 constexpr int SAMPLE_THREADS = 256;
 
@@ -77,6 +78,10 @@ struct QueueView {
     float* __restrict__ ray_logT; // [Q] forward log-transmittance (-1e3 when stopped)
     float4* __restrict__ ray_Y;   // [Q][8] SH basis value of channels 4q..4q+3 (0 for padding)
     float* __restrict__ ray_accum;// [Q] what is left of the reference's accum behind the foreground (MSI)
+    // per-ray block table for K3: (first record, count) of the ray's first BLK_TABLE blocks and the
+    // number of blocks, so that K3 need not walk the chain header by header (NULL: ship mode)
+    int2* __restrict__ blk_table; // [Q][BLK_TABLE]
+    int* __restrict__ ray_nblk;   // [Q]
     // ship mode (record shipping between slabs): the record array is n_regions sub-arrays of
     // region_cap records, region k filled by rank k; counts[k] = records in region k this step
     const int* __restrict__ counts;
@@ -185,6 +190,7 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv, SlabView sl, ShipV
     // ship mode: destination of the block whose header is still pending, that block, its size
     int cur_dest = -1, pend_blk = -1, pend_n = 0;
     unsigned visited = 0u;
+    int n_blk = 0;            // blocks of this ray so far (non-ship modes)
 
     // slab mode: t-interval in which the x coordinate can fall into the slab (one cell of margin;
     // the outermost slabs are open-ended because locate() clamps)
@@ -325,11 +331,13 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv, SlabView sl, ShipV
                         r4[3] = make_int4(__float_as_int(__fsub_rn(my_before, pcnt)), __float_as_int(sigma),
                                           __float_as_int(ws), (int)ray_id);
                     }
-                    if (lane == 0) {  // block header and chain: always written by lane 0
+                    if (lane == 0) {  // block header, chain and table: always written by lane 0
                         reinterpret_cast<int4*>(qv.rec + base)[5] = make_int4(n, -1, 0, 0);
                         if (prev_blk >= 0) qv.rec[prev_blk].blk_next = base;
                         else first_blk = base;
+                        if (n_blk < BLK_TABLE) qv.blk_table[ray_id * BLK_TABLE + n_blk] = make_int2(base, n);
                     }
+                    ++n_blk;
                     prev_blk = base;
                 }
             }
@@ -365,6 +373,7 @@ trace_kernel(GridView g, Opts opt, MarchArgs a, QueueView qv, SlabView sl, ShipV
     if (lane == 0) {
         if (!SLAB && !hit) first_blk = -2;  // the seed kernel tells "missed the grid" from "no active sample"
         qv.ray_first[ray_id] = first_blk;
+        qv.ray_nblk[ray_id] = n_blk;
         qv.ray_logT[ray_id] = logT_fwd;
         if (COUNT) {
             atomicAdd(a.counters + 0, (unsigned long long)cnt[0]);
@@ -404,6 +413,23 @@ __device__ __forceinline__ void red_quad(float* __restrict__ p, int qi, int D, f
     }
 }
 
+// cp.async (LDGSTS) staging of records: the sample-parallel kernels walk records whose addresses are
+// known iterations ahead, so the next records travel global -> shared memory while the current one is
+// processed, at no register cost (ncu, r2: half of K4's stall samples sat on the first use of the
+// record it had just asked for).
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+#ifndef QM_RING
+#define QM_RING 4   // records in flight per 8-lane group (96 bytes of shared memory each)
+#endif
+
 __device__ __forceinline__ void corner_weights(float px, float py, float pz, float* wq) {
     const float ax = 1.f - px, ay = 1.f - py, az = 1.f - pz;
     const float yz00 = ay * az, yz01 = ay * pz, yz10 = py * az, yz11 = py * pz;
@@ -428,16 +454,42 @@ shade_kernel(GridView g, QueueView qv, float* __restrict__ rgb_out, SlabView sl,
     const int D = g.sh_dim, B = g.basis_dim;
     int ce[4];  // colour of each of this lane's channels (lane constant)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) ce[e] = (qi * 4 + e < D) ? (qi * 4 + e) / B : -1;
+    for (int e = 0; e < 4; ++e) {   // channel j belongs to colour j / B (j < 3B: two compares, no division)
+        const int j = qi * 4 + e;
+        ce[e] = (j < D) ? (j >= B) + (j >= 2 * B) : -1;
+    }
     const float* shq = g.sh + (qi * 4 < D ? qi * 4 : 0);
     const unsigned gmask = 0xffu << (threadIdx.x & 24);  // the 8 lanes that share a sample
     const int groups = (gridDim.x * blockDim.x) >> 3;
-    for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; s < n; s += groups) {
+    // the group's next QM_RING records (s, s + groups, ...) are on their way into shared memory:
+    // lane q < 4 copies 16-byte chunk q (links, links, pos + weight, transmittance / sigma / ray)
+    __shared__ int4 ring[SAMPLE_THREADS / 8][QM_RING][4];
+    int4 (*const my_ring)[4] = ring[threadIdx.x >> 3];
+    auto stage = [&](int s, int k) {
+        if (s < n && qi < 4)
+            cp_async16(&my_ring[k % QM_RING][qi],
+                       reinterpret_cast<const int4*>(qv.rec + region_index<MODE>(rg, s, cur1)) + qi);
+        cp_async_commit();   // (an empty group keeps the count per iteration uniform)
+    };
+    const int s_first = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+#pragma unroll
+    for (int k = 0; k < QM_RING; ++k) stage(s_first + k * groups, k);
+    int k = 0;
+    for (int s = s_first; s < n; s += groups, ++k) {
         const int si = region_index<MODE>(rg, s, cur0);
-        const Record* r = qv.rec + si;
+        cp_async_wait<QM_RING - 1>();   // this lane's chunk of record s has landed ...
+        __syncwarp(gmask);              // ... and so have the other lanes'
+        const int4(&slot)[4] = my_ring[k % QM_RING];
+        const int4 la = slot[0];
+        const int4 lb = slot[1];
+        float4 pw = *reinterpret_cast<const float4*>(&slot[2]);
+        const float4 st = *reinterpret_cast<const float4*>(&slot[3]);
+        const int ray = __float_as_int(st.w);
 #if QM_GATHER_AHEAD & 1
-        if (s + groups < n) {  // lane q of the group pulls corner q of the next record
-            const int32_t ln = __ldcg(&qv.rec[region_index<MODE>(rg, s + groups, cur1)].lk[qi]);
+        if (s + groups < n) {  // lane q of the group pulls corner q of the next record towards L2
+            cp_async_wait<QM_RING - 2>();
+            __syncwarp(gmask);
+            const int32_t ln = reinterpret_cast<const int32_t*>(&my_ring[(k + 1) % QM_RING][0])[qi];
             if (ln >= 0) {
                 const float* row = g.sh + (size_t)ln * (unsigned)g.sh_stride;
                 prefetch_l2(row);
@@ -445,14 +497,11 @@ shade_kernel(GridView g, QueueView qv, float* __restrict__ rgb_out, SlabView sl,
             }
         }
 #endif
-        const int4 la = __ldcg(reinterpret_cast<const int4*>(r));
-        const int4 lb = __ldcg(reinterpret_cast<const int4*>(r) + 1);
-        float4 pw = __ldcg(reinterpret_cast<const float4*>(r) + 2);
-        const int ray = __ldcg(&r->ray);
+        __syncwarp(gmask);              // everybody has read slot k: refill it
+        stage(s + QM_RING * groups, k + QM_RING);
         if (SLAB) {
             // pw.w is the slab-local log-transmittance before the sample (cuvol.cu:170-178 with the
             // entry value added); a sample behind the stop threshold is dead for K3 / K4 too
-            const float4 st = __ldcg(reinterpret_cast<const float4*>(r) + 3);
             const float lt_in = __ldg(sl.lt_in + ray);
             const float before = __fadd_rn(lt_in, pw.w);
             if (fexp(before) < sl.stop_thresh) {
@@ -560,14 +609,63 @@ seed_kernel(Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
     }
     const float lt_in = REL ? __ldg(sl.lt_in + ray_id) : 0.f;
     if (SLAB) accum = __ldg(sl.accum_start + ray_id);  // seed and beta term of the whole ray
-    while (blk >= 0) {
-        const int count = __ldcg(&qv.rec[blk].blk_count);
-        const int next = __ldcg(&qv.rec[blk].blk_next);
-        bool on = lane < count;
-        Record* r = qv.rec + blk + (on ? lane : 0);
-        const float4 pw = __ldcg(reinterpret_cast<const float4*>(r) + 2);
-        const float4 st = __ldcg(reinterpret_cast<const float4*>(r) + 3);
-        const float4 co = __ldcg(reinterpret_cast<const float4*>(r) + 4);
+    // The ray's blocks in sample order.  With the block table (written by K1) the addresses of all
+    // blocks are known up front: block b+1's records are loaded while block b is scanned, instead of
+    // one dependent header -> records round trip per block (the kernel was pure L2 latency: 31 us at
+    // 8 % issue utilisation).  Blocks behind the table, and ship mode, walk the chain.
+    const bool use_table = MODE != 2 && qv.blk_table != nullptr;
+    const int n_tab = use_table ? min(__ldcg(qv.ray_nblk + ray_id), BLK_TABLE) : 0;
+    int2 ent = make_int2(-1, 0);     // lane j: table entry j of the current window of 32 blocks
+    if (n_tab > 0 && lane < n_tab) ent = __ldcg(qv.blk_table + ray_id * BLK_TABLE + lane);
+    int tb = 0;                      // next table entry
+    // current block: its records in registers
+    int cur = blk, cur_count = 0, cur_next = -1;
+    float4 pw, st, co;
+    auto load_block = [&](int b, int count_hint, int& count, int& next, float4& q_pw, float4& q_st, float4& q_co) {
+        // count_hint >= 0: from the table (no header read needed for the addresses)
+        count = count_hint >= 0 ? count_hint : __ldcg(&qv.rec[b].blk_count);
+        const Record* r = qv.rec + b + (lane < count ? lane : 0);
+        q_pw = __ldcg(reinterpret_cast<const float4*>(r) + 2);
+        q_st = __ldcg(reinterpret_cast<const float4*>(r) + 3);
+        q_co = __ldcg(reinterpret_cast<const float4*>(r) + 4);
+        next = -1;
+    };
+    if (n_tab > 0) {
+        cur = __shfl_sync(FULL, ent.x, 0);
+        load_block(cur, __shfl_sync(FULL, ent.y, 0), cur_count, cur_next, pw, st, co);
+        tb = 1;
+    } else {
+        load_block(cur, -1, cur_count, cur_next, pw, st, co);
+        cur_next = __ldcg(&qv.rec[cur].blk_next);
+    }
+    while (cur >= 0) {
+        // issue the next block's loads before touching this block's data
+        int nxt = -1, nxt_count = 0, nxt_next = -1;
+        float4 npw = make_float4(0.f, 0.f, 0.f, 0.f), nst = npw, nco = npw;
+        if (tb > 0) {   // table mode
+            if (tb < n_tab) {
+                if ((tb & 31) == 0) ent = (tb + lane < n_tab) ? __ldcg(qv.blk_table + ray_id * BLK_TABLE + tb + lane)
+                                                              : make_int2(-1, 0);
+                nxt = __shfl_sync(FULL, ent.x, tb & 31);
+                load_block(nxt, __shfl_sync(FULL, ent.y, tb & 31), nxt_count, nxt_next, npw, nst, nco);
+                ++tb;
+            } else if (n_tab == BLK_TABLE) {    // the table is full: the rest of the ray hangs off the chain
+                nxt = __ldcg(&qv.rec[cur].blk_next);
+                tb = 0;
+                if (nxt >= 0) {
+                    load_block(nxt, -1, nxt_count, nxt_next, npw, nst, nco);
+                    nxt_next = __ldcg(&qv.rec[nxt].blk_next);
+                }
+            }
+        } else {
+            nxt = cur_next;
+            if (nxt >= 0) {
+                load_block(nxt, -1, nxt_count, nxt_next, npw, nst, nco);
+                nxt_next = __ldcg(&qv.rec[nxt].blk_next);
+            }
+        }
+        bool on = lane < cur_count;
+        Record* r = qv.rec + cur + (on ? lane : 0);
         if (REL) on = on && pw.w >= 0.f;  // dead: behind the stop threshold
         const float w = pw.w, after = REL ? __fadd_rn(lt_in, st.x) : st.x, sigma = st.y, ws = st.z;
         const float col[3] = {co.x, co.y, co.z};
@@ -598,7 +696,12 @@ seed_kernel(Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
             if (a.sparsity_loss > 0.f) cgs += a.sparsity_loss * (4 * sigma / (1 + 2 * (sigma * sigma)));
             reinterpret_cast<float4*>(r)[4] = make_float4(gc[0], gc[1], gc[2], cgs);
         }
-        blk = next;
+        cur = nxt;
+        cur_count = nxt_count;
+        cur_next = nxt_next;
+        pw = npw;
+        st = nst;
+        co = nco;
     }
     if (!SLAB && a.accum_out != nullptr && lane == 0) a.accum_out[ray_id] = accum - beta_term;
 }
@@ -624,7 +727,10 @@ scatter_kernel(GridView g, QueueView qv, GradView gr, int64_t gsh_stride, int64_
     const int D = g.sh_dim, B = g.basis_dim;
     int ce[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) ce[e] = (qi * 4 + e < D) ? (qi * 4 + e) / B : -1;
+    for (int e = 0; e < 4; ++e) {   // channel j belongs to colour j / B (j < 3B: two compares, no division)
+        const int j = qi * 4 + e;
+        ce[e] = (j < D) ? (j >= B) + (j >= 2 * B) : -1;
+    }
     const bool quad_on = qi * 4 < D;
     const int groups = (gridDim.x * blockDim.x) >> 3;
     const int per = (n + groups - 1) / groups;
@@ -675,43 +781,68 @@ scatter_kernel(GridView g, QueueView qv, GradView gr, int64_t gsh_stride, int64_
         }
     };
 
+    // records s .. s+QM_RING-1 of this group's run are on their way into shared memory: lane q < 5
+    // copies 16-byte chunk q (links, links, pos + weight, ray, dL/dcolour + dL/dsigma)
+    __shared__ int4 ring[SAMPLE_THREADS / 8][QM_RING][5];
+    int4 (*const my_ring)[5] = ring[threadIdx.x >> 3];
+    const unsigned gmask = 0xffu << (threadIdx.x & 24);
+    auto stage = [&](int s) {
+        if (s < s1 && qi < 5)
+            cp_async16(&my_ring[(s - s0) % QM_RING][qi],
+                       reinterpret_cast<const int4*>(qv.rec + region_index<MODE>(rg, s, cur0)) + qi);
+        cp_async_commit();   // (an empty group keeps the count per iteration uniform)
+    };
+#pragma unroll
+    for (int k = 0; k < QM_RING; ++k) stage(s0 + k);
+
+    int32_t lown = -1;  // SLOTS: this lane's corner link of the pending cell (pa / pb are not kept)
     for (int s = s0; s < s1; ++s) {
-        const Record* r = qv.rec + region_index<MODE>(rg, s, cur0);
-        const int4 la = __ldcg(reinterpret_cast<const int4*>(r));
-        const int4 lb = __ldcg(reinterpret_cast<const int4*>(r) + 1);
-        const float4 pw = __ldcg(reinterpret_cast<const float4*>(r) + 2);
-        const float4 gg = __ldcg(reinterpret_cast<const float4*>(r) + 4);
-        const int ray = __ldcg(&r->ray);
+        cp_async_wait<QM_RING - 1>();   // this lane's chunk of record s has landed ...
+        __syncwarp(gmask);              // ... and so have the other lanes'
+        const int4(&slot)[5] = my_ring[(s - s0) % QM_RING];
+        const float4 pw = *reinterpret_cast<const float4*>(&slot[2]);
+        const int ray = slot[3].w;
+        const float4 gg = *reinterpret_cast<const float4*>(&slot[4]);
+        const int32_t ln = reinterpret_cast<const int32_t*>(&slot[0])[qi];   // corner qi of record s
+        int4 la = make_int4(0, 0, 0, 0), lb = la;
+        if (!SLOTS) {
+            la = slot[0];
+            lb = slot[1];
+        }
+        __syncwarp(gmask);              // everybody has read the slot: refill it
+        stage(s + QM_RING);
         if (SLAB && pw.w < 0.f) continue;  // dead sample
         if (ray != cur_ray) {
             Y = __ldcg(qv.ray_Y + (int64_t)ray * 8 + qi);
             cur_ray = ray;
         }
-        const bool same = have && la.x == pa.x && la.y == pa.y && la.z == pa.z && la.w == pa.w &&
-                          lb.x == pb.x && lb.y == pb.y && lb.z == pb.z && lb.w == pb.w;
+        // same cell as the pending one?  SLOTS (64-register cap): each lane compares its own corner and
+        // the group votes; otherwise all eight links are at hand for the flush anyway
+        bool same;
+        if (SLOTS) same = have && (__ballot_sync(gmask, ln == lown) & gmask) == gmask;
+        else same = have && la.x == pa.x && la.y == pa.y && la.z == pa.z && la.w == pa.w &&
+                    lb.x == pb.x && lb.y == pb.y && lb.z == pb.z && lb.w == pb.w;
         if (!same) {
             if (have) flush();
-            pa = la;
-            pb = lb;
+            if (!SLOTS) {
+                pa = la;
+                pb = lb;
+            }
+            lown = ln;
             have = true;
             dacc = 0.f;
 #pragma unroll
             for (int q = 0; q < 8; ++q)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) acc[q][e] = 0.f;
-            {  // lane q pulls the grad row of corner q towards L2 for the flush one sample later
-                int32_t ln = la.x;
-                const int32_t Ls[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
-#pragma unroll
-                for (int q = 1; q < 8; ++q) ln = (qi == q) ? Ls[q] : ln;
-                if (SLOTS) {  // rank query for this lane's corner; the slot row is prefetched instead
-                    sown = ln >= 0 ? slot_of(sm, ln) : -1;
-                    if (sown >= 0) prefetch_l2(sm.grad + (size_t)(unsigned)sown * (unsigned)sm.width);
-                } else if (ln >= 0) {
-                    const float* row = gr.grad_sh + (int64_t)ln * gsh_stride;
-                    prefetch_l2(row);
-                    prefetch_l2(row + (D - 1));
-                }
+            // lane q pulls the grad row of corner q towards L2 for the flush one sample later
+            if (SLOTS) {  // rank query for this lane's corner; the slot row is prefetched instead
+                sown = ln >= 0 ? slot_of(sm, ln) : -1;
+                if (sown >= 0) prefetch_l2(sm.grad + (size_t)(unsigned)sown * (unsigned)sm.width);
+            } else if (ln >= 0) {
+                const float* row = gr.grad_sh + (int64_t)ln * gsh_stride;
+                prefetch_l2(row);
+                prefetch_l2(row + (D - 1));
             }
         }
         float wq[8];
@@ -748,8 +879,8 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 }  // namespace
 
 size_t queue_workspace_bytes(int64_t n_rays, int64_t records) {
-    return 256 + align_up((size_t)n_rays * 4, 256) * 3 + align_up((size_t)n_rays * 8 * 16, 256) +
-           (size_t)records * sizeof(Record);
+    return 256 + align_up((size_t)n_rays * 4, 256) * 4 + align_up((size_t)n_rays * 8 * 16, 256) +
+           align_up((size_t)n_rays * BLK_TABLE * 8, 256) + (size_t)records * sizeof(Record);
 }
 
 // Carves the workspace; false if it cannot hold even a minimal queue.
@@ -771,6 +902,10 @@ static bool carve_queue(void* workspace, size_t workspace_bytes, int64_t n_rays,
     p += align_up((size_t)n_rays * 4, 256);
     qv.ray_Y = reinterpret_cast<float4*>(p);
     p += align_up((size_t)n_rays * 8 * 16, 256);
+    qv.blk_table = reinterpret_cast<int2*>(p);
+    p += align_up((size_t)n_rays * BLK_TABLE * 8, 256);
+    qv.ray_nblk = reinterpret_cast<int*>(p);
+    p += align_up((size_t)n_rays * 4, 256);
     qv.rec = reinterpret_cast<Record*>(p);
     const size_t cap = (workspace_bytes - fixed) / sizeof(Record);
     qv.capacity = (int)(cap > (size_t)0x7ff00000 ? (size_t)0x7ff00000 : cap);
@@ -948,6 +1083,8 @@ bool carve_ship(void* workspace, size_t bytes, int64_t n_rays_global, int n_slab
     qv.ray_logT = reinterpret_cast<float*>(p);
     p += align_up((size_t)n_rays_global * 4, 256);
     qv.ray_accum = nullptr;
+    qv.blk_table = nullptr;
+    qv.ray_nblk = nullptr;
     qv.ray_Y = reinterpret_cast<float4*>(p);
     p += align_up((size_t)n_rays_global * 8 * 16, 256);
     qv.rec = reinterpret_cast<Record*>(p);

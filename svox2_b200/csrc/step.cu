@@ -250,13 +250,19 @@ __device__ __forceinline__ void rmsprop_update(float& d, float& rms, float g, fl
     d = fmaxf(__fsub_rn(d, __fdiv_rn(__fmul_rn(lr, g), __fadd_rn(sqrtf(rms), eps))), minval);
 }
 
+// A/B on B200 (profiles/r2_ab_variants.txt): 2 passes in flight at ptxas' 64 registers (8 CTAs of 128
+// threads = 32 warps per SM) against 1 pass capped at 40 registers (12 CTAs = 48 warps per SM, no
+// spills): the latter is 3 us per step faster in two separate runs; 48 / 32 registers spill and lose.
 #ifndef SLOT_OPT_PASSES
-#define SLOT_OPT_PASSES 2
+#define SLOT_OPT_PASSES 1
 #endif
 #ifndef SLOT_OPT_BLOCKS
-#define SLOT_OPT_BLOCKS 8
+#define SLOT_OPT_BLOCKS 12
 #endif
-__global__ void __launch_bounds__(OPT_THREADS)
+#ifndef SLOT_OPT_MINBLOCKS
+#define SLOT_OPT_MINBLOCKS 12
+#endif
+__global__ void __launch_bounds__(OPT_THREADS, SLOT_OPT_MINBLOCKS)
 slot_rmsprop_kernel(SlotOptArgs a) {
     constexpr int U = SLOT_OPT_PASSES;
     const int lane = threadIdx.x & 31;
