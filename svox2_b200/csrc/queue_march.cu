@@ -53,6 +53,9 @@ namespace {
 // 0.376 -> 0.400 ms) and keeps 80 registers.
 #define QM_SCATTER_BLOCKS 4
 #endif
+#ifndef QM_DENSE_SCATTER_BLOCKS
+#define QM_DENSE_SCATTER_BLOCKS 3
+#endif
 
 constexpr int BLK_TABLE = 64;      // blocks per ray kept in the table (later ones: chain only)
 constexpr int TRACE_THREADS = 64;
@@ -440,8 +443,14 @@ __device__ __forceinline__ void corner_weights(float px, float py, float pz, flo
 // ---------------------------------------------------------------------------------------
 // K2: gather + colours, 8 lanes per sample
 // ---------------------------------------------------------------------------------------
+#ifndef QM_SHADE_BLOCKS
+// min resident CTAs per SM asked of ptxas: 4 = a 64-register cap.  The variant that also marks the
+// touched rows needs 79 registers on its own (3 CTAs per SM); capped it spills 36 bytes and the fused
+// step gains 9 us (profiles/r2_ab_variants.txt, sh4).  The plain variant needs 62 either way.
+#define QM_SHADE_BLOCKS 4
+#endif
 template <bool VEC, int MODE, bool MARK>
-__global__ void __launch_bounds__(SAMPLE_THREADS)
+__global__ void __launch_bounds__(SAMPLE_THREADS, QM_SHADE_BLOCKS)
 shade_kernel(GridView g, QueueView qv, float* __restrict__ rgb_out, SlabView sl, SlotMap sm) {
     constexpr bool SLAB = MODE == 1, SHIP = MODE == 2;
     if (*qv.overflow) return;
@@ -714,7 +723,7 @@ seed_kernel(Opts opt, MarchArgs a, QueueView qv, SlabView sl) {
 // registers; consecutive samples that fall into the same cell (~35 % at step 0.5) are merged
 // before the REDs leave the SM.  The basis table of the ray is re-read only when the ray changes.
 template <bool VEC, int MODE, bool SLOTS>
-__global__ void __launch_bounds__(SAMPLE_THREADS, SLOTS ? QM_SCATTER_BLOCKS : 3)
+__global__ void __launch_bounds__(SAMPLE_THREADS, SLOTS ? QM_SCATTER_BLOCKS : QM_DENSE_SCATTER_BLOCKS)
 scatter_kernel(GridView g, QueueView qv, GradView gr, int64_t gsh_stride, int64_t gd_stride, SlotMap sm) {
     constexpr bool SLAB = MODE == 1;
     if (*qv.overflow) return;
@@ -737,7 +746,7 @@ scatter_kernel(GridView g, QueueView qv, GradView gr, int64_t gsh_stride, int64_
     const int gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     const int s0 = min(n, gid * per), s1 = min(n, s0 + per);
 
-    int4 pa = make_int4(0, 0, 0, 0), pb = make_int4(0, 0, 0, 0);  // links of the pending cell
+    int32_t lown = -1;  // this lane's corner link (corner qi) of the pending cell
     float acc[8][4];
     float dacc = 0.f;
     bool have = false;
@@ -746,11 +755,10 @@ scatter_kernel(GridView g, QueueView qv, GradView gr, int64_t gsh_stride, int64_
 
     int sown = -1;  // SLOTS: slot of this lane's corner of the pending cell
     auto flush = [&]() {
-        const int32_t L[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+        const unsigned gm = 0xffu << (threadIdx.x & 24);
+        const int lane0 = threadIdx.x & 24;
         if (SLOTS) {
             // compact gradient rows: SH and density gradients of a row land in ONE slot row
-            const unsigned gm = 0xffu << (threadIdx.x & 24);
-            const int lane0 = threadIdx.x & 24;
             float* const base = sm.grad + 4 * qi;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -764,19 +772,18 @@ scatter_kernel(GridView g, QueueView qv, GradView gr, int64_t gsh_stride, int64_
                 *reinterpret_cast<uint16_t*>(sm.flags + 2 * (size_t)(unsigned)sown) = 0x0101;  // both masks
             }
         } else {
-            if (quad_on) {
+            // (the eight links of the cell live one per lane: a shuffle per corner instead of eight
+            // registers per lane)
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    if (L[q] >= 0)
-                        red_quad<VEC>(gr.grad_sh + (int64_t)L[q] * gsh_stride + 4 * qi, qi, D, acc[q][0],
-                                      acc[q][1], acc[q][2], acc[q][3]);
+            for (int q = 0; q < 8; ++q) {
+                const int32_t Lq = __shfl_sync(gm, lown, lane0 + q);
+                if (quad_on && Lq >= 0)
+                    red_quad<VEC>(gr.grad_sh + (int64_t)Lq * gsh_stride + 4 * qi, qi, D, acc[q][0],
+                                  acc[q][1], acc[q][2], acc[q][3]);
             }
-            int32_t Lown = L[0];
-#pragma unroll
-            for (int q = 1; q < 8; ++q) Lown = (qi == q) ? L[q] : Lown;
-            if (Lown >= 0) {
-                atomicAdd(gr.grad_density + (int64_t)Lown * gd_stride, dacc);
-                if (gr.mask) gr.mask[Lown] = 1;
+            if (lown >= 0) {
+                atomicAdd(gr.grad_density + (int64_t)lown * gd_stride, dacc);
+                if (gr.mask) gr.mask[lown] = 1;
             }
         }
     };
@@ -795,7 +802,6 @@ scatter_kernel(GridView g, QueueView qv, GradView gr, int64_t gsh_stride, int64_
 #pragma unroll
     for (int k = 0; k < QM_RING; ++k) stage(s0 + k);
 
-    int32_t lown = -1;  // SLOTS: this lane's corner link of the pending cell (pa / pb are not kept)
     for (int s = s0; s < s1; ++s) {
         cp_async_wait<QM_RING - 1>();   // this lane's chunk of record s has landed ...
         __syncwarp(gmask);              // ... and so have the other lanes'
@@ -804,11 +810,6 @@ scatter_kernel(GridView g, QueueView qv, GradView gr, int64_t gsh_stride, int64_
         const int ray = slot[3].w;
         const float4 gg = *reinterpret_cast<const float4*>(&slot[4]);
         const int32_t ln = reinterpret_cast<const int32_t*>(&slot[0])[qi];   // corner qi of record s
-        int4 la = make_int4(0, 0, 0, 0), lb = la;
-        if (!SLOTS) {
-            la = slot[0];
-            lb = slot[1];
-        }
         __syncwarp(gmask);              // everybody has read the slot: refill it
         stage(s + QM_RING);
         if (SLAB && pw.w < 0.f) continue;  // dead sample
@@ -816,18 +817,10 @@ scatter_kernel(GridView g, QueueView qv, GradView gr, int64_t gsh_stride, int64_
             Y = __ldcg(qv.ray_Y + (int64_t)ray * 8 + qi);
             cur_ray = ray;
         }
-        // same cell as the pending one?  SLOTS (64-register cap): each lane compares its own corner and
-        // the group votes; otherwise all eight links are at hand for the flush anyway
-        bool same;
-        if (SLOTS) same = have && (__ballot_sync(gmask, ln == lown) & gmask) == gmask;
-        else same = have && la.x == pa.x && la.y == pa.y && la.z == pa.z && la.w == pa.w &&
-                    lb.x == pb.x && lb.y == pb.y && lb.z == pb.z && lb.w == pb.w;
+        // same cell as the pending one?  Each lane compares its own corner and the group votes.
+        const bool same = have && (__ballot_sync(gmask, ln == lown) & gmask) == gmask;
         if (!same) {
             if (have) flush();
-            if (!SLOTS) {
-                pa = la;
-                pb = lb;
-            }
             lown = ln;
             have = true;
             dacc = 0.f;
