@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--workload", default="c3")
+    ap.add_argument("--e2e", action="store_true", help="profile bench.py's end-to-end loop (pinned H2D per step, loss D2H)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "timeline.json"))
     args = ap.parse_args()
     import svox2_b200 as sv
@@ -53,10 +54,50 @@ def main():
         trainer.step(sv.Rays(*batches[i % bench.POOL][:2]), batches[i % bench.POOL][2], global_batch=bench.BATCH)
     torch.cuda.synchronize()
     from torch.profiler import ProfilerActivity, profile
+    def e2e_loop(steps):    # the loop of bench.py's e2e leg
+        host = [tuple(x.cpu().pin_memory() for x in b) for b in batches]
+        copy_stream, loss_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        main_stream = torch.cuda.current_stream(dev)
+        stage = [tuple(torch.empty_like(x, device=dev) for x in host[0]) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        free = [torch.cuda.Event() for _ in range(2)]
+        loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+        loss_ev = [torch.cuda.Event() for _ in range(2)]
+
+        def prefetch(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(free[i & 1])
+                for dst, src in zip(stage[i & 1], host[i % bench.POOL]):
+                    dst.copy_(src, non_blocking=True)
+                ready[i & 1].record(copy_stream)
+
+        for ev in free:
+            ev.record(main_stream)
+        prefetch(0)
+        for i in range(steps):
+            if i + 1 < steps:
+                prefetch(i + 1)
+            main_stream.wait_event(ready[i & 1])
+            o, d, g = stage[i & 1]
+            trainer.step(sv.Rays(o, d), g, global_batch=bench.BATCH)
+            free[i & 1].record(main_stream)
+            with torch.cuda.stream(loss_stream):
+                loss_stream.wait_event(free[i & 1])
+                loss_host[i & 1].copy_(trainer.last_mse, non_blocking=True)
+                loss_ev[i & 1].record(loss_stream)
+            if i > 0:
+                loss_ev[(i - 1) & 1].synchronize()
+        torch.cuda.synchronize()
+
+    if args.e2e:
+        e2e_loop(4)
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        for i in range(args.steps):
-            trainer.step(sv.Rays(*batches[i % bench.POOL][:2]), batches[i % bench.POOL][2],
-                         global_batch=bench.BATCH)
+        if args.e2e:
+            e2e_loop(args.steps)
+        else:
+            for i in range(args.steps):
+                trainer.step(sv.Rays(*batches[i % bench.POOL][:2]), batches[i % bench.POOL][2],
+                             global_batch=bench.BATCH)
         torch.cuda.synchronize()
     evs = []
     for e in prof.profiler.kineto_results.events():     # raw CUPTI activity records (stream ids included)
@@ -83,7 +124,7 @@ def main():
         busy_end = base
         idle = 0.0
         for e in one:
-            tag = "main" if e["stream"] == main_stream else "side"
+            tag = "main" if e["stream"] == main_stream else ("s%s" % e["stream"])[:4]
             print("  %-4s +%8.1f us  %7.1f us  %s" % (tag, e["start_us"] - base, e["dur_us"], e["name"][:70]))
             if tag == "main":
                 idle += max(0.0, e["start_us"] - busy_end)
