@@ -246,8 +246,13 @@ tv_grad_sparse_kernel(const int32_t* __restrict__ links, int X, int Y, int Z,
 #ifndef TV_VEC_PASSES
 #define TV_VEC_PASSES 2
 #endif
+#ifdef TV_VEC_MINBLOCKS      // A/B: register cap through resident CTAs per SM
+template <bool SLOTS>
+__global__ void __launch_bounds__(TV_THREADS, TV_VEC_MINBLOCKS)
+#else
 template <bool SLOTS>
 __global__ void __launch_bounds__(TV_THREADS)
+#endif
 tv_grad_sparse_vec_kernel(const int32_t* __restrict__ links, int X, int Y, int Z,
                           const float* __restrict__ data, int64_t stride,
                           const int32_t* __restrict__ rand_cells, int64_t cell_start, int start_dim,
