@@ -530,15 +530,13 @@ def run_ours(args):
     for i in range(args.warmup):
         step(*batches[i % POOL])
     barrier()
-    # single GPU: the end-to-end loop below repeats the SAME K training steps as the device-resident
+    # the end-to-end loop below repeats the SAME K training steps as the device-resident
     # loop (state after the warm-up restored, same TV seeds), so that the two numbers differ by the
     # end-to-end overhead only.  (A grid that has trained K steps longer is a different workload: the
     # optimiser alone went from 0.23 to 0.28-0.33 ms per step over 400 steps in tools/timeline.py.)
-    snapshot = None
-    if world == 1:
-        snapshot = {k: getattr(grid, k).detach().clone() for k in ("density_data", "sh_data", "density_rms", "sh_rms")
-                    if getattr(grid, k, None) is not None}
-        rng_state = np.random.get_state()
+    snapshot = {k: getattr(grid, k).detach().clone() for k in ("density_data", "sh_data", "density_rms", "sh_rms")
+                if getattr(grid, k, None) is not None}    # (N > 1: every rank its own arrays, slab and halo rows alike)
+    rng_state = np.random.get_state()
     if sampler:
         sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -554,12 +552,13 @@ def run_ours(args):
         trainer.check_overflow()
     touched = (int(grid.sparse_grad_indexer.sum()), int(grid.sparse_sh_grad_indexer.sum()))
 
-    if snapshot is not None:
-        with torch.no_grad():
-            for k, v in snapshot.items():
-                getattr(grid, k).detach().copy_(v)
-        np.random.set_state(rng_state)
-        snapshot = None
+    barrier()
+    with torch.no_grad():
+        for k, v in snapshot.items():
+            getattr(grid, k).detach().copy_(v)
+    np.random.set_state(rng_state)
+    snapshot = None
+    barrier()
     # end to end: pinned host inputs -> H2D, step, D2H of the loss, every step.  The loss of step i
     # lands in a double-buffered pinned scalar and is read while step i+1 is already enqueued (the
     # driver in svox2_b200/train.py never blocks on the step it just launched either).
@@ -725,7 +724,7 @@ def run_ours(args):
                 "ms_per_step": ms_e2e / args.steps, "last_loss": loss_val,
                 "loss_readback": "every step, one step late (double-buffered pinned scalar, D2H on a side stream behind the step)",
                 "h2d": "pinned host -> double-buffered device staging on a copy stream, one step ahead",
-                "state": "parameters / RMS state / TV seeds of the start of the device-timed loop restored first: the same K steps" if world == 1 else "continues from the state the device-timed loop left"},
+                "state": "parameters / RMS state / TV seeds of the start of the device-timed loop restored first: the same K steps"},
         "gpu_launches": trainer.kernels_per_step * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "fused call: trace + shade + seed + scatter kernels",
