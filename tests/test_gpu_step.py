@@ -101,3 +101,46 @@ def test_fused_step_queue_overflow_is_reported():
     tr.step(rays, gt)
     tr.check_overflow()             # 64 per ray is plenty for this scene
     assert tr._step_ws.status()[0][0] > 0
+
+
+def test_rays_longer_than_the_block_table():
+    """A tube grid of 2304 cells in z crossed end to end: ~120 record blocks per ray, more than the
+    64 entries of K1's per-ray block table, so K3 goes table -> chain inside one ray.  The reference
+    result is the operator sequence on a second grid: its queue (512 records per ray on average)
+    overflows for these rays and the lattice kernel -- a different implementation -- redoes the batch."""
+    sc = make_scene(reso=(6, 6, 2304), basis_dim=4, seed=11, n_rays=48, sparse=False, accel=False)
+    rng = np.random.default_rng(5)
+    n = 48
+    o = np.zeros((n, 3), np.float32)
+    o[:, :2] = rng.uniform(-0.3, 0.3, (n, 2))
+    o[:, 2] = -1.02     # (the march never goes past t = 2000 grid units, render_util.cuh:581: start at the face)
+    d = np.zeros((n, 3), np.float32)
+    d[:, :2] = rng.uniform(-0.02, 0.02, (n, 2))
+    d[:, 2] = 1.0
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    sc["origins"], sc["dirs"] = o, d.astype(np.float32)
+    sc["rgb_gt"] = rng.uniform(0, 1, (n, 3)).astype(np.float32)
+    sc["density"] = (sc["density"] * 0.05).astype(np.float32)     # keep the rays alive to the far end
+    a, b = make_grid(sv, sc), make_grid(sv, sc)
+    for g in (a, b):
+        set_opt(g, **OPTS["default"])
+    hyper = dict(HYPER, tv_sparsity=0.01)
+    fused = ShardedTrainer(a, fused=True, **hyper)
+    plain = ShardedTrainer(b, fused=False, **hyper)
+    rays, gt = sv.Rays(t(sc["origins"]), t(sc["dirs"])), t(sc["rgb_gt"])
+    counters = torch.zeros(4, dtype=torch.int64, device="cuda")
+    from svox2_b200 import csrc as C
+    C.volume_render_cuvol(a._to_cpp(), rays._to_cpp(), a.opt._to_cpp(), _counters=counters)
+    assert counters[2].item() / n > 64 * 32, "the scene must give more than 64 full blocks per ray"
+    np.random.seed(3)
+    ra = fused.step(rays, gt)
+    np.random.seed(3)
+    rb = plain.step(rays, gt)
+    torch.cuda.synchronize()
+    st = fused.export_masks()
+    assert st[1] == 0 and st[2] == 0                                        # the fused step's queue held them
+    assert (ra - rb).abs().max().item() < 1e-5
+    assert torch.equal(a.sparse_grad_indexer, b.sparse_grad_indexer)
+    assert torch.equal(a.sparse_sh_grad_indexer, b.sparse_sh_grad_indexer)
+    assert rel_err(_np(a.density_rms), _np(b.density_rms)) < 1e-4           # rms = g^2 after the first step
+    assert rel_err(_np(a.sh_rms), _np(b.sh_rms)) < 1e-4
