@@ -1,7 +1,7 @@
 // Fused train step: opt/opt.py's inner loop (opt.py:474-603) as ONE C-ABI call on a compact
 // per-step gradient buffer (slots.cuh).
 //
-//   reference (per batch)                                  here (one call, 10 launches, no host sync)
+//   reference (per batch)                                  here (one call, 11 launches, no host sync)
 //   ----------------------------------------------------   -------------------------------------------
 //   volume_render_fused   (svox2.py:1072-1142)              clear | trace | shade (+ touched-row bits)
 //   inplace_tv_grad       (svox2.py:1731-1766)              tv_mark | rank scan (slot numbering)
